@@ -1,0 +1,74 @@
+"""ctypes binding of the C-ABI library (``include/pitchextractor_b200.h``).
+
+The product path is CUDA-only: if ``libpe_b200.so`` is missing or a call fails, a ``RuntimeError`` is raised --
+there is no CPU / eager fallback.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpe_b200.so")
+
+PE_OUT_F32, PE_OUT_BF16, PE_OUT_F32_ATOMIC = 0, 1, 2
+PE_ACT_NONE, PE_ACT_GELU = 0, 1
+PE_AUX_NONE, PE_AUX_ADD, PE_AUX_GELU_GRAD = 0, 1, 2
+
+_ERRORS = {-1: "bad shape / argument", -2: "workspace too small", -3: "device is not sm_100 (B200)",
+           -4: "CUDA driver entry point unavailable", -5: "kernel launch failed"}
+
+
+class Epilogue(ctypes.Structure):
+    _fields_ = [
+        ("out", ctypes.c_void_p), ("ldc", ctypes.c_longlong), ("out_mode", ctypes.c_int), ("act", ctypes.c_int),
+        ("out2", ctypes.c_void_p), ("ld2", ctypes.c_longlong), ("bias", ctypes.c_void_p),
+        ("aux", ctypes.c_void_p), ("ld_aux", ctypes.c_longlong), ("aux_mode", ctypes.c_int),
+        ("drop_thresh", ctypes.c_uint), ("drop_scale", ctypes.c_float), ("drop_seed", ctypes.c_ulonglong),
+        ("alpha", ctypes.c_float), ("stats", ctypes.c_void_p),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                "pitchextractor_b200: %s not found -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)" % LIB_PATH)
+        _lib = ctypes.CDLL(LIB_PATH)
+        _lib.pe_version.restype = ctypes.c_int
+    return _lib
+
+
+def ptr(t):
+    """Device pointer of a tensor (or None)."""
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError("pitchextractor_b200.%s failed: %s (rc=%d)" % (what, _ERRORS.get(rc, "unknown"), rc))
+
+
+def call(name, *args):
+    fn = getattr(lib(), name)
+    fn.restype = ctypes.c_int
+    check(fn(*args), name)
+
+
+def drop_thresh(p_drop):
+    """uint32 keep threshold and scale for dropout probability p_drop (0 disables)."""
+    if p_drop <= 0.0:
+        return 0, 1.0
+    keep = 1.0 - p_drop
+    return min(int(keep * 4294967296.0), 4294967295), 1.0 / keep

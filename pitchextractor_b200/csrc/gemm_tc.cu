@@ -1,0 +1,496 @@
+// tcgen05 / TMEM / TMA tile engine: one warp-specialised kernel that serves
+//   mode 0  plain GEMM          D[M,N] = sum_k A(m,k) B(n,k)            (linear fwd / dgrad / wgrad)
+//   mode 1  3x3 conv (+1x1)     implicit GEMM over NHWC pixels, taps walked by shifted 4-D TMA boxes
+//   mode 2  conv weight grad    contraction over pixels, both operands MN-major straight from NHWC
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warps 2..5 = epilogue
+// (TMEM -> registers -> fused bias / GELU / dropout / residual -> global).  Accumulators live in TMEM.
+#include "common.cuh"
+#include "../../include/pitchextractor_b200.h"
+
+namespace pe {
+
+constexpr int kBlockM = 128;
+constexpr int kRowBytes = 128;             // one swizzle-128B row: 64 bf16 (or 32 tf32) along the contiguous dim
+constexpr int kATileBytes = kBlockM * kRowBytes;  // 16 KB
+constexpr int kNumThreads = 192;
+
+struct TcParams {
+  int mode;  // 0 gemm, 1 conv fwd, 2 conv wgrad
+  int kind;  // 0 bf16, 1 tf32
+  int a_mn, b_mn;
+  int M, N;        // output extents used for masking
+  int block_n;     // columns per CTA tile (multiple of 16, <= 256)
+  int tmem_cols;   // power of two >= max(32, block_n)
+  int stages;
+  int kb_total, kb_per_split;
+  int a_boxes, b_boxes;  // number of 64-wide TMA boxes for MN-major operands
+  // conv geometry
+  int H, W, tw, th, tiles_w, tiles_h;
+  int c1_chunks, c2_chunks;
+  int taps;  // wgrad: 9 or 1
+  pe_epilogue ep;
+};
+
+struct TileCoord {
+  int m0, n0;           // gemm: first row / col of the tile
+  int b, h0, w0;        // conv: image index and patch origin
+};
+
+__device__ __forceinline__ void decode_conv_tile(const TcParams& p, int tile, int& b, int& h0, int& w0) {
+  const int per_img = p.tiles_h * p.tiles_w;
+  b = tile / per_img;
+  const int r = tile - b * per_img;
+  h0 = (r / p.tiles_w) * p.th;
+  w0 = (r % p.tiles_w) * p.tw;
+}
+
+__global__ void __launch_bounds__(kNumThreads, 1)
+tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_a2,
+               const __grid_constant__ CUtensorMap tma_b, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-B alignment is required by the 128-B swizzle; dynamic smem base is only guaranteed 16 B.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_tile_bytes = p.block_n * kRowBytes;
+  const int stage_bytes = kATileBytes + b_tile_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tmem_full_bar = empty_bar + p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int kb_end = min(p.kb_total, kb_begin + p.kb_per_split);
+  const int num_kb = kb_end - kb_begin;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    if (p.mode == 1 && p.c2_chunks > 0) tma_prefetch_desc(&tma_a2);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile coordinates
+  int m0 = 0, n0 = 0, img = 0, h0 = 0, w0 = 0, tap = 0;
+  if (p.mode == 0) {
+    m0 = blockIdx.x * kBlockM;
+    n0 = blockIdx.y * p.block_n;
+  } else if (p.mode == 1) {
+    decode_conv_tile(p, blockIdx.x, img, h0, w0);
+    n0 = blockIdx.y * p.block_n;
+  } else {
+    m0 = blockIdx.x * kBlockM;  // Cout tile
+    tap = blockIdx.y;           // 0..taps-1
+  }
+
+  if (num_kb > 0) {
+    if (warp == 0) {
+      // ------------------------------------------------------------------ TMA producer
+      if (lane == 0) {
+        const int elems_per_row = p.kind == 0 ? 64 : 32;
+        for (int i = 0; i < num_kb; ++i) {
+          const int kb = kb_begin + i;
+          const int s = i % p.stages;
+          const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          uint8_t* sa = smem + (size_t)s * stage_bytes;
+          uint8_t* sb = sa + kATileBytes;
+          mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+          if (p.mode == 0) {
+            const int k0 = kb * elems_per_row;
+            if (!p.a_mn) {
+              tma_load_2d(&tma_a, &full_bar[s], sa, k0, m0);
+            } else {
+              for (int j = 0; j < p.a_boxes; ++j)
+                tma_load_2d(&tma_a, &full_bar[s], sa + j * (elems_per_row * kRowBytes), m0 + j * elems_per_row, k0);
+            }
+            if (!p.b_mn) {
+              tma_load_2d(&tma_b, &full_bar[s], sb, k0, n0);
+            } else {
+              for (int j = 0; j < p.b_boxes; ++j)
+                tma_load_2d(&tma_b, &full_bar[s], sb + j * (elems_per_row * kRowBytes), n0 + j * elems_per_row, k0);
+            }
+          } else if (p.mode == 1) {
+            const int main_kb = 9 * p.c1_chunks;
+            if (kb < main_kb) {
+              const int t = kb / p.c1_chunks;
+              const int c0 = (kb - t * p.c1_chunks) * 64;
+              tma_load_4d(&tma_a, &full_bar[s], sa, c0, w0 + (t % 3) - 1, h0 + (t / 3) - 1, img);
+            } else {
+              tma_load_4d(&tma_a2, &full_bar[s], sa, (kb - main_kb) * 64, w0, h0, img);
+            }
+            tma_load_2d(&tma_b, &full_bar[s], sb, kb * 64, n0);
+          } else {
+            // k-block = one 64-pixel patch; A = dy (Cout-major), B = shifted x (Cin-major)
+            int pb, ph0, pw0;
+            decode_conv_tile(p, kb, pb, ph0, pw0);
+            const int dh = p.taps == 9 ? (tap / 3) - 1 : 0;
+            const int dw = p.taps == 9 ? (tap % 3) - 1 : 0;
+            for (int j = 0; j < p.a_boxes; ++j)
+              tma_load_4d(&tma_a, &full_bar[s], sa + j * (64 * kRowBytes), m0 + j * 64, pw0, ph0, pb);
+            for (int j = 0; j < p.b_boxes; ++j)
+              tma_load_4d(&tma_b, &full_bar[s], sb + j * (64 * kRowBytes), j * 64, pw0 + dw, ph0 + dh, pb);
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ------------------------------------------------------------------ MMA issuer
+      if (lane == 0) {
+        const uint32_t idesc =
+            umma_idesc(p.kind == 0 ? UMMA_BF16 : UMMA_TF32, kBlockM, p.block_n, p.a_mn, p.b_mn);
+        // bytes to advance the descriptor start address per UMMA_K step (16 bf16 / 8 tf32)
+        const int k_rows = p.kind == 0 ? 16 : 8;
+        const uint32_t a_step = p.a_mn ? (uint32_t)(k_rows * kRowBytes) : 32u;
+        const uint32_t b_step = p.b_mn ? (uint32_t)(k_rows * kRowBytes) : 32u;
+        const int block_k_rows = p.kind == 0 ? 64 : 32;
+        // MN-major: 64-wide (bf16) MN blocks are separate TMA boxes, block_k_rows * 128 B apart
+        const uint32_t a_lbo = p.a_mn ? (uint32_t)(block_k_rows * kRowBytes) : 16u;
+        const uint32_t b_lbo = p.b_mn ? (uint32_t)(block_k_rows * kRowBytes) : 16u;
+        for (int i = 0; i < num_kb; ++i) {
+          const int s = i % p.stages;
+          const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t sb = sa + kATileBytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = umma_desc_sw128(sa + k * a_step, a_lbo, 1024);
+            const uint64_t db = umma_desc_sw128(sb + k * b_step, b_lbo, 1024);
+            if (p.kind == 0)
+              tc_mma_bf16(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            else
+              tc_mma_tf32(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
+        }
+        tc_commit(tmem_full_bar);
+      }
+    }
+  }
+
+  if (warp >= 2) {
+    // -------------------------------------------------------------------- epilogue
+    const pe_epilogue& ep = p.ep;
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;
+    long long grow;  // global output row
+    bool row_ok;
+    if (p.mode == 1) {
+      const int h = h0 + r / p.tw, w = w0 + r % p.tw;
+      row_ok = (h < p.H) && (w < p.W);
+      grow = ((long long)img * p.H + h) * p.W + w;
+    } else {
+      grow = m0 + r;
+      row_ok = grow < p.M;
+    }
+    const int col_base = (p.mode == 2) ? 0 : n0;
+    const long long out_col_off = (p.mode == 2) ? (long long)tap * p.N : 0;  // wgrad: tap-major weight columns
+    if (num_kb > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+    }
+    const int nchunks = p.block_n / 32 + ((p.block_n % 32) ? 1 : 0);
+    for (int c = 0; c < nchunks; ++c) {
+      uint32_t v[32];
+      if (num_kb > 0) {
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+      if (!row_ok) continue;
+      const int col0 = col_base + c * 32;
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * ep.alpha;
+      if (ep.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.N) f[j] += __ldg(ep.bias + col0 + j);
+      }
+      const bool full = (col0 + 32 <= p.N) && (c * 32 + 32 <= p.block_n);
+      if (ep.act == PE_ACT_GELU) {
+        if (ep.out2) {
+          __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(ep.out2) + grow * ep.ld2 + col0;
+          if (full) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8)
+              *reinterpret_cast<uint4*>(o2 + j) = make_uint4(pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]),
+                                                             pack_bf16(f[j + 4], f[j + 5]), pack_bf16(f[j + 6], f[j + 7]));
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N && c * 32 + j < p.block_n) o2[j] = __float2bfloat16(f[j]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+      }
+      if (ep.drop_thresh) {
+        const unsigned long long e0 = (unsigned long long)grow * (unsigned long long)p.N + (unsigned long long)col0;
+        if ((e0 & 3ull) == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const uint4 rb = dropout_bits4(ep.drop_seed, (e0 + j) >> 2);
+            f[j + 0] = rb.x < ep.drop_thresh ? f[j + 0] * ep.drop_scale : 0.f;
+            f[j + 1] = rb.y < ep.drop_thresh ? f[j + 1] * ep.drop_scale : 0.f;
+            f[j + 2] = rb.z < ep.drop_thresh ? f[j + 2] * ep.drop_scale : 0.f;
+            f[j + 3] = rb.w < ep.drop_thresh ? f[j + 3] * ep.drop_scale : 0.f;
+          }
+        } else {
+          for (int j = 0; j < 32; ++j)
+            f[j] = dropout_keep(ep.drop_seed, e0 + j, ep.drop_thresh) ? f[j] * ep.drop_scale : 0.f;
+        }
+      }
+      if (ep.aux_mode != PE_AUX_NONE) {
+        const __nv_bfloat16* ax = reinterpret_cast<const __nv_bfloat16*>(ep.aux) + grow * ep.ld_aux + col0;
+        float a[32];
+        if (full) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            const uint4 u = *reinterpret_cast<const uint4*>(ax + j);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 x2 = __bfloat1622float2(h2[t]);
+              a[j + 2 * t] = x2.x;
+              a[j + 2 * t + 1] = x2.y;
+            }
+          }
+        } else {
+          for (int j = 0; j < 32; ++j)
+            a[j] = (col0 + j < p.N && c * 32 + j < p.block_n) ? __bfloat162float(ax[j]) : 0.f;
+        }
+        if (ep.aux_mode == PE_AUX_ADD) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] += a[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] *= gelu_erf_grad(a[j]);
+        }
+      }
+      if (ep.out_mode == PE_OUT_BF16) {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + grow * ep.ldc + out_col_off + col0;
+        if (full) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8)
+            *reinterpret_cast<uint4*>(o + j) = make_uint4(pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]),
+                                                          pack_bf16(f[j + 4], f[j + 5]), pack_bf16(f[j + 6], f[j + 7]));
+        } else {
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N && c * 32 + j < p.block_n) o[j] = __float2bfloat16(f[j]);
+        }
+      } else if (ep.out_mode == PE_OUT_F32) {
+        float* o = reinterpret_cast<float*>(ep.out) + grow * ep.ldc + out_col_off + col0;
+        if (full) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+        } else {
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N && c * 32 + j < p.block_n) o[j] = f[j];
+        }
+      } else {
+        float* o = reinterpret_cast<float*>(ep.out) + grow * ep.ldc + out_col_off + col0;
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.N && c * 32 + j < p.block_n) atomicAdd(o + j, f[j]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+}  // namespace pe
+
+// =================================================================================================
+// host launchers
+// =================================================================================================
+using pe::TcParams;
+
+static int pow2_cols(int n) {
+  int c = 32;
+  while (c < n) c <<= 1;
+  return c;
+}
+
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, TcParams& p, dim3 grid,
+                     cudaStream_t stream) {
+  const int stage_bytes = pe::kATileBytes + p.block_n * pe::kRowBytes;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2) return PE_ERR_BAD_SHAPE;
+  p.stages = stages;
+  p.tmem_cols = pow2_cols(p.block_n);
+  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 1) * sizeof(uint64_t) + 16 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(pe::tc_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+        cudaSuccess)
+      return PE_ERR_LAUNCH;
+    attr_set = true;
+  }
+  pe::tc_tile_kernel<<<grid, pe::kNumThreads, smem, stream>>>(ta, ta2, tb, p);
+  return cudaGetLastError() == cudaSuccess ? PE_OK : PE_ERR_LAUNCH;
+}
+
+static void default_ep(pe_epilogue& e) {
+  if (e.alpha == 0.f) e.alpha = 1.f;
+}
+
+extern "C" int pe_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, int M,
+                            int N, int K, const pe_epilogue* ep, int splits, pe_stream_t stream) {
+  if (int rc = pe_host::check_arch()) return rc;
+  if (!A || !B || !ep || !ep->out || M <= 0 || N <= 0 || K <= 0) return PE_ERR_BAD_SHAPE;
+  if ((lda % 8) || (ldb % 8) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
+    return PE_ERR_BAD_SHAPE;
+  if (splits < 1) splits = 1;
+  if (splits > 1 && ep->out_mode != PE_OUT_F32_ATOMIC) return PE_ERR_BAD_SHAPE;
+  TcParams p{};
+  p.mode = 0;
+  p.kind = 0;
+  p.a_mn = a_mn ? 1 : 0;
+  p.b_mn = b_mn ? 1 : 0;
+  p.M = M;
+  p.N = N;
+  // tile width: as wide as N allows (<= 256); MN-major B needs whole 64-wide boxes
+  int bn = N >= 256 ? 256 : ((N + 15) / 16) * 16;
+  if (p.b_mn) bn = ((bn + 63) / 64) * 64;
+  if (bn > 256) bn = 256;
+  p.block_n = bn;
+  p.a_boxes = 2;
+  p.b_boxes = bn / 64;
+  p.kb_total = (K + 63) / 64;
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  p.ep = *ep;
+  default_ep(p.ep);
+
+  CUtensorMap ta, tb;
+  {
+    uint64_t dims[2], str[1];
+    uint32_t box[2];
+    if (!p.a_mn) { dims[0] = (uint64_t)K; dims[1] = (uint64_t)M; box[0] = 64; box[1] = 128; }
+    else         { dims[0] = (uint64_t)M; dims[1] = (uint64_t)K; box[0] = 64; box[1] = 64; }
+    str[0] = (uint64_t)lda * 2;
+    if (int rc = pe_host::encode_tmap(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, dims, str, box)) return rc;
+    if (!p.b_mn) { dims[0] = (uint64_t)K; dims[1] = (uint64_t)N; box[0] = 64; box[1] = (uint32_t)bn; }
+    else         { dims[0] = (uint64_t)N; dims[1] = (uint64_t)K; box[0] = 64; box[1] = 64; }
+    str[0] = (uint64_t)ldb * 2;
+    if (int rc = pe_host::encode_tmap(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, B, dims, str, box)) return rc;
+  }
+  dim3 grid((M + 127) / 128, (N + bn - 1) / bn, splits);
+  return launch_tc(ta, ta, tb, p, grid, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// patch shapes: 128-pixel output tiles (fwd) and 64-pixel contraction blocks (wgrad) that tile W in 5 columns
+static bool conv_patch(int W, int pixels, int& tw, int& th) {
+  // choose the widest tw <= 16 dividing `pixels` such that tiles cover W with little waste
+  int best = 0;
+  for (int cand = 16; cand >= 1; cand >>= 1) {
+    if (pixels % cand) continue;
+    if (W % cand == 0) { best = cand; break; }
+  }
+  if (!best) best = (W >= 16) ? 16 : (W >= 8 ? 8 : (W >= 4 ? 4 : 2));
+  tw = best;
+  th = pixels / tw;
+  return th <= 256;
+}
+
+static int nhwc_tmap(CUtensorMap* m, const void* base, int B, int H, int W, int C, int tw, int th) {
+  uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+  uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+  uint32_t box[4] = {64, (uint32_t)tw, (uint32_t)th, 1};
+  return pe_host::encode_tmap(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, str, box);
+}
+
+extern "C" int pe_conv3x3_nhwc(const void* x, const void* x2, const void* w, int B, int H, int W, int C1, int C2,
+                               int Cout, const pe_epilogue* ep, pe_stream_t stream) {
+  if (int rc = pe_host::check_arch()) return rc;
+  if (!x || !w || !ep || !ep->out || B <= 0 || H <= 0 || W <= 0) return PE_ERR_BAD_SHAPE;
+  if (C1 % 64 || C2 % 64 || C1 <= 0 || Cout % 16 || Cout <= 0 || (C2 > 0 && !x2)) return PE_ERR_BAD_SHAPE;
+  TcParams p{};
+  p.mode = 1;
+  p.kind = 0;
+  p.H = H;
+  p.W = W;
+  if (!conv_patch(W, 128, p.tw, p.th)) return PE_ERR_BAD_SHAPE;
+  p.tiles_w = (W + p.tw - 1) / p.tw;
+  p.tiles_h = (H + p.th - 1) / p.th;
+  p.c1_chunks = C1 / 64;
+  p.c2_chunks = C2 / 64;
+  p.M = B * H * W;
+  p.N = Cout;
+  p.block_n = Cout > 256 ? 256 : Cout;
+  p.kb_total = 9 * p.c1_chunks + p.c2_chunks;
+  p.kb_per_split = p.kb_total;
+  p.ep = *ep;
+  default_ep(p.ep);
+  CUtensorMap ta, ta2, tb;
+  if (int rc = nhwc_tmap(&ta, x, B, H, W, C1, p.tw, p.th)) return rc;
+  ta2 = ta;
+  if (C2 > 0)
+    if (int rc = nhwc_tmap(&ta2, x2, B, H, W, C2, p.tw, p.th)) return rc;
+  {
+    const int Ktot = 9 * C1 + C2;
+    uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)Cout};
+    uint64_t str[1] = {(uint64_t)Ktot * 2};
+    uint32_t box[2] = {64, (uint32_t)p.block_n};
+    if (int rc = pe_host::encode_tmap(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w, dims, str, box)) return rc;
+  }
+  dim3 grid(B * p.tiles_h * p.tiles_w, (Cout + p.block_n - 1) / p.block_n, 1);
+  return launch_tc(ta, ta2, tb, p, grid, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int pe_conv_wgrad_nhwc(const void* dy, const void* x, float* dw, long long ldw, int B, int H, int W, int C,
+                                  int Cout, int taps, int splits, pe_stream_t stream) {
+  if (int rc = pe_host::check_arch()) return rc;
+  if (!dy || !x || !dw || B <= 0 || H <= 0 || W <= 0) return PE_ERR_BAD_SHAPE;
+  if (C % 64 || C <= 0 || C > 256 || Cout % 8 || Cout <= 0 || (taps != 9 && taps != 1)) return PE_ERR_BAD_SHAPE;
+  TcParams p{};
+  p.mode = 2;
+  p.kind = 0;
+  p.a_mn = 1;
+  p.b_mn = 1;
+  p.H = H;
+  p.W = W;
+  if (!conv_patch(W, 64, p.tw, p.th)) return PE_ERR_BAD_SHAPE;
+  p.tiles_w = (W + p.tw - 1) / p.tw;
+  p.tiles_h = (H + p.th - 1) / p.th;
+  p.taps = taps;
+  p.M = Cout;
+  p.N = C;
+  p.block_n = C;
+  p.a_boxes = 2;
+  p.b_boxes = C / 64;
+  p.kb_total = B * p.tiles_h * p.tiles_w;
+  if (splits < 1) splits = 1;
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  pe_epilogue e{};
+  e.out = dw;
+  e.ldc = ldw;
+  e.out_mode = PE_OUT_F32_ATOMIC;
+  e.alpha = 1.f;
+  p.ep = e;
+  CUtensorMap ta, tb;
+  if (int rc = nhwc_tmap(&ta, dy, B, H, W, Cout, p.tw, p.th)) return rc;
+  if (int rc = nhwc_tmap(&tb, x, B, H, W, C, p.tw, p.th)) return rc;
+  dim3 grid((Cout + 127) / 128, taps, splits);
+  return launch_tc(ta, ta, tb, p, grid, reinterpret_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,67 @@
+// Host-side plumbing shared by every C-ABI entry point: driver entry-point lookup for the tensor-map
+// encoder, device queries, version.
+#include "common.cuh"
+#include "../../include/pitchextractor_b200.h"
+
+#include <cudaTypedefs.h>
+#include <mutex>
+
+namespace pe_host {
+
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+static std::once_flag g_encode_once;
+
+static void load_encode() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+      qres == cudaDriverEntryPointSuccess) {
+    g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  }
+}
+
+int encode_tmap(CUtensorMap* map, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box) {
+  std::call_once(g_encode_once, load_encode);
+  if (!g_encode) return PE_ERR_DRIVER;
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[5];
+  cuuint32_t bdim[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  CUresult r = g_encode(map, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? PE_OK : PE_ERR_DRIVER;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+int check_arch() {
+  static int ok = -100;
+  if (ok == -100) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return PE_ERR_ARCH;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    ok = (major == 10) ? PE_OK : PE_ERR_ARCH;
+  }
+  return ok;
+}
+
+}  // namespace pe_host
+
+extern "C" int pe_version(void) { return 100; }
+extern "C" int pe_check_device(void) { return pe_host::check_arch(); }

@@ -1,0 +1,79 @@
+"""Thin Python wrappers over the C-ABI kernels: argument marshalling only (no arithmetic on this side)."""
+import ctypes
+
+import torch
+
+from . import _lib as L
+from ._lib import Epilogue, call, ptr, stream
+
+c_int, c_ll, c_size = ctypes.c_int, ctypes.c_longlong, ctypes.c_size_t
+
+
+def make_epilogue(out, out_mode=None, bias=None, act=L.PE_ACT_NONE, out2=None, aux=None, aux_mode=L.PE_AUX_NONE,
+                  p_drop=0.0, seed=0, alpha=1.0, ldc=None):
+    ep = Epilogue()
+    ep.out = out.data_ptr()
+    ep.ldc = out.stride(-2) if ldc is None else ldc
+    if out_mode is None:
+        out_mode = L.PE_OUT_BF16 if out.dtype == torch.bfloat16 else L.PE_OUT_F32
+    ep.out_mode = out_mode
+    ep.act = act
+    if out2 is not None:
+        ep.out2, ep.ld2 = out2.data_ptr(), out2.stride(-2)
+    if bias is not None:
+        assert bias.dtype == torch.float32
+        ep.bias = bias.data_ptr()
+    if aux is not None:
+        assert aux.dtype == torch.bfloat16
+        ep.aux, ep.ld_aux, ep.aux_mode = aux.data_ptr(), aux.stride(-2), aux_mode
+    ep.drop_thresh, ep.drop_scale = L.drop_thresh(p_drop)
+    ep.drop_seed = seed
+    ep.alpha = alpha
+    return ep
+
+
+def gemm(a, b, out, M, N, K, a_mn=False, b_mn=False, splits=1, **epkw):
+    """out[M,N] (op)= sum_k A(m,k) B(n,k).  a: [M,K] (or [K,M] if a_mn), b: [N,K] (or [K,N] if b_mn), bf16."""
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+    ep = make_epilogue(out, **epkw)
+    call("pe_gemm_bf16", ptr(a), c_ll(a.stride(0)), c_int(int(a_mn)), ptr(b), c_ll(b.stride(0)), c_int(int(b_mn)),
+         c_int(M), c_int(N), c_int(K), ctypes.byref(ep), c_int(splits), stream())
+    return out
+
+
+def conv3x3(x, w, out, x2=None, **epkw):
+    """x [B,H,W,C1] bf16 NHWC, x2 [B,H,W,C2] or None, w [Cout, 9*C1+C2] bf16, out [B,H,W,Cout]."""
+    B, H, W, C1 = x.shape
+    C2 = 0 if x2 is None else x2.shape[-1]
+    Cout = w.shape[0]
+    assert w.shape[1] == 9 * C1 + C2 and x.is_contiguous() and w.is_contiguous()
+    ep = make_epilogue(out, ldc=Cout, **epkw)
+    call("pe_conv3x3_nhwc", ptr(x), ptr(x2), ptr(w), c_int(B), c_int(H), c_int(W), c_int(C1), c_int(C2), c_int(Cout),
+         ctypes.byref(ep), stream())
+    return out
+
+
+def conv_wgrad(dy, x, dw, taps=9, splits=0, col_offset=0):
+    """dw[Cout, col_offset + tap*C + ci] += sum_p dy[p,co] x[p+tap,ci]; dw fp32 [Cout, ldw]."""
+    B, H, W, Cout = dy.shape
+    C = x.shape[-1]
+    if splits <= 0:
+        splits = max(1, min(64, (148 * 2) // (taps * ((Cout + 127) // 128))))
+    base = ctypes.c_void_p(dw.data_ptr() + 4 * col_offset)
+    call("pe_conv_wgrad_nhwc", ptr(dy), ptr(x), base, c_ll(dw.stride(0)), c_int(B), c_int(H), c_int(W), c_int(C),
+         c_int(Cout), c_int(taps), c_int(splits), stream())
+    return dw
+
+
+def logmel(wave, tables, out_bmt=None, out_btm=None, crop=None, T_out=0, power_ws=None):
+    """wave [B,L] fp32 cuda -> normalised log-mel; tables from ``logmel_tables``."""
+    B, Lw = wave.shape
+    n_fft, hop, n_mels = tables["n_fft"], tables["hop"], tables["n_mels"]
+    T = 1 + Lw // hop
+    n_bins = n_fft // 2 + 1
+    if power_ws is None or power_ws.numel() < B * T * n_bins:
+        power_ws = torch.empty(B * T * n_bins, device=wave.device, dtype=torch.float32)
+    call("pe_logmel_f32", ptr(wave), c_int(B), c_int(Lw), c_int(n_fft), c_int(hop), c_int(n_mels),
+         ptr(tables["basis"]), c_int(tables["basis"].stride(0)), ptr(tables["fb"]), ptr(power_ws),
+         c_size(power_ws.numel() * 4), ptr(out_bmt), ptr(out_btm), ptr(crop), c_int(T_out), stream())
+    return power_ws

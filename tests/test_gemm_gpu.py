@@ -1,0 +1,128 @@
+"""tcgen05 tile engine vs a plain torch fp32 reference of the same op (GPU)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(shape, device="cuda", generator=g) * scale).to(torch.bfloat16)
+
+
+def _close(got, ref, rtol=2e-2, atol=None):
+    got, ref = got.float(), ref.float()
+    atol = atol if atol is not None else 1e-2 * ref.abs().max().item()
+    err = (got - ref).abs()
+    bad = err > atol + rtol * ref.abs()
+    assert not bad.any(), "max err %.4g (ref max %.4g), %d bad" % (err.max().item(), ref.abs().max().item(),
+                                                                   int(bad.sum()))
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (256, 256, 512), (384, 1536, 512), (200, 80, 72), (12288, 512, 1536)])
+def test_gemm_kmajor(built_lib, M, N, K):
+    from pitchextractor_b200 import ops
+    Kp = (K + 7) // 8 * 8
+    a = _rand((M, Kp), 1)[:, :K]
+    b = _rand((N, Kp), 2)[:, :K]
+    out = torch.empty(M, N, device="cuda", dtype=torch.float32)
+    ops.gemm(a, b, out, M, N, K)
+    torch.cuda.synchronize()
+    _close(out, a.float() @ b.float().t())
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (256, 256, 192), (512, 1536, 1000)])
+def test_gemm_mn_major(built_lib, a_mn, b_mn, M, N, K):
+    from pitchextractor_b200 import ops
+    a = _rand((M, K), 3)
+    b = _rand((N, K), 4)
+    a_arg = a.t().contiguous() if a_mn else a
+    b_arg = b.t().contiguous() if b_mn else b
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a_arg, b_arg, out, M, N, K, a_mn=a_mn, b_mn=b_mn)
+    torch.cuda.synchronize()
+    _close(out, a.float() @ b.float().t())
+
+
+def test_gemm_splitk_atomic(built_lib):
+    from pitchextractor_b200 import ops, _lib as L
+    M, N, K = 1536, 512, 4096  # weight-gradient shape: contraction over tokens
+    dy = _rand((K, M), 5)
+    x = _rand((K, N), 6)
+    out = torch.zeros(M, N, device="cuda", dtype=torch.float32)
+    ops.gemm(dy, x, out, M, N, K, a_mn=True, b_mn=True, splits=8, out_mode=L.PE_OUT_F32_ATOMIC)
+    torch.cuda.synchronize()
+    _close(out, dy.float().t() @ x.float())
+
+
+def test_gemm_epilogues(built_lib):
+    from pitchextractor_b200 import ops, _lib as L
+    M, N, K = 384, 1536, 512
+    a, b = _rand((M, K), 7, 0.5), _rand((N, K), 8, 0.1)
+    bias = torch.randn(N, device="cuda")
+    ref = a.float() @ b.float().t() + bias
+    # bias + GELU with pre-activation copy
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    pre = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, b, out, M, N, K, bias=bias, act=L.PE_ACT_GELU, out2=pre)
+    torch.cuda.synchronize()
+    _close(pre, ref)
+    _close(out, torch.nn.functional.gelu(ref))
+    # residual add, fp32 out
+    res = _rand((M, N), 9)
+    out32 = torch.empty(M, N, device="cuda", dtype=torch.float32)
+    ops.gemm(a, b, out32, M, N, K, bias=bias, aux=res, aux_mode=L.PE_AUX_ADD)
+    torch.cuda.synchronize()
+    _close(out32, ref + res.float())
+    # gelu-grad multiply
+    ops.gemm(a, b, out32, M, N, K, aux=res, aux_mode=L.PE_AUX_GELU_GRAD)
+    torch.cuda.synchronize()
+    x = res.float().requires_grad_()
+    torch.nn.functional.gelu(x).sum().backward()
+    _close(out32, (a.float() @ b.float().t()) * x.grad)
+    # dropout: deterministic in (seed, index); keep-rate and scaling
+    ops.gemm(a, b, out32, M, N, K, bias=bias, p_drop=0.25, seed=1234)
+    out_b = torch.empty_like(out32)
+    ops.gemm(a, b, out_b, M, N, K, bias=bias, p_drop=0.25, seed=1234)
+    torch.cuda.synchronize()
+    assert torch.equal(out32, out_b)
+    kept = out32 != 0
+    assert abs(kept.float().mean().item() - 0.75) < 0.01
+    _close(out32[kept], (ref / 0.75)[kept])
+
+
+@pytest.mark.parametrize("B,H,W,C1,C2,Cout", [(1, 16, 16, 64, 0, 64), (2, 192, 80, 64, 0, 64), (2, 192, 40, 128, 64, 128),
+                                              (2, 192, 20, 192, 128, 192), (3, 192, 10, 256, 192, 256),
+                                              (1, 10, 12, 64, 0, 128)])
+def test_conv3x3(built_lib, B, H, W, C1, C2, Cout):
+    from pitchextractor_b200 import ops
+    x = _rand((B, H, W, C1), 10)
+    w = _rand((Cout, 3, 3, C1), 11, 0.05)
+    x2 = _rand((B, H, W, C2), 12) if C2 else None
+    w2 = _rand((Cout, C2), 13, 0.05) if C2 else None
+    wcat = torch.cat([w.reshape(Cout, -1)] + ([w2] if C2 else []), dim=1).contiguous()
+    out = torch.empty(B, H, W, Cout, device="cuda", dtype=torch.bfloat16)
+    ops.conv3x3(x, wcat, out, x2=x2)
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), padding=1)
+    if C2:
+        ref = ref + torch.nn.functional.conv2d(x2.float().permute(0, 3, 1, 2), w2.float()[:, :, None, None])
+    _close(out, ref.permute(0, 2, 3, 1))
+
+
+@pytest.mark.parametrize("B,H,W,C,Cout,taps", [(2, 192, 80, 64, 64, 9), (2, 192, 40, 64, 128, 9), (2, 192, 20, 192, 192, 9),
+                                               (2, 192, 10, 256, 256, 9), (2, 192, 40, 64, 128, 1), (1, 10, 12, 64, 72, 9)])
+def test_conv_wgrad(built_lib, B, H, W, C, Cout, taps):
+    from pitchextractor_b200 import ops
+    x = _rand((B, H, W, C), 14)
+    dy = _rand((B, H, W, Cout), 15, 0.1)
+    dw = torch.zeros(Cout, taps * C, device="cuda", dtype=torch.float32)
+    ops.conv_wgrad(dy, x, dw, taps=taps)
+    torch.cuda.synchronize()
+    xs = x.float().permute(0, 3, 1, 2).requires_grad_(False)
+    wt = torch.zeros(Cout, C, 3 if taps == 9 else 1, 3 if taps == 9 else 1, device="cuda", requires_grad=True)
+    y = torch.nn.functional.conv2d(xs, wt, padding=1 if taps == 9 else 0)
+    y.backward(dy.float().permute(0, 3, 1, 2))
+    ref = wt.grad.permute(0, 2, 3, 1).reshape(Cout, taps * C)
+    _close(dw, ref)
