@@ -1,0 +1,283 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: JDCNet training segments/s (log-mel + forward + losses + backward + AdamW step).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path (one process per GPU)
+  python bench.py --impl reference [--gpus N] [--steps K] ...    # the reference's CPU step (oracle port), rank 0 only
+
+Workload (BASELINE.json configs[1], north_star): JDCNet with the Transformer sequence model (4 layers, d=512, 8 heads,
+FFN 1536 -- Configs/config.yml:16-24), batch 64 segments per GPU, each a synthetic 58 624-sample 24 kHz segment
+(pitchextractor_b200/synthetic.py) -> 192 log-mel frames, bf16 tensor-core operands with fp32 accumulation.
+One JSON line is printed by rank 0 (contract: task statement).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+SEG = 58624
+FRAMES = 192
+MODEL_CFG = dict(model_type="transformer", num_layers=4, dropout=0.1, nhead=8, dim_feedforward=1536, max_len=2048)
+# algorithmic training flops per segment, 3 x forward: conv trunk 13.39 + transformers 8.66 GFLOP
+FLOPS_PER_SEGMENT = 3.0 * (13.39e9 + 8.66e9)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sustained=p["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=5)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_pool(batch, n_batches, rank):
+    """Host (pinned) pool of synthetic batches: waves, f0 [B,192], sil [B,192], crops."""
+    from pitchextractor_b200 import synthetic
+    from pitchextractor_b200.meldataset import align_length
+    pool = []
+    for i in range(n_batches):
+        waves, f0_full = synthetic.make_batch(batch, seed=1234 + 1000 * rank + i)
+        rng = np.random.default_rng([99, rank, i])
+        crops = rng.integers(0, f0_full.shape[1] - FRAMES, size=batch).astype(np.int32)
+        f0 = np.stack([align_length(f0_full[b], f0_full.shape[1])[c:c + FRAMES] for b, c in enumerate(crops)])
+        sil = (f0 == 0).astype(np.float32)
+        pool.append(tuple(torch.from_numpy(a).pin_memory() for a in (waves, f0.astype(np.float32), sil, crops)))
+    return pool
+
+
+def run_ours(args):
+    from pitchextractor_b200 import JDCNet, Trainer, build_optimizer, ops, _lib
+    from pitchextractor_b200.parallel import init_from_env
+    import torch.distributed as dist
+    rank, world, local_rank = init_from_env("nccl")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    B = args.batch
+    torch.manual_seed(0)
+    model = JDCNet(num_class=1, sequence_model_config=dict(MODEL_CFG)).to(dev)
+    opt, sched = build_optimizer({"params": model.parameters(), "optimizer_params": {},
+                                  "scheduler_params": {"max_lr": 3e-4, "pct_start": 0.0, "epochs": 100,
+                                                       "steps_per_epoch": 1000}})
+    trainer = Trainer(model=model, criterion=None, optimizer=opt, scheduler=sched, config={},
+                      loss_config={"lambda_f0": 0.1}, device=dev)
+    model.train()
+    pool = make_pool(B, args.pool, rank)
+    dpool = [tuple(t.to(dev) for t in b) for b in pool]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    resident = lambda i: trainer.run_async(dpool[i % len(dpool)])
+    host = lambda i: trainer.run(pool[i % len(pool)])
+    for i in range(args.warmup):
+        resident(i)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    n0 = _lib.launch_count
+    ms = timed(resident, args.steps)
+    launches = _lib.launch_count - n0
+    clocks = sampler.stop()
+    last = trainer.run(pool[0])
+    # end to end: host (pinned) buffers in, python floats out, every step
+    for i in range(min(2, args.warmup)):
+        host(i)
+    ms_e2e = timed(host, args.steps)
+    h2d = sum(t.numel() * t.element_size() for t in pool[0])
+    # dominant kernel: the tcgen05 tile engine (implicit-GEMM conv / GEMM / weight-gradient launches)
+    ops.PROFILE = []
+    barrier()
+    for i in range(min(3, args.steps)):
+        resident(i)
+    torch.cuda.synchronize()
+    prof, ops.PROFILE = ops.PROFILE, None
+    tc_ms = sum(a.elapsed_time(b) for _, a, b, _ in prof)
+    tc_flops = sum(f for _, _, _, f in prof)
+    n_prof_steps = min(3, args.steps)
+    # log-mel alone (second headline metric)
+    from pitchextractor_b200.mel import LogMel
+    lm = LogMel(dev)
+    w = dpool[0][0]
+    for _ in range(3):
+        lm(w, T_out=FRAMES, layout="btm")
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        lm(w, T_out=FRAMES, layout="btm")
+    e1.record()
+    torch.cuda.synchronize()
+    lm_ms = e0.elapsed_time(e1) / 10
+    if rank != 0:
+        return
+    pk = peaks()
+    seg_s = world * B * args.steps / (ms / 1e3)
+    frames = B * (1 + SEG // 300)
+    line = {
+        "metric": "train_segments_per_s", "value": seg_s, "unit": "segments/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "JDCNet Transformer (4L d512 h8 ffn1536) train step incl. log-mel, batch %d/GPU, "
+                               "24 kHz 58624-sample segments -> 192 frames (BASELINE configs[1])" % B,
+                   "global_batch": world * B, "parallelism": "dp%d" % world,
+                   "l2": "working set (>1 GB activations/step) exceeds the 126 MB L2; inputs cycle over %d batches" % len(pool)},
+        "e2e": {"value": world * B * args.steps / (ms_e2e / 1e3), "unit": "segments/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 12},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "tc_tile_kernel (tcgen05 implicit-GEMM conv / GEMM / wgrad)",
+                     "achieved": tc_flops / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else None, "peak": pk["tf_sustained"],
+                     "unit": "TFLOP/s",
+                     "frac": (tc_flops / (tc_ms / 1e3) / 1e12 / pk["tf_sustained"]) if tc_ms > 0 else None,
+                     "traffic": None, "peak_source": pk["src"] + " (sustained bf16)",
+                     "launches_per_step": len(prof) // max(1, n_prof_steps), "ms_per_step": tc_ms / max(1, n_prof_steps),
+                     "step_frac_of_bf16_peak": seg_s / world * FLOPS_PER_SEGMENT / (pk["tf_sustained"] * 1e12)},
+        "logmel": {"frames_per_s": frames / (lm_ms / 1e3), "ms": lm_ms, "bound": "hbm",
+                   "achieved_gbs": frames * 1520.0 / (lm_ms / 1e3) / 1e9, "peak_gbs": pk["hbm"],
+                   "frac": frames * 1520.0 / (lm_ms / 1e3) / 1e9 / pk["hbm"]},
+        "loss_last": last,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(sample_batch=args.cpu_sample, steps=1, warmup=1)
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(sample_batch, steps, warmup):
+    """Oracle port of reference Trainer.run on the host cores (fp32; AMP / checkpointing are off on CPU in the
+    reference too, trainer.py:64,103), on a bounded sample of the workload."""
+    from oracle import jdcnet_torch as J, train_step as TS
+    from pitchextractor_b200 import synthetic
+    from pitchextractor_b200.model import JDCNet
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    sd = JDCNet(num_class=1, sequence_model_config=dict(MODEL_CFG)).state_dict()
+    ref = TS.ReferenceStep(sd, J.default_config("transformer"))
+    waves, f0 = synthetic.make_batch(sample_batch, seed=4321)
+    crops = np.arange(sample_batch) % 4
+    for _ in range(warmup):
+        ref.step(waves, f0, crops)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ref.step(waves, f0, crops)
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": sample_batch / dt, "unit": "segments/s", "cores": cores, "kind": "port",
+            "sample": "%d step(s) of %d segments (of the 64-segment batch), per-sample CPU log-mel + fp32 fwd/bwd + AdamW"
+                      % (steps, sample_batch), "s_per_step": dt}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    from oracle import jdcnet_torch as J, train_step as TS
+    from pitchextractor_b200 import synthetic
+    from pitchextractor_b200.model import JDCNet
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    sb = args.cpu_sample
+    sd = JDCNet(num_class=1, sequence_model_config=dict(MODEL_CFG)).state_dict()
+    ref = TS.ReferenceStep(sd, J.default_config("transformer"))
+    waves, f0 = synthetic.make_batch(sb, seed=4321)
+    crops = np.arange(sb) % 4
+    for _ in range(args.warmup):
+        ref.step(waves, f0, crops)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        last = ref.step(waves, f0, crops)
+    dt = time.perf_counter() - t0
+    v = sb * args.steps / dt
+    sample = ("each step = %d segments (bounded sample of the %d-segment batch): per-sample CPU log-mel + fp32 "
+              "forward/backward + AdamW, %d host threads" % (sb, args.batch, cores))
+    print(json.dumps({
+        "impl": "reference", "metric": "train_segments_per_s", "value": v, "unit": "segments/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "JDCNet Transformer (4L d512 h8 ffn1536) train step incl. log-mel, batch %d/GPU, "
+                               "24 kHz 58624-sample segments -> 192 frames (BASELINE configs[1])" % args.batch,
+                   "global_batch": args.batch, "parallelism": "cpu"},
+        "cpu_baseline": {"value": v, "unit": "segments/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "loss_last": last}), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="segments per GPU per step")
+    ap.add_argument("--pool", type=int, default=3, help="distinct synthetic batches cycled through")
+    ap.add_argument("--cpu-sample", type=int, default=8, help="segments per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

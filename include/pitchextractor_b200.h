@@ -99,6 +99,88 @@ int pe_logmel_f32(const float* wave, int B, int L, int n_fft, int hop, int n_mel
                   int ld_basis, const float* fb, float* power, size_t power_bytes, float* out_bmt, float* out_btm,
                   const int* crop, int T_out, pe_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Conv trunk, memory-bound passes over NHWC bf16 activations (model.py:23-57,143-175).
+ * ------------------------------------------------------------------------------------------------ */
+/* Conv2d(1->64, 3x3, pad 1, no bias) (model.py:24): x[b][t][f] fp32 with element strides (sb, st, sf) -> y bf16
+ * [B][T][F][64]; w fp32 [64][9]. */
+int pe_stem_conv_fwd(const float* x, long long sb, long long st, long long sf, int B, int T, int F, const float* w,
+                     void* y, pe_stream_t stream);
+/* its weight gradient: dw[64][9] += sum_p dy[p][c] x[p+tap] */
+int pe_stem_conv_wgrad(const float* x, long long sb, long long st, long long sf, int B, int T, int F, const void* dy,
+                       float* dw, pe_stream_t stream);
+/* nn.BatchNorm2d training statistics (model.py:25,37,54,150,159): sums[0][c] += sum x, sums[1][c] += sum x^2 over
+ * x bf16 [rows][C]; caller zeroes sums (fp64 [2][C]). */
+int pe_bn_stats(const void* x, long long rows, int C, double* sums, pe_stream_t stream);
+/* batch mean / biased variance -> scale = gamma*rstd, shift = beta - mean*scale, saved mean / rstd; updates
+ * running_mean / running_var (momentum, unbiased variance) and num_batches_tracked as torch does (may be NULL). */
+int pe_bn_finalize(const double* sums, double count, const float* gamma, const float* beta, float eps, float momentum,
+                   float* scale, float* shift, float* mean, float* rstd, float* running_mean, float* running_var,
+                   long long* num_batches_tracked, int C, pe_stream_t stream);
+/* eval mode: scale / shift from the running statistics */
+int pe_bn_eval_params(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                      float eps, float* scale, float* shift, float* mean, float* rstd, int C, pe_stream_t stream);
+/* y = Dropout(MaxPool2d((1,k))(LeakyReLU(x*scale + shift))) (model.py:36-41,149-153; scale == NULL: pure max-pool,
+ * model.py:45-49).  x bf16 [rows][W][C]; output pixel (row, wo) written at out + (row*Wo+wo)*ld_out + c_off, and/or
+ * in the sequence layout out_seq[row][c*Wo + wo] (model.py:93,112). */
+int pe_bn_act_pool_fwd(const void* x, long long rows, int W, int C, int k, const float* scale, const float* shift,
+                       float slope, unsigned drop_thresh, float drop_scale, unsigned long long seed, void* out,
+                       long long ld_out, int c_off, void* out_seq, pe_stream_t stream);
+/* backward of the block above through dropout, max-pool, LeakyReLU and the BatchNorm batch statistics:
+ * dx bf16 [rows][W][C]; dgamma / dbeta accumulated (+=); sums is a zeroed fp64 [2][C] scratch. */
+int pe_bn_act_pool_bwd(const void* x, long long rows, int W, int C, int k, const float* scale, const float* shift,
+                       const float* mean, const float* rstd, float slope, unsigned drop_thresh, float drop_scale,
+                       unsigned long long seed, const void* dout, long long ld_dout, int c_off, const void* dout_seq,
+                       double* sums, float* dgamma, float* dbeta, void* dx, pe_stream_t stream);
+/* backward of the auxiliary max-pools: dx[argmax of each window] += dout */
+int pe_maxpool_bwd_add(const void* x, long long rows, int W, int C, int k, const void* dout, long long ld_dout,
+                       int c_off, void* dx, pe_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sequence model passes (model.py:178-256; torch/nn/modules/transformer.py:961-982).
+ * ------------------------------------------------------------------------------------------------ */
+/* out = LayerNorm(x (+ pe[m % T])) over D in {256,512,768}; x is fp32 (x_f32) or bf16 (x_bf16); out bf16;
+ * mean / rstd fp32 [M] saved for the backward pass. */
+int pe_layernorm_fwd(const float* x_f32, const void* x_bf16, const float* pe_table, int T, int D, const float* gamma,
+                     const float* beta, float eps, long long M, void* out, float* mean, float* rstd,
+                     pe_stream_t stream);
+/* dx (bf16) and, optionally, dx_masked = dropout-masked dx (gradient entering the preceding Linear);
+ * dgamma, dbeta, dbias (= column sums of dx_masked) accumulated (+=). */
+int pe_layernorm_bwd(const void* dy, const float* x_f32, const void* x_bf16, const float* pe_table, int T, int D,
+                     const float* gamma, const float* mean, const float* rstd, long long M, void* dx, void* dx_masked,
+                     unsigned drop_thresh, float drop_scale, unsigned long long seed, float* dgamma, float* dbeta,
+                     float* dbias, pe_stream_t stream);
+/* out[n] += sum_m x[m][n], x bf16 [M][ld] (bias gradients) */
+int pe_colsum_bf16(const void* x, long long M, int N, long long ld, float* out, pe_stream_t stream);
+/* multi-head softmax attention with dropout on the probabilities (nn.MultiheadAttention inside
+ * nn.TransformerEncoderLayer, model.py:231-239): qkv bf16 [B*T][3*H*64] -> ctx bf16 [B*T][H*64], lse fp32 [B][H][T] */
+int pe_attn_fwd(const void* qkv, int B, int T, int H, int head_dim, unsigned drop_thresh, float drop_scale,
+                unsigned long long seed, void* ctx, float* lse, pe_stream_t stream);
+int pe_attn_bwd(const void* qkv, const void* ctx, const void* dctx, const float* lse, int B, int T, int H,
+                int head_dim, unsigned drop_thresh, float drop_scale, unsigned long long seed, void* dqkv, float* delta,
+                pe_stream_t stream);
+/* heads (num_class == 1) + losses (model.py:96-98,115-117; train.py:104-106; trainer.py:237-239):
+ * f0 = hc.wc + bc, logit = hd.(wd[0]+wd[1]) + bd[0]+bd[1]; loss_out = {total, lambda*SmoothL1, BCE}.
+ * When dhc != NULL also writes dL/dhc, dL/dhd (bf16) and accumulates the head parameter gradients; with gc_ext /
+ * gd_ext (fp32 [M]) the output gradients are supplied by the caller instead of derived from the losses. */
+int pe_heads_loss(const void* hc, const void* hd, long long M, int D, const float* wc, const float* bc, const float* wd,
+                  const float* bd, const float* f0_target, const float* sil_target, float lambda_f0, float grad_scale,
+                  float* f0_pred, float* sil_logit, double* loss_acc, float* loss_out, const float* gc_ext,
+                  const float* gd_ext, void* dhc, void* dhd, float* dwc, float* dbc, float* dwd, float* dbd,
+                  pe_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Parameter passes (optimizers.py:54-64).
+ * ------------------------------------------------------------------------------------------------ */
+/* torch.optim.AdamW step over a flat fp32 arena; also writes the bf16 working copy when p_bf16 != NULL. */
+int pe_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+             float weight_decay, long long step, float grad_scale, void* p_bf16, pe_stream_t stream);
+int pe_cast_bf16(const float* x, void* y, long long n, pe_stream_t stream);
+/* tensor-core operand layouts of a conv weight w fp32 [Cout][9][Cin] (+ 1x1 shortcut w2 [Cout][C2] or, for the data
+ * gradient, [C2][Cin]): w_fwd bf16 [Cout][9*Cin + C2]; w_dgrad bf16 [Cin][9*Cout + C2] with flipped taps. */
+int pe_conv_weight_prep(const float* w, int Cout, int Cin, const float* w2, int C2, void* w_fwd, void* w_dgrad,
+                        pe_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,2 +1,8 @@
 """pitchextractor_b200 -- B200-native (sm_100a) implementation of the PitchExtractor training hot path."""
 __version__ = "0.1.0"
+
+from .mel import LogMel, DEFAULT_MEL_PARAMS  # noqa: E402,F401
+from .model import JDCNet, ResBlock, SequenceModel, SinusoidalPositionalEncoding  # noqa: E402,F401
+from .meldataset import MelDataset, Collater, build_dataloader, align_length  # noqa: E402,F401
+from .optimizers import build_optimizer, FusedAdamW  # noqa: E402,F401
+from .trainer import Trainer  # noqa: E402,F401

@@ -60,10 +60,17 @@ def check(rc, what):
         raise RuntimeError("pitchextractor_b200.%s failed: %s (rc=%d)" % (what, _ERRORS.get(rc, "unknown"), rc))
 
 
+# kernels launched per C-ABI call (for bench.py's gpu_launches count)
+_LAUNCHES_PER_CALL = {"pe_logmel_f32": 2, "pe_bn_act_pool_bwd": 3, "pe_attn_bwd": 2, "pe_heads_loss": 2}
+launch_count = 0
+
+
 def call(name, *args):
+    global launch_count
     fn = getattr(lib(), name)
     fn.restype = ctypes.c_int
     check(fn(*args), name)
+    launch_count += _LAUNCHES_PER_CALL.get(name, 1)
 
 
 def drop_thresh(p_drop):

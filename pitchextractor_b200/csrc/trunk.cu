@@ -1,0 +1,562 @@
+// Memory-bound passes of the JDCNet conv trunk over NHWC bf16 activations (reference model.py:23-57,143-175):
+// stem convolution (Cin = 1), BatchNorm batch statistics / finalize, fused BN-apply + LeakyReLU + MaxPool(1,k)
+// (+ Dropout) forward, the matching two-pass BatchNorm backward, and the auxiliary max-pools of the detector
+// branch.  All kernels are coalesced 16-byte-vector passes; per-channel reductions use fp32 partials per CTA and
+// fp64 atomics across CTAs.
+#include "common.cuh"
+#include "../../include/pitchextractor_b200.h"
+
+namespace pe {
+
+__device__ __forceinline__ void ld8(const __nv_bfloat16* p, float* f) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 v = __bfloat1622float2(h[i]);
+    f[2 * i] = v.x;
+    f[2 * i + 1] = v.y;
+  }
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const float* f) {
+  *reinterpret_cast<uint4*>(p) =
+      make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+}
+
+// ---------------------------------------------------------------------------------------------
+// stem: Conv2d(1 -> 64, 3x3, pad 1, no bias) on x[b][t][f] (arbitrary strides) -> y[b][t][f][64] bf16
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+stem_conv_fwd_kernel(const float* __restrict__ x, long long sb, long long st, long long sf, int B, int T, int F,
+                     const float* __restrict__ w /*[64][9]*/, __nv_bfloat16* __restrict__ y) {
+  __shared__ float ws[9][64];
+  for (int i = threadIdx.x; i < 576; i += 256) ws[i % 9][i / 9] = w[i];
+  __syncthreads();
+  const int g = threadIdx.x & 7;
+  const long long p = (long long)blockIdx.x * 32 + (threadIdx.x >> 3);
+  const long long P = (long long)B * T * F;
+  if (p >= P) return;
+  const int f = (int)(p % F);
+  const int t = (int)((p / F) % T);
+  const int b = (int)(p / ((long long)F * T));
+  float xv[9];
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const int tt = t + kh - 1, ff = f + kw - 1;
+      xv[kh * 3 + kw] = (tt >= 0 && tt < T && ff >= 0 && ff < F) ? __ldg(x + b * sb + tt * st + ff * sf) : 0.f;
+    }
+  float o[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float a = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) a = fmaf(xv[k], ws[k][g * 8 + c], a);
+    o[c] = a;
+  }
+  st8(y + p * 64 + g * 8, o);
+}
+
+// dw[c][tap] += sum_p dy[p][c] * x[p + tap]
+__global__ void __launch_bounds__(256)
+stem_conv_wgrad_kernel(const float* __restrict__ x, long long sb, long long st, long long sf, int B, int T, int F,
+                       const __nv_bfloat16* __restrict__ dy, float* __restrict__ dw, int pixels_per_cta) {
+  __shared__ float red[576];
+  for (int i = threadIdx.x; i < 576; i += 256) red[i] = 0.f;
+  __syncthreads();
+  const int g = threadIdx.x & 7;
+  const int ty = threadIdx.x >> 3;  // 32 pixel lanes
+  const long long P = (long long)B * T * F;
+  const long long p0 = (long long)blockIdx.x * pixels_per_cta;
+  const long long p1 = min(P, p0 + pixels_per_cta);
+  float acc[8][9];
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[c][k] = 0.f;
+  for (long long p = p0 + ty; p < p1; p += 32) {
+    const int f = (int)(p % F);
+    const int t = (int)((p / F) % T);
+    const int b = (int)(p / ((long long)F * T));
+    float xv[9];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int tt = t + kh - 1, ff = f + kw - 1;
+        xv[kh * 3 + kw] = (tt >= 0 && tt < T && ff >= 0 && ff < F) ? __ldg(x + b * sb + tt * st + ff * sf) : 0.f;
+      }
+    float d[8];
+    ld8(dy + p * 64 + g * 8, d);
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+#pragma unroll
+      for (int k = 0; k < 9; ++k) acc[c][k] = fmaf(d[c], xv[k], acc[c][k]);
+  }
+  // lanes with equal g inside a warp: lane = g + 8*j, j = 0..3
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      float v = acc[c][k];
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if ((threadIdx.x & 31) < 8) atomicAdd(&red[(g * 8 + c) * 9 + k], v);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 576; i += 256) atomicAdd(dw + i, red[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// BatchNorm2d (training) statistics over x[rows][C] bf16 -> sums[0][c] = sum x, sums[1][c] = sum x^2 (fp64 atomics)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int C, double* __restrict__ sums,
+                int rows_per_cta) {
+  extern __shared__ float sred[];  // [2][C]
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sred[i] = 0.f;
+  __syncthreads();
+  const int cg = C >> 3;
+  const int ry = blockDim.x / cg;
+  const int tx = threadIdx.x % cg, ty = threadIdx.x / cg;
+  float s[8], ss[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = ss[i] = 0.f;
+  if (ty < ry) {
+    const long long r0 = (long long)blockIdx.x * rows_per_cta;
+    const long long r1 = min(rows, r0 + rows_per_cta);
+    for (long long r = r0 + ty; r < r1; r += ry) {
+      float v[8];
+      ld8(x + r * C + tx * 8, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[i] += v[i];
+        ss[i] = fmaf(v[i], v[i], ss[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(&sred[tx * 8 + i], s[i]);
+      atomicAdd(&sred[C + tx * 8 + i], ss[i]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(sums + i, (double)sred[i]);
+}
+
+// mean / biased var -> scale, shift (+ saved mean, rstd) and the running-stat update of nn.BatchNorm2d
+// (momentum 0.1, unbiased running variance, num_batches_tracked += 1).
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum, float* scale,
+                                   float* shift, float* mean_out, float* rstd_out, float* running_mean,
+                                   float* running_var, long long* nbt, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && nbt) *nbt += 1;
+  if (c >= C) return;
+  const double mean = sums[c] / count;
+  double var = sums[C + c] / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const double rstd = 1.0 / sqrt(var + (double)eps);
+  const float sc = (float)((double)gamma[c] * rstd);
+  scale[c] = sc;
+  shift[c] = (float)((double)beta[c] - mean * (double)gamma[c] * rstd);
+  mean_out[c] = (float)mean;
+  rstd_out[c] = (float)rstd;
+  if (running_mean) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+// eval mode: scale / shift from the running statistics
+__global__ void bn_eval_params_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ running_mean, const float* __restrict__ running_var,
+                                      float eps, float* scale, float* shift, float* mean_out, float* rstd_out, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float rstd = rsqrtf(running_var[c] + eps);
+  scale[c] = gamma[c] * rstd;
+  shift[c] = beta[c] - running_mean[c] * gamma[c] * rstd;
+  if (mean_out) mean_out[c] = running_mean[c];
+  if (rstd_out) rstd_out[c] = rstd;
+}
+
+// ---------------------------------------------------------------------------------------------
+// y = Dropout(MaxPool_(1,k)(LeakyReLU(x * scale + shift)));  scale == NULL => pure max-pool of x.
+// x: [rows][W][C];  out: pixel (row, wo) at out + (row*Wo + wo) * ld_out + c_off;  optional second copy in the
+// sequence-model layout out_seq[row][c*Wo + wo] (model.py:93,112 permute+view).
+// ---------------------------------------------------------------------------------------------
+struct PoolGeom {
+  long long rows;
+  int W, C, k, Wo;
+};
+
+__global__ void __launch_bounds__(256)
+bn_act_pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, PoolGeom g, const float* __restrict__ scale,
+                       const float* __restrict__ shift, float slope, unsigned drop_thresh, float drop_scale,
+                       unsigned long long seed, __nv_bfloat16* __restrict__ out, long long ld_out, int c_off,
+                       __nv_bfloat16* __restrict__ out_seq) {
+  const int cg = g.C >> 3;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = g.rows * g.Wo * cg;
+  if (idx >= total) return;
+  const int tx = (int)(idx % cg);
+  const int wo = (int)((idx / cg) % g.Wo);
+  const long long row = idx / ((long long)cg * g.Wo);
+  float sc[8], sh[8];
+  if (scale) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      sc[i] = __ldg(scale + tx * 8 + i);
+      sh[i] = __ldg(shift + tx * 8 + i);
+    }
+  }
+  float best[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) best[i] = -INFINITY;
+  const __nv_bfloat16* xp = x + ((row * g.W + (long long)wo * g.k) * g.C + tx * 8);
+  for (int j = 0; j < g.k; ++j) {
+    float v[8];
+    ld8(xp + (long long)j * g.C, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float z = v[i];
+      if (scale) {
+        z = fmaf(z, sc[i], sh[i]);
+        z = z > 0.f ? z : z * slope;
+      }
+      best[i] = fmaxf(best[i], z);
+    }
+  }
+  if (drop_thresh) {
+    const unsigned long long e0 = (unsigned long long)((row * g.Wo + wo) * g.C + tx * 8);
+    const uint4 r0 = dropout_bits4(seed, e0 >> 2), r1 = dropout_bits4(seed, (e0 >> 2) + 1);
+    const unsigned rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) best[i] = rr[i] < drop_thresh ? best[i] * drop_scale : 0.f;
+  }
+  if (out) st8(out + (row * g.Wo + wo) * ld_out + c_off + tx * 8, best);
+  if (out_seq) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      out_seq[row * ((long long)g.C * g.Wo) + (long long)(tx * 8 + i) * g.Wo + wo] = __float2bfloat16(best[i]);
+  }
+}
+
+// Gradient routing shared by the two backward passes: for one window (row, wo) and 8 channels recompute
+// z_j = lrelu(bn(x_j)), the first arg-max j*, and g* = dout * dropout * lrelu'(.) at j*.
+struct BnBwdArgs {
+  const __nv_bfloat16* x;
+  PoolGeom g;
+  const float* scale;
+  const float* shift;
+  const float* mean;
+  const float* rstd;
+  float slope;
+  unsigned drop_thresh;
+  float drop_scale;
+  unsigned long long seed;
+  const __nv_bfloat16* dout;      // NHWC consumer gradient (may be NULL)
+  long long ld_dout;
+  int c_off;
+  const __nv_bfloat16* dout_seq;  // sequence-layout consumer gradient (may be NULL)
+};
+
+__device__ __forceinline__ void bn_bwd_route(const BnBwdArgs& a, long long row, int wo, int tx, const float* sc,
+                                             const float* sh, int* jstar, float* gstar) {
+  const PoolGeom& g = a.g;
+  float best[8], pre[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    best[i] = -INFINITY;
+    jstar[i] = 0;
+    pre[i] = 0.f;
+  }
+  const __nv_bfloat16* xp = a.x + ((row * g.W + (long long)wo * g.k) * g.C + tx * 8);
+  for (int j = 0; j < g.k; ++j) {
+    float v[8];
+    ld8(xp + (long long)j * g.C, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float zp = fmaf(v[i], sc[i], sh[i]);
+      const float z = zp > 0.f ? zp : zp * a.slope;
+      if (z > best[i]) {
+        best[i] = z;
+        jstar[i] = j;
+        pre[i] = zp;
+      }
+    }
+  }
+  float go[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) go[i] = 0.f;
+  if (a.dout) {
+    float d[8];
+    ld8(a.dout + (row * g.Wo + wo) * a.ld_dout + a.c_off + tx * 8, d);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) go[i] += d[i];
+  }
+  if (a.dout_seq) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      go[i] += __bfloat162float(a.dout_seq[row * ((long long)g.C * g.Wo) + (long long)(tx * 8 + i) * g.Wo + wo]);
+  }
+  if (a.drop_thresh) {
+    const unsigned long long e0 = (unsigned long long)((row * g.Wo + wo) * g.C + tx * 8);
+    const uint4 r0 = dropout_bits4(a.seed, e0 >> 2), r1 = dropout_bits4(a.seed, (e0 >> 2) + 1);
+    const unsigned rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) go[i] = rr[i] < a.drop_thresh ? go[i] * a.drop_scale : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) gstar[i] = go[i] * (pre[i] > 0.f ? 1.f : a.slope);
+}
+
+// pass 1: sums[0][c] = sum g, sums[1][c] = sum g * xhat
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(BnBwdArgs a, double* __restrict__ sums, int windows_per_cta) {
+  extern __shared__ float sred[];  // [2][C]
+  const PoolGeom& g = a.g;
+  for (int i = threadIdx.x; i < 2 * g.C; i += blockDim.x) sred[i] = 0.f;
+  __syncthreads();
+  const int cg = g.C >> 3;
+  const int ry = blockDim.x / cg;
+  const int tx = threadIdx.x % cg, ty = threadIdx.x / cg;
+  if (ty < ry) {
+    float sc[8], sh[8], mu[8], rs[8], s[8], sx[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      sc[i] = a.scale[tx * 8 + i];
+      sh[i] = a.shift[tx * 8 + i];
+      mu[i] = a.mean[tx * 8 + i];
+      rs[i] = a.rstd[tx * 8 + i];
+      s[i] = sx[i] = 0.f;
+    }
+    const long long nwin = g.rows * g.Wo;
+    const long long w0 = (long long)blockIdx.x * windows_per_cta;
+    const long long w1 = min(nwin, w0 + windows_per_cta);
+    for (long long wi = w0 + ty; wi < w1; wi += ry) {
+      const long long row = wi / g.Wo;
+      const int wo = (int)(wi - row * g.Wo);
+      int js[8];
+      float gs[8];
+      bn_bwd_route(a, row, wo, tx, sc, sh, js, gs);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float xv = __bfloat162float(a.x[(row * g.W + (long long)wo * g.k + js[i]) * g.C + tx * 8 + i]);
+        s[i] += gs[i];
+        sx[i] = fmaf(gs[i], (xv - mu[i]) * rs[i], sx[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(&sred[tx * 8 + i], s[i]);
+      atomicAdd(&sred[g.C + tx * 8 + i], sx[i]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * g.C; i += blockDim.x) atomicAdd(sums + i, (double)sred[i]);
+}
+
+// dgamma += sum g*xhat, dbeta += sum g
+__global__ void bn_bwd_params_kernel(const double* __restrict__ sums, float* dgamma, float* dbeta, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  dbeta[c] += (float)sums[c];
+  dgamma[c] += (float)sums[C + c];
+}
+
+// pass 2: dx = scale * (g - mean_g - xhat * mean_gx) for every input element (pooled-away elements have g = 0)
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(BnBwdArgs a, const double* __restrict__ sums, double count, __nv_bfloat16* __restrict__ dx) {
+  const PoolGeom& g = a.g;
+  const int cg = g.C >> 3;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = g.rows * g.Wo * cg;
+  if (idx >= total) return;
+  const int tx = (int)(idx % cg);
+  const int wo = (int)((idx / cg) % g.Wo);
+  const long long row = idx / ((long long)cg * g.Wo);
+  float sc[8], sh[8], mu[8], rs[8], mg[8], mgx[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = tx * 8 + i;
+    sc[i] = a.scale[c];
+    sh[i] = a.shift[c];
+    mu[i] = a.mean[c];
+    rs[i] = a.rstd[c];
+    mg[i] = (float)(sums[c] / count);
+    mgx[i] = (float)(sums[g.C + c] / count);
+  }
+  int js[8];
+  float gs[8];
+  bn_bwd_route(a, row, wo, tx, sc, sh, js, gs);
+  const int jend = (wo == g.Wo - 1) ? (g.W - wo * g.k) : g.k;  // last window also owns the floor-dropped columns
+  const long long base = (row * g.W + (long long)wo * g.k) * g.C + tx * 8;
+  for (int j = 0; j < jend; ++j) {
+    float v[8], o[8];
+    ld8(a.x + base + (long long)j * g.C, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float xhat = (v[i] - mu[i]) * rs[i];
+      const float gi = (j == js[i]) ? gs[i] : 0.f;
+      o[i] = sc[i] * (gi - mg[i] - xhat * mgx[i]);
+    }
+    st8(dx + base + (long long)j * g.C, o);
+  }
+}
+
+// aux max-pool backward (model.py:45-49,103-105): dx[argmax window] += dout
+__global__ void __launch_bounds__(256)
+maxpool_bwd_add_kernel(const __nv_bfloat16* __restrict__ x, PoolGeom g, const __nv_bfloat16* __restrict__ dout,
+                       long long ld_dout, int c_off, __nv_bfloat16* __restrict__ dx) {
+  const int cg = g.C >> 3;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = g.rows * g.Wo * cg;
+  if (idx >= total) return;
+  const int tx = (int)(idx % cg);
+  const int wo = (int)((idx / cg) % g.Wo);
+  const long long row = idx / ((long long)cg * g.Wo);
+  float best[8];
+  int js[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    best[i] = -INFINITY;
+    js[i] = 0;
+  }
+  const long long base = (row * g.W + (long long)wo * g.k) * g.C + tx * 8;
+  for (int j = 0; j < g.k; ++j) {
+    float v[8];
+    ld8(x + base + (long long)j * g.C, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (v[i] > best[i]) {
+        best[i] = v[i];
+        js[i] = j;
+      }
+  }
+  float d[8];
+  ld8(dout + (row * g.Wo + wo) * ld_dout + c_off + tx * 8, d);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    __nv_bfloat16* p = dx + base + (long long)js[i] * g.C + i;
+    *p = __float2bfloat16(__bfloat162float(*p) + d[i]);
+  }
+}
+
+}  // namespace pe
+
+// =================================================================================================
+// C-ABI
+// =================================================================================================
+using namespace pe;
+#define PE_ST(s) reinterpret_cast<cudaStream_t>(s)
+#define PE_LAUNCH_RC() (cudaGetLastError() == cudaSuccess ? PE_OK : PE_ERR_LAUNCH)
+
+extern "C" int pe_stem_conv_fwd(const float* x, long long sb, long long st, long long sf, int B, int T, int F,
+                                const float* w, void* y, pe_stream_t stream) {
+  if (int rc = pe_host::check_arch()) return rc;
+  if (!x || !w || !y || B <= 0 || T <= 0 || F <= 0) return PE_ERR_BAD_SHAPE;
+  const long long P = (long long)B * T * F;
+  stem_conv_fwd_kernel<<<(unsigned)((P + 31) / 32), 256, 0, PE_ST(stream)>>>(x, sb, st, sf, B, T, F, w,
+                                                                             (__nv_bfloat16*)y);
+  return PE_LAUNCH_RC();
+}
+
+extern "C" int pe_stem_conv_wgrad(const float* x, long long sb, long long st, long long sf, int B, int T, int F,
+                                  const void* dy, float* dw, pe_stream_t stream) {
+  if (int rc = pe_host::check_arch()) return rc;
+  if (!x || !dy || !dw || B <= 0 || T <= 0 || F <= 0) return PE_ERR_BAD_SHAPE;
+  const long long P = (long long)B * T * F;
+  const int per = 4096;
+  stem_conv_wgrad_kernel<<<(unsigned)((P + per - 1) / per), 256, 0, PE_ST(stream)>>>(
+      x, sb, st, sf, B, T, F, (const __nv_bfloat16*)dy, dw, per);
+  return PE_LAUNCH_RC();
+}
+
+static bool chan_ok(int C) { return C > 0 && (C % 8) == 0 && C <= 2048; }
+
+extern "C" int pe_bn_stats(const void* x, long long rows, int C, double* sums, pe_stream_t stream) {
+  if (int rc = pe_host::check_arch()) return rc;
+  if (!x || !sums || rows <= 0 || !chan_ok(C) || C / 8 > 256) return PE_ERR_BAD_SHAPE;
+  const int per = 2048;
+  bn_stats_kernel<<<(unsigned)((rows + per - 1) / per), 256, 2 * C * sizeof(float), PE_ST(stream)>>>(
+      (const __nv_bfloat16*)x, rows, C, sums, per);
+  return PE_LAUNCH_RC();
+}
+
+extern "C" int pe_bn_finalize(const double* sums, double count, const float* gamma, const float* beta, float eps,
+                              float momentum, float* scale, float* shift, float* mean, float* rstd,
+                              float* running_mean, float* running_var, long long* num_batches_tracked, int C,
+                              pe_stream_t stream) {
+  if (int rc = pe_host::check_arch()) return rc;
+  if (!sums || !gamma || !beta || !scale || !shift || !mean || !rstd || C <= 0 || count <= 0) return PE_ERR_BAD_SHAPE;
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, PE_ST(stream)>>>(sums, count, gamma, beta, eps, momentum, scale, shift,
+                                                                 mean, rstd, running_mean, running_var,
+                                                                 num_batches_tracked, C);
+  return PE_LAUNCH_RC();
+}
+
+extern "C" int pe_bn_eval_params(const float* gamma, const float* beta, const float* running_mean,
+                                 const float* running_var, float eps, float* scale, float* shift, float* mean,
+                                 float* rstd, int C, pe_stream_t stream) {
+  if (int rc = pe_host::check_arch()) return rc;
+  if (!gamma || !beta || !running_mean || !running_var || !scale || !shift || C <= 0) return PE_ERR_BAD_SHAPE;
+  bn_eval_params_kernel<<<(C + 127) / 128, 128, 0, PE_ST(stream)>>>(gamma, beta, running_mean, running_var, eps, scale,
+                                                                    shift, mean, rstd, C);
+  return PE_LAUNCH_RC();
+}
+
+extern "C" int pe_bn_act_pool_fwd(const void* x, long long rows, int W, int C, int k, const float* scale,
+                                  const float* shift, float slope, unsigned drop_thresh, float drop_scale,
+                                  unsigned long long seed, void* out, long long ld_out, int c_off, void* out_seq,
+                                  pe_stream_t stream) {
+  if (int rc = pe_host::check_arch()) return rc;
+  if (!x || rows <= 0 || W <= 0 || !chan_ok(C) || k <= 0 || k > W || (!out && !out_seq) || ((scale == 0) != (shift == 0)))
+    return PE_ERR_BAD_SHAPE;
+  PoolGeom g{rows, W, C, k, W / k};
+  const long long total = rows * g.Wo * (C / 8);
+  bn_act_pool_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, PE_ST(stream)>>>(
+      (const __nv_bfloat16*)x, g, scale, shift, slope, drop_thresh, drop_scale, seed, (__nv_bfloat16*)out, ld_out, c_off,
+      (__nv_bfloat16*)out_seq);
+  return PE_LAUNCH_RC();
+}
+
+extern "C" int pe_bn_act_pool_bwd(const void* x, long long rows, int W, int C, int k, const float* scale,
+                                  const float* shift, const float* mean, const float* rstd, float slope,
+                                  unsigned drop_thresh, float drop_scale, unsigned long long seed, const void* dout,
+                                  long long ld_dout, int c_off, const void* dout_seq, double* sums /* [2][C], zeroed */,
+                                  float* dgamma, float* dbeta, void* dx, pe_stream_t stream) {
+  if (int rc = pe_host::check_arch()) return rc;
+  if (!x || !scale || !shift || !mean || !rstd || !sums || !dx || rows <= 0 || W <= 0 || !chan_ok(C) || C / 8 > 256 ||
+      k <= 0 || k > W || (!dout && !dout_seq))
+    return PE_ERR_BAD_SHAPE;
+  BnBwdArgs a{};
+  a.x = (const __nv_bfloat16*)x;
+  a.g = PoolGeom{rows, W, C, k, W / k};
+  a.scale = scale; a.shift = shift; a.mean = mean; a.rstd = rstd;
+  a.slope = slope; a.drop_thresh = drop_thresh; a.drop_scale = drop_scale; a.seed = seed;
+  a.dout = (const __nv_bfloat16*)dout; a.ld_dout = ld_dout; a.c_off = c_off;
+  a.dout_seq = (const __nv_bfloat16*)dout_seq;
+  const long long nwin = rows * a.g.Wo;
+  const int per = 2048;
+  bn_bwd_reduce_kernel<<<(unsigned)((nwin + per - 1) / per), 256, 2 * C * sizeof(float), PE_ST(stream)>>>(a, sums, per);
+  if (dgamma && dbeta) bn_bwd_params_kernel<<<(C + 127) / 128, 128, 0, PE_ST(stream)>>>(sums, dgamma, dbeta, C);
+  const long long total = nwin * (C / 8);
+  bn_bwd_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, PE_ST(stream)>>>(a, sums, (double)rows * W,
+                                                                                  (__nv_bfloat16*)dx);
+  return PE_LAUNCH_RC();
+}
+
+extern "C" int pe_maxpool_bwd_add(const void* x, long long rows, int W, int C, int k, const void* dout,
+                                  long long ld_dout, int c_off, void* dx, pe_stream_t stream) {
+  if (int rc = pe_host::check_arch()) return rc;
+  if (!x || !dout || !dx || rows <= 0 || W <= 0 || !chan_ok(C) || k <= 0 || k > W) return PE_ERR_BAD_SHAPE;
+  PoolGeom g{rows, W, C, k, W / k};
+  const long long total = rows * g.Wo * (C / 8);
+  maxpool_bwd_add_kernel<<<(unsigned)((total + 255) / 256), 256, 0, PE_ST(stream)>>>(
+      (const __nv_bfloat16*)x, g, (const __nv_bfloat16*)dout, ld_dout, c_off, (__nv_bfloat16*)dx);
+  return PE_LAUNCH_RC();
+}

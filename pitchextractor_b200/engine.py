@@ -1,0 +1,513 @@
+"""Kernel engine of JDCNet: owns the flat parameter / gradient arenas and the activation buffers and enqueues the
+sm_100a kernels of one forward (+ backward) pass on the current CUDA stream.
+
+Data layout in HBM
+  * parameters: one flat fp32 arena (master) + one flat bf16 arena (tensor-core operands, re-cast every step) + one
+    flat fp32 gradient arena; every ``nn.Parameter`` / ``.grad`` is a view.
+  * activations: NHWC bf16 ([B, T, F, C]; T = 192 frames on H, mel bins on W), sequence tensors [B*T, D] bf16, pre-LN
+    residual sums fp32.  Everything the backward pass needs is kept (no recompute): 180 GB of HBM make activation
+    checkpointing (reference trainer.py:227-233) unnecessary.
+  * dropout masks are never stored: Philox keyed by (site seed, element index) is replayed in the backward kernels.
+"""
+import ctypes
+
+import torch
+
+from . import _lib as L
+from . import ops
+from ._lib import call, ptr, stream
+
+c_int, c_ll, c_f, c_d, c_u, c_ull = (ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_double, ctypes.c_uint,
+                                     ctypes.c_ulonglong)
+BN_EPS, BN_MOMENTUM, LN_EPS = 1e-5, 0.1, 1e-5
+NULL = None
+
+
+def _align(n, a=64):
+    return (n + a - 1) // a * a
+
+
+class _OutputGrad(torch.autograd.Function):
+    """One autograd node for the whole network: forward ran in the engine, backward replays the engine's backward
+    kernels and accumulates into the parameters' ``.grad`` views."""
+
+    @staticmethod
+    def forward(ctx, engine, token, *params):
+        ctx.engine = engine
+        ctx.token = token
+        cls, det = engine._out_cls, engine._out_det
+        return cls.clone(), det.clone()
+
+    @staticmethod
+    def backward(ctx, dcls, ddet):
+        eng = ctx.engine
+        if ctx.token != eng._fwd_token:
+            raise RuntimeError("pitchextractor_b200: backward through a stale forward (activations were overwritten)")
+        eng.backward_from_output_grads(dcls, ddet)
+        return (None, None) + tuple(None for _ in range(len(eng.params)))
+
+
+class Engine:
+    def __init__(self, model, device):
+        L.check(L.lib().pe_check_device(), "pe_check_device")
+        self.model = model
+        self.device = device
+        self.slope = float(model.leaky_relu_slope)
+        sc = model.sequence_classifier
+        self.seq_type = sc.model_type
+        self.seq_dim = sc.output_dim
+        self.num_layers = sc.num_layers
+        self.nhead = sc.nhead
+        self.ff = sc.dim_feedforward
+        self.p_seq = float(sc.dropout)
+        self.p_trunk = 0.5  # nn.Dropout(p=0.5) in pool_block / detector_conv (model.py:40,56)
+        if model.num_class != 1:
+            raise NotImplementedError("the fused heads kernel implements num_class == 1 (Configs/config.yml:17)")
+        if self.seq_type != "transformer":
+            raise NotImplementedError("bilstm sequence model: recurrence kernels not built yet")
+        self.step_seed = 0x5EED0000
+        self.dropout_enabled = True
+        self._bufs = {}
+        self._fwd_token = 0
+        self.on_grads_ready = None  # callback(tag) for the data-parallel gradient reducer
+        self._pack()
+
+    # ------------------------------------------------------------------ parameter arenas
+    def _pack(self):
+        named = list(self.model.named_parameters())
+        self.names = [n for n, _ in named]
+        self.params = [p for _, p in named]
+        offs, total = [], 0
+        for p in self.params:
+            offs.append(total)
+            total += _align(p.numel())
+        self.total = total
+        dev = self.device
+        self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.flat_grad = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.flat_bf16 = torch.zeros(total, device=dev, dtype=torch.bfloat16)
+        self.view, self.gview, self.bview, self.offset = {}, {}, {}, {}
+        for name, p, off in zip(self.names, self.params, offs):
+            n = p.numel()
+            if p.dim() == 4:  # conv weight: channels-last physical order [Cout][kh][kw][Cin]
+                co, ci, kh, kw = p.shape
+                mk = lambda buf: buf[off:off + n].view(co, kh, kw, ci).permute(0, 3, 1, 2)
+            else:
+                mk = lambda buf, shape=p.shape: buf[off:off + n].view(shape)
+            v = mk(self.flat)
+            v.copy_(p.data)
+            p.data = v
+            p.grad = mk(self.flat_grad)
+            self.view[name], self.gview[name], self.bview[name], self.offset[name] = v, p.grad, mk(self.flat_bf16), off
+        # fused operand layouts of the convolution weights (bf16)
+        self.wops = {}
+        for blk, cin, cout in (("conv_block", 64, 64),):
+            self.wops[blk + ".3.dgrad"] = torch.empty(cin, 9 * cout, device=dev, dtype=torch.bfloat16)
+        for i, (cin, cout) in enumerate(((64, 128), (128, 192), (192, 256)), 1):
+            r = "res_block%d" % i
+            self.wops[r + ".B.fwd"] = torch.empty(cout, 9 * cout + cin, device=dev, dtype=torch.bfloat16)
+            self.wops[r + ".B.dgrad"] = torch.empty(cout, 9 * cout, device=dev, dtype=torch.bfloat16)
+            self.wops[r + ".A.dgrad"] = torch.empty(cin, 9 * cout + cout, device=dev, dtype=torch.bfloat16)
+        nbn = 9
+        self.bn_sums = torch.zeros(2 * nbn, 2, 256, device=dev, dtype=torch.float64)  # fwd + bwd scratch per BN
+        self.bn_aff = torch.zeros(nbn, 4, 256, device=dev, dtype=torch.float32)       # scale, shift, mean, rstd
+        self.bn_index = {}
+        self.loss_acc = torch.zeros(2, device=dev, dtype=torch.float64)
+        self.loss_out = torch.zeros(3, device=dev, dtype=torch.float32)
+        from .optimizers import register_engine
+        register_engine(self)
+
+    def mat(self, name, rows, cols, arena="bf16"):
+        """[rows, cols] row-major view of a parameter's storage in the bf16 / fp32 / grad arena."""
+        buf = {"bf16": self.flat_bf16, "f32": self.flat, "grad": self.flat_grad}[arena]
+        off = self.offset[name]
+        return buf[off:off + rows * cols].view(rows, cols)
+
+    def attach_grads(self):
+        """(Re)attach the ``.grad`` views (an optimizer's zero_grad(set_to_none=True) drops them)."""
+        for name, p in zip(self.names, self.params):
+            if p.grad is None or p.grad.data_ptr() != self.gview[name].data_ptr():
+                p.grad = self.gview[name]
+
+    def zero_grad(self):
+        self.flat_grad.zero_()
+        self.attach_grads()
+
+    def refresh_weights(self):
+        """bf16 working copies of the (possibly just updated) fp32 master weights + conv operand layouts."""
+        call("pe_cast_bf16", ptr(self.flat), ptr(self.flat_bf16), c_ll(self.total), stream())
+        V = self.view
+        prep = lambda w, co, ci, w2, c2, fwd, dgrad: call(
+            "pe_conv_weight_prep", ptr(w), c_int(co), c_int(ci), ptr(w2), c_int(c2), ptr(fwd), ptr(dgrad), stream())
+        prep(V["conv_block.3.weight"], 64, 64, None, 0, None, self.wops["conv_block.3.dgrad"])
+        for i, (cin, cout) in enumerate(((64, 128), (128, 192), (192, 256)), 1):
+            r = "res_block%d" % i
+            wA, wB, wS = V[r + ".conv.0.weight"], V[r + ".conv.3.weight"], V[r + ".conv1by1.weight"]
+            prep(wB, cout, cout, wS, cin, self.wops[r + ".B.fwd"], None)
+            prep(wB, cout, cout, None, 0, None, self.wops[r + ".B.dgrad"])
+            prep(wA, cout, cin, wS, cout, None, self.wops[r + ".A.dgrad"])
+
+    # ------------------------------------------------------------------ buffers
+    def buf(self, name, shape, dtype=torch.bfloat16):
+        t = self._bufs.get(name)
+        if t is None or t.shape != torch.Size(shape) or t.dtype != dtype:
+            t = torch.empty(shape, device=self.device, dtype=dtype)
+            self._bufs[name] = t
+        return t
+
+    def _seed(self, site):
+        return (self.step_seed << 8) + site
+
+    def _drop(self, p, training):
+        if not training or not self.dropout_enabled or p <= 0.0:
+            return 0, 1.0
+        return L.drop_thresh(p)
+
+    # ------------------------------------------------------------------ BatchNorm helpers
+    def _bn_slot(self, prefix):
+        if prefix not in self.bn_index:
+            self.bn_index[prefix] = len(self.bn_index)
+        return self.bn_index[prefix]
+
+    def _bn_prepare(self, prefix, x, rows, C, training):
+        """Batch statistics (training) or running statistics (eval) -> scale / shift / mean / rstd for this BN."""
+        i = self._bn_slot(prefix)
+        aff = self.bn_aff[i]
+        sc, sh, mu, rs = aff[0], aff[1], aff[2], aff[3]
+        m = self.model.get_submodule(prefix)
+        if training:
+            sums = self.bn_sums[2 * i]
+            call("pe_bn_stats", ptr(x), c_ll(rows), c_int(C), ptr(sums), stream())
+            call("pe_bn_finalize", ptr(sums), c_d(float(rows)), ptr(m.weight), ptr(m.bias), c_f(BN_EPS),
+                 c_f(BN_MOMENTUM), ptr(sc), ptr(sh), ptr(mu), ptr(rs), ptr(m.running_mean), ptr(m.running_var),
+                 ptr(m.num_batches_tracked), c_int(C), stream())
+        else:
+            call("pe_bn_eval_params", ptr(m.weight), ptr(m.bias), ptr(m.running_mean), ptr(m.running_var), c_f(BN_EPS),
+                 ptr(sc), ptr(sh), ptr(mu), ptr(rs), c_int(C), stream())
+        return sc, sh, mu, rs
+
+    def _act_pool(self, x, rows, W, C, k, aff, out=None, ld_out=0, c_off=0, out_seq=None, drop=(0, 1.0), seed=0):
+        sc, sh = (aff[0], aff[1]) if aff is not None else (None, None)
+        call("pe_bn_act_pool_fwd", ptr(x), c_ll(rows), c_int(W), c_int(C), c_int(k), ptr(sc), ptr(sh), c_f(self.slope),
+             c_u(drop[0]), c_f(drop[1]), c_ull(seed), ptr(out), c_ll(ld_out), c_int(c_off), ptr(out_seq), stream())
+
+    def _act_pool_bwd(self, prefix, x, rows, W, C, k, dx, dout=None, ld_dout=0, c_off=0, dout_seq=None, drop=(0, 1.0),
+                      seed=0):
+        i = self._bn_slot(prefix)
+        aff = self.bn_aff[i]
+        sums = self.bn_sums[2 * i + 1]
+        g = self.gview
+        call("pe_bn_act_pool_bwd", ptr(x), c_ll(rows), c_int(W), c_int(C), c_int(k), ptr(aff[0]), ptr(aff[1]),
+             ptr(aff[2]), ptr(aff[3]), c_f(self.slope), c_u(drop[0]), c_f(drop[1]), c_ull(seed), ptr(dout),
+             c_ll(ld_dout), c_int(c_off), ptr(dout_seq), ptr(sums), ptr(g[prefix + ".weight"]), ptr(g[prefix + ".bias"]),
+             ptr(dx), stream())
+
+    # ------------------------------------------------------------------ forward
+    def _prep_input(self, x):
+        """Accept the reference layouts: model input [B,1,T,80] (possibly the transposed view of a [B,1,80,T] mel)."""
+        if x.dim() != 4 or x.shape[1] != 1:
+            raise ValueError("JDCNet expects input of shape [B, 1, T, n_mels]")
+        if x.device != self.device or x.dtype != torch.float32:
+            x = x.to(self.device, torch.float32)
+        B, _, T, F = x.shape
+        if F != 80:
+            raise ValueError("the conv trunk is built for 80 mel bins (width 80 -> 40 -> 20 -> 10 -> 2)")
+        if T > 256:
+            raise ValueError("sequence kernels are built for segments of at most 256 frames (reference uses 192)")
+        return x, B, T, F
+
+    def forward_core(self, x, training):
+        x, B, T, F = self._prep_input(x)
+        self._x, self._B, self._T = x, B, T
+        self._training = training
+        self._fwd_token += 1
+        self.step_seed += 1
+        if training:
+            self.bn_sums.zero_()
+        self.refresh_weights()
+        V, W16 = self.view, self.bview
+        BT = B * T
+        st = stream
+        # ---- conv_block (model.py:23-28)
+        Y1 = self.buf("Y1", (B, T, 80, 64))
+        call("pe_stem_conv_fwd", ptr(x), c_ll(x.stride(0)), c_ll(x.stride(2)), c_ll(x.stride(3)), c_int(B), c_int(T),
+             c_int(F), ptr(V["conv_block.0.weight"]), ptr(Y1), st())
+        aff = self._bn_prepare("conv_block.1", Y1, BT * 80, 64, training)
+        Z1 = self.buf("Z1", (B, T, 80, 64))
+        self._act_pool(Y1, BT, 80, 64, 1, aff, out=Z1, ld_out=64)
+        R = self.buf("R0", (B, T, 80, 64))
+        ops.conv3x3(Z1, self.mat("conv_block.3.weight", 64, 576), R)
+        # ---- residual blocks (model.py:143-175)
+        width = 80
+        for i, (cin, cout) in enumerate(((64, 128), (128, 192), (192, 256)), 1):
+            r = "res_block%d" % i
+            aff = self._bn_prepare(r + ".pre_conv.0", R, BT * width, cin, training)
+            P = self.buf("P%d" % i, (B, T, width // 2, cin))
+            self._act_pool(R, BT, width, cin, 2, aff, out=P, ld_out=cin)
+            width //= 2
+            U = self.buf("U%d" % i, (B, T, width, cout))
+            ops.conv3x3(P, self.mat(r + ".conv.0.weight", cout, 9 * cin), U)
+            aff = self._bn_prepare(r + ".conv.1", U, BT * width, cout, training)
+            Vv = self.buf("V%d" % i, (B, T, width, cout))
+            self._act_pool(U, BT, width, cout, 1, aff, out=Vv, ld_out=cout)
+            R = self.buf("R%d" % i, (B, T, width, cout))
+            ops.conv3x3(Vv, self.wops[r + ".B.fwd"], R, x2=P)
+        # ---- pool_block + auxiliary max-pools + concat (model.py:36-49,103-108)
+        CAT = self.buf("CAT", (B, T, 2, 640))
+        SEQC = self.buf("SEQC", (BT, 512))
+        aff = self._bn_prepare("pool_block.0", R, BT * 10, 256, training)
+        self._act_pool(R, BT, 10, 256, 4, aff, out=CAT, ld_out=640, c_off=384, out_seq=SEQC,
+                       drop=self._drop(self.p_trunk, training), seed=self._seed(1))
+        self._act_pool(self._bufs["R0"], BT, 80, 64, 40, None, out=CAT, ld_out=640, c_off=0)
+        self._act_pool(self._bufs["R1"], BT, 40, 128, 20, None, out=CAT, ld_out=640, c_off=64)
+        self._act_pool(self._bufs["R2"], BT, 20, 192, 10, None, out=CAT, ld_out=640, c_off=192)
+        # ---- detector_conv (model.py:52-57): 1x1 conv == GEMM over the 640 concatenated channels
+        DD = self.buf("DD", (BT * 2, 256))
+        ops.gemm(CAT.view(BT * 2, 640), self.mat("detector_conv.0.weight", 256, 640), DD, BT * 2, 256, 640)
+        aff = self._bn_prepare("detector_conv.1", DD, BT * 2, 256, training)
+        SEQD = self.buf("SEQD", (BT, 512))
+        self._act_pool(DD, BT, 2, 256, 1, aff, out=None, out_seq=SEQD, drop=self._drop(self.p_trunk, training),
+                       seed=self._seed(2))
+        # ---- sequence models (model.py:94,113)
+        Hc = self._transformer_fwd("sequence_classifier", "c", SEQC, B, T, training, 16)
+        Hd = self._transformer_fwd("sequence_detector", "d", SEQD, B, T, training, 64)
+        self._Hc, self._Hd = Hc, Hd
+        return Hc, Hd
+
+    def _transformer_fwd(self, prefix, tag, X, B, T, training, site0):
+        V, W16 = self.view, self.bview
+        M, D, FF, H = B * T, 512, self.ff, self.nhead
+        sm = self.model.get_submodule(prefix)
+        pe = sm.pos_encoding.pe
+        drop = self._drop(self.p_seq, training)
+        pdrop = self.p_seq if drop[0] else 0.0
+        Hcur = self.buf(tag + "H0", (M, D))
+        stats = self.buf(tag + "lnstats", (2 * self.num_layers + 1, 2, M), torch.float32)
+        call("pe_layernorm_fwd", None, ptr(X), ptr(pe), c_int(T), c_int(D), ptr(V[prefix + ".layer_norm.weight"]),
+             ptr(V[prefix + ".layer_norm.bias"]), c_f(LN_EPS), c_ll(M), ptr(Hcur), ptr(stats[0, 0]), ptr(stats[0, 1]),
+             stream())
+        for l in range(self.num_layers):
+            q = "%s.model.layers.%d." % (prefix, l)
+            t = "%s%d" % (tag, l)
+            site = site0 + 8 * l
+            QKV = self.buf(t + "QKV", (M, 3 * D))
+            ops.gemm(Hcur, W16[q + "self_attn.in_proj_weight"], QKV, M, 3 * D, D, bias=V[q + "self_attn.in_proj_bias"])
+            CTX = self.buf(t + "CTX", (M, D))
+            LSE = self.buf(t + "LSE", (B, H, T), torch.float32)
+            call("pe_attn_fwd", ptr(QKV), c_int(B), c_int(T), c_int(H), c_int(64), c_u(drop[0]), c_f(drop[1]),
+                 c_ull(self._seed(site + 0)), ptr(CTX), ptr(LSE), stream())
+            S1 = self.buf(t + "S1", (M, D), torch.float32)
+            ops.gemm(CTX, W16[q + "self_attn.out_proj.weight"], S1, M, D, D, bias=V[q + "self_attn.out_proj.bias"],
+                     p_drop=pdrop, seed=self._seed(site + 1), aux=Hcur, aux_mode=L.PE_AUX_ADD)
+            H1 = self.buf(t + "H1", (M, D))
+            call("pe_layernorm_fwd", ptr(S1), None, None, c_int(T), c_int(D), ptr(V[q + "norm1.weight"]),
+                 ptr(V[q + "norm1.bias"]), c_f(LN_EPS), c_ll(M), ptr(H1), ptr(stats[2 * l + 1, 0]),
+                 ptr(stats[2 * l + 1, 1]), stream())
+            U = self.buf(t + "U", (M, FF))
+            G = self.buf(t + "G", (M, FF))
+            ops.gemm(H1, W16[q + "linear1.weight"], G, M, FF, D, bias=V[q + "linear1.bias"], act=L.PE_ACT_GELU, out2=U,
+                     p_drop=pdrop, seed=self._seed(site + 2))
+            S2 = self.buf(t + "S2", (M, D), torch.float32)
+            ops.gemm(G, W16[q + "linear2.weight"], S2, M, D, FF, bias=V[q + "linear2.bias"], p_drop=pdrop,
+                     seed=self._seed(site + 3), aux=H1, aux_mode=L.PE_AUX_ADD)
+            Hn = self.buf(t + "H2", (M, D))
+            call("pe_layernorm_fwd", ptr(S2), None, None, c_int(T), c_int(D), ptr(V[q + "norm2.weight"]),
+                 ptr(V[q + "norm2.bias"]), c_f(LN_EPS), c_ll(M), ptr(Hn), ptr(stats[2 * l + 2, 0]),
+                 ptr(stats[2 * l + 2, 1]), stream())
+            Hcur = Hn
+        return Hcur
+
+    # ------------------------------------------------------------------ heads
+    def _heads(self, f0, sil, lambda_f0, grad_scale, want_grad, gc_ext=None, gd_ext=None):
+        V, g = self.view, self.gview
+        M, D = self._B * self._T, self.seq_dim
+        self._pred_f0 = self.buf("pred_f0", (M,), torch.float32)
+        self._pred_sil = self.buf("pred_sil", (M,), torch.float32)
+        dHc = self.buf("dHc", (M, D)) if want_grad else None
+        dHd = self.buf("dHd", (M, D)) if want_grad else None
+        self.loss_acc.zero_()
+        gw = lambda n: ptr(g[n]) if want_grad else None
+        call("pe_heads_loss", ptr(self._Hc), ptr(self._Hd), c_ll(M), c_int(D), ptr(V["classifier.weight"]),
+             ptr(V["classifier.bias"]), ptr(V["detector.weight"]), ptr(V["detector.bias"]), ptr(f0), ptr(sil),
+             c_f(lambda_f0), c_f(grad_scale), ptr(self._pred_f0), ptr(self._pred_sil),
+             ptr(self.loss_acc) if f0 is not None else None, ptr(self.loss_out) if f0 is not None else None,
+             ptr(gc_ext), ptr(gd_ext), ptr(dHc), ptr(dHd), gw("classifier.weight"), gw("classifier.bias"),
+             gw("detector.weight"), gw("detector.bias"), stream())
+        return dHc, dHd
+
+    # ------------------------------------------------------------------ backward
+    def _wgrad_linear(self, dY, X, name, M_out, N_in, tokens):
+        """grad(weight[name]) [M_out, N_in] += dY^T X, contraction over tokens, split-K with fp32 atomics."""
+        tiles = ((M_out + 127) // 128) * ((N_in + 255) // 256)
+        splits = max(1, min((tokens + 63) // 64, (296 + tiles - 1) // tiles))
+        ops.gemm(dY, X, self.mat(name, M_out, N_in, "grad"), M_out, N_in, tokens, a_mn=True, b_mn=True, splits=splits,
+                 out_mode=L.PE_OUT_F32_ATOMIC)
+
+    def _transformer_bwd(self, prefix, tag, X, dH, B, T, site0):
+        V, W16, g = self.view, self.bview, self.gview
+        M, D, FF, H = B * T, 512, self.ff, self.nhead
+        training = self._training
+        drop = self._drop(self.p_seq, training)
+        pdrop = self.p_seq if drop[0] else 0.0
+        stats = self._bufs[tag + "lnstats"]
+        sm = self.model.get_submodule(prefix)
+        dS = self.buf(tag + "dS", (M, D))
+        dSm = self.buf(tag + "dSm", (M, D))
+        dU = self.buf(tag + "dU", (M, FF))
+        dH1 = self.buf(tag + "dH1", (M, D))
+        dCTX = self.buf(tag + "dCTX", (M, D))
+        dQKV = self.buf(tag + "dQKV", (M, 3 * D))
+        delta = self.buf(tag + "delta", (B, H, T), torch.float32)
+        for l in reversed(range(self.num_layers)):
+            q = "%s.model.layers.%d." % (prefix, l)
+            t = "%s%d" % (tag, l)
+            site = site0 + 8 * l
+            Hin = self._bufs[tag + "H0"] if l == 0 else self._bufs["%s%dH2" % (tag, l - 1)]
+            QKV, CTX, LSE = self._bufs[t + "QKV"], self._bufs[t + "CTX"], self._bufs[t + "LSE"]
+            S1, H1, U, G, S2 = (self._bufs[t + k] for k in ("S1", "H1", "U", "G", "S2"))
+            # norm2 backward (+ linear2 output dropout, linear2.bias gradient)
+            call("pe_layernorm_bwd", ptr(dH), ptr(S2), None, None, c_int(T), c_int(D), ptr(V[q + "norm2.weight"]),
+                 ptr(stats[2 * l + 2, 0]), ptr(stats[2 * l + 2, 1]), c_ll(M), ptr(dS), ptr(dSm), c_u(drop[0]),
+                 c_f(drop[1]), c_ull(self._seed(site + 3)), ptr(g[q + "norm2.weight"]), ptr(g[q + "norm2.bias"]),
+                 ptr(g[q + "linear2.bias"]), stream())
+            # linear2: dG -> through dropout and GELU' -> dU ; weight gradient
+            ops.gemm(dSm, W16[q + "linear2.weight"], dU, M, FF, D, b_mn=True, p_drop=pdrop, seed=self._seed(site + 2),
+                     aux=U, aux_mode=L.PE_AUX_GELU_GRAD)
+            self._wgrad_linear(dSm, G, q + "linear2.weight", D, FF, M)
+            # linear1: dH1 = dU W1 + dS (residual) ; weight / bias gradients
+            ops.gemm(dU, W16[q + "linear1.weight"], dH1, M, D, FF, b_mn=True, aux=dS, aux_mode=L.PE_AUX_ADD)
+            self._wgrad_linear(dU, H1, q + "linear1.weight", FF, D, M)
+            call("pe_colsum_bf16", ptr(dU), c_ll(M), c_int(FF), c_ll(FF), ptr(g[q + "linear1.bias"]), stream())
+            # norm1 backward (+ out_proj output dropout, out_proj.bias gradient)
+            call("pe_layernorm_bwd", ptr(dH1), ptr(S1), None, None, c_int(T), c_int(D), ptr(V[q + "norm1.weight"]),
+                 ptr(stats[2 * l + 1, 0]), ptr(stats[2 * l + 1, 1]), c_ll(M), ptr(dS), ptr(dSm), c_u(drop[0]),
+                 c_f(drop[1]), c_ull(self._seed(site + 1)), ptr(g[q + "norm1.weight"]), ptr(g[q + "norm1.bias"]),
+                 ptr(g[q + "self_attn.out_proj.bias"]), stream())
+            # out_proj
+            ops.gemm(dSm, W16[q + "self_attn.out_proj.weight"], dCTX, M, D, D, b_mn=True)
+            self._wgrad_linear(dSm, CTX, q + "self_attn.out_proj.weight", D, D, M)
+            # attention
+            call("pe_attn_bwd", ptr(QKV), ptr(CTX), ptr(dCTX), ptr(LSE), c_int(B), c_int(T), c_int(H), c_int(64),
+                 c_u(drop[0]), c_f(drop[1]), c_ull(self._seed(site + 0)), ptr(dQKV), ptr(delta), stream())
+            # in_proj: dH = dQKV Wqkv + dS (residual)
+            dHn = self.buf(tag + "dHin%d" % (l & 1), (M, D))
+            ops.gemm(dQKV, W16[q + "self_attn.in_proj_weight"], dHn, M, D, 3 * D, b_mn=True, aux=dS,
+                     aux_mode=L.PE_AUX_ADD)
+            self._wgrad_linear(dQKV, Hin, q + "self_attn.in_proj_weight", 3 * D, D, M)
+            call("pe_colsum_bf16", ptr(dQKV), c_ll(M), c_int(3 * D), c_ll(3 * D), ptr(g[q + "self_attn.in_proj_bias"]),
+                 stream())
+            dH = dHn
+        dX = self.buf(tag + "dX", (M, D))
+        call("pe_layernorm_bwd", ptr(dH), None, ptr(X), ptr(sm.pos_encoding.pe), c_int(T), c_int(D),
+             ptr(V[prefix + ".layer_norm.weight"]), ptr(stats[0, 0]), ptr(stats[0, 1]), c_ll(M), ptr(dX), None, c_u(0),
+             c_f(1.0), c_ull(0), ptr(g[prefix + ".layer_norm.weight"]), ptr(g[prefix + ".layer_norm.bias"]), None,
+             stream())
+        return dX
+
+    def backward_core(self, dHc, dHd):
+        """Backward of everything below the heads; accumulates into the gradient arena."""
+        B, T = self._B, self._T
+        BT = B * T
+        training = self._training
+        W16, g, bufs = self.bview, self.gview, self._bufs
+        notify = self.on_grads_ready or (lambda tag: None)
+        dSEQD = self._transformer_bwd("sequence_detector", "d", bufs["SEQD"], dHd, B, T, 64)
+        notify("sequence_detector+heads")
+        dSEQC = self._transformer_bwd("sequence_classifier", "c", bufs["SEQC"], dHc, B, T, 16)
+        notify("sequence_classifier")
+        tdrop = self._drop(self.p_trunk, training)
+        # detector_conv
+        dDD = self.buf("dDD", (BT * 2, 256))
+        self._act_pool_bwd("detector_conv.1", bufs["DD"], BT, 2, 256, 1, dDD, dout_seq=dSEQD, drop=tdrop,
+                           seed=self._seed(2))
+        dCAT = self.buf("dCAT", (BT * 2, 640))
+        ops.gemm(dDD, self.mat("detector_conv.0.weight", 256, 640), dCAT, BT * 2, 640, 256, b_mn=True)
+        self._wgrad_linear(dDD, bufs["CAT"].view(BT * 2, 640), "detector_conv.0.weight", 256, 640, BT * 2)
+        # pool_block
+        dR = self.buf("dR3", (B, T, 10, 256))
+        self._act_pool_bwd("pool_block.0", bufs["R3"], BT, 10, 256, 4, dR, dout=dCAT, ld_dout=640, c_off=384,
+                           dout_seq=dSEQC, drop=tdrop, seed=self._seed(1))
+        width = 10
+        aux = {2: (10, 192), 1: (20, 64), 0: (40, 0)}  # aux max-pool window / concat channel offset per source R_k
+        for i, (cin, cout) in reversed(list(enumerate(((64, 128), (128, 192), (192, 256)), 1))):
+            r = "res_block%d" % i
+            P, U, Vv = bufs["P%d" % i], bufs["U%d" % i], bufs["V%d" % i]
+            gB = self.mat(r + ".conv.3.weight", cout, 9 * cout, "grad")
+            gS = self.mat(r + ".conv1by1.weight", cout, cin, "grad")
+            gA = self.mat(r + ".conv.0.weight", cout, 9 * cin, "grad")
+            # conv B + shortcut
+            dV = self.buf("dV%d" % i, (B, T, width, cout))
+            ops.conv3x3(dR, self.wops[r + ".B.dgrad"], dV)
+            ops.conv_wgrad(dR, Vv, gB, taps=9)
+            ops.conv_wgrad(dR, P, gS, taps=1)
+            dU = self.buf("dU%d" % i, (B, T, width, cout))
+            self._act_pool_bwd(r + ".conv.1", U, BT, width, cout, 1, dU, dout=dV, ld_dout=cout)
+            # conv A (+ shortcut data gradient fused as extra K columns)
+            dP = self.buf("dP%d" % i, (B, T, width, cin))
+            ops.conv3x3(dU, self.wops[r + ".A.dgrad"], dP, x2=dR)
+            ops.conv_wgrad(dU, P, gA, taps=9)
+            # pre_conv BN/LReLU/pool backward -> gradient of the block input
+            Rin = bufs["R%d" % (i - 1)]
+            dRin = self.buf("dR%d" % (i - 1), (B, T, width * 2, cin))
+            self._act_pool_bwd(r + ".pre_conv.0", Rin, BT, width * 2, cin, 2, dRin, dout=dP, ld_dout=cin)
+            k_aux, c_off = aux[i - 1]
+            call("pe_maxpool_bwd_add", ptr(Rin), c_ll(BT), c_int(width * 2), c_int(cin), c_int(k_aux), ptr(dCAT),
+                 c_ll(640), c_int(c_off), ptr(dRin), stream())
+            dR = dRin
+            width *= 2
+        # conv_block
+        dZ1 = self.buf("dZ1", (B, T, 80, 64))
+        ops.conv3x3(dR, self.wops["conv_block.3.dgrad"], dZ1)
+        ops.conv_wgrad(dR, bufs["Z1"], self.mat("conv_block.3.weight", 64, 576, "grad"), taps=9)
+        dY1 = self.buf("dY1", (B, T, 80, 64))
+        self._act_pool_bwd("conv_block.1", bufs["Y1"], BT, 80, 64, 1, dY1, dout=dZ1, ld_dout=64)
+        x = self._x
+        call("pe_stem_conv_wgrad", ptr(x), c_ll(x.stride(0)), c_ll(x.stride(2)), c_ll(x.stride(3)), c_int(B), c_int(T),
+             c_int(80), ptr(dY1), ptr(g["conv_block.0.weight"]), stream())
+        notify("trunk")
+
+    # ------------------------------------------------------------------ public entry points
+    def train_step(self, mel, f0, sil, lambda_f0=0.1, grad_scale=1.0):
+        """mel [B,1,80,T] (reference batch layout) -> fills .grad, returns device tensor [loss, f0, sil]."""
+        x = mel.transpose(-1, -2)  # trainer.py:235
+        self.zero_grad()
+        self.forward_core(x, training=True)
+        f0 = f0.to(self.device, torch.float32).contiguous().view(-1)
+        sil = sil.to(self.device, torch.float32).contiguous().view(-1)
+        dHc, dHd = self._heads(f0, sil, lambda_f0, grad_scale, want_grad=True)
+        self.backward_core(dHc, dHd)
+        return self.loss_out
+
+    def eval_loss(self, mel, f0, sil, lambda_f0=0.1):
+        self.forward_core(mel.transpose(-1, -2), training=False)
+        f0 = f0.to(self.device, torch.float32).contiguous().view(-1)
+        sil = sil.to(self.device, torch.float32).contiguous().view(-1)
+        self._heads(f0, sil, lambda_f0, 1.0, want_grad=False)
+        return self.loss_out
+
+    def autograd_forward(self, x):
+        training = self.model.training
+        self.forward_core(x, training=training)
+        B, T = self._B, self._T
+        self._predict_only()
+        self._out_cls = self._pred_f0.view(B, T, 1)
+        self._out_det = self._pred_sil.view(B, T)
+        if torch.is_grad_enabled() and training:
+            return _OutputGrad.apply(self, self._fwd_token, *self.params)
+        return self._out_cls.clone(), self._out_det.clone()
+
+    def _predict_only(self):
+        M = self._B * self._T
+        zeros = self.buf("zero_targets", (M,), torch.float32)
+        zeros.zero_()
+        self._heads(zeros, zeros, 0.0, 1.0, want_grad=False)
+
+    def backward_from_output_grads(self, dcls, ddet):
+        M = self._B * self._T
+        gc = dcls.to(torch.float32).contiguous().view(M)
+        gd = ddet.to(torch.float32).contiguous().view(M)
+        if any(p.grad is None for p in self.params):
+            self.flat_grad.zero_()  # grads were dropped by zero_grad(set_to_none=True): start from zero
+        self.attach_grads()
+        dHc, dHd = self._heads(None, None, 0.0, 1.0, want_grad=True, gc_ext=gc, gd_ext=gd)
+        self.backward_core(dHc, dHd)

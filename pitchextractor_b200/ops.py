@@ -8,6 +8,26 @@ from ._lib import Epilogue, call, ptr, stream
 
 c_int, c_ll, c_size = ctypes.c_int, ctypes.c_longlong, ctypes.c_size_t
 
+# When set to a list, every tensor-core tile-engine launch appends (tag, start_event, end_event, algorithmic_flops):
+# bench.py uses it to time the dominant kernel with CUDA events on the launching stream.
+PROFILE = None
+
+
+class _Timed:
+    def __init__(self, tag, flops):
+        self.tag, self.flops = tag, flops
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if PROFILE is not None:
+            self.e1.record()
+            PROFILE.append((self.tag, self.e0, self.e1, self.flops))
+
 
 def make_epilogue(out, out_mode=None, bias=None, act=L.PE_ACT_NONE, out2=None, aux=None, aux_mode=L.PE_AUX_NONE,
                   p_drop=0.0, seed=0, alpha=1.0, ldc=None):
@@ -36,8 +56,9 @@ def gemm(a, b, out, M, N, K, a_mn=False, b_mn=False, splits=1, **epkw):
     """out[M,N] (op)= sum_k A(m,k) B(n,k).  a: [M,K] (or [K,M] if a_mn), b: [N,K] (or [K,N] if b_mn), bf16."""
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     ep = make_epilogue(out, **epkw)
-    call("pe_gemm_bf16", ptr(a), c_ll(a.stride(0)), c_int(int(a_mn)), ptr(b), c_ll(b.stride(0)), c_int(int(b_mn)),
-         c_int(M), c_int(N), c_int(K), ctypes.byref(ep), c_int(splits), stream())
+    with _Timed("gemm", 2.0 * M * N * K):
+        call("pe_gemm_bf16", ptr(a), c_ll(a.stride(0)), c_int(int(a_mn)), ptr(b), c_ll(b.stride(0)), c_int(int(b_mn)),
+             c_int(M), c_int(N), c_int(K), ctypes.byref(ep), c_int(splits), stream())
     return out
 
 
@@ -48,8 +69,9 @@ def conv3x3(x, w, out, x2=None, **epkw):
     Cout = w.shape[0]
     assert w.shape[1] == 9 * C1 + C2 and x.is_contiguous() and w.is_contiguous()
     ep = make_epilogue(out, ldc=Cout, **epkw)
-    call("pe_conv3x3_nhwc", ptr(x), ptr(x2), ptr(w), c_int(B), c_int(H), c_int(W), c_int(C1), c_int(C2), c_int(Cout),
-         ctypes.byref(ep), stream())
+    with _Timed("conv", 2.0 * B * H * W * Cout * (9 * C1 + C2)):
+        call("pe_conv3x3_nhwc", ptr(x), ptr(x2), ptr(w), c_int(B), c_int(H), c_int(W), c_int(C1), c_int(C2),
+             c_int(Cout), ctypes.byref(ep), stream())
     return out
 
 
@@ -60,8 +82,9 @@ def conv_wgrad(dy, x, dw, taps=9, splits=0, col_offset=0):
     if splits <= 0:
         splits = max(1, min(64, (148 * 2) // (taps * ((Cout + 127) // 128))))
     base = ctypes.c_void_p(dw.data_ptr() + 4 * col_offset)
-    call("pe_conv_wgrad_nhwc", ptr(dy), ptr(x), base, c_ll(dw.stride(0)), c_int(B), c_int(H), c_int(W), c_int(C),
-         c_int(Cout), c_int(taps), c_int(splits), stream())
+    with _Timed("wgrad", 2.0 * B * H * W * Cout * C * taps):
+        call("pe_conv_wgrad_nhwc", ptr(dy), ptr(x), base, c_ll(dw.stride(0)), c_int(B), c_int(H), c_int(W), c_int(C),
+             c_int(Cout), c_int(taps), c_int(splits), stream())
     return dw
 
 

@@ -1,0 +1,162 @@
+"""``Trainer`` with the reference's constructor and methods (reference trainer.py:32-291), driving the fused CUDA step.
+
+Differences that follow from the B200 design (documented, not hidden):
+  * mixed precision is always bf16-operands / fp32-accumulate inside the kernels; no GradScaler is needed (the
+    reference autocasts to fp16 and scales, trainer.py:63-102).  ``use_mixed_precision`` is accepted and ignored.
+  * ``gradient_checkpointing`` is accepted and ignored: activations are kept in HBM, so the reference's double
+    BatchNorm running-stat update under checkpointing does not happen here.
+  * a batch may carry waveforms instead of mels (``Collater(return_wave=True)``): the log-mel then runs on the GPU.
+  * under torch.distributed (one process per GPU) gradients are all-reduced in overlapped buckets.
+"""
+import logging
+import os
+from collections import defaultdict
+
+import numpy as np
+import torch
+import torch.distributed as dist
+from tqdm import tqdm
+
+from .mel import LogMel
+from .parallel import GradReducer, broadcast_parameters, bucket_ranges
+
+logger = logging.getLogger(__name__)
+logger.setLevel(logging.DEBUG)
+
+
+class Trainer(object):
+    def __init__(self, model=None, criterion=None, optimizer=None, scheduler=None, config={}, loss_config={},
+                 device=torch.device("cpu"), logger=logger, train_dataloader=None, val_dataloader=None,
+                 initial_steps=0, initial_epochs=0, use_mixed_precision=False, gradient_checkpointing=False,
+                 checkpoint_use_reentrant=None):
+        self.steps, self.epochs = initial_steps, initial_epochs
+        self.model, self.criterion, self.optimizer, self.scheduler = model, criterion, optimizer, scheduler
+        self.train_dataloader, self.val_dataloader = train_dataloader, val_dataloader
+        self.config, self.loss_config = config, loss_config
+        self.device = torch.device(device)
+        self.logger = logger
+        self.finish_train = False
+        if self.device.type != "cuda":
+            raise RuntimeError("pitchextractor_b200.Trainer runs on a CUDA (sm_100a) device; there is no CPU fallback")
+        self.use_amp = True  # bf16 tensor-core operands, fp32 accumulation / master weights
+        self.gradient_checkpointing = False
+        if gradient_checkpointing:
+            self.logger.info("gradient_checkpointing ignored: activations stay resident in HBM")
+        self._logmel = None
+        self._reducer = None
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.sync_every_step = True  # reference semantics: run() returns python floats (3 .item() syncs there, 1 here)
+
+    # ------------------------------------------------------------------ checkpoints (trainer.py:138-195)
+    def save_checkpoint(self, checkpoint_path):
+        state = {"optimizer": self.optimizer.state_dict(), "scheduler": self.scheduler.state_dict(),
+                 "steps": self.steps, "epochs": self.epochs,
+                 "model": {k: v.detach().clone().contiguous() for k, v in self.model.state_dict().items()}}
+        d = os.path.dirname(checkpoint_path)
+        if d and not os.path.exists(d):
+            os.makedirs(d)
+        torch.save(state, checkpoint_path)
+
+    def load_checkpoint(self, checkpoint_path, load_only_params=False):
+        state = torch.load(checkpoint_path, map_location="cpu")
+        self._load(state["model"], self.model)
+        if not load_only_params:
+            self.steps, self.epochs = state["steps"], state["epochs"]
+            self.optimizer.load_state_dict(state["optimizer"])
+            state["scheduler"].update(**self.config.get("scheduler_params", {}))
+            self.scheduler.load_state_dict(state["scheduler"])
+
+    def _load(self, states, model, force_load=True):
+        """Shape-tolerant copy: missing keys are skipped, mismatching shapes copy the overlapping corner."""
+        own = model.state_dict()
+        for key, val in states.items():
+            if key not in own:
+                continue
+            val = val.data if isinstance(val, torch.nn.Parameter) else val
+            dst = own[key]
+            if val.shape == dst.shape:
+                dst.copy_(val)
+                continue
+            self.logger.info("%s does not have same shape" % key)
+            if not force_load or val.dim() != dst.dim():
+                continue
+            corner = tuple(slice(0, min(a, b)) for a, b in zip(val.shape, dst.shape))
+            dst[corner].copy_(val[corner])
+
+    @staticmethod
+    def get_gradient_norm(model):
+        return float(np.sqrt(sum(p.grad.data.norm(2).item() ** 2 for p in model.parameters())))
+
+    def _get_lr(self):
+        return self.optimizer.param_groups[0]["lr"]
+
+    # ------------------------------------------------------------------ one step (trainer.py:219-252)
+    def _mel_from_batch(self, batch):
+        """-> (mel-like model input, f0, sil).  batch = (mels [B,1,80,192], f0, sil) or (waves, f0, sil, crops)."""
+        if len(batch) == 4:
+            waves, f0, sil, crops = batch
+            if self._logmel is None:
+                self._logmel = LogMel(self.device)
+            x = self._logmel(waves.to(self.device, non_blocking=True), crop=crops.to(self.device, non_blocking=True),
+                             T_out=192, layout="btm")  # [B, 192, 80] == the transposed model input
+            return x[:, None].transpose(-1, -2), f0, sil  # present it as the reference's [B,1,80,192] view
+        x, f0, sil = batch
+        return x.to(self.device, non_blocking=True), f0, sil
+
+    def _ensure_parallel(self):
+        if self.world > 1 and self._reducer is None:
+            eng = self.model.engine
+            broadcast_parameters(eng.flat)
+            for b in self.model.buffers():
+                if b.dtype.is_floating_point:
+                    dist.broadcast(b, src=0)
+            offs = [eng.offset[n] for n in eng.names]
+            self._reducer = GradReducer(eng.flat_grad, bucket_ranges(eng.names, offs, eng.total))
+            eng.on_grads_ready = self._reducer.ready
+            if hasattr(self.optimizer, "grad_scale"):
+                self.optimizer.grad_scale = 1.0 / self.world
+
+    def run_async(self, batch):
+        """One optimisation step; returns the device tensor [loss, f0, sil] without synchronising."""
+        self._ensure_parallel()
+        x, f0, sil = self._mel_from_batch(batch)
+        f0 = f0.to(self.device, non_blocking=True)
+        sil = sil.to(self.device, non_blocking=True)
+        if self._reducer is not None:
+            self._reducer.begin_step()
+        losses = self.model.train_step_loss(x, f0, sil, self.loss_config["lambda_f0"])
+        if self._reducer is not None:
+            self._reducer.wait()
+            if not hasattr(self.optimizer, "grad_scale"):
+                self.model.engine.flat_grad.mul_(1.0 / self.world)
+        self.optimizer.step()
+        self.scheduler.step()
+        self.steps += 1
+        return losses
+
+    def run(self, batch):
+        losses = self.run_async(batch).tolist()  # one device->host read of 3 floats
+        return {"loss": losses[0], "f0": losses[1], "sil": losses[2]}
+
+    def _train_epoch(self):
+        self.epochs += 1
+        train_losses = defaultdict(list)
+        self.model.train()
+        for _, batch in enumerate(tqdm(self.train_dataloader, desc="[train]"), 1):
+            for key, value in self.run(batch).items():
+                train_losses["train/%s" % key].append(value)
+        train_losses = {key: np.mean(value) for key, value in train_losses.items()}
+        train_losses["train/learning_rate"] = self._get_lr()
+        return train_losses
+
+    @torch.no_grad()
+    def _eval_epoch(self):
+        self.model.eval()
+        eval_losses = defaultdict(list)
+        for _, batch in enumerate(tqdm(self.val_dataloader, desc="[eval]"), 1):
+            x, f0, sil = self._mel_from_batch(batch)
+            out = self.model.engine.eval_loss(x, f0, sil, self.loss_config["lambda_f0"]).tolist()
+            eval_losses["eval/loss"].append(out[0])
+            eval_losses["eval/f0"].append(out[1])
+            eval_losses["eval/sil"].append(out[2])
+        return {key: np.mean(value) for key, value in eval_losses.items()}
