@@ -159,6 +159,8 @@ int pe_attn_fwd(const void* qkv, int B, int T, int H, int head_dim, unsigned dro
 int pe_attn_bwd(const void* qkv, const void* ctx, const void* dctx, const float* lse, int B, int T, int H,
                 int head_dim, unsigned drop_thresh, float drop_scale, unsigned long long seed, void* dqkv, float* delta,
                 pe_stream_t stream);
+/* T == 192 runs on the tcgen05 kernels, other lengths on the fp32 SIMT kernels; on != 0 forces SIMT (cross-checks) */
+int pe_attn_set_simt(int on);
 /* heads (num_class == 1) + losses (model.py:96-98,115-117; train.py:104-106; trainer.py:237-239):
  * f0 = hc.wc + bc, logit = hd.(wd[0]+wd[1]) + bd[0]+bd[1]; loss_out = {total, lambda*SmoothL1, BCE}.
  * When dhc != NULL also writes dL/dhc, dL/dhd (bf16) and accumulates the head parameter gradients; with gc_ext /

@@ -60,6 +60,15 @@ __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t e, uint32_t
   return v < keep_thresh;
 }
 
+// attention-probability dropout: keep iff fmix32(seed, element) < thresh.  A counter hash instead of Philox because
+// the attention backward walks the mask in both row- and column-major order.
+__host__ __device__ __forceinline__ uint32_t attn_drop_hash(unsigned long long seed, unsigned long long e) {
+  uint32_t h = (uint32_t)e * 0x9E3779B1u ^ ((uint32_t)(e >> 32) * 0x85EBCA77u) ^ (uint32_t)seed ^
+               ((uint32_t)(seed >> 32) * 0xC2B2AE3Du);
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h;
+}
+
 // ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------

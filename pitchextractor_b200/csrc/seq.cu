@@ -173,30 +173,43 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ xf
   }
 }
 
-// out[n] += sum_m x[m][n]  (bias gradients of Linear layers)
+// out[n] += sum_m x[m][n]  (bias gradients of Linear layers).  CTA = 64 column groups (512 columns) x 4 row lanes.
 __global__ void __launch_bounds__(256)
 colsum_kernel(const __nv_bfloat16* __restrict__ x, long long M, int N, long long ld, int rows_per_cta,
               float* __restrict__ out) {
+  __shared__ float red[4][512];
   const int cg = N >> 3;
-  const int cpb = min(cg, 256);           // column groups handled per pass by this CTA
-  const int ry = 256 / cpb;
-  const int tx = threadIdx.x % cpb, ty = threadIdx.x / cpb;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int gcol = blockIdx.y * 64 + tx;
   const long long m0 = (long long)blockIdx.x * rows_per_cta;
   const long long m1 = min(M, m0 + rows_per_cta);
-  for (int g0 = blockIdx.y * cpb; g0 < cg; g0 += gridDim.y * cpb) {
-    const int gcol = g0 + tx;
-    if (gcol >= cg || ty >= ry) continue;
-    float s[8];
+  float s[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s[j] = 0.f;
-    for (long long m = m0 + ty; m < m1; m += ry) {
+  for (int j = 0; j < 8; ++j) s[j] = 0.f;
+  if (gcol < cg) {
+    long long m = m0 + ty;
+    for (; m + 12 < m1; m += 16) {  // 4 independent 16-byte loads in flight
+      float v0[8], v1[8], v2[8], v3[8];
+      ld8b(x + m * ld + gcol * 8, v0);
+      ld8b(x + (m + 4) * ld + gcol * 8, v1);
+      ld8b(x + (m + 8) * ld + gcol * 8, v2);
+      ld8b(x + (m + 12) * ld + gcol * 8, v3);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] += (v0[j] + v1[j]) + (v2[j] + v3[j]);
+    }
+    for (; m < m1; m += 4) {
       float v[8];
       ld8b(x + m * ld + gcol * 8, v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) s[j] += v[j];
     }
+  }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(out + gcol * 8 + j, s[j]);
+  for (int j = 0; j < 8; ++j) red[ty][tx * 8 + j] = s[j];
+  __syncthreads();
+  for (int c = threadIdx.x; c < 512; c += 256) {
+    const int col = blockIdx.y * 512 + c;
+    if (col < N) atomicAdd(out + col, red[0][c] + red[1][c] + red[2][c] + red[3][c]);
   }
 }
 
@@ -287,7 +300,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int T, int H, float scale
       const float p = __expf(s[jj] - mx);
       l += p;
       float pd = p;
-      if (drop_thresh) pd = dropout_keep(seed, e_row + j0 + jj, drop_thresh) ? p * drop_scale : 0.f;
+      if (drop_thresh) pd = attn_drop_hash(seed, e_row + j0 + jj) < drop_thresh ? p * drop_scale : 0.f;
       axpy64(o, pd, Vs + (j0 + jj) * HD);
     }
   }
@@ -343,7 +356,7 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
   for (int j = 0; j < T; ++j) {
     const float p = __expf(dot64(qr, Ks + j * HD) - L);
     float dp = dot64(dor, Vs + j * HD);
-    if (drop_thresh) dp = dropout_keep(seed, e_row + j, drop_thresh) ? dp * drop_scale : 0.f;
+    if (drop_thresh) dp = attn_drop_hash(seed, e_row + j) < drop_thresh ? dp * drop_scale : 0.f;
     axpy64(dq, p * (dp - dl), Ks + j * HD);
   }
   __nv_bfloat16* op = dqkv + row * ld + h * HD;
@@ -396,7 +409,7 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
   // pass A: dV_j = sum_q dropout(P)_qj dO_q
   for (int q = 0; q < T; ++q) {
     float p = __expf(dot64(kr, Qs + q * HD) - Ls[q]);
-    if (drop_thresh) p = dropout_keep(seed, e_base + (unsigned long long)q * T, drop_thresh) ? p * drop_scale : 0.f;
+    if (drop_thresh) p = attn_drop_hash(seed, e_base + (unsigned long long)q * T) < drop_thresh ? p * drop_scale : 0.f;
     axpy64(acc, p, dOs + q * HD);
   }
   __nv_bfloat16* ov = dqkv + ((long long)b * T + j) * ld + 2 * D + h * HD;
@@ -417,7 +430,7 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
   for (int q = 0; q < T; ++q) {
     const float p = __expf(dot64(kr, Qs + q * HD) - Ls[q]);
     float dp = dot64(vr, dOs + q * HD);
-    if (drop_thresh) dp = dropout_keep(seed, e_base + (unsigned long long)q * T, drop_thresh) ? dp * drop_scale : 0.f;
+    if (drop_thresh) dp = attn_drop_hash(seed, e_base + (unsigned long long)q * T) < drop_thresh ? dp * drop_scale : 0.f;
     axpy64(acc, p * (dp - Dl[q]), Qs + q * HD);
   }
   __nv_bfloat16* ok = dqkv + ((long long)b * T + j) * ld + D + h * HD;
@@ -617,18 +630,31 @@ extern "C" int pe_layernorm_bwd(const void* dy, const float* x_f32, const void* 
 extern "C" int pe_colsum_bf16(const void* x, long long M, int N, long long ld, float* out, pe_stream_t stream) {
   if (int rc = pe_host::check_arch()) return rc;
   if (!x || !out || M <= 0 || N <= 0 || (N % 8) || (ld % 8)) return PE_ERR_BAD_SHAPE;
-  const int per = 512;
-  dim3 grid((unsigned)((M + per - 1) / per), 1);
+  const int per = 256;
+  dim3 grid((unsigned)((M + per - 1) / per), (unsigned)((N / 8 + 63) / 64));
   colsum_kernel<<<grid, 256, 0, PE_ST(stream)>>>((const __nv_bfloat16*)x, M, N, ld, per, out);
   return PE_LAUNCH_RC();
 }
 
 static int attn_threads(int T) { return ((T + 31) / 32) * 32; }
 
+// tcgen05 kernels for the T = 192 segment length (attn_tc.cu); other lengths use the SIMT kernels above
+int pe_attn_fwd_tc(const void* qkv, int B, int H, unsigned drop_thresh, float drop_scale, unsigned long long seed,
+                   void* ctx, float* lse, cudaStream_t stream);
+int pe_attn_bwd_tc(const void* qkv, const void* ctx, const void* dctx, const float* lse, int B, int H,
+                   unsigned drop_thresh, float drop_scale, unsigned long long seed, void* dqkv, cudaStream_t stream);
+static bool g_attn_force_simt = false;
+extern "C" int pe_attn_set_simt(int on) {
+  g_attn_force_simt = on != 0;
+  return PE_OK;
+}
+
 extern "C" int pe_attn_fwd(const void* qkv, int B, int T, int H, int head_dim, unsigned drop_thresh, float drop_scale,
                            unsigned long long seed, void* ctx, float* lse, pe_stream_t stream) {
   if (int rc = pe_host::check_arch()) return rc;
   if (!qkv || !ctx || !lse || B <= 0 || T <= 0 || T > 256 || H <= 0 || head_dim != HD) return PE_ERR_BAD_SHAPE;
+  if (T == 192 && !g_attn_force_simt)
+    return pe_attn_fwd_tc(qkv, B, H, drop_thresh, drop_scale, seed, ctx, lse, PE_ST(stream));
   const size_t smem = 2ull * T * HD * sizeof(float);
   static bool attr = false;
   if (!attr) {
@@ -647,6 +673,8 @@ extern "C" int pe_attn_bwd(const void* qkv, const void* ctx, const void* dctx, c
   if (int rc = pe_host::check_arch()) return rc;
   if (!qkv || !ctx || !dctx || !lse || !dqkv || !delta || B <= 0 || T <= 0 || T > 256 || H <= 0 || head_dim != HD)
     return PE_ERR_BAD_SHAPE;
+  if (T == 192 && !g_attn_force_simt)
+    return pe_attn_bwd_tc(qkv, ctx, dctx, lse, B, H, drop_thresh, drop_scale, seed, dqkv, PE_ST(stream));
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

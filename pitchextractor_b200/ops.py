@@ -100,3 +100,20 @@ def logmel(wave, tables, out_bmt=None, out_btm=None, crop=None, T_out=0, power_w
          ptr(tables["basis"]), c_int(tables["basis"].stride(0)), ptr(tables["fb"]), ptr(power_ws),
          c_size(power_ws.numel() * 4), ptr(out_bmt), ptr(out_btm), ptr(crop), c_int(T_out), stream())
     return power_ws
+
+
+def attn_fwd(qkv, B, T, H, ctx, lse, p_drop=0.0, seed=0):
+    th, sc = L.drop_thresh(p_drop)
+    call("pe_attn_fwd", ptr(qkv), c_int(B), c_int(T), c_int(H), c_int(64), ctypes.c_uint(th), ctypes.c_float(sc),
+         ctypes.c_ulonglong(seed), ptr(ctx), ptr(lse), stream())
+
+
+def attn_bwd(qkv, ctx, dctx, lse, B, T, H, dqkv, delta, p_drop=0.0, seed=0):
+    th, sc = L.drop_thresh(p_drop)
+    call("pe_attn_bwd", ptr(qkv), ptr(ctx), ptr(dctx), ptr(lse), c_int(B), c_int(T), c_int(H), c_int(64),
+         ctypes.c_uint(th), ctypes.c_float(sc), ctypes.c_ulonglong(seed), ptr(dqkv), ptr(delta), stream())
+
+
+def colsum(x, out):
+    M, N = x.shape
+    call("pe_colsum_bf16", ptr(x), c_ll(M), c_int(N), c_ll(x.stride(0)), ptr(out), stream())
