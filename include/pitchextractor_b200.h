@@ -127,11 +127,12 @@ int pe_bn_act_pool_fwd(const void* x, long long rows, int W, int C, int k, const
                        float slope, unsigned drop_thresh, float drop_scale, unsigned long long seed, void* out,
                        long long ld_out, int c_off, void* out_seq, pe_stream_t stream);
 /* backward of the block above through dropout, max-pool, LeakyReLU and the BatchNorm batch statistics:
- * dx bf16 [rows][W][C]; dgamma / dbeta accumulated (+=); sums is a zeroed fp64 [2][C] scratch. */
+ * dx bf16 [rows][W][C]; dgamma / dbeta accumulated (+=); sums is a zeroed fp64 [2][C] scratch, coef an fp32 [2][C]
+ * scratch; k in {1, 2, 4}. */
 int pe_bn_act_pool_bwd(const void* x, long long rows, int W, int C, int k, const float* scale, const float* shift,
                        const float* mean, const float* rstd, float slope, unsigned drop_thresh, float drop_scale,
                        unsigned long long seed, const void* dout, long long ld_dout, int c_off, const void* dout_seq,
-                       double* sums, float* dgamma, float* dbeta, void* dx, pe_stream_t stream);
+                       double* sums, float* coef, float* dgamma, float* dbeta, void* dx, pe_stream_t stream);
 /* backward of the auxiliary max-pools: dx[argmax of each window] += dout */
 int pe_maxpool_bwd_add(const void* x, long long rows, int W, int C, int k, const void* dout, long long ld_dout,
                        int c_off, void* dx, pe_stream_t stream);

@@ -74,7 +74,15 @@ def call(name, *args):
 
 
 def drop_thresh(p_drop):
-    """uint32 keep threshold and scale for dropout probability p_drop (0 disables)."""
+    """16-bit keep threshold (Philox lanes) and the exactly matching scale for dropout probability p_drop."""
+    if p_drop <= 0.0:
+        return 0, 1.0
+    t = max(1, min(65535, int(round((1.0 - p_drop) * 65536.0))))
+    return t, 65536.0 / t
+
+
+def attn_drop_thresh(p_drop):
+    """32-bit keep threshold (hash) and scale for the attention-probability dropout."""
     if p_drop <= 0.0:
         return 0, 1.0
     keep = 1.0 - p_drop

@@ -49,15 +49,21 @@ __device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t k
   }
   return make_uint4(c0, c1, c2, c3);
 }
-// keep-mask for 4 consecutive elements starting at index 4*q; p_keep_u32 = keep probability * 2^32
-__device__ __forceinline__ uint4 dropout_bits4(uint64_t seed, uint64_t q) {
-  return philox4x32((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)seed, (uint32_t)(seed >> 32));
-}
-// single element keep decision (element index e): uses lane e&3 of block e>>2
-__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t e, uint32_t keep_thresh) {
-  const uint4 r = dropout_bits4(seed, e >> 2);
-  const uint32_t v = (e & 3) == 0 ? r.x : (e & 3) == 1 ? r.y : (e & 3) == 2 ? r.z : r.w;
-  return v < keep_thresh;
+// Dropout keep decisions for the 8 consecutive elements [8q, 8q+8): bit i of the result is set iff 16-bit lane i of
+// one Philox block is below thresh16 (= keep probability * 65536).  Every dropout site indexes elements the same
+// way in its forward and backward kernels, so masks are never stored.
+__device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint64_t q, uint32_t thresh16) {
+  const uint4 r = philox4x32((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)seed, (uint32_t)(seed >> 32));
+  uint32_t m = 0;
+  m |= (uint32_t)((r.x & 0xFFFFu) < thresh16) << 0;
+  m |= (uint32_t)((r.x >> 16) < thresh16) << 1;
+  m |= (uint32_t)((r.y & 0xFFFFu) < thresh16) << 2;
+  m |= (uint32_t)((r.y >> 16) < thresh16) << 3;
+  m |= (uint32_t)((r.z & 0xFFFFu) < thresh16) << 4;
+  m |= (uint32_t)((r.z >> 16) < thresh16) << 5;
+  m |= (uint32_t)((r.w & 0xFFFFu) < thresh16) << 6;
+  m |= (uint32_t)((r.w >> 16) < thresh16) << 7;
+  return m;
 }
 
 // attention-probability dropout: keep iff fmix32(seed, element) < thresh.  A counter hash instead of Philox because
@@ -220,9 +226,21 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// erf by Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7, far below bf16 resolution): one ex2, one rcp, a few FMAs
+__device__ __forceinline__ float erf_fast(float x) {
+  const float ax = fabsf(x);
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = __expf(-ax * ax);
+  const float r = fmaf(-p * t, e, 1.0f);
+  return copysignf(r, x);
+}
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+  const float cdf = 0.5f * (1.0f + erf_fast(x * 0.70710678118654752f));
   const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
   return cdf + x * pdf;
 }

@@ -10,9 +10,10 @@
 namespace pe {
 
 constexpr int kBlockM = 128;
-constexpr int kRowBytes = 128;             // one swizzle-128B row: 64 bf16 (or 32 tf32) along the contiguous dim
+constexpr int kRowBytes = 128;                    // one swizzle-128B row: 64 bf16 (or 32 tf32) along the contiguous dim
 constexpr int kATileBytes = kBlockM * kRowBytes;  // 16 KB
-constexpr int kNumThreads = 192;
+constexpr int kNumEpiWarps = 8;
+constexpr int kNumThreads = 64 + 32 * kNumEpiWarps;  // warp 0 = TMA, warp 1 = MMA, warps 2..9 = epilogue
 
 struct TcParams {
   int mode;  // 0 gemm, 1 conv fwd, 2 conv wgrad
@@ -20,20 +21,17 @@ struct TcParams {
   int a_mn, b_mn;
   int M, N;        // output extents used for masking
   int block_n;     // columns per CTA tile (multiple of 16, <= 256)
-  int tmem_cols;   // power of two >= max(32, block_n)
+  int tmem_cols;   // power of two >= 2 * block_n (two accumulator stages)
+  int acc_stride;  // TMEM column offset of accumulator stage 1
   int stages;
   int kb_total, kb_per_split;
   int a_boxes, b_boxes;  // number of 64-wide TMA boxes for MN-major operands
+  int tiles_x, tiles_y, tiles_z, num_tiles;  // persistent tile space (x fastest)
   // conv geometry
   int H, W, tw, th, tiles_w, tiles_h;
   int c1_chunks, c2_chunks;
   int taps;  // wgrad: 9 or 1
   pe_epilogue ep;
-};
-
-struct TileCoord {
-  int m0, n0;           // gemm: first row / col of the tile
-  int b, h0, w0;        // conv: image index and patch origin
 };
 
 __device__ __forceinline__ void decode_conv_tile(const TcParams& p, int tile, int& b, int& h0, int& w0) {
@@ -44,25 +42,36 @@ __device__ __forceinline__ void decode_conv_tile(const TcParams& p, int tile, in
   w0 = (r % p.tiles_w) * p.tw;
 }
 
+struct TileCoord {
+  int tx, ty, tz;
+};
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile) {
+  TileCoord c;
+  c.tx = tile % p.tiles_x;
+  const int r = tile / p.tiles_x;
+  c.ty = r % p.tiles_y;
+  c.tz = r / p.tiles_y;
+  return c;
+}
+
+// Persistent, warp-specialised tile engine: every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the smem
+// operand ring and the two TMEM accumulator stages are shared by consecutive tiles, so the epilogue of tile i overlaps
+// the TMA + MMA main loop of tile i + 1.
 __global__ void __launch_bounds__(kNumThreads, 1)
 tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_a2,
                const __grid_constant__ CUtensorMap tma_b, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // 1024-B alignment is required by the 128-B swizzle; dynamic smem base is only guaranteed 16 B.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_tile_bytes = p.block_n * kRowBytes;
   const int stage_bytes = kATileBytes + b_tile_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + p.stages;
-  uint64_t* tmem_full_bar = empty_bar + p.stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + p.stages;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  const int kb_begin = blockIdx.z * p.kb_per_split;
-  const int kb_end = min(p.kb_total, kb_begin + p.kb_per_split);
-  const int num_kb = kb_end - kb_begin;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -74,7 +83,10 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], kNumEpiWarps);
+    }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -83,28 +95,28 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // tile coordinates
-  int m0 = 0, n0 = 0, img = 0, h0 = 0, w0 = 0, tap = 0;
-  if (p.mode == 0) {
-    m0 = blockIdx.x * kBlockM;
-    n0 = blockIdx.y * p.block_n;
-  } else if (p.mode == 1) {
-    decode_conv_tile(p, blockIdx.x, img, h0, w0);
-    n0 = blockIdx.y * p.block_n;
-  } else {
-    m0 = blockIdx.x * kBlockM;  // Cout tile
-    tap = blockIdx.y;           // 0..taps-1
-  }
-
-  if (num_kb > 0) {
-    if (warp == 0) {
-      // ------------------------------------------------------------------ TMA producer
-      if (lane == 0) {
-        const int elems_per_row = p.kind == 0 ? 64 : 32;
-        for (int i = 0; i < num_kb; ++i) {
-          const int kb = kb_begin + i;
-          const int s = i % p.stages;
-          const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const int elems_per_row = p.kind == 0 ? 64 : 32;
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, tile);
+        const int kb_begin = tc.tz * p.kb_per_split;
+        const int kb_end = min(p.kb_total, kb_begin + p.kb_per_split);
+        int m0 = 0, n0 = 0, img = 0, h0 = 0, w0 = 0;
+        if (p.mode == 0) {
+          m0 = tc.tx * kBlockM;
+          n0 = tc.ty * p.block_n;
+        } else if (p.mode == 1) {
+          decode_conv_tile(p, tc.tx, img, h0, w0);
+          n0 = tc.ty * p.block_n;
+        } else {
+          m0 = tc.tx * kBlockM;  // Cout tile; tc.ty = tap
+        }
+        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1u;
           mbar_wait(&empty_bar[s], ph ^ 1u);
           uint8_t* sa = smem + (size_t)s * stage_bytes;
           uint8_t* sb = sa + kATileBytes;
@@ -137,6 +149,7 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             // k-block = one 64-pixel patch; A = dy (Cout-major), B = shifted x (Cin-major)
             int pb, ph0, pw0;
             decode_conv_tile(p, kb, pb, ph0, pw0);
+            const int tap = tc.ty;
             const int dh = p.taps == 9 ? (tap / 3) - 1 : 0;
             const int dw = p.taps == 9 ? (tap % 3) - 1 : 0;
             for (int j = 0; j < p.a_boxes; ++j)
@@ -146,22 +159,30 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           }
         }
       }
-    } else if (warp == 1) {
-      // ------------------------------------------------------------------ MMA issuer
-      if (lane == 0) {
-        const uint32_t idesc =
-            umma_idesc(p.kind == 0 ? UMMA_BF16 : UMMA_TF32, kBlockM, p.block_n, p.a_mn, p.b_mn);
-        // bytes to advance the descriptor start address per UMMA_K step (16 bf16 / 8 tf32)
-        const int k_rows = p.kind == 0 ? 16 : 8;
-        const uint32_t a_step = p.a_mn ? (uint32_t)(k_rows * kRowBytes) : 32u;
-        const uint32_t b_step = p.b_mn ? (uint32_t)(k_rows * kRowBytes) : 32u;
-        const int block_k_rows = p.kind == 0 ? 64 : 32;
-        // MN-major: 64-wide (bf16) MN blocks are separate TMA boxes, block_k_rows * 128 B apart
-        const uint32_t a_lbo = p.a_mn ? (uint32_t)(block_k_rows * kRowBytes) : 16u;
-        const uint32_t b_lbo = p.b_mn ? (uint32_t)(block_k_rows * kRowBytes) : 16u;
-        for (int i = 0; i < num_kb; ++i) {
-          const int s = i % p.stages;
-          const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(p.kind == 0 ? UMMA_BF16 : UMMA_TF32, kBlockM, p.block_n, p.a_mn, p.b_mn);
+      const int k_rows = p.kind == 0 ? 16 : 8;  // UMMA_K
+      const uint32_t a_step = p.a_mn ? (uint32_t)(k_rows * kRowBytes) : 32u;
+      const uint32_t b_step = p.b_mn ? (uint32_t)(k_rows * kRowBytes) : 32u;
+      const int block_k_rows = p.kind == 0 ? 64 : 32;
+      // MN-major: 64-wide (bf16) MN blocks are separate TMA boxes, block_k_rows * 128 B apart
+      const uint32_t a_lbo = p.a_mn ? (uint32_t)(block_k_rows * kRowBytes) : 16u;
+      const uint32_t b_lbo = p.b_mn ? (uint32_t)(block_k_rows * kRowBytes) : 16u;
+      uint32_t it = 0, local = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
+        const TileCoord tc = decode_tile(p, tile);
+        const int kb_begin = tc.tz * p.kb_per_split;
+        const int num_kb = min(p.kb_total, kb_begin + p.kb_per_split) - kb_begin;
+        const uint32_t acc = local & 1u;
+        mbar_wait(&tmem_empty_bar[acc], ((local >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.acc_stride;
+        for (int i = 0; i < num_kb; ++i, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1u;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
@@ -171,143 +192,151 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             const uint64_t da = umma_desc_sw128(sa + k * a_step, a_lbo, 1024);
             const uint64_t db = umma_desc_sw128(sb + k * b_step, b_lbo, 1024);
             if (p.kind == 0)
-              tc_mma_bf16(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+              tc_mma_bf16(d_tmem, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
             else
-              tc_mma_tf32(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+              tc_mma_tf32(d_tmem, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
           }
           tc_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
         }
-        tc_commit(tmem_full_bar);
+        tc_commit(&tmem_full_bar[acc]);
       }
     }
-  }
-
-  if (warp >= 2) {
-    // -------------------------------------------------------------------- epilogue
+  } else {
+    // -------------------------------------------------------------------- epilogue (8 warps, 2 per TMEM lane quarter)
     const pe_epilogue& ep = p.ep;
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int q = warp & 3;              // TMEM lane quarter this warp may access
+    const int pair = (warp - 2) >> 2;    // which of the two warps of the quarter: takes chunks c with (c & 1) == pair
     const int r = q * 32 + lane;
-    long long grow;  // global output row
-    bool row_ok;
-    if (p.mode == 1) {
-      const int h = h0 + r / p.tw, w = w0 + r % p.tw;
-      row_ok = (h < p.H) && (w < p.W);
-      grow = ((long long)img * p.H + h) * p.W + w;
-    } else {
-      grow = m0 + r;
-      row_ok = grow < p.M;
-    }
-    const int col_base = (p.mode == 2) ? 0 : n0;
-    const long long out_col_off = (p.mode == 2) ? (long long)tap * p.N : 0;  // wgrad: tap-major weight columns
-    if (num_kb > 0) {
-      mbar_wait(tmem_full_bar, 0);
-      tc_fence_after();
-    }
-    const int nchunks = p.block_n / 32 + ((p.block_n % 32) ? 1 : 0);
-    for (int c = 0; c < nchunks; ++c) {
-      uint32_t v[32];
-      if (num_kb > 0) {
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-        tmem_ld_wait();
+    const int nchunks = (p.block_n + 31) / 32;
+    uint32_t local = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
+      const TileCoord tc = decode_tile(p, tile);
+      int m0 = 0, n0 = 0, img = 0, h0 = 0, w0 = 0;
+      long long grow;
+      bool row_ok;
+      long long out_col_off = 0;
+      if (p.mode == 1) {
+        decode_conv_tile(p, tc.tx, img, h0, w0);
+        n0 = tc.ty * p.block_n;
+        const int h = h0 + r / p.tw, w = w0 + r % p.tw;
+        row_ok = (h < p.H) && (w < p.W);
+        grow = ((long long)img * p.H + h) * p.W + w;
       } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0u;
+        m0 = tc.tx * kBlockM;
+        if (p.mode == 0) n0 = tc.ty * p.block_n;
+        else out_col_off = (long long)tc.ty * p.N;  // wgrad: tap-major weight columns
+        grow = m0 + r;
+        row_ok = grow < p.M;
       }
-      if (!row_ok) continue;
-      const int col0 = col_base + c * 32;
-      float f[32];
+      const uint32_t acc = local & 1u;
+      mbar_wait(&tmem_full_bar[acc], (local >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + acc * (uint32_t)p.acc_stride + ((uint32_t)(q * 32) << 16);
+      for (int c = pair; c < nchunks; c += 2) {
+        uint32_t v[32];
+        tmem_ld32(t_row + (uint32_t)(c * 32), v);
+        tmem_ld_wait();
+        if (!row_ok) continue;
+        const int col0 = n0 + c * 32;
+        float f[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * ep.alpha;
-      if (ep.bias) {
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * ep.alpha;
+        const bool full = (col0 + 32 <= p.N) && (c * 32 + 32 <= p.block_n);
+        if (ep.bias) {
+          if (full) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (col0 + j < p.N) f[j] += __ldg(ep.bias + col0 + j);
-      }
-      const bool full = (col0 + 32 <= p.N) && (c * 32 + 32 <= p.block_n);
-      if (ep.act == PE_ACT_GELU) {
-        if (ep.out2) {
-          __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(ep.out2) + grow * ep.ld2 + col0;
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
+              f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) f[j] += __ldg(ep.bias + col0 + j);
+          }
+        }
+        if (ep.act == PE_ACT_GELU) {
+          if (ep.out2) {
+            __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(ep.out2) + grow * ep.ld2 + col0;
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8)
+                *reinterpret_cast<uint4*>(o2 + j) = make_uint4(pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]),
+                                                               pack_bf16(f[j + 4], f[j + 5]), pack_bf16(f[j + 6], f[j + 7]));
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N && c * 32 + j < p.block_n) o2[j] = __float2bfloat16(f[j]);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+        }
+        if (ep.drop_thresh) {  // element index row * N + col; N % 8 == 0 is enforced by the launcher
+          const unsigned long long e0 = (unsigned long long)grow * (unsigned long long)p.N + (unsigned long long)col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            const uint32_t km = dropout_keep8(ep.drop_seed, (e0 + j) >> 3, ep.drop_thresh);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) f[j + t] = ((km >> t) & 1u) ? f[j + t] * ep.drop_scale : 0.f;
+          }
+        }
+        if (ep.aux_mode != PE_AUX_NONE) {
+          const __nv_bfloat16* ax = reinterpret_cast<const __nv_bfloat16*>(ep.aux) + grow * ep.ld_aux + col0;
+          float a[32];
+          if (full) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const uint4 u = *reinterpret_cast<const uint4*>(ax + j);
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float2 x2 = __bfloat1622float2(h2[t]);
+                a[j + 2 * t] = x2.x;
+                a[j + 2 * t + 1] = x2.y;
+              }
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              a[j] = (col0 + j < p.N && c * 32 + j < p.block_n) ? __bfloat162float(ax[j]) : 0.f;
+          }
+          if (ep.aux_mode == PE_AUX_ADD) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] += a[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] *= gelu_erf_grad(a[j]);
+          }
+        }
+        if (ep.out_mode == PE_OUT_BF16) {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + grow * ep.ldc + out_col_off + col0;
           if (full) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8)
-              *reinterpret_cast<uint4*>(o2 + j) = make_uint4(pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]),
-                                                             pack_bf16(f[j + 4], f[j + 5]), pack_bf16(f[j + 6], f[j + 7]));
+              *reinterpret_cast<uint4*>(o + j) = make_uint4(pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]),
+                                                            pack_bf16(f[j + 4], f[j + 5]), pack_bf16(f[j + 6], f[j + 7]));
           } else {
             for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N && c * 32 + j < p.block_n) o2[j] = __float2bfloat16(f[j]);
+              if (col0 + j < p.N && c * 32 + j < p.block_n) o[j] = __float2bfloat16(f[j]);
           }
-        }
+        } else if (ep.out_mode == PE_OUT_F32) {
+          float* o = reinterpret_cast<float*>(ep.out) + grow * ep.ldc + out_col_off + col0;
+          if (full) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-      }
-      if (ep.drop_thresh) {
-        const unsigned long long e0 = (unsigned long long)grow * (unsigned long long)p.N + (unsigned long long)col0;
-        if ((e0 & 3ull) == 0) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const uint4 rb = dropout_bits4(ep.drop_seed, (e0 + j) >> 2);
-            f[j + 0] = rb.x < ep.drop_thresh ? f[j + 0] * ep.drop_scale : 0.f;
-            f[j + 1] = rb.y < ep.drop_thresh ? f[j + 1] * ep.drop_scale : 0.f;
-            f[j + 2] = rb.z < ep.drop_thresh ? f[j + 2] * ep.drop_scale : 0.f;
-            f[j + 3] = rb.w < ep.drop_thresh ? f[j + 3] * ep.drop_scale : 0.f;
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N && c * 32 + j < p.block_n) o[j] = f[j];
           }
         } else {
+          float* o = reinterpret_cast<float*>(ep.out) + grow * ep.ldc + out_col_off + col0;
           for (int j = 0; j < 32; ++j)
-            f[j] = dropout_keep(ep.drop_seed, e0 + j, ep.drop_thresh) ? f[j] * ep.drop_scale : 0.f;
+            if (col0 + j < p.N && c * 32 + j < p.block_n) atomicAdd(o + j, f[j]);
         }
       }
-      if (ep.aux_mode != PE_AUX_NONE) {
-        const __nv_bfloat16* ax = reinterpret_cast<const __nv_bfloat16*>(ep.aux) + grow * ep.ld_aux + col0;
-        float a[32];
-        if (full) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            const uint4 u = *reinterpret_cast<const uint4*>(ax + j);
-            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const float2 x2 = __bfloat1622float2(h2[t]);
-              a[j + 2 * t] = x2.x;
-              a[j + 2 * t + 1] = x2.y;
-            }
-          }
-        } else {
-          for (int j = 0; j < 32; ++j)
-            a[j] = (col0 + j < p.N && c * 32 + j < p.block_n) ? __bfloat162float(ax[j]) : 0.f;
-        }
-        if (ep.aux_mode == PE_AUX_ADD) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] += a[j];
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] *= gelu_erf_grad(a[j]);
-        }
-      }
-      if (ep.out_mode == PE_OUT_BF16) {
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + grow * ep.ldc + out_col_off + col0;
-        if (full) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8)
-            *reinterpret_cast<uint4*>(o + j) = make_uint4(pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]),
-                                                          pack_bf16(f[j + 4], f[j + 5]), pack_bf16(f[j + 6], f[j + 7]));
-        } else {
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.N && c * 32 + j < p.block_n) o[j] = __float2bfloat16(f[j]);
-        }
-      } else if (ep.out_mode == PE_OUT_F32) {
-        float* o = reinterpret_cast<float*>(ep.out) + grow * ep.ldc + out_col_off + col0;
-        if (full) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-        } else {
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.N && c * 32 + j < p.block_n) o[j] = f[j];
-        }
-      } else {
-        float* o = reinterpret_cast<float*>(ep.out) + grow * ep.ldc + out_col_off + col0;
-        for (int j = 0; j < 32; ++j)
-          if (col0 + j < p.N && c * 32 + j < p.block_n) atomicAdd(o + j, f[j]);
-      }
+      // hand the accumulator stage back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
     }
   }
 
@@ -329,15 +358,21 @@ static int pow2_cols(int n) {
   return c;
 }
 
-static int launch_tc(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, TcParams& p, dim3 grid,
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, TcParams& p, dim3 tiles,
                      cudaStream_t stream) {
   const int stage_bytes = pe::kATileBytes + p.block_n * pe::kRowBytes;
   int stages = (200 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) return PE_ERR_BAD_SHAPE;
   p.stages = stages;
-  p.tmem_cols = pow2_cols(p.block_n);
-  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 1) * sizeof(uint64_t) + 16 + 1024;
+  p.tmem_cols = pow2_cols(2 * p.block_n);
+  p.acc_stride = p.tmem_cols / 2;
+  p.tiles_x = (int)tiles.x;
+  p.tiles_y = (int)tiles.y;
+  p.tiles_z = (int)tiles.z;
+  p.num_tiles = p.tiles_x * p.tiles_y * p.tiles_z;
+  if (p.ep.drop_thresh && (p.N % 8)) return PE_ERR_BAD_SHAPE;
+  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 4) * sizeof(uint64_t) + 16 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(pe::tc_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
@@ -345,6 +380,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtens
       return PE_ERR_LAUNCH;
     attr_set = true;
   }
+  const int grid = p.num_tiles < pe_host::num_sms() ? p.num_tiles : pe_host::num_sms();
   pe::tc_tile_kernel<<<grid, pe::kNumThreads, smem, stream>>>(ta, ta2, tb, p);
   return cudaGetLastError() == cudaSuccess ? PE_OK : PE_ERR_LAUNCH;
 }
@@ -368,10 +404,16 @@ extern "C" int pe_gemm_bf16(const void* A, long long lda, int a_mn, const void* 
   p.b_mn = b_mn ? 1 : 0;
   p.M = M;
   p.N = N;
-  // tile width: as wide as N allows (<= 256); MN-major B needs whole 64-wide boxes
+  // tile width: as wide as N allows (<= 256), narrowed when that fills the SMs' tile rounds better;
+  // MN-major B needs whole 64-wide boxes
   int bn = N >= 256 ? 256 : ((N + 15) / 16) * 16;
   if (p.b_mn) bn = ((bn + 63) / 64) * 64;
   if (bn > 256) bn = 256;
+  if (bn == 256 && splits == 1) {
+    const long long mt = (M + 127) / 128, sms = pe_host::num_sms();
+    const long long r256 = (mt * ((N + 255) / 256) + sms - 1) / sms, r128 = (mt * ((N + 127) / 128) + sms - 1) / sms;
+    if (r128 * (128 + 48) < r256 * (256 + 48)) bn = 128;
+  }
   p.block_n = bn;
   p.a_boxes = 2;
   p.b_boxes = bn / 64;

@@ -143,10 +143,9 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ xf
       if (dxm) {
         if (drop_thresh) {
           const unsigned long long e0 = (unsigned long long)(m * D + c);
-          const uint4 r0 = dropout_bits4(seed, e0 >> 2), r1 = dropout_bits4(seed, (e0 >> 2) + 1);
-          const unsigned rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+          const uint32_t km = dropout_keep8(seed, e0 >> 3, drop_thresh);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = rr[j] < drop_thresh ? o[j] * drop_scale : 0.f;
+          for (int j = 0; j < 8; ++j) o[j] = ((km >> j) & 1u) ? o[j] * drop_scale : 0.f;
         }
         st8b(dxm + m * D + c, o);
       }

@@ -126,7 +126,20 @@ bn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int C, doub
   if (ty < ry) {
     const long long r0 = (long long)blockIdx.x * rows_per_cta;
     const long long r1 = min(rows, r0 + rows_per_cta);
-    for (long long r = r0 + ty; r < r1; r += ry) {
+    long long r = r0 + ty;
+    for (; r + 3LL * ry < r1; r += 4LL * ry) {  // four independent 16-byte loads in flight per thread
+      float v0[8], v1[8], v2[8], v3[8];
+      ld8(x + r * C + tx * 8, v0);
+      ld8(x + (r + ry) * C + tx * 8, v1);
+      ld8(x + (r + 2LL * ry) * C + tx * 8, v2);
+      ld8(x + (r + 3LL * ry) * C + tx * 8, v3);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[i] += (v0[i] + v1[i]) + (v2[i] + v3[i]);
+        ss[i] += fmaf(v0[i], v0[i], v1[i] * v1[i]) + fmaf(v2[i], v2[i], v3[i] * v3[i]);
+      }
+    }
+    for (; r < r1; r += ry) {
       float v[8];
       ld8(x + r * C + tx * 8, v);
 #pragma unroll
@@ -232,10 +245,9 @@ bn_act_pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, PoolGeom g, const fl
   }
   if (drop_thresh) {
     const unsigned long long e0 = (unsigned long long)((row * g.Wo + wo) * g.C + tx * 8);
-    const uint4 r0 = dropout_bits4(seed, e0 >> 2), r1 = dropout_bits4(seed, (e0 >> 2) + 1);
-    const unsigned rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+    const uint32_t km = dropout_keep8(seed, e0 >> 3, drop_thresh);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) best[i] = rr[i] < drop_thresh ? best[i] * drop_scale : 0.f;
+    for (int i = 0; i < 8; ++i) best[i] = ((km >> i) & 1u) ? best[i] * drop_scale : 0.f;
   }
   if (out) st8(out + (row * g.Wo + wo) * ld_out + c_off + tx * 8, best);
   if (out_seq) {
@@ -245,15 +257,14 @@ bn_act_pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, PoolGeom g, const fl
   }
 }
 
-// Gradient routing shared by the two backward passes: for one window (row, wo) and 8 channels recompute
-// z_j = lrelu(bn(x_j)), the first arg-max j*, and g* = dout * dropout * lrelu'(.) at j*.
+// Backward of y = Dropout(MaxPool(1,K)(LeakyReLU(BN_train(x)))) in two coalesced passes.  For one window (row, wo) and 8
+// channels a thread recomputes z_j = lrelu(x_j*scale + shift), the first arg-max j*, and g* = dout * dropout * lrelu'.
+// Per-channel constants live in shared memory (registers are kept low so that 32+ warps per SM hide HBM latency).
 struct BnBwdArgs {
   const __nv_bfloat16* x;
   PoolGeom g;
   const float* scale;
   const float* shift;
-  const float* mean;
-  const float* rstd;
   float slope;
   unsigned drop_thresh;
   float drop_scale;
@@ -264,39 +275,29 @@ struct BnBwdArgs {
   const __nv_bfloat16* dout_seq;  // sequence-layout consumer gradient (may be NULL)
 };
 
-__device__ __forceinline__ void bn_bwd_route(const BnBwdArgs& a, long long row, int wo, int tx, const float* sc,
-                                             const float* sh, int* jstar, float* gstar) {
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+__device__ __forceinline__ float bf16_at(const uint4& q, int i) {
+  const uint32_t w = i < 2 ? q.x : i < 4 ? q.y : i < 6 ? q.z : q.w;
+  return (i & 1) ? bf16_hi(w) : bf16_lo(w);
+}
+
+// loads the K-window and the consumer gradient, returns per channel: jstar, g*, x at jstar
+template <int K>
+__device__ __forceinline__ void bn_bwd_route(const BnBwdArgs& a, const float* s_sc, const float* s_sh, long long row,
+                                             int wo, int tx, uint4* xv, int* jstar, float* gstar, float* xstar) {
   const PoolGeom& g = a.g;
-  float best[8], pre[8];
+  const __nv_bfloat16* xp = a.x + ((row * g.W + (long long)wo * K) * g.C + tx * 8);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    best[i] = -INFINITY;
-    jstar[i] = 0;
-    pre[i] = 0.f;
-  }
-  const __nv_bfloat16* xp = a.x + ((row * g.W + (long long)wo * g.k) * g.C + tx * 8);
-  for (int j = 0; j < g.k; ++j) {
-    float v[8];
-    ld8(xp + (long long)j * g.C, v);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float zp = fmaf(v[i], sc[i], sh[i]);
-      const float z = zp > 0.f ? zp : zp * a.slope;
-      if (z > best[i]) {
-        best[i] = z;
-        jstar[i] = j;
-        pre[i] = zp;
-      }
-    }
-  }
+  for (int j = 0; j < K; ++j) xv[j] = __ldg(reinterpret_cast<const uint4*>(xp + (long long)j * g.C));
   float go[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) go[i] = 0.f;
   if (a.dout) {
-    float d[8];
-    ld8(a.dout + (row * g.Wo + wo) * a.ld_dout + a.c_off + tx * 8, d);
+    const uint4 d = __ldg(reinterpret_cast<const uint4*>(a.dout + (row * g.Wo + wo) * a.ld_dout + a.c_off + tx * 8));
 #pragma unroll
-    for (int i = 0; i < 8; ++i) go[i] += d[i];
+    for (int i = 0; i < 8; ++i) go[i] = bf16_at(d, i);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) go[i] = 0.f;
   }
   if (a.dout_seq) {
 #pragma unroll
@@ -305,73 +306,122 @@ __device__ __forceinline__ void bn_bwd_route(const BnBwdArgs& a, long long row, 
   }
   if (a.drop_thresh) {
     const unsigned long long e0 = (unsigned long long)((row * g.Wo + wo) * g.C + tx * 8);
-    const uint4 r0 = dropout_bits4(a.seed, e0 >> 2), r1 = dropout_bits4(a.seed, (e0 >> 2) + 1);
-    const unsigned rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+    const uint32_t km = dropout_keep8(a.seed, e0 >> 3, a.drop_thresh);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) go[i] = rr[i] < a.drop_thresh ? go[i] * a.drop_scale : 0.f;
+    for (int i = 0; i < 8; ++i) go[i] = ((km >> i) & 1u) ? go[i] * a.drop_scale : 0.f;
   }
+  const float4 sc0 = *reinterpret_cast<const float4*>(s_sc + tx * 8), sc1 = *reinterpret_cast<const float4*>(s_sc + tx * 8 + 4);
+  const float4 sh0 = *reinterpret_cast<const float4*>(s_sh + tx * 8), sh1 = *reinterpret_cast<const float4*>(s_sh + tx * 8 + 4);
+  const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+  const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
 #pragma unroll
-  for (int i = 0; i < 8; ++i) gstar[i] = go[i] * (pre[i] > 0.f ? 1.f : a.slope);
+  for (int i = 0; i < 8; ++i) {
+    float best = -INFINITY, pre = 0.f, xs = 0.f;
+    int js = 0;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const float xj = bf16_at(xv[j], i);
+      const float zp = fmaf(xj, sc[i], sh[i]);
+      const float z = zp > 0.f ? zp : zp * a.slope;
+      if (z > best) {
+        best = z;
+        js = j;
+        pre = zp;
+        xs = xj;
+      }
+    }
+    jstar[i] = js;
+    xstar[i] = xs;
+    gstar[i] = go[i] * (pre > 0.f ? 1.f : a.slope);
+  }
 }
 
-// pass 1: sums[0][c] = sum g, sums[1][c] = sum g * xhat
+// pass 1: sums[0][c] += sum g, sums[1][c] += sum g * x   (raw x; centred / scaled in fp64 by the params kernel)
+template <int K>
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(BnBwdArgs a, double* __restrict__ sums, int windows_per_cta) {
-  extern __shared__ float sred[];  // [2][C]
+  extern __shared__ __align__(16) float sm[];  // sc[C] | sh[C] | red[2][C]
   const PoolGeom& g = a.g;
-  for (int i = threadIdx.x; i < 2 * g.C; i += blockDim.x) sred[i] = 0.f;
+  float* s_sc = sm;
+  float* s_sh = sm + g.C;
+  float* red = sm + 2 * g.C;
+  for (int i = threadIdx.x; i < g.C; i += blockDim.x) {
+    s_sc[i] = a.scale[i];
+    s_sh[i] = a.shift[i];
+    red[i] = 0.f;
+    red[g.C + i] = 0.f;
+  }
   __syncthreads();
   const int cg = g.C >> 3;
   const int ry = blockDim.x / cg;
   const int tx = threadIdx.x % cg, ty = threadIdx.x / cg;
   if (ty < ry) {
-    float sc[8], sh[8], mu[8], rs[8], s[8], sx[8];
+    float s[8], sx[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      sc[i] = a.scale[tx * 8 + i];
-      sh[i] = a.shift[tx * 8 + i];
-      mu[i] = a.mean[tx * 8 + i];
-      rs[i] = a.rstd[tx * 8 + i];
-      s[i] = sx[i] = 0.f;
-    }
+    for (int i = 0; i < 8; ++i) s[i] = sx[i] = 0.f;
     const long long nwin = g.rows * g.Wo;
     const long long w0 = (long long)blockIdx.x * windows_per_cta;
     const long long w1 = min(nwin, w0 + windows_per_cta);
+#pragma unroll 2
     for (long long wi = w0 + ty; wi < w1; wi += ry) {
       const long long row = wi / g.Wo;
       const int wo = (int)(wi - row * g.Wo);
+      uint4 xv[K];
       int js[8];
-      float gs[8];
-      bn_bwd_route(a, row, wo, tx, sc, sh, js, gs);
+      float gs[8], xs[8];
+      bn_bwd_route<K>(a, s_sc, s_sh, row, wo, tx, xv, js, gs, xs);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float xv = __bfloat162float(a.x[(row * g.W + (long long)wo * g.k + js[i]) * g.C + tx * 8 + i]);
         s[i] += gs[i];
-        sx[i] = fmaf(gs[i], (xv - mu[i]) * rs[i], sx[i]);
+        sx[i] = fmaf(gs[i], xs[i], sx[i]);
       }
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      atomicAdd(&sred[tx * 8 + i], s[i]);
-      atomicAdd(&sred[g.C + tx * 8 + i], sx[i]);
+      atomicAdd(&red[tx * 8 + i], s[i]);
+      atomicAdd(&red[g.C + tx * 8 + i], sx[i]);
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * g.C; i += blockDim.x) atomicAdd(sums + i, (double)sred[i]);
+  for (int i = threadIdx.x; i < 2 * g.C; i += blockDim.x) atomicAdd(sums + i, (double)red[i]);
 }
 
-// dgamma += sum g*xhat, dbeta += sum g
-__global__ void bn_bwd_params_kernel(const double* __restrict__ sums, float* dgamma, float* dbeta, int C) {
+// dbeta += S_g, dgamma += rstd * (S_gx - mean * S_g); coefficients of pass 2: dx = scale*g - A*x + B with
+// A = scale*rstd*mgx, B = A*mean - scale*mg, mg = S_g / n, mgx = rstd * (S_gx - mean*S_g) / n
+__global__ void bn_bwd_params_kernel(const double* __restrict__ sums, double count, const float* __restrict__ scale,
+                                     const float* __restrict__ mean, const float* __restrict__ rstd, float* dgamma,
+                                     float* dbeta, float* __restrict__ coef, int C) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  dbeta[c] += (float)sums[c];
-  dgamma[c] += (float)sums[C + c];
+  const double sg = sums[c], sgx = sums[C + c];
+  const double mu = mean[c], rs = rstd[c], sc = scale[c];
+  const double sgxh = rs * (sgx - mu * sg);
+  if (dbeta) dbeta[c] += (float)sg;
+  if (dgamma) dgamma[c] += (float)sgxh;
+  const double mg = sg / count, mgx = sgxh / count;
+  const double A = sc * rs * mgx;
+  coef[c] = (float)A;
+  coef[C + c] = (float)(A * mu - sc * mg);
 }
 
-// pass 2: dx = scale * (g - mean_g - xhat * mean_gx) for every input element (pooled-away elements have g = 0)
+// pass 2: dx for every input element (pooled-away elements have g = 0; the last window also owns the columns that
+// the floor of W / K drops)
+template <int K>
 __global__ void __launch_bounds__(256)
-bn_bwd_apply_kernel(BnBwdArgs a, const double* __restrict__ sums, double count, __nv_bfloat16* __restrict__ dx) {
+bn_bwd_apply_kernel(BnBwdArgs a, const float* __restrict__ coef, __nv_bfloat16* __restrict__ dx) {
+  extern __shared__ __align__(16) float sm[];  // sc | sh | A | B
   const PoolGeom& g = a.g;
+  float* s_sc = sm;
+  float* s_sh = sm + g.C;
+  float* s_A = sm + 2 * g.C;
+  float* s_B = sm + 3 * g.C;
+  for (int i = threadIdx.x; i < g.C; i += blockDim.x) {
+    s_sc[i] = a.scale[i];
+    s_sh[i] = a.shift[i];
+    s_A[i] = coef[i];
+    s_B[i] = coef[g.C + i];
+  }
+  __syncthreads();
   const int cg = g.C >> 3;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = g.rows * g.Wo * cg;
@@ -379,32 +429,33 @@ bn_bwd_apply_kernel(BnBwdArgs a, const double* __restrict__ sums, double count, 
   const int tx = (int)(idx % cg);
   const int wo = (int)((idx / cg) % g.Wo);
   const long long row = idx / ((long long)cg * g.Wo);
-  float sc[8], sh[8], mu[8], rs[8], mg[8], mgx[8];
+  uint4 xv[K];
+  int js[8];
+  float gs[8], xs[8];
+  bn_bwd_route<K>(a, s_sc, s_sh, row, wo, tx, xv, js, gs, xs);
+  const long long base = (row * g.W + (long long)wo * K) * g.C + tx * 8;
+  float sg[8], A[8], Bc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int c = tx * 8 + i;
-    sc[i] = a.scale[c];
-    sh[i] = a.shift[c];
-    mu[i] = a.mean[c];
-    rs[i] = a.rstd[c];
-    mg[i] = (float)(sums[c] / count);
-    mgx[i] = (float)(sums[g.C + c] / count);
+    sg[i] = s_sc[tx * 8 + i] * gs[i];
+    A[i] = s_A[tx * 8 + i];
+    Bc[i] = s_B[tx * 8 + i];
   }
-  int js[8];
-  float gs[8];
-  bn_bwd_route(a, row, wo, tx, sc, sh, js, gs);
-  const int jend = (wo == g.Wo - 1) ? (g.W - wo * g.k) : g.k;  // last window also owns the floor-dropped columns
-  const long long base = (row * g.W + (long long)wo * g.k) * g.C + tx * 8;
-  for (int j = 0; j < jend; ++j) {
-    float v[8], o[8];
-    ld8(a.x + base + (long long)j * g.C, v);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float xhat = (v[i] - mu[i]) * rs[i];
-      const float gi = (j == js[i]) ? gs[i] : 0.f;
-      o[i] = sc[i] * (gi - mg[i] - xhat * mgx[i]);
-    }
+  for (int j = 0; j < K; ++j) {
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = fmaf(-A[i], bf16_at(xv[j], i), Bc[i]) + (j == js[i] ? sg[i] : 0.f);
     st8(dx + base + (long long)j * g.C, o);
+  }
+  if (wo == g.Wo - 1) {
+    for (int j = K; j < g.W - wo * K; ++j) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(a.x + base + (long long)j * g.C));
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = fmaf(-A[i], bf16_at(q, i), Bc[i]);
+      st8(dx + base + (long long)j * g.C, o);
+    }
   }
 }
 
@@ -528,25 +579,37 @@ extern "C" int pe_bn_act_pool_bwd(const void* x, long long rows, int W, int C, i
                                   const float* shift, const float* mean, const float* rstd, float slope,
                                   unsigned drop_thresh, float drop_scale, unsigned long long seed, const void* dout,
                                   long long ld_dout, int c_off, const void* dout_seq, double* sums /* [2][C], zeroed */,
-                                  float* dgamma, float* dbeta, void* dx, pe_stream_t stream) {
+                                  float* coef /* [2][C] scratch */, float* dgamma, float* dbeta, void* dx,
+                                  pe_stream_t stream) {
   if (int rc = pe_host::check_arch()) return rc;
-  if (!x || !scale || !shift || !mean || !rstd || !sums || !dx || rows <= 0 || W <= 0 || !chan_ok(C) || C / 8 > 256 ||
-      k <= 0 || k > W || (!dout && !dout_seq))
+  if (!x || !scale || !shift || !mean || !rstd || !sums || !coef || !dx || rows <= 0 || W <= 0 || !chan_ok(C) ||
+      C / 8 > 256 || (k != 1 && k != 2 && k != 4) || k > W || (!dout && !dout_seq))
     return PE_ERR_BAD_SHAPE;
   BnBwdArgs a{};
   a.x = (const __nv_bfloat16*)x;
   a.g = PoolGeom{rows, W, C, k, W / k};
-  a.scale = scale; a.shift = shift; a.mean = mean; a.rstd = rstd;
+  a.scale = scale; a.shift = shift;
   a.slope = slope; a.drop_thresh = drop_thresh; a.drop_scale = drop_scale; a.seed = seed;
   a.dout = (const __nv_bfloat16*)dout; a.ld_dout = ld_dout; a.c_off = c_off;
   a.dout_seq = (const __nv_bfloat16*)dout_seq;
   const long long nwin = rows * a.g.Wo;
-  const int per = 2048;
-  bn_bwd_reduce_kernel<<<(unsigned)((nwin + per - 1) / per), 256, 2 * C * sizeof(float), PE_ST(stream)>>>(a, sums, per);
-  if (dgamma && dbeta) bn_bwd_params_kernel<<<(C + 127) / 128, 128, 0, PE_ST(stream)>>>(sums, dgamma, dbeta, C);
+  const int per = 1024;
+  const unsigned g1 = (unsigned)((nwin + per - 1) / per);
   const long long total = nwin * (C / 8);
-  bn_bwd_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, PE_ST(stream)>>>(a, sums, (double)rows * W,
-                                                                                  (__nv_bfloat16*)dx);
+  const unsigned g2 = (unsigned)((total + 255) / 256);
+  const size_t sm1 = 4 * C * sizeof(float), sm2 = 4 * C * sizeof(float);
+  cudaStream_t st = PE_ST(stream);
+#define PE_BN_BWD(K)                                                                                      \
+  do {                                                                                                    \
+    bn_bwd_reduce_kernel<K><<<g1, 256, sm1, st>>>(a, sums, per);                                          \
+    bn_bwd_params_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, (double)rows * W, scale, mean, rstd, dgamma, dbeta, \
+                                                          coef, C);                                       \
+    bn_bwd_apply_kernel<K><<<g2, 256, sm2, st>>>(a, coef, (__nv_bfloat16*)dx);                            \
+  } while (0)
+  if (k == 1) PE_BN_BWD(1);
+  else if (k == 2) PE_BN_BWD(2);
+  else PE_BN_BWD(4);
+#undef PE_BN_BWD
   return PE_LAUNCH_RC();
 }
 

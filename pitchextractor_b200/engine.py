@@ -111,6 +111,7 @@ class Engine:
         nbn = 9
         self.bn_sums = torch.zeros(2 * nbn, 2, 256, device=dev, dtype=torch.float64)  # fwd + bwd scratch per BN
         self.bn_aff = torch.zeros(nbn, 4, 256, device=dev, dtype=torch.float32)       # scale, shift, mean, rstd
+        self.bn_coef = torch.zeros(nbn, 2, 256, device=dev, dtype=torch.float32)      # pass-2 coefficients (backward)
         self.bn_index = {}
         self.loss_acc = torch.zeros(2, device=dev, dtype=torch.float64)
         self.loss_out = torch.zeros(3, device=dev, dtype=torch.float32)
@@ -199,8 +200,8 @@ class Engine:
         g = self.gview
         call("pe_bn_act_pool_bwd", ptr(x), c_ll(rows), c_int(W), c_int(C), c_int(k), ptr(aff[0]), ptr(aff[1]),
              ptr(aff[2]), ptr(aff[3]), c_f(self.slope), c_u(drop[0]), c_f(drop[1]), c_ull(seed), ptr(dout),
-             c_ll(ld_dout), c_int(c_off), ptr(dout_seq), ptr(sums), ptr(g[prefix + ".weight"]), ptr(g[prefix + ".bias"]),
-             ptr(dx), stream())
+             c_ll(ld_dout), c_int(c_off), ptr(dout_seq), ptr(sums), ptr(self.bn_coef[i]), ptr(g[prefix + ".weight"]),
+             ptr(g[prefix + ".bias"]), ptr(dx), stream())
 
     # ------------------------------------------------------------------ forward
     def _prep_input(self, x):
@@ -280,6 +281,7 @@ class Engine:
         sm = self.model.get_submodule(prefix)
         pe = sm.pos_encoding.pe
         drop = self._drop(self.p_seq, training)
+        adrop = L.attn_drop_thresh(self.p_seq if drop[0] else 0.0)
         pdrop = self.p_seq if drop[0] else 0.0
         Hcur = self.buf(tag + "H0", (M, D))
         stats = self.buf(tag + "lnstats", (2 * self.num_layers + 1, 2, M), torch.float32)
@@ -294,7 +296,7 @@ class Engine:
             ops.gemm(Hcur, W16[q + "self_attn.in_proj_weight"], QKV, M, 3 * D, D, bias=V[q + "self_attn.in_proj_bias"])
             CTX = self.buf(t + "CTX", (M, D))
             LSE = self.buf(t + "LSE", (B, H, T), torch.float32)
-            call("pe_attn_fwd", ptr(QKV), c_int(B), c_int(T), c_int(H), c_int(64), c_u(drop[0]), c_f(drop[1]),
+            call("pe_attn_fwd", ptr(QKV), c_int(B), c_int(T), c_int(H), c_int(64), c_u(adrop[0]), c_f(adrop[1]),
                  c_ull(self._seed(site + 0)), ptr(CTX), ptr(LSE), stream())
             S1 = self.buf(t + "S1", (M, D), torch.float32)
             ops.gemm(CTX, W16[q + "self_attn.out_proj.weight"], S1, M, D, D, bias=V[q + "self_attn.out_proj.bias"],
@@ -348,6 +350,7 @@ class Engine:
         M, D, FF, H = B * T, 512, self.ff, self.nhead
         training = self._training
         drop = self._drop(self.p_seq, training)
+        adrop = L.attn_drop_thresh(self.p_seq if drop[0] else 0.0)
         pdrop = self.p_seq if drop[0] else 0.0
         stats = self._bufs[tag + "lnstats"]
         sm = self.model.get_submodule(prefix)
@@ -388,7 +391,7 @@ class Engine:
             self._wgrad_linear(dSm, CTX, q + "self_attn.out_proj.weight", D, D, M)
             # attention
             call("pe_attn_bwd", ptr(QKV), ptr(CTX), ptr(dCTX), ptr(LSE), c_int(B), c_int(T), c_int(H), c_int(64),
-                 c_u(drop[0]), c_f(drop[1]), c_ull(self._seed(site + 0)), ptr(dQKV), ptr(delta), stream())
+                 c_u(adrop[0]), c_f(adrop[1]), c_ull(self._seed(site + 0)), ptr(dQKV), ptr(delta), stream())
             # in_proj: dH = dQKV Wqkv + dS (residual)
             dHn = self.buf(tag + "dHin%d" % (l & 1), (M, D))
             ops.gemm(dQKV, W16[q + "self_attn.in_proj_weight"], dHn, M, D, 3 * D, b_mn=True, aux=dS,

@@ -103,13 +103,13 @@ def logmel(wave, tables, out_bmt=None, out_btm=None, crop=None, T_out=0, power_w
 
 
 def attn_fwd(qkv, B, T, H, ctx, lse, p_drop=0.0, seed=0):
-    th, sc = L.drop_thresh(p_drop)
+    th, sc = L.attn_drop_thresh(p_drop)
     call("pe_attn_fwd", ptr(qkv), c_int(B), c_int(T), c_int(H), c_int(64), ctypes.c_uint(th), ctypes.c_float(sc),
          ctypes.c_ulonglong(seed), ptr(ctx), ptr(lse), stream())
 
 
 def attn_bwd(qkv, ctx, dctx, lse, B, T, H, dqkv, delta, p_drop=0.0, seed=0):
-    th, sc = L.drop_thresh(p_drop)
+    th, sc = L.attn_drop_thresh(p_drop)
     call("pe_attn_bwd", ptr(qkv), ptr(ctx), ptr(dctx), ptr(lse), c_int(B), c_int(T), c_int(H), c_int(64),
          ctypes.c_uint(th), ctypes.c_float(sc), ctypes.c_ulonglong(seed), ptr(dqkv), ptr(delta), stream())
 
