@@ -26,6 +26,7 @@ struct TcParams {
   int stages;
   int kb_total, kb_per_split;
   int a_boxes, b_boxes;  // number of 64-wide TMA boxes for MN-major operands
+  int tx_bytes;          // bytes the TMA loads of one k-block deliver (mbarrier expect_tx)
   int tiles_x, tiles_y, tiles_z, num_tiles;  // persistent tile space (x fastest)
   // conv geometry
   int H, W, tw, th, tiles_w, tiles_h;
@@ -120,7 +121,7 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           mbar_wait(&empty_bar[s], ph ^ 1u);
           uint8_t* sa = smem + (size_t)s * stage_bytes;
           uint8_t* sb = sa + kATileBytes;
-          mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+          mbar_arrive_expect_tx(&full_bar[s], (uint32_t)p.tx_bytes);
           if (p.mode == 0) {
             const int k0 = kb * elems_per_row;
             if (!p.a_mn) {
@@ -146,16 +147,22 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
             tma_load_2d(&tma_b, &full_bar[s], sb, kb * 64, n0);
           } else {
-            // k-block = one 64-pixel patch; A = dy (Cout-major), B = shifted x (Cin-major)
+            // k-block = one 64-pixel patch; A = dy (Cout-major); B = x shifted by the tap(s) this tile owns: output
+            // column n = tap * Cin + ci, 64-wide boxes, several taps per tile when Cin is small (A is loaded once)
             int pb, ph0, pw0;
             decode_conv_tile(p, kb, pb, ph0, pw0);
-            const int tap = tc.ty;
-            const int dh = p.taps == 9 ? (tap / 3) - 1 : 0;
-            const int dw = p.taps == 9 ? (tap % 3) - 1 : 0;
+            const int cin = p.c1_chunks * 64;
             for (int j = 0; j < p.a_boxes; ++j)
               tma_load_4d(&tma_a, &full_bar[s], sa + j * (64 * kRowBytes), m0 + j * 64, pw0, ph0, pb);
-            for (int j = 0; j < p.b_boxes; ++j)
-              tma_load_4d(&tma_b, &full_bar[s], sb + j * (64 * kRowBytes), j * 64, pw0 + dw, ph0 + dh, pb);
+            for (int j = 0; j < p.b_boxes; ++j) {
+              const int col = tc.ty * p.block_n + j * 64;
+              const int tap = col / cin;
+              const int dh = p.taps == 9 ? (tap / 3) - 1 : 0;
+              const int dw = p.taps == 9 ? (tap % 3) - 1 : 0;
+              // columns past the last tap are loaded from beyond the channel extent: TMA zero-fills them
+              tma_load_4d(&tma_b, &full_bar[s], sb + j * (64 * kRowBytes), tap < p.taps ? col - tap * cin : cin,
+                          pw0 + dw, ph0 + dh, pb);
+            }
           }
         }
       }
@@ -223,8 +230,7 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         grow = ((long long)img * p.H + h) * p.W + w;
       } else {
         m0 = tc.tx * kBlockM;
-        if (p.mode == 0) n0 = tc.ty * p.block_n;
-        else out_col_off = (long long)tc.ty * p.N;  // wgrad: tap-major weight columns
+        n0 = tc.ty * p.block_n;  // wgrad: columns are tap-major (n = tap * Cin + ci), several taps per tile
         grow = m0 + r;
         row_ok = grow < p.M;
       }
@@ -329,8 +335,14 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           }
         } else {
           float* o = reinterpret_cast<float*>(ep.out) + grow * ep.ldc + out_col_off + col0;
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.N && c * 32 + j < p.block_n) atomicAdd(o + j, f[j]);
+          if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)  // 16-byte vector reductions: 4x fewer L2 atomic operations
+              atomicAdd(reinterpret_cast<float4*>(o + j), make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]));
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N && c * 32 + j < p.block_n) atomicAdd(o + j, f[j]);
+          }
         }
       }
       // hand the accumulator stage back to the MMA warp
@@ -366,6 +378,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtens
   if (stages < 2) return PE_ERR_BAD_SHAPE;
   p.stages = stages;
   p.tmem_cols = pow2_cols(2 * p.block_n);
+  p.tx_bytes = p.mode == 2 ? (p.a_boxes + p.b_boxes) * 64 * pe::kRowBytes : stage_bytes;
   p.acc_stride = p.tmem_cols / 2;
   p.tiles_x = (int)tiles.x;
   p.tiles_y = (int)tiles.y;
@@ -404,16 +417,11 @@ extern "C" int pe_gemm_bf16(const void* A, long long lda, int a_mn, const void* 
   p.b_mn = b_mn ? 1 : 0;
   p.M = M;
   p.N = N;
-  // tile width: as wide as N allows (<= 256), narrowed when that fills the SMs' tile rounds better;
+  // tile width: as wide as N allows (<= 256): one 128x256 tile reads 87 flops per operand byte;
   // MN-major B needs whole 64-wide boxes
   int bn = N >= 256 ? 256 : ((N + 15) / 16) * 16;
   if (p.b_mn) bn = ((bn + 63) / 64) * 64;
   if (bn > 256) bn = 256;
-  if (bn == 256 && splits == 1) {
-    const long long mt = (M + 127) / 128, sms = pe_host::num_sms();
-    const long long r256 = (mt * ((N + 255) / 256) + sms - 1) / sms, r128 = (mt * ((N + 127) / 128) + sms - 1) / sms;
-    if (r128 * (128 + 48) < r256 * (256 + 48)) bn = 128;
-  }
   p.block_n = bn;
   p.a_boxes = 2;
   p.b_boxes = bn / 64;
@@ -515,13 +523,23 @@ extern "C" int pe_conv_wgrad_nhwc(const void* dy, const void* x, float* dw, long
   p.tiles_w = (W + p.tw - 1) / p.tw;
   p.tiles_h = (H + p.th - 1) / p.th;
   p.taps = taps;
+  p.c1_chunks = C / 64;
   p.M = Cout;
-  p.N = C;
-  p.block_n = C;
-  p.a_boxes = 2;
-  p.b_boxes = C / 64;
+  p.N = taps * C;
+  // several taps per tile when that keeps the tile <= 256 columns: dy is then loaded once for all of them
+  int group = 1;
+  if (taps == 9) group = C == 64 ? 3 : (C == 128 ? 2 : 1);
+  p.block_n = group * C;
+  p.a_boxes = Cout > 64 ? 2 : 1;  // rows >= Cout of the accumulator are never stored: skip their operand box
+  p.b_boxes = p.block_n / 64;
   p.kb_total = B * p.tiles_h * p.tiles_w;
-  if (splits < 1) splits = 1;
+  const int n_tiles = (p.N + p.block_n - 1) / p.block_n;
+  const int m_tiles = (Cout + 127) / 128;
+  if (splits < 1) {
+    splits = pe_host::num_sms() / (m_tiles * n_tiles);
+    if (splits < 1) splits = 1;
+  }
+  if (splits > p.kb_total) splits = p.kb_total;
   p.kb_per_split = (p.kb_total + splits - 1) / splits;
   splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
   pe_epilogue e{};
@@ -533,6 +551,6 @@ extern "C" int pe_conv_wgrad_nhwc(const void* dy, const void* x, float* dw, long
   CUtensorMap ta, tb;
   if (int rc = nhwc_tmap(&ta, dy, B, H, W, Cout, p.tw, p.th)) return rc;
   if (int rc = nhwc_tmap(&tb, x, B, H, W, C, p.tw, p.th)) return rc;
-  dim3 grid((Cout + 127) / 128, taps, splits);
+  dim3 grid(m_tiles, n_tiles, splits);
   return launch_tc(ta, ta, tb, p, grid, reinterpret_cast<cudaStream_t>(stream));
 }

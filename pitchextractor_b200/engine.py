@@ -341,7 +341,7 @@ class Engine:
     def _wgrad_linear(self, dY, X, name, M_out, N_in, tokens):
         """grad(weight[name]) [M_out, N_in] += dY^T X, contraction over tokens, split-K with fp32 atomics."""
         tiles = ((M_out + 127) // 128) * ((N_in + 255) // 256)
-        splits = max(1, min((tokens + 63) // 64, (296 + tiles - 1) // tiles))
+        splits = max(1, min((tokens + 63) // 64, 148 // tiles))  # one persistent round of <= 148 tiles
         ops.gemm(dY, X, self.mat(name, M_out, N_in, "grad"), M_out, N_in, tokens, a_mn=True, b_mn=True, splits=splits,
                  out_mode=L.PE_OUT_F32_ATOMIC)
 

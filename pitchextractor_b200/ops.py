@@ -79,8 +79,6 @@ def conv_wgrad(dy, x, dw, taps=9, splits=0, col_offset=0):
     """dw[Cout, col_offset + tap*C + ci] += sum_p dy[p,co] x[p+tap,ci]; dw fp32 [Cout, ldw]."""
     B, H, W, Cout = dy.shape
     C = x.shape[-1]
-    if splits <= 0:
-        splits = max(1, min(64, (148 * 2) // (taps * ((Cout + 127) // 128))))
     base = ctypes.c_void_p(dw.data_ptr() + 4 * col_offset)
     with _Timed("wgrad", 2.0 * B * H * W * Cout * C * taps):
         call("pe_conv_wgrad_nhwc", ptr(dy), ptr(x), base, c_ll(dw.stride(0)), c_int(B), c_int(H), c_int(W), c_int(C),
