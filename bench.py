@@ -93,6 +93,8 @@ def run_ours(args):
     from pitchextractor_b200 import JDCNet, Trainer, build_optimizer, ops, _lib
     from pitchextractor_b200.parallel import init_from_env
     import torch.distributed as dist
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line
     rank, world, local_rank = init_from_env("nccl")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -166,6 +168,9 @@ def run_ours(args):
     e1.record()
     torch.cuda.synchronize()
     lm_ms = e0.elapsed_time(e1) / 10
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     pk = peaks()
