@@ -27,8 +27,13 @@ import torch  # noqa: E402
 SEG = 58624
 FRAMES = 192
 MODEL_CFG = dict(model_type="transformer", num_layers=4, dropout=0.1, nhead=8, dim_feedforward=1536, max_len=2048)
-# algorithmic training flops per segment, 3 x forward: conv trunk 13.39 + transformers 8.66 GFLOP
-FLOPS_PER_SEGMENT = 3.0 * (13.39e9 + 8.66e9)
+# algorithmic training flops per segment, 3 x forward: conv trunk 13.39 GFLOP + transformers 8.66
+# (or BiLSTMs 10.27)
+FLOPS_PER_SEGMENT = {"transformer": 3.0 * (13.39e9 + 8.66e9), "bilstm": 3.0 * (13.39e9 + 10.27e9)}
+WORKLOAD = {"transformer": "JDCNet Transformer (4L d512 h8 ffn1536) train step incl. log-mel, batch %d/GPU, 24 kHz "
+                           "58624-sample segments -> 192 frames (BASELINE configs[1])",
+            "bilstm": "JDCNet BiLSTM (4L h384 bidirectional) train step incl. log-mel, batch %d/GPU, 24 kHz "
+                      "58624-sample segments -> 192 frames (BASELINE configs[3] at 512/GPU, configs[0] at 16)"}
 
 
 def peaks():
@@ -100,7 +105,8 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     B = args.batch
     torch.manual_seed(0)
-    model = JDCNet(num_class=1, sequence_model_config=dict(MODEL_CFG)).to(dev)
+    cfg = dict(MODEL_CFG, model_type=args.model)
+    model = JDCNet(num_class=1, sequence_model_config=cfg).to(dev)
     opt, sched = build_optimizer({"params": model.parameters(), "optimizer_params": {},
                                   "scheduler_params": {"max_lr": 3e-4, "pct_start": 0.0, "epochs": 100,
                                                        "steps_per_epoch": 1000}})
@@ -180,8 +186,7 @@ def run_ours(args):
         "metric": "train_segments_per_s", "value": seg_s, "unit": "segments/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "JDCNet Transformer (4L d512 h8 ffn1536) train step incl. log-mel, batch %d/GPU, "
-                               "24 kHz 58624-sample segments -> 192 frames (BASELINE configs[1])" % B,
+        "config": {"workload": WORKLOAD[args.model] % B,
                    "global_batch": world * B, "parallelism": "dp%d" % world,
                    "l2": "working set (>1 GB activations/step) exceeds the 126 MB L2; inputs cycle over %d batches" % len(pool)},
         "e2e": {"value": world * B * args.steps / (ms_e2e / 1e3), "unit": "segments/s", "h2d_bytes_per_step": h2d,
@@ -194,18 +199,18 @@ def run_ours(args):
                      "frac": (tc_flops / (tc_ms / 1e3) / 1e12 / pk["tf_sustained"]) if tc_ms > 0 else None,
                      "traffic": None, "peak_source": pk["src"] + " (sustained bf16)",
                      "launches_per_step": len(prof) // max(1, n_prof_steps), "ms_per_step": tc_ms / max(1, n_prof_steps),
-                     "step_frac_of_bf16_peak": seg_s / world * FLOPS_PER_SEGMENT / (pk["tf_sustained"] * 1e12)},
+                     "step_frac_of_bf16_peak": seg_s / world * FLOPS_PER_SEGMENT[args.model] / (pk["tf_sustained"] * 1e12)},
         "logmel": {"frames_per_s": frames / (lm_ms / 1e3), "ms": lm_ms, "bound": "hbm",
                    "achieved_gbs": frames * 1520.0 / (lm_ms / 1e3) / 1e9, "peak_gbs": pk["hbm"],
                    "frac": frames * 1520.0 / (lm_ms / 1e3) / 1e9 / pk["hbm"]},
         "loss_last": last,
     }
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(sample_batch=args.cpu_sample, steps=1, warmup=1)
+        line["cpu_baseline"] = cpu_baseline(sample_batch=args.cpu_sample, steps=1, warmup=1, model=args.model)
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline(sample_batch, steps, warmup):
+def cpu_baseline(sample_batch, steps, warmup, model="transformer"):
     """Oracle port of reference Trainer.run on the host cores (fp32; AMP / checkpointing are off on CPU in the
     reference too, trainer.py:64,103), on a bounded sample of the workload."""
     from oracle import jdcnet_torch as J, train_step as TS
@@ -214,8 +219,8 @@ def cpu_baseline(sample_batch, steps, warmup):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(0)
-    sd = JDCNet(num_class=1, sequence_model_config=dict(MODEL_CFG)).state_dict()
-    ref = TS.ReferenceStep(sd, J.default_config("transformer"))
+    sd = JDCNet(num_class=1, sequence_model_config=dict(MODEL_CFG, model_type=model)).state_dict()
+    ref = TS.ReferenceStep(sd, J.default_config(model))
     waves, f0 = synthetic.make_batch(sample_batch, seed=4321)
     crops = np.arange(sample_batch) % 4
     for _ in range(warmup):
@@ -241,8 +246,8 @@ def run_reference(args):
     torch.set_num_threads(cores)
     torch.manual_seed(0)
     sb = args.cpu_sample
-    sd = JDCNet(num_class=1, sequence_model_config=dict(MODEL_CFG)).state_dict()
-    ref = TS.ReferenceStep(sd, J.default_config("transformer"))
+    sd = JDCNet(num_class=1, sequence_model_config=dict(MODEL_CFG, model_type=args.model)).state_dict()
+    ref = TS.ReferenceStep(sd, J.default_config(args.model))
     waves, f0 = synthetic.make_batch(sb, seed=4321)
     crops = np.arange(sb) % 4
     for _ in range(args.warmup):
@@ -258,8 +263,7 @@ def run_reference(args):
         "impl": "reference", "metric": "train_segments_per_s", "value": v, "unit": "segments/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "JDCNet Transformer (4L d512 h8 ffn1536) train step incl. log-mel, batch %d/GPU, "
-                               "24 kHz 58624-sample segments -> 192 frames (BASELINE configs[1])" % args.batch,
+        "config": {"workload": WORKLOAD[args.model] % args.batch,
                    "global_batch": args.batch, "parallelism": "cpu"},
         "cpu_baseline": {"value": v, "unit": "segments/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -273,6 +277,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="segments per GPU per step")
+    ap.add_argument("--model", default="transformer", choices=["transformer", "bilstm"],
+                    help="sequence model (default: the configuration the metric is quoted on)")
     ap.add_argument("--pool", type=int, default=3, help="distinct synthetic batches cycled through")
     ap.add_argument("--cpu-sample", type=int, default=8, help="segments per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")

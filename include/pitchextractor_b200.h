@@ -173,6 +173,29 @@ int pe_heads_loss(const void* hc, const void* hd, long long M, int D, const floa
                   pe_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * BiLSTM sequence model (model.py:218-228 -> torch.nn.LSTM; gates i,f,g,o, torch/nn/modules/rnn.py:842-847).
+ * One call advances the four recurrences of a layer (2 sequence models x 2 directions) by one time step; hidden
+ * size 384.  Arrays indexed [model] (2 entries) or [model*2 + direction] (4 entries); all pointers device memory.
+ *   gx : fp32 [B][T][2*1536]  input projection x W_ih^T on entry, activated gates (kept for the backward) on exit
+ *   c  : fp32 [B][T][2*384]   cell state;   y : bf16 [B][T][2*384] hidden state (direction d at columns d*384)
+ * ------------------------------------------------------------------------------------------------ */
+int pe_lstm_step_fwd(int B, int T, int hidden, int step, float* const* gx, float* const* c, void* const* y,
+                     const void* const* w_hh /* bf16 [1536][384] */, const float* const* b_ih,
+                     const float* const* b_hh, pe_stream_t stream);
+/* backward step `step` (0 = the last forward step of each direction): dg bf16 [B][T][2*1536] receives the
+ * pre-activation gate gradients, dc fp32 [B][2*384] carries dL/dc between calls, dy bf16 [B][T][2*384] is dL/dy. */
+int pe_lstm_step_bwd(int B, int T, int hidden, int step, const float* const* gates, const float* const* c,
+                     const void* const* dy, void* const* dg, float* const* dc, const void* const* w_hh,
+                     pe_stream_t stream);
+/* y = dropout(x) on n bf16 elements (n % 8 == 0); the same call with the same seed back-propagates */
+int pe_dropout_bf16(const void* x, void* y, long long n, unsigned drop_thresh, float drop_scale,
+                    unsigned long long seed, pe_stream_t stream);
+/* dw[Cout][ldw] += sum_{b,t} dy[b][t][co] x[b][t][ci] over strided [B][T][.] token views (row / image strides in
+ * elements); the recurrent weight gradient is this with dy and x shifted by one time step.  C <= 256. */
+int pe_wgrad_tokens(const void* dy, long long dy_ld, long long dy_img, const void* x, long long x_ld, long long x_img,
+                    float* dw, long long ldw, int B, int T, int C, int Cout, int splits, pe_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Parameter passes (optimizers.py:54-64).
  * ------------------------------------------------------------------------------------------------ */
 /* torch.optim.AdamW step over a flat fp32 arena; also writes the bf16 working copy when p_bf16 != NULL. */

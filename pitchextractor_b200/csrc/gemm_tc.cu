@@ -554,3 +554,63 @@ extern "C" int pe_conv_wgrad_nhwc(const void* dy, const void* x, float* dw, long
   dim3 grid(m_tiles, n_tiles, splits);
   return launch_tc(ta, ta, tb, p, grid, reinterpret_cast<cudaStream_t>(stream));
 }
+
+// Weight gradient of a per-token linear map with strided token views: dw[Cout][ldw] += sum_{b,t} dy[b][t][co] * x[b][t][ci]
+// for t in [0, T), where dy / x are [B][T][.] views with arbitrary row and image strides (elements).  Used for the
+// recurrent LSTM weights, where dy and x are the same activations shifted by one time step.  C <= 256 per call.
+extern "C" int pe_wgrad_tokens(const void* dy, long long dy_ld, long long dy_img, const void* x, long long x_ld,
+                               long long x_img, float* dw, long long ldw, int B, int T, int C, int Cout, int splits,
+                               pe_stream_t stream) {
+  if (int rc = pe_host::check_arch()) return rc;
+  if (!dy || !x || !dw || B <= 0 || T <= 0 || C % 64 || C <= 0 || C > 256 || Cout % 8 || Cout <= 0)
+    return PE_ERR_BAD_SHAPE;
+  if ((dy_ld % 8) || (x_ld % 8) || (dy_img % 8) || (x_img % 8)) return PE_ERR_BAD_SHAPE;
+  TcParams p{};
+  p.mode = 2;
+  p.kind = 0;
+  p.a_mn = 1;
+  p.b_mn = 1;
+  p.H = T;
+  p.W = 1;
+  p.tw = 1;
+  p.th = 64;
+  p.tiles_w = 1;
+  p.tiles_h = (T + 63) / 64;
+  p.taps = 1;
+  p.c1_chunks = C / 64;
+  p.M = Cout;
+  p.N = C;
+  p.block_n = C;
+  p.a_boxes = Cout > 64 ? 2 : 1;
+  p.b_boxes = C / 64;
+  p.kb_total = B * p.tiles_h;
+  const int m_tiles = (Cout + 127) / 128;
+  if (splits < 1) {
+    splits = pe_host::num_sms() / m_tiles;
+    if (splits < 1) splits = 1;
+  }
+  if (splits > p.kb_total) splits = p.kb_total;
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  pe_epilogue e{};
+  e.out = dw;
+  e.ldc = ldw;
+  e.out_mode = PE_OUT_F32_ATOMIC;
+  e.alpha = 1.f;
+  p.ep = e;
+  CUtensorMap ta, tb;
+  {
+    uint64_t dims[4] = {(uint64_t)Cout, 1, (uint64_t)T, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)dy_ld * 2, (uint64_t)dy_ld * 2, (uint64_t)dy_img * 2};
+    uint32_t box[4] = {64, 1, 64, 1};
+    if (int rc = pe_host::encode_tmap(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dy, dims, str, box)) return rc;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)C, 1, (uint64_t)T, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)x_ld * 2, (uint64_t)x_ld * 2, (uint64_t)x_img * 2};
+    uint32_t box[4] = {64, 1, 64, 1};
+    if (int rc = pe_host::encode_tmap(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x, dims, str, box)) return rc;
+  }
+  dim3 grid(m_tiles, 1, splits);
+  return launch_tc(ta, ta, tb, p, grid, reinterpret_cast<cudaStream_t>(stream));
+}

@@ -63,8 +63,9 @@ class Engine:
         self.p_trunk = 0.5  # nn.Dropout(p=0.5) in pool_block / detector_conv (model.py:40,56)
         if model.num_class != 1:
             raise NotImplementedError("the fused heads kernel implements num_class == 1 (Configs/config.yml:17)")
-        if self.seq_type != "transformer":
-            raise NotImplementedError("bilstm sequence model: recurrence kernels not built yet")
+        if self.seq_type == "bilstm" and (sc.hidden_size != 384 or not sc.bidirectional):
+            raise NotImplementedError("the LSTM recurrence kernels are built for hidden_size 384, bidirectional")
+        self.p_lstm = float(getattr(sc, "lstm_dropout", 0.0))
         self.step_seed = 0x5EED0000
         self.dropout_enabled = True
         self._bufs = {}
@@ -270,8 +271,11 @@ class Engine:
         self._act_pool(DD, BT, 2, 256, 1, aff, out=None, out_seq=SEQD, drop=self._drop(self.p_trunk, training),
                        seed=self._seed(2))
         # ---- sequence models (model.py:94,113)
-        Hc = self._transformer_fwd("sequence_classifier", "c", SEQC, B, T, training, 16)
-        Hd = self._transformer_fwd("sequence_detector", "d", SEQD, B, T, training, 64)
+        if self.seq_type == "transformer":
+            Hc = self._transformer_fwd("sequence_classifier", "c", SEQC, B, T, training, 16)
+            Hd = self._transformer_fwd("sequence_detector", "d", SEQD, B, T, training, 64)
+        else:
+            Hc, Hd = self._bilstm_fwd(SEQC, SEQD, B, T, training)
         self._Hc, self._Hd = Hc, Hd
         return Hc, Hd
 
@@ -318,6 +322,106 @@ class Engine:
                  ptr(stats[2 * l + 2, 1]), stream())
             Hcur = Hn
         return Hcur
+
+
+    # ------------------------------------------------------------------ BiLSTM sequence models (model.py:218-228)
+    _LSTM_MODELS = ("sequence_classifier", "sequence_detector")
+
+    @staticmethod
+    def _ptrs(tensors, ctype=ctypes.c_void_p):
+        return (ctype * len(tensors))(*[t.data_ptr() for t in tensors])
+
+    def _lstm_names(self, layer):
+        out = []
+        for prefix in self._LSTM_MODELS:
+            for sfx in ("", "_reverse"):
+                out.append((prefix, "l%d%s" % (layer, sfx)))
+        return out  # index = model * 2 + direction
+
+    def _bilstm_fwd(self, Xc, Xd, B, T, training):
+        V, W16 = self.view, self.bview
+        M, Hh, G = B * T, 384, 1536
+        drop = self._drop(self.p_lstm, training)
+        X = [Xc, Xd]
+        Y = None
+        for l in range(self.num_layers):
+            In = 512 if l == 0 else 2 * Hh
+            if l > 0:
+                for mi in range(2):
+                    if drop[0]:  # nn.LSTM inter-layer dropout (not after the last layer)
+                        Xl = self.buf("lx%d_%d" % (mi, l), (M, 2 * Hh))
+                        call("pe_dropout_bf16", ptr(Y[mi]), ptr(Xl), c_ll(M * 2 * Hh), c_u(drop[0]), c_f(drop[1]),
+                             c_ull(self._seed(128 + 4 * l + mi)), stream())
+                        X[mi] = Xl
+                    else:
+                        X[mi] = Y[mi]
+            names = self._lstm_names(l)
+            GX = [self.buf("lgx%d_%d" % (mi, l), (M, 2 * G), torch.float32) for mi in range(2)]
+            for r, (prefix, sfx) in enumerate(names):
+                mi, d = r >> 1, r & 1
+                ops.gemm(X[mi], W16["%s.model.weight_ih_%s" % (prefix, sfx)], GX[mi][:, d * G:(d + 1) * G], M, G, In)
+            self._bufs["lxin%d_0" % l], self._bufs["lxin%d_1" % l] = X[0], X[1]
+            Y = [self.buf("ly%d_%d" % (mi, l), (M, 2 * Hh)) for mi in range(2)]
+            C = [self.buf("lc%d_%d" % (mi, l), (M, 2 * Hh), torch.float32) for mi in range(2)]
+            gx_a, c_a, y_a = self._ptrs(GX), self._ptrs(C), self._ptrs(Y)
+            whh = self._ptrs([W16["%s.model.weight_hh_%s" % n] for n in names])
+            bih = self._ptrs([V["%s.model.bias_ih_%s" % n] for n in names])
+            bhh = self._ptrs([V["%s.model.bias_hh_%s" % n] for n in names])
+            st = stream()
+            for s in range(T):
+                call("pe_lstm_step_fwd", c_int(B), c_int(T), c_int(Hh), c_int(s), gx_a, c_a, y_a, whh, bih, bhh, st)
+        return Y[0], Y[1]
+
+    def _bilstm_bwd(self, dHc, dHd, B, T):
+        W16, g, bufs = self.bview, self.gview, self._bufs
+        M, Hh, G = B * T, 384, 1536
+        drop = self._drop(self.p_lstm, self._training)
+        dY = [dHc, dHd]
+        for l in reversed(range(self.num_layers)):
+            In = 512 if l == 0 else 2 * Hh
+            names = self._lstm_names(l)
+            GX = [bufs["lgx%d_%d" % (mi, l)] for mi in range(2)]
+            C = [bufs["lc%d_%d" % (mi, l)] for mi in range(2)]
+            Y = [bufs["ly%d_%d" % (mi, l)] for mi in range(2)]
+            X = [bufs["lxin%d_%d" % (l, mi)] for mi in range(2)]
+            dG = [self.buf("ldg%d" % mi, (M, 2 * G)) for mi in range(2)]
+            dc = [self.buf("ldc%d" % mi, (B, 2 * Hh), torch.float32) for mi in range(2)]
+            gx_a, c_a, dy_a, dg_a, dc_a = (self._ptrs(GX), self._ptrs(C), self._ptrs(dY), self._ptrs(dG), self._ptrs(dc))
+            whh = self._ptrs([W16["%s.model.weight_hh_%s" % n] for n in names])
+            st = stream()
+            for s in range(T):
+                call("pe_lstm_step_bwd", c_int(B), c_int(T), c_int(Hh), c_int(s), gx_a, c_a, dy_a, dg_a, dc_a, whh, st)
+            dX = [None, None]
+            for r, (prefix, sfx) in enumerate(names):
+                mi, d = r >> 1, r & 1
+                dGd = dG[mi][:, d * G:(d + 1) * G]
+                w_ih = "%s.model.weight_ih_%s" % (prefix, sfx)
+                w_hh = "%s.model.weight_hh_%s" % (prefix, sfx)
+                self._wgrad_linear(dGd, X[mi], w_ih, G, In, M)
+                for bname in ("bias_ih", "bias_hh"):
+                    call("pe_colsum_bf16", ptr(dGd), c_ll(M), c_int(G), c_ll(2 * G),
+                         ptr(g["%s.model.%s_%s" % (prefix, bname, sfx)]), stream())
+                # recurrent weights: dW_hh += sum_t dgates_t^T h_{t-1} (time-shifted token views)
+                dg_off, y_off = (1, 0) if d == 0 else (0, 1)
+                gw = self.mat(w_hh, G, Hh, "grad")
+                for c0 in (0, 192):
+                    call("pe_wgrad_tokens",
+                         ctypes.c_void_p(dG[mi].data_ptr() + 2 * (dg_off * 2 * G + d * G)), c_ll(2 * G), c_ll(T * 2 * G),
+                         ctypes.c_void_p(Y[mi].data_ptr() + 2 * (y_off * 2 * Hh + d * Hh + c0)), c_ll(2 * Hh),
+                         c_ll(T * 2 * Hh), ctypes.c_void_p(gw.data_ptr() + 4 * c0), c_ll(Hh), c_int(B), c_int(T - 1),
+                         c_int(192), c_int(G), c_int(0), stream())
+                # input gradient (both directions accumulate into the same tensor)
+                if d == 0:
+                    dX[mi] = self.buf("ldx%d_%d" % (mi, l & 1), (M, In))
+                    ops.gemm(dGd, W16[w_ih], dX[mi], M, In, G, b_mn=True)
+                else:
+                    ops.gemm(dGd, W16[w_ih], dX[mi], M, In, G, b_mn=True, aux=dX[mi], aux_mode=L.PE_AUX_ADD)
+            if l > 0 and drop[0]:
+                for mi in range(2):
+                    call("pe_dropout_bf16", ptr(dX[mi]), ptr(dX[mi]), c_ll(M * In), c_u(drop[0]), c_f(drop[1]),
+                         c_ull(self._seed(128 + 4 * l + mi)), stream())
+            dY = dX
+        return dY[0], dY[1]
 
     # ------------------------------------------------------------------ heads
     def _heads(self, f0, sil, lambda_f0, grad_scale, want_grad, gc_ext=None, gd_ext=None):
@@ -414,10 +518,15 @@ class Engine:
         training = self._training
         W16, g, bufs = self.bview, self.gview, self._bufs
         notify = self.on_grads_ready or (lambda tag: None)
-        dSEQD = self._transformer_bwd("sequence_detector", "d", bufs["SEQD"], dHd, B, T, 64)
-        notify("sequence_detector+heads")
-        dSEQC = self._transformer_bwd("sequence_classifier", "c", bufs["SEQC"], dHc, B, T, 16)
-        notify("sequence_classifier")
+        if self.seq_type == "transformer":
+            dSEQD = self._transformer_bwd("sequence_detector", "d", bufs["SEQD"], dHd, B, T, 64)
+            notify("sequence_detector+heads")
+            dSEQC = self._transformer_bwd("sequence_classifier", "c", bufs["SEQC"], dHc, B, T, 16)
+            notify("sequence_classifier")
+        else:
+            dSEQC, dSEQD = self._bilstm_bwd(dHc, dHd, B, T)
+            notify("sequence_detector+heads")
+            notify("sequence_classifier")
         tdrop = self._drop(self.p_trunk, training)
         # detector_conv
         dDD = self.buf("dDD", (BT * 2, 256))

@@ -21,26 +21,27 @@ def _inputs(B, seed=0):
     return mel, f0, sil
 
 
-def _model(seed=0):
+def _model(seed=0, model_type="transformer"):
     from pitchextractor_b200.model import JDCNet
     torch.manual_seed(seed)
-    cfg = dict(model_type="transformer", num_layers=4, dropout=0.1, nhead=8, dim_feedforward=1536, max_len=2048)
+    cfg = dict(model_type=model_type, num_layers=4, dropout=0.1, nhead=8, dim_feedforward=1536, max_len=2048)
     m = JDCNet(num_class=1, sequence_model_config=cfg)
     # make BN affine / biases non-trivial so their gradients and the folded scale/shift are exercised
     g = torch.Generator().manual_seed(seed + 1)
     for n, p in m.named_parameters():
-        if p.dim() == 1:
+        if p.dim() == 1 and "model.bias_" not in n:
             p.data.add_(0.1 * torch.randn(p.shape, generator=g))
     return m
 
 
-def test_forward_backward_parity(built_lib):
+@pytest.mark.parametrize("model_type", ["transformer", "bilstm"])
+def test_forward_backward_parity(built_lib, model_type):
     from oracle import jdcnet_torch as J
     B = 2
     mel, f0, sil = _inputs(B)
-    m = _model()
+    m = _model(model_type=model_type)
     sd = {k: v.detach().clone().float() for k, v in m.state_dict().items()}
-    cfg = J.default_config("transformer")
+    cfg = J.default_config(model_type)
     ref = J.loss_and_grads(sd, mel, f0, sil, cfg)
     m = m.cuda()
     eng = m.engine
@@ -79,11 +80,12 @@ def test_forward_backward_parity(built_lib):
     assert not bad, bad[:10]
 
 
-def test_eval_forward_parity(built_lib):
+@pytest.mark.parametrize("model_type", ["transformer", "bilstm"])
+def test_eval_forward_parity(built_lib, model_type):
     from oracle import jdcnet_torch as J
     B = 3
     mel, f0, sil = _inputs(B, seed=3)
-    m = _model(seed=3)
+    m = _model(seed=3, model_type=model_type)
     g = torch.Generator().manual_seed(9)
     for n, b in m.named_buffers():
         if n.endswith("running_mean"):
@@ -91,7 +93,7 @@ def test_eval_forward_parity(built_lib):
         if n.endswith("running_var"):
             b.copy_(0.5 + torch.rand(b.shape, generator=g))
     sd = {k: v.detach().clone().float() for k, v in m.state_dict().items()}
-    cls, det = J.jdcnet_forward(sd, mel.transpose(-1, -2), J.default_config("transformer"), training=False)
+    cls, det = J.jdcnet_forward(sd, mel.transpose(-1, -2), J.default_config(model_type), training=False)
     m = m.cuda().eval()
     with torch.no_grad():
         c2, d2 = m(mel.cuda().transpose(-1, -2))
