@@ -79,6 +79,10 @@ int pe_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long lon
 int pe_conv3x3_nhwc(const void* x, const void* x2, const void* w, int B, int H, int W, int C1, int C2, int Cout,
                     const pe_epilogue* ep, pe_stream_t stream);
 
+/* tuning aid: when buf != NULL the tile engine writes per-CTA cycle counters [grid][4] = {main-loop total, MMA thread
+ * waiting for operands, MMA thread waiting for a free accumulator stage, TMA thread waiting for a free smem slot} */
+int pe_tc_set_debug(long long* buf);
+
 /* Weight gradient of the convolution above: dw[Cout][taps*C + ...] += sum_pixels dy[p][co] * x[p+tap][ci].
  * dy: [B][H][W][Cout] bf16, x: [B][H][W][C] bf16, dw: fp32 [Cout][ldw] at column offset tap*C (3x3, taps=9) or
  * a single centre tap (taps=1, the 1x1 shortcut).  Accumulates atomically (caller zeroes dw). */
@@ -174,19 +178,19 @@ int pe_heads_loss(const void* hc, const void* hd, long long M, int D, const floa
 
 /* ------------------------------------------------------------------------------------------------
  * BiLSTM sequence model (model.py:218-228 -> torch.nn.LSTM; gates i,f,g,o, torch/nn/modules/rnn.py:842-847).
- * One call advances the four recurrences of a layer (2 sequence models x 2 directions) by one time step; hidden
- * size 384.  Arrays indexed [model] (2 entries) or [model*2 + direction] (4 entries); all pointers device memory.
+ * One call advances the four recurrences of a layer (2 sequence models x 2 directions) through time steps
+ * [step_begin, step_end) (one dependent launch per step); hidden size 384.  Arrays indexed [model] (2 entries) or [model*2 + direction] (4 entries); all pointers device memory.
  *   gx : fp32 [B][T][2*1536]  input projection x W_ih^T on entry, activated gates (kept for the backward) on exit
  *   c  : fp32 [B][T][2*384]   cell state;   y : bf16 [B][T][2*384] hidden state (direction d at columns d*384)
  * ------------------------------------------------------------------------------------------------ */
-int pe_lstm_step_fwd(int B, int T, int hidden, int step, float* const* gx, float* const* c, void* const* y,
-                     const void* const* w_hh /* bf16 [1536][384] */, const float* const* b_ih,
-                     const float* const* b_hh, pe_stream_t stream);
-/* backward step `step` (0 = the last forward step of each direction): dg bf16 [B][T][2*1536] receives the
+int pe_lstm_steps_fwd(int B, int T, int hidden, int step_begin, int step_end, float* const* gx, float* const* c,
+                      void* const* y, const void* const* w_hh /* bf16 [1536][384] */, const float* const* b_ih,
+                      const float* const* b_hh, pe_stream_t stream);
+/* backward steps (step 0 = the last forward step of each direction): dg bf16 [B][T][2*1536] receives the
  * pre-activation gate gradients, dc fp32 [B][2*384] carries dL/dc between calls, dy bf16 [B][T][2*384] is dL/dy. */
-int pe_lstm_step_bwd(int B, int T, int hidden, int step, const float* const* gates, const float* const* c,
-                     const void* const* dy, void* const* dg, float* const* dc, const void* const* w_hh,
-                     pe_stream_t stream);
+int pe_lstm_steps_bwd(int B, int T, int hidden, int step_begin, int step_end, const float* const* gates,
+                      const float* const* c, const void* const* dy, void* const* dg, float* const* dc,
+                      const void* const* w_hh, pe_stream_t stream);
 /* y = dropout(x) on n bf16 elements (n % 8 == 0); the same call with the same seed back-propagates */
 int pe_dropout_bf16(const void* x, void* y, long long n, unsigned drop_thresh, float drop_scale,
                     unsigned long long seed, pe_stream_t stream);

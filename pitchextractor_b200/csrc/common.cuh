@@ -106,15 +106,25 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
   return ok;
 }
 // Bounded wait: a pipeline bug must surface as a launch failure, never as a hung GPU.
+static __device__ __noinline__ void mbar_timeout_trap() {
+  printf("pe: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
-      printf("pe: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z,
-             threadIdx.x);
-      __trap();
-    }
+    if (++spins > (1u << 26)) mbar_timeout_trap();
+  }
+}
+// Same, for warps that wait much longer than a pipeline stage (epilogue waiting for a whole main loop): sleep between
+// probes so the spinning does not take issue slots from the MMA / TMA threads that share the SM sub-partition.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(64);
+    if (++spins > (1u << 24)) mbar_timeout_trap();
   }
 }
 

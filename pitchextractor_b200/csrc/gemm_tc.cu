@@ -6,6 +6,7 @@
 // (TMEM -> registers -> fused bias / GELU / dropout / residual -> global).  Accumulators live in TMEM.
 #include "common.cuh"
 #include "../../include/pitchextractor_b200.h"
+#include <cstdlib>
 
 namespace pe {
 
@@ -32,6 +33,7 @@ struct TcParams {
   int H, W, tw, th, tiles_w, tiles_h;
   int c1_chunks, c2_chunks;
   int taps;  // wgrad: 9 or 1
+  long long* dbg;  // optional [gridDim.x][4] cycle counters (tuning): total, mma wait-full, mma wait-tmem, tma wait-empty
   pe_epilogue ep;
 };
 
@@ -100,7 +102,9 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       const int elems_per_row = p.kind == 0 ? 64 : 32;
-      uint32_t it = 0;
+      int stage = 0;
+      uint32_t phase = 0;
+      long long w_empty = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(p, tile);
         const int kb_begin = tc.tz * p.kb_per_split;
@@ -115,10 +119,15 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         } else {
           m0 = tc.tx * kBlockM;  // Cout tile; tc.ty = tap
         }
-        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1u;
-          mbar_wait(&empty_bar[s], ph ^ 1u);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          const int s = stage;
+          const long long c0 = p.dbg ? clock64() : 0;
+          mbar_wait(&empty_bar[s], phase ^ 1u);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+          if (p.dbg) w_empty += clock64() - c0;
           uint8_t* sa = smem + (size_t)s * stage_bytes;
           uint8_t* sb = sa + kATileBytes;
           mbar_arrive_expect_tx(&full_bar[s], (uint32_t)p.tx_bytes);
@@ -166,6 +175,7 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           }
         }
       }
+      if (p.dbg) p.dbg[blockIdx.x * 4 + 3] = w_empty;
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
@@ -178,34 +188,55 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       // MN-major: 64-wide (bf16) MN blocks are separate TMA boxes, block_k_rows * 128 B apart
       const uint32_t a_lbo = p.a_mn ? (uint32_t)(block_k_rows * kRowBytes) : 16u;
       const uint32_t b_lbo = p.b_mn ? (uint32_t)(block_k_rows * kRowBytes) : 16u;
-      uint32_t it = 0, local = 0;
+      uint32_t local = 0;
+      int stage = 0;
+      uint32_t phase = 0;
+      long long w_full = 0, w_tmem = 0;
+      const long long t_begin = p.dbg ? clock64() : 0;
+      // descriptor templates: everything but the 14-bit start-address field is loop invariant
+      const uint64_t da0 = umma_desc_sw128(0, a_lbo, 1024), db0 = umma_desc_sw128(0, b_lbo, 1024);
+      const uint32_t a_inc = a_step >> 4, b_inc = b_step >> 4;
+      const uint32_t smem_base = smem_u32(smem);
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
         const TileCoord tc = decode_tile(p, tile);
         const int kb_begin = tc.tz * p.kb_per_split;
         const int num_kb = min(p.kb_total, kb_begin + p.kb_per_split) - kb_begin;
         const uint32_t acc = local & 1u;
+        const long long c1 = p.dbg ? clock64() : 0;
         mbar_wait(&tmem_empty_bar[acc], ((local >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator stage
+        if (p.dbg) w_tmem += clock64() - c1;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.acc_stride;
-        for (int i = 0; i < num_kb; ++i, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1u;
-          mbar_wait(&full_bar[s], ph);
+        for (int i = 0; i < num_kb; ++i) {
+          const long long c2 = p.dbg ? clock64() : 0;
+          mbar_wait(&full_bar[stage], phase);
+          if (p.dbg) w_full += clock64() - c2;
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint32_t sb = sa + kATileBytes;
+          const uint32_t sa = (smem_base + (uint32_t)stage * (uint32_t)stage_bytes) >> 4;
+          const uint32_t sb = sa + (kATileBytes >> 4);
+          if (p.kind == 0) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t da = umma_desc_sw128(sa + k * a_step, a_lbo, 1024);
-            const uint64_t db = umma_desc_sw128(sb + k * b_step, b_lbo, 1024);
-            if (p.kind == 0)
-              tc_mma_bf16(d_tmem, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
-            else
-              tc_mma_tf32(d_tmem, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)
+              tc_mma_bf16(d_tmem, da0 | (uint64_t)(sa + k * a_inc), db0 | (uint64_t)(sb + k * b_inc), idesc,
+                          (i > 0 || k > 0) ? 1u : 0u);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc_mma_tf32(d_tmem, da0 | (uint64_t)(sa + k * a_inc), db0 | (uint64_t)(sb + k * b_inc), idesc,
+                          (i > 0 || k > 0) ? 1u : 0u);
           }
-          tc_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
+          tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
         }
         tc_commit(&tmem_full_bar[acc]);
+      }
+      if (p.dbg) {
+        p.dbg[blockIdx.x * 4 + 0] = clock64() - t_begin;
+        p.dbg[blockIdx.x * 4 + 1] = w_full;
+        p.dbg[blockIdx.x * 4 + 2] = w_tmem;
       }
     }
   } else {
@@ -235,7 +266,7 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         row_ok = grow < p.M;
       }
       const uint32_t acc = local & 1u;
-      mbar_wait(&tmem_full_bar[acc], (local >> 1) & 1u);
+      mbar_wait_relaxed(&tmem_full_bar[acc], (local >> 1) & 1u);
       tc_fence_after();
       const uint32_t t_row = tmem_base + acc * (uint32_t)p.acc_stride + ((uint32_t)(q * 32) << 16);
       for (int c = pair; c < nchunks; c += 2) {
@@ -364,6 +395,12 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 // =================================================================================================
 using pe::TcParams;
 
+static long long* g_tc_dbg = nullptr;
+extern "C" int pe_tc_set_debug(long long* buf) {
+  g_tc_dbg = buf;
+  return PE_OK;
+}
+
 static int pow2_cols(int n) {
   int c = 32;
   while (c < n) c <<= 1;
@@ -375,6 +412,10 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtens
   const int stage_bytes = pe::kATileBytes + p.block_n * pe::kRowBytes;
   int stages = (200 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;
+  if (const char* env = getenv("PE_TC_STAGES")) {  // tuning knob
+    const int v = atoi(env);
+    if (v >= 2 && v < stages) stages = v;
+  }
   if (stages < 2) return PE_ERR_BAD_SHAPE;
   p.stages = stages;
   p.tmem_cols = pow2_cols(2 * p.block_n);
@@ -384,6 +425,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtens
   p.tiles_y = (int)tiles.y;
   p.tiles_z = (int)tiles.z;
   p.num_tiles = p.tiles_x * p.tiles_y * p.tiles_z;
+  p.dbg = g_tc_dbg;
   if (p.ep.drop_thresh && (p.N % 8)) return PE_ERR_BAD_SHAPE;
   const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 4) * sizeof(uint64_t) + 16 + 1024;
   static bool attr_set = false;

@@ -372,17 +372,18 @@ static int lstm_maps(LstmMaps* m, const void* const* act, int act_cols, int B, i
   return PE_OK;
 }
 
-extern "C" int pe_lstm_step_fwd(int B, int T, int hidden, int step, float* const* gx, float* const* c, void* const* y,
-                                const void* const* w_hh, const float* const* b_ih, const float* const* b_hh,
-                                pe_stream_t stream) {
+extern "C" int pe_lstm_steps_fwd(int B, int T, int hidden, int step_begin, int step_end, float* const* gx,
+                                 float* const* c, void* const* y, const void* const* w_hh, const float* const* b_ih,
+                                 const float* const* b_hh, pe_stream_t stream) {
   if (int rc = pe_host::check_arch()) return rc;
-  if (hidden != LH || B <= 0 || T <= 0 || step < 0 || step >= T || !gx || !c || !y || !w_hh || !b_ih || !b_hh)
+  if (hidden != LH || B <= 0 || T <= 0 || step_begin < 0 || step_end > T || step_begin >= step_end || !gx || !c || !y ||
+      !w_hh || !b_ih || !b_hh)
     return PE_ERR_BAD_SHAPE;
   LstmMaps maps;
   const void* act[2] = {y[0], y[1]};
   if (int rc = lstm_maps(&maps, act, 2 * LH, B, T, w_hh, false)) return rc;
   LstmStepParams p{};
-  p.B = B; p.T = T; p.step = step; p.first = step == 0;
+  p.B = B; p.T = T;
   for (int i = 0; i < 2; ++i) {
     p.gx[i] = gx[i]; p.c[i] = c[i]; p.y[i] = (__nv_bfloat16*)y[i];
   }
@@ -397,21 +398,26 @@ extern "C" int pe_lstm_step_fwd(int B, int T, int hidden, int step, float* const
     attr = true;
   }
   dim3 grid(LH / 64, (B + 127) / 128, 4);
-  lstm_step_fwd_kernel<<<grid, L_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(maps, p);
+  for (int s = step_begin; s < step_end; ++s) {  // the time steps are dependent launches on the same stream
+    p.step = s;
+    p.first = s == 0;
+    lstm_step_fwd_kernel<<<grid, L_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(maps, p);
+  }
   return cudaGetLastError() == cudaSuccess ? PE_OK : PE_ERR_LAUNCH;
 }
 
-extern "C" int pe_lstm_step_bwd(int B, int T, int hidden, int step, const float* const* gates, const float* const* c,
-                                const void* const* dy, void* const* dg, float* const* dc, const void* const* w_hh,
-                                pe_stream_t stream) {
+extern "C" int pe_lstm_steps_bwd(int B, int T, int hidden, int step_begin, int step_end, const float* const* gates,
+                                 const float* const* c, const void* const* dy, void* const* dg, float* const* dc,
+                                 const void* const* w_hh, pe_stream_t stream) {
   if (int rc = pe_host::check_arch()) return rc;
-  if (hidden != LH || B <= 0 || T <= 0 || step < 0 || step >= T || !gates || !c || !dy || !dg || !dc || !w_hh)
+  if (hidden != LH || B <= 0 || T <= 0 || step_begin < 0 || step_end > T || step_begin >= step_end || !gates || !c ||
+      !dy || !dg || !dc || !w_hh)
     return PE_ERR_BAD_SHAPE;
   LstmMaps maps;
   const void* act[2] = {dg[0], dg[1]};
   if (int rc = lstm_maps(&maps, act, 2 * LG, B, T, w_hh, true)) return rc;
   LstmStepParams p{};
-  p.B = B; p.T = T; p.step = step; p.first = step == 0;
+  p.B = B; p.T = T;
   for (int i = 0; i < 2; ++i) {
     p.gx[i] = const_cast<float*>(gates[i]); p.c[i] = const_cast<float*>(c[i]);
     p.dy[i] = (const __nv_bfloat16*)dy[i]; p.dg[i] = (__nv_bfloat16*)dg[i]; p.dc[i] = dc[i];
@@ -424,7 +430,11 @@ extern "C" int pe_lstm_step_bwd(int B, int T, int hidden, int step, const float*
     attr = true;
   }
   dim3 grid(LH / 64, (B + 127) / 128, 4);
-  lstm_step_bwd_kernel<<<grid, L_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(maps, p);
+  for (int s = step_begin; s < step_end; ++s) {
+    p.step = s;
+    p.first = s == 0;
+    lstm_step_bwd_kernel<<<grid, L_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(maps, p);
+  }
   return cudaGetLastError() == cudaSuccess ? PE_OK : PE_ERR_LAUNCH;
 }
 

@@ -367,9 +367,9 @@ class Engine:
             whh = self._ptrs([W16["%s.model.weight_hh_%s" % n] for n in names])
             bih = self._ptrs([V["%s.model.bias_ih_%s" % n] for n in names])
             bhh = self._ptrs([V["%s.model.bias_hh_%s" % n] for n in names])
-            st = stream()
-            for s in range(T):
-                call("pe_lstm_step_fwd", c_int(B), c_int(T), c_int(Hh), c_int(s), gx_a, c_a, y_a, whh, bih, bhh, st)
+            call("pe_lstm_steps_fwd", c_int(B), c_int(T), c_int(Hh), c_int(0), c_int(T), gx_a, c_a, y_a, whh, bih, bhh,
+                 stream())
+            L.launch_count += T - 1
         return Y[0], Y[1]
 
     def _bilstm_bwd(self, dHc, dHd, B, T):
@@ -388,9 +388,9 @@ class Engine:
             dc = [self.buf("ldc%d" % mi, (B, 2 * Hh), torch.float32) for mi in range(2)]
             gx_a, c_a, dy_a, dg_a, dc_a = (self._ptrs(GX), self._ptrs(C), self._ptrs(dY), self._ptrs(dG), self._ptrs(dc))
             whh = self._ptrs([W16["%s.model.weight_hh_%s" % n] for n in names])
-            st = stream()
-            for s in range(T):
-                call("pe_lstm_step_bwd", c_int(B), c_int(T), c_int(Hh), c_int(s), gx_a, c_a, dy_a, dg_a, dc_a, whh, st)
+            call("pe_lstm_steps_bwd", c_int(B), c_int(T), c_int(Hh), c_int(0), c_int(T), gx_a, c_a, dy_a, dg_a, dc_a, whh,
+                 stream())
+            L.launch_count += T - 1
             dX = [None, None]
             for r, (prefix, sfx) in enumerate(names):
                 mi, d = r >> 1, r & 1

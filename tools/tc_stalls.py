@@ -1,0 +1,31 @@
+"""Where the tile engine's MMA / TMA threads wait (tuning aid, GPU only)."""
+import ctypes, os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pitchextractor_b200 import ops, _lib
+dbg = torch.zeros(148, 4, dtype=torch.int64, device="cuda")
+lib = _lib.lib()
+
+def show(tag):
+    torch.cuda.synchronize()
+    d = dbg.float().mean(0).tolist()
+    print("%-34s main-loop %8.0f cyc | mma waits operands %5.1f%% | mma waits accumulator %5.1f%% | tma waits slot %5.1f%%" % (
+        tag, d[0], 100 * d[1] / max(d[0], 1), 100 * d[2] / max(d[0], 1), 100 * d[3] / max(d[0], 1)), flush=True)
+
+def gemm(M, N, K):
+    a = torch.randn(M, K, device="cuda").to(torch.bfloat16); b = torch.randn(N, K, device="cuda").to(torch.bfloat16)
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, b, out, M, N, K); torch.cuda.synchronize()
+    lib.pe_tc_set_debug(ctypes.c_void_p(dbg.data_ptr())); dbg.zero_()
+    ops.gemm(a, b, out, M, N, K); show("gemm M=%d N=%d K=%d" % (M, N, K)); lib.pe_tc_set_debug(None)
+
+def conv(B, H, W, C1, C2, Cout):
+    x = torch.randn(B, H, W, C1, device="cuda").to(torch.bfloat16)
+    x2 = torch.randn(B, H, W, C2, device="cuda").to(torch.bfloat16) if C2 else None
+    w = torch.randn(Cout, 9 * C1 + C2, device="cuda").to(torch.bfloat16)
+    out = torch.empty(B, H, W, Cout, device="cuda", dtype=torch.bfloat16)
+    ops.conv3x3(x, w, out, x2=x2); torch.cuda.synchronize()
+    lib.pe_tc_set_debug(ctypes.c_void_p(dbg.data_ptr())); dbg.zero_()
+    ops.conv3x3(x, w, out, x2=x2); show("conv W=%d C=%d->%d" % (W, C1, Cout)); lib.pe_tc_set_debug(None)
+
+gemm(12288, 1536, 512); gemm(12288, 512, 1536); gemm(12288, 256, 2048)
+conv(64, 192, 80, 64, 0, 64); conv(64, 192, 40, 128, 64, 128); conv(64, 192, 10, 256, 192, 256)
