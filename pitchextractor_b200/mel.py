@@ -53,6 +53,51 @@ def windowed_dft_basis(n_fft, win_length=None):
     return torch.from_numpy(basis)
 
 
+def dft32_operand_images():
+    """fp16 operand images (hi, lo, hi * 2^-11) of the real 64 x 64 form of the 32-point complex DFT matrix
+    F[(c', k), (c, n)] (c, c' in {re, im}), laid out as a 128-byte-swizzled K-major [64 rows x 128 B] tcgen05 operand."""
+    k = np.arange(32)[:, None]
+    n = np.arange(32)[None, :]
+    ang = 2.0 * np.pi * ((k * n) % 32) / 32.0
+    F = np.zeros((64, 64))
+    F[:32, :32], F[:32, 32:] = np.cos(ang), np.sin(ang)
+    F[32:, :32], F[32:, 32:] = -np.sin(ang), np.cos(ang)
+    hi = F.astype(np.float16)
+    lo = (F - hi.astype(np.float64)).astype(np.float16)
+    hi_s = (hi.astype(np.float64) * 2.0 ** -11).astype(np.float16)
+    out = np.zeros((3, 64 * 64), dtype=np.float16)
+    o = np.arange(64)[:, None]
+    kk = np.arange(64)[None, :]
+    elem = (o * 128 + (((kk >> 3) ^ (o & 7)) << 4) + (kk & 7) * 2) // 2
+    for i, mat in enumerate((hi, lo, hi_s)):
+        out[i, elem.reshape(-1)] = mat.reshape(-1)
+    return torch.from_numpy(out)
+
+
+def four_step_twiddles():
+    """[2, 32, 32] fp32: cos / sin of 2 pi k1 n2 / 1024, indexed [k1][n2]."""
+    k1 = np.arange(32)[:, None]
+    n2 = np.arange(32)[None, :]
+    ang = 2.0 * np.pi * (k1 * n2) / 1024.0
+    return torch.from_numpy(np.stack([np.cos(ang), np.sin(ang)]).astype(np.float32))
+
+
+def banded_filterbank(fb):
+    """fb [n_bins, n_mels] -> (start, count, offset int32 [n_mels], weights fp32 [nnz]): each mel filter is one
+    contiguous band of bins."""
+    fb = fb.cpu().numpy()
+    starts, counts, offs, weights = [], [], [], []
+    for m in range(fb.shape[1]):
+        nz = np.nonzero(fb[:, m])[0]
+        lo, hi = (int(nz[0]), int(nz[-1]) + 1) if nz.size else (0, 1)
+        starts.append(lo)
+        counts.append(hi - lo)
+        offs.append(len(weights))
+        weights.extend(fb[lo:hi, m].tolist())
+    to_i = lambda a: torch.tensor(a, dtype=torch.int32)
+    return to_i(starts), to_i(counts), to_i(offs), torch.tensor(weights, dtype=torch.float32)
+
+
 _TABLE_CACHE = {}
 
 
@@ -60,11 +105,23 @@ def logmel_tables(device, sample_rate=24000, n_fft=1024, win_length=1024, hop_le
     """Immutable constant tables, built once per (device, params)."""
     key = (str(device), sample_rate, n_fft, win_length, hop_length, n_mels)
     if key not in _TABLE_CACHE:
-        _TABLE_CACHE[key] = {
+        fb = mel_filterbank(sample_rate, n_fft, n_mels)
+        tab = {
             "n_fft": n_fft, "hop": hop_length, "n_mels": n_mels, "sr": sample_rate,
             "basis": windowed_dft_basis(n_fft, win_length).to(device),
-            "fb": mel_filterbank(sample_rate, n_fft, n_mels).to(device),
+            "fb": fb.to(device),
+            "tc": n_fft == 1024 and hop_length % 4 == 0 and n_mels <= 128,
         }
+        if tab["tc"]:
+            win = np.zeros(n_fft)
+            left = (n_fft - win_length) // 2
+            win[left:left + win_length] = 0.5 - 0.5 * np.cos(2.0 * np.pi * np.arange(win_length) / win_length)
+            st, cnt, off, w = banded_filterbank(fb)
+            tab.update(win=torch.from_numpy(win.astype(np.float32)).to(device), fmat=dft32_operand_images().to(device),
+                       tw=four_step_twiddles().to(device), mel_start=st.to(device), mel_count=cnt.to(device),
+                       mel_off=off.to(device), mel_w=w.to(device), mel_nnz=int(w.numel()))
+            tab["tc"] = tab["mel_nnz"] <= 2048
+        _TABLE_CACHE[key] = tab
     return _TABLE_CACHE[key]
 
 
@@ -72,7 +129,9 @@ class LogMel:
     """Batched replacement of ``(log(1e-5 + MelSpectrogram(wave)) + 4) / 4``: wave [B, L] fp32 (cuda) ->
     [B, n_mels, T] with T = 1 + L // hop.  CUDA-only."""
 
-    def __init__(self, device="cuda", **mel_params):
+    def __init__(self, device="cuda", impl="auto", **mel_params):
+        """impl: "auto" (tcgen05 four-step kernel when n_fft == 1024, else the fp32 SIMT kernels), "tc" or "simt"."""
+        self.impl = impl
         params = dict(DEFAULT_MEL_PARAMS)
         params.update(mel_params)
         if "win_len" in params and "win_length" not in mel_params:
@@ -98,11 +157,22 @@ class LogMel:
         n_mels = self.params["n_mels"]
         shape = (B, n_mels, To) if layout == "bmt" else (B, To, n_mels)
         out = torch.empty(shape, device=self.device, dtype=torch.float32)
-        need = B * T * (self.params["n_fft"] // 2 + 1)
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.empty(need, device=self.device, dtype=torch.float32)
         if crop is not None:
             crop = crop.to(self.device, torch.int32).contiguous()
-        ops.logmel(wave, self.tables, out_bmt=out if layout == "bmt" else None,
-                   out_btm=out if layout == "btm" else None, crop=crop, T_out=To, power_ws=self._ws)
+        use_tc = self.tables["tc"] if self.impl == "auto" else self.impl == "tc"
+        if use_tc and not self.tables["tc"]:
+            raise RuntimeError("the tcgen05 log-mel kernel needs n_fft == 1024, hop % 4 == 0, n_mels <= 128")
+        if use_tc:
+            need = B * ((Lw + self.params["n_fft"] + 3) // 4 * 4)
+        else:
+            need = B * T * (self.params["n_fft"] // 2 + 1)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, device=self.device, dtype=torch.float32)
+        kw = dict(out_bmt=out if layout == "bmt" else None, out_btm=out if layout == "btm" else None, crop=crop, T_out=To)
+        if use_tc:
+            if crop is not None or To != T:
+                out.zero_()  # rows past the end of an item stay zero (Collater padding, meldataset.py:804-816)
+            ops.logmel_tc(wave, self.tables, ws=self._ws, **kw)
+        else:
+            ops.logmel(wave, self.tables, power_ws=self._ws, **kw)
         return out

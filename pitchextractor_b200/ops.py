@@ -115,3 +115,13 @@ def attn_bwd(qkv, ctx, dctx, lse, B, T, H, dqkv, delta, p_drop=0.0, seed=0):
 def colsum(x, out):
     M, N = x.shape
     call("pe_colsum_bf16", ptr(x), c_ll(M), c_int(N), c_ll(x.stride(0)), ptr(out), stream())
+
+
+def logmel_tc(wave, tables, ws, out_bmt=None, out_btm=None, crop=None, T_out=0):
+    """tcgen05 four-step log-mel (n_fft 1024); ws: fp32 workspace for the reflect-padded waveform."""
+    B, Lw = wave.shape
+    t = tables
+    call("pe_logmel_tc", ptr(wave), c_int(B), c_int(Lw), c_int(t["n_fft"]), c_int(t["hop"]), c_int(t["n_mels"]),
+         ptr(t["win"]), ptr(t["fmat"]), ptr(t["tw"]), ptr(t["mel_start"]), ptr(t["mel_count"]), ptr(t["mel_off"]),
+         ptr(t["mel_w"]), c_int(t["mel_nnz"]), ptr(ws), c_size(ws.numel() * 4), ptr(out_bmt), ptr(out_btm), ptr(crop),
+         c_int(T_out), stream())

@@ -21,13 +21,17 @@ def _signals():
     }
 
 
-def test_logmel_segment_parity(built_lib):
+IMPLS = ["tc", "simt"]
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_logmel_segment_parity(built_lib, impl):
     from oracle import logmel_np
     from pitchextractor_b200.mel import LogMel
     sigs = _signals()
     names = list(sigs)
     wave = torch.from_numpy(np.stack([sigs[n] for n in names])).cuda()
-    y = LogMel("cuda")(wave).cpu().numpy()
+    y = LogMel("cuda", impl=impl)(wave).cpu().numpy()
     assert y.shape == (len(names), 80, 196)
     for i, n in enumerate(names):
         ref = logmel_np.log_mel(sigs[n])
@@ -38,27 +42,44 @@ def test_logmel_segment_parity(built_lib):
         assert err.max() <= tol * max(1.0, np.abs(ref).max()), (n, err.max())
 
 
-@pytest.mark.parametrize("L,B", [(24000, 3), (600, 2), (1025, 1), (240000, 2)])
-def test_logmel_lengths(built_lib, L, B):
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("L,B", [(24000, 3), (600, 2), (1025, 1), (240000, 2), (58624, 64)])
+def test_logmel_lengths(built_lib, L, B, impl):
     from oracle import logmel_np
     from pitchextractor_b200.mel import LogMel
     rng = np.random.default_rng(L)
     w = (0.2 * rng.standard_normal((B, L))).astype(np.float32)
-    y = LogMel("cuda")(torch.from_numpy(w).cuda()).cpu().numpy()
+    y = LogMel("cuda", impl=impl)(torch.from_numpy(w).cuda()).cpu().numpy()
     for b in range(B):
         ref = logmel_np.log_mel(w[b])
         assert y[b].shape == ref.shape
         assert np.abs(y[b] - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max())
 
 
-def test_logmel_crop_and_layout(built_lib):
+@pytest.mark.parametrize("impl", IMPLS)
+def test_logmel_crop_and_layout(built_lib, impl):
     from oracle import logmel_np
     from pitchextractor_b200.mel import LogMel
     rng = np.random.default_rng(7)
     w = (0.1 * rng.standard_normal((4, SEG))).astype(np.float32)
     crop = torch.tensor([0, 1, 3, 4], dtype=torch.int32)
-    y = LogMel("cuda")(torch.from_numpy(w).cuda(), crop=crop, T_out=192, layout="btm").cpu().numpy()
+    y = LogMel("cuda", impl=impl)(torch.from_numpy(w).cuda(), crop=crop, T_out=192, layout="btm").cpu().numpy()
     assert y.shape == (4, 192, 80)
     for b in range(4):
         ref = logmel_np.log_mel(w[b])[:, int(crop[b]):int(crop[b]) + 192].T
         assert np.abs(y[b] - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_logmel_zero_padding_past_the_end(built_lib, impl):
+    """Collater semantics (meldataset.py:804-816): frames past the end of a short item are zero."""
+    from oracle import logmel_np
+    from pitchextractor_b200.mel import LogMel
+    rng = np.random.default_rng(11)
+    w = (0.1 * rng.standard_normal((2, 24000))).astype(np.float32)  # 81 frames
+    y = LogMel("cuda", impl=impl)(torch.from_numpy(w).cuda(), T_out=192).cpu().numpy()
+    assert y.shape == (2, 80, 192)
+    for b in range(2):
+        ref = logmel_np.log_mel(w[b])
+        assert np.abs(y[b, :, :81] - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max())
+        assert (y[b, :, 81:] == 0).all()
