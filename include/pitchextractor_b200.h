@@ -107,12 +107,16 @@ int pe_logmel_f32(const float* wave, int B, int L, int n_fft, int hop, int n_mel
  *   win [1024] fp32 window;  fmat: 3 x [64][64] fp16 operand images (hi, lo, hi * 2^-11) of the 32-point complex DFT
  *   matrix in the 128-byte-swizzled K-major layout;  tw [2][32][32] fp32 cos / sin of 2 pi k1 n2 / 1024;
  *   mel_start / mel_count / mel_off [n_mels] + mel_w [mel_nnz]: banded filterbank;  xpad: fp32 workspace
- *   [B][round_up(L + 1024, 4)] for the reflect-padded waveform.  Output frames t with 0 <= t - crop[b] < T_out are
+ *   [B][round_up(L, 4)], used only when L % 4 != 0 (rows are re-strided to 16 bytes); the reflect padding happens
+ *   inside the kernel.  Output frames t with 0 <= t - crop[b] < T_out are
  *   written (the caller zero-fills the outputs when padding rows are possible). */
 int pe_logmel_tc(const float* wave, int B, int L, int n_fft, int hop, int n_mels, const float* win, const void* fmat,
                  const float* tw, const int* mel_start, const int* mel_count, const int* mel_off, const float* mel_w,
                  int mel_nnz, float* xpad, size_t xpad_bytes, float* out_bmt, float* out_btm, const int* crop,
                  int T_out, pe_stream_t stream);
+
+/* tuning aid: per-CTA cycle counters of the tcgen05 log-mel worker phases, [grid][8] */
+int pe_logmel_set_debug(long long* buf);
 
 /* ------------------------------------------------------------------------------------------------
  * Conv trunk, memory-bound passes over NHWC bf16 activations (model.py:23-57,143-175).

@@ -61,7 +61,7 @@ def check(rc, what):
 
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches count)
-_LAUNCHES_PER_CALL = {"pe_logmel_f32": 2, "pe_logmel_tc": 2, "pe_bn_act_pool_bwd": 3, "pe_attn_bwd": 2, "pe_heads_loss": 2}
+_LAUNCHES_PER_CALL = {"pe_logmel_f32": 2, "pe_bn_act_pool_bwd": 3, "pe_attn_bwd": 2, "pe_heads_loss": 2}
 launch_count = 0
 
 
