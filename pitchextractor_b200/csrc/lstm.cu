@@ -53,6 +53,7 @@ lstm_step_fwd_kernel(const __grid_constant__ LstmMaps maps, const LstmStepParams
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int u0 = blockIdx.x * 64, b0 = blockIdx.y * 128, rec = blockIdx.z;
   const int model = rec >> 1, dir = rec & 1;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // let the next step's prologue start early
   const int t = dir ? p.T - 1 - p.step : p.step;
   const int t_prev = dir ? t + 1 : t - 1;
 
@@ -69,6 +70,9 @@ lstm_step_fwd_kernel(const __grid_constant__ LstmMaps maps, const LstmStepParams
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: the prologue above overlapped the previous time step; everything below reads what
+  // that step wrote
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (!p.first) {
     if (warp == 0 && lane == 0) {
@@ -193,6 +197,7 @@ lstm_step_bwd_kernel(const __grid_constant__ LstmMaps maps, const LstmStepParams
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int u0 = blockIdx.x * 64, b0 = blockIdx.y * 128, rec = blockIdx.z;
   const int model = rec >> 1, dir = rec & 1;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // the backward pass walks each direction's own time order in reverse
   const int t = dir ? p.step : p.T - 1 - p.step;
   const int t_next = dir ? t - 1 : t + 1;   // processed one launch earlier
@@ -212,6 +217,7 @@ lstm_step_bwd_kernel(const __grid_constant__ LstmMaps maps, const LstmStepParams
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (!p.first) {
     if (warp == 0 && lane == 0) {
@@ -398,10 +404,20 @@ extern "C" int pe_lstm_steps_fwd(int B, int T, int hidden, int step_begin, int s
     attr = true;
   }
   dim3 grid(LH / 64, (B + 127) / 128, 4);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(L_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr_pdl[1];
+  attr_pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr_pdl[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr_pdl;
+  cfg.numAttrs = 1;
   for (int s = step_begin; s < step_end; ++s) {  // the time steps are dependent launches on the same stream
     p.step = s;
     p.first = s == 0;
-    lstm_step_fwd_kernel<<<grid, L_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(maps, p);
+    if (cudaLaunchKernelEx(&cfg, lstm_step_fwd_kernel, maps, p) != cudaSuccess) return PE_ERR_LAUNCH;
   }
   return cudaGetLastError() == cudaSuccess ? PE_OK : PE_ERR_LAUNCH;
 }
@@ -430,10 +446,20 @@ extern "C" int pe_lstm_steps_bwd(int B, int T, int hidden, int step_begin, int s
     attr = true;
   }
   dim3 grid(LH / 64, (B + 127) / 128, 4);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(L_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr_pdl[1];
+  attr_pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr_pdl[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr_pdl;
+  cfg.numAttrs = 1;
   for (int s = step_begin; s < step_end; ++s) {
     p.step = s;
     p.first = s == 0;
-    lstm_step_bwd_kernel<<<grid, L_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(maps, p);
+    if (cudaLaunchKernelEx(&cfg, lstm_step_bwd_kernel, maps, p) != cudaSuccess) return PE_ERR_LAUNCH;
   }
   return cudaGetLastError() == cudaSuccess ? PE_OK : PE_ERR_LAUNCH;
 }
