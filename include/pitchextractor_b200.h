@@ -39,11 +39,14 @@ int pe_check_device(void); /* PE_OK iff the current device is sm_100 */
 /* ------------------------------------------------------------------------------------------------
  * Fused epilogue description shared by the tensor-core GEMM / implicit-GEMM convolution.
  *   v = acc (+ bias[col]);  if act==GELU {out2 = bf16(v); v = gelu(v)};  if drop_thresh {v = keep ? v*drop_scale : 0};
- *   if aux_mode==ADD v += aux; if aux_mode==GELU_GRAD v *= gelu'(aux);  store (fp32 | bf16 | atomic fp32 add).
+ *   (act==GELU_SAVE_GRAD: out2 = bf16(gelu'(v) * dropout factor) instead, i.e. d out / d v, so that the backward GEMM
+ *   only multiplies: aux_mode==MUL)
+ *   if aux_mode==ADD v += aux; if aux_mode==GELU_GRAD v *= gelu'(aux); if aux_mode==MUL v *= aux;
+ *   store (fp32 | bf16 | atomic fp32 add).
  * ------------------------------------------------------------------------------------------------ */
 enum { PE_OUT_F32 = 0, PE_OUT_BF16 = 1, PE_OUT_F32_ATOMIC = 2 };
-enum { PE_ACT_NONE = 0, PE_ACT_GELU = 1 };
-enum { PE_AUX_NONE = 0, PE_AUX_ADD = 1, PE_AUX_GELU_GRAD = 2 };
+enum { PE_ACT_NONE = 0, PE_ACT_GELU = 1, PE_ACT_GELU_SAVE_GRAD = 2 };
+enum { PE_AUX_NONE = 0, PE_AUX_ADD = 1, PE_AUX_GELU_GRAD = 2, PE_AUX_MUL = 3 };
 
 typedef struct pe_epilogue {
   void* out;           /* [M][ldc] */
@@ -60,7 +63,16 @@ typedef struct pe_epilogue {
   float drop_scale;              /* 1/keep_prob */
   unsigned long long drop_seed;
   float alpha;                   /* scale applied to the accumulator first (1.0f for none) */
-  float* stats;        /* optional [2][N] fp32: per-column sum and sum of squares of the STORED value (atomic) */
+  /* optional per-column reductions of the STORED value v over all rows (N <= 256), accumulated atomically in fp64:
+   *   stats_mode 1: stats[0][n] += sum v,  stats[1][n] += sum v^2            (BatchNorm batch statistics)
+   *   stats_mode 2: g = v * lrelu'(x*scale + shift); stats[0][n] += sum g, stats[1][n] += sum g*x
+   *                 (first pass of the BatchNorm backward; x = stats_x bf16 [M][N], the BN input) */
+  double* stats;
+  int stats_mode;
+  const void* stats_x;
+  const float* stats_scale;
+  const float* stats_shift;
+  float stats_slope;
 } pe_epilogue;
 
 /* D[M,N] = sum_k A(m,k) * B(n,k), bf16 operands, fp32 accumulation in TMEM (tcgen05.mma kind::f16).
@@ -147,11 +159,13 @@ int pe_bn_act_pool_fwd(const void* x, long long rows, int W, int C, int k, const
                        long long ld_out, int c_off, void* out_seq, pe_stream_t stream);
 /* backward of the block above through dropout, max-pool, LeakyReLU and the BatchNorm batch statistics:
  * dx bf16 [rows][W][C]; dgamma / dbeta accumulated (+=); sums is a zeroed fp64 [2][C] scratch, coef an fp32 [2][C]
- * scratch; k in {1, 2, 4}. */
+ * scratch; k in {1, 2, 4}.  sums_ready != 0: the reduction pass already ran (fused in the producing convolution's
+ * epilogue, pe_epilogue.stats_mode 2) and is skipped. */
 int pe_bn_act_pool_bwd(const void* x, long long rows, int W, int C, int k, const float* scale, const float* shift,
                        const float* mean, const float* rstd, float slope, unsigned drop_thresh, float drop_scale,
                        unsigned long long seed, const void* dout, long long ld_dout, int c_off, const void* dout_seq,
-                       double* sums, float* coef, float* dgamma, float* dbeta, void* dx, pe_stream_t stream);
+                       double* sums, int sums_ready, float* coef, float* dgamma, float* dbeta, void* dx,
+                       pe_stream_t stream);
 /* backward of the auxiliary max-pools: dx[argmax of each window] += dout */
 int pe_maxpool_bwd_add(const void* x, long long rows, int W, int C, int k, const void* dout, long long ld_dout,
                        int c_off, void* dx, pe_stream_t stream);

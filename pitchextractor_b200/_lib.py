@@ -12,8 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpe_b200.so")
 
 PE_OUT_F32, PE_OUT_BF16, PE_OUT_F32_ATOMIC = 0, 1, 2
-PE_ACT_NONE, PE_ACT_GELU = 0, 1
-PE_AUX_NONE, PE_AUX_ADD, PE_AUX_GELU_GRAD = 0, 1, 2
+PE_ACT_NONE, PE_ACT_GELU, PE_ACT_GELU_SAVE_GRAD = 0, 1, 2
+PE_AUX_NONE, PE_AUX_ADD, PE_AUX_GELU_GRAD, PE_AUX_MUL = 0, 1, 2, 3
 
 _ERRORS = {-1: "bad shape / argument", -2: "workspace too small", -3: "device is not sm_100 (B200)",
            -4: "CUDA driver entry point unavailable", -5: "kernel launch failed"}
@@ -25,7 +25,9 @@ class Epilogue(ctypes.Structure):
         ("out2", ctypes.c_void_p), ("ld2", ctypes.c_longlong), ("bias", ctypes.c_void_p),
         ("aux", ctypes.c_void_p), ("ld_aux", ctypes.c_longlong), ("aux_mode", ctypes.c_int),
         ("drop_thresh", ctypes.c_uint), ("drop_scale", ctypes.c_float), ("drop_seed", ctypes.c_ulonglong),
-        ("alpha", ctypes.c_float), ("stats", ctypes.c_void_p),
+        ("alpha", ctypes.c_float), ("stats", ctypes.c_void_p), ("stats_mode", ctypes.c_int),
+        ("stats_x", ctypes.c_void_p), ("stats_scale", ctypes.c_void_p), ("stats_shift", ctypes.c_void_p),
+        ("stats_slope", ctypes.c_float),
     ]
 
 

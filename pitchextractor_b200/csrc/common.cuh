@@ -264,6 +264,20 @@ __device__ __forceinline__ float erf_fast(float x) {
   const float r = fmaf(-p * t, e, 1.0f);
   return copysignf(r, x);
 }
+// gelu(x) and gelu'(x) with one exponential: exp(-(x/sqrt2)^2) of the erf approximation is sqrt(2 pi) * pdf(x)
+__device__ __forceinline__ void gelu_erf_both(float x, float& g, float& gp) {
+  const float ax = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = __expf(-ax * ax);
+  const float er = copysignf(fmaf(-p * t, e, 1.0f), x);
+  const float cdf = 0.5f * (1.0f + er);
+  g = x * cdf;
+  gp = fmaf(x * 0.39894228040143268f, e, cdf);
+}
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float cdf = 0.5f * (1.0f + erf_fast(x * 0.70710678118654752f));

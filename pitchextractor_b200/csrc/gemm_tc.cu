@@ -72,6 +72,7 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   uint64_t* tmem_full_bar = empty_bar + p.stages;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);  // [2][256] per-CTA column partial sums (ep.stats)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -93,6 +94,8 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  if (p.ep.stats_mode)
+    for (int i = threadIdx.x; i < 512; i += kNumThreads) s_stats[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -273,12 +276,13 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         uint32_t v[32];
         tmem_ld32(t_row + (uint32_t)(c * 32), v);
         tmem_ld_wait();
-        if (!row_ok) continue;
+        if (!row_ok && !ep.stats_mode) continue;
         const int col0 = n0 + c * 32;
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * ep.alpha;
         const bool full = (col0 + 32 <= p.N) && (c * 32 + 32 <= p.block_n);
+        if (row_ok) {  // rows outside the tensor only take part in the column-statistics shuffles below
         if (ep.bias) {
           if (full) {
 #pragma unroll
@@ -291,6 +295,35 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               if (col0 + j < p.N) f[j] += __ldg(ep.bias + col0 + j);
           }
         }
+        if (ep.act == PE_ACT_GELU_SAVE_GRAD) {
+          // out = dropout(gelu(v)); out2 = d out / d v = gelu'(v) * dropout factor (the backward GEMM just multiplies)
+          float gp[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) gelu_erf_both(f[j], f[j], gp[j]);
+          if (ep.drop_thresh) {
+            const unsigned long long e0 = (unsigned long long)grow * (unsigned long long)p.N + (unsigned long long)col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const uint32_t km = dropout_keep8(ep.drop_seed, (e0 + j) >> 3, ep.drop_thresh);
+#pragma unroll
+              for (int t = 0; t < 8; ++t) {
+                const float sc = ((km >> t) & 1u) ? ep.drop_scale : 0.f;
+                f[j + t] *= sc;
+                gp[j + t] *= sc;
+              }
+            }
+          }
+          __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(ep.out2) + grow * ep.ld2 + col0;
+          if (full) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8)
+              *reinterpret_cast<uint4*>(o2 + j) = make_uint4(pack_bf16(gp[j], gp[j + 1]), pack_bf16(gp[j + 2], gp[j + 3]),
+                                                             pack_bf16(gp[j + 4], gp[j + 5]), pack_bf16(gp[j + 6], gp[j + 7]));
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N && c * 32 + j < p.block_n) o2[j] = __float2bfloat16(gp[j]);
+          }
+        } else {
         if (ep.act == PE_ACT_GELU) {
           if (ep.out2) {
             __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(ep.out2) + grow * ep.ld2 + col0;
@@ -316,6 +349,7 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             for (int t = 0; t < 8; ++t) f[j + t] = ((km >> t) & 1u) ? f[j + t] * ep.drop_scale : 0.f;
           }
         }
+        }
         if (ep.aux_mode != PE_AUX_NONE) {
           const __nv_bfloat16* ax = reinterpret_cast<const __nv_bfloat16*>(ep.aux) + grow * ep.ld_aux + col0;
           float a[32];
@@ -338,10 +372,62 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           if (ep.aux_mode == PE_AUX_ADD) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] += a[j];
+          } else if (ep.aux_mode == PE_AUX_MUL) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] *= a[j];
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] *= gelu_erf_grad(a[j]);
           }
+        }
+        }
+        if (ep.stats_mode) {
+          // per-column sums over the 32 rows of this warp by a transposing butterfly (31 shuffles per quantity), then
+          // one shared-memory atomic per column; the CTA flushes its partials to the fp64 global sums once, at the end
+          float sa[32], sb[32];
+          const bool colok = full;
+          if (ep.stats_mode == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float v = (row_ok && colok) ? (ep.out_mode == PE_OUT_BF16 ? __bfloat162float(__float2bfloat16(f[j])) : f[j]) : 0.f;
+              sa[j] = v;
+              sb[j] = v * v;
+            }
+          } else {
+            const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(ep.stats_x) + grow * (long long)p.N + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 u = make_uint4(0u, 0u, 0u, 0u);
+              if (row_ok && colok) u = *reinterpret_cast<const uint4*>(xp + j);
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+              for (int t = 0; t < 8; ++t) {
+                const float2 x2 = __bfloat1622float2(h2[t >> 1]);
+                const float x = (t & 1) ? x2.y : x2.x;
+                const float z = fmaf(x, __ldg(ep.stats_scale + min(col0 + j + t, p.N - 1)), __ldg(ep.stats_shift + min(col0 + j + t, p.N - 1)));
+                const float v = (row_ok && colok) ? __bfloat162float(__float2bfloat16(f[j + t])) : 0.f;
+                const float g = v * (z > 0.f ? 1.f : ep.stats_slope);
+                sa[j + t] = g;
+                sb[j + t] = g * x;
+              }
+            }
+          }
+#pragma unroll
+          for (int s = 16; s >= 1; s >>= 1) {
+            const bool up = (lane & s) != 0;
+#pragma unroll
+            for (int i = 0; i < s; ++i) {
+              const float send_a = up ? sa[i] : sa[i + s], keep_a = up ? sa[i + s] : sa[i];
+              const float send_b = up ? sb[i] : sb[i + s], keep_b = up ? sb[i + s] : sb[i];
+              sa[i] = keep_a + __shfl_xor_sync(0xffffffffu, send_a, s);
+              sb[i] = keep_b + __shfl_xor_sync(0xffffffffu, send_b, s);
+            }
+          }
+          if (colok) {
+            atomicAdd(&s_stats[col0 + lane], sa[0]);
+            atomicAdd(&s_stats[256 + col0 + lane], sb[0]);
+          }
+          if (!row_ok) continue;
         }
         if (ep.out_mode == PE_OUT_BF16) {
           __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + grow * ep.ldc + out_col_off + col0;
@@ -381,6 +467,13 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
     }
+    if (ep.stats_mode) {
+      asm volatile("bar.sync 2, 256;" ::: "memory");  // the 8 epilogue warps
+      for (int i = threadIdx.x - 64; i < 2 * p.N; i += 32 * kNumEpiWarps) {
+        const int which = i / p.N, col = i - which * p.N;
+        atomicAdd(ep.stats + (long long)which * p.N + col, (double)s_stats[which * 256 + col]);
+      }
+    }
   }
 
   tc_fence_before();
@@ -410,7 +503,7 @@ static int pow2_cols(int n) {
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, TcParams& p, dim3 tiles,
                      cudaStream_t stream) {
   const int stage_bytes = pe::kATileBytes + p.block_n * pe::kRowBytes;
-  int stages = (200 * 1024) / stage_bytes;
+  int stages = (198 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;
   if (const char* env = getenv("PE_TC_STAGES")) {  // tuning knob
     const int v = atoi(env);
@@ -427,7 +520,12 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtens
   p.num_tiles = p.tiles_x * p.tiles_y * p.tiles_z;
   p.dbg = g_tc_dbg;
   if (p.ep.drop_thresh && (p.N % 8)) return PE_ERR_BAD_SHAPE;
-  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 4) * sizeof(uint64_t) + 16 + 1024;
+  if (p.ep.act == PE_ACT_GELU_SAVE_GRAD && !p.ep.out2) return PE_ERR_BAD_SHAPE;
+  if (p.ep.stats_mode) {
+    if (!p.ep.stats || p.N > 256 || (p.N % 32) || p.tiles_y != 1 || p.mode == 2) return PE_ERR_BAD_SHAPE;
+    if (p.ep.stats_mode == 2 && (!p.ep.stats_x || !p.ep.stats_scale || !p.ep.stats_shift)) return PE_ERR_BAD_SHAPE;
+  }
+  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 4) * sizeof(uint64_t) + 16 + 2048 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(pe::tc_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=

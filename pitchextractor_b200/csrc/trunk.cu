@@ -579,8 +579,8 @@ extern "C" int pe_bn_act_pool_bwd(const void* x, long long rows, int W, int C, i
                                   const float* shift, const float* mean, const float* rstd, float slope,
                                   unsigned drop_thresh, float drop_scale, unsigned long long seed, const void* dout,
                                   long long ld_dout, int c_off, const void* dout_seq, double* sums /* [2][C], zeroed */,
-                                  float* coef /* [2][C] scratch */, float* dgamma, float* dbeta, void* dx,
-                                  pe_stream_t stream) {
+                                  int sums_ready, float* coef /* [2][C] scratch */, float* dgamma, float* dbeta,
+                                  void* dx, pe_stream_t stream) {
   if (int rc = pe_host::check_arch()) return rc;
   if (!x || !scale || !shift || !mean || !rstd || !sums || !coef || !dx || rows <= 0 || W <= 0 || !chan_ok(C) ||
       C / 8 > 256 || (k != 1 && k != 2 && k != 4) || k > W || (!dout && !dout_seq))
@@ -601,7 +601,7 @@ extern "C" int pe_bn_act_pool_bwd(const void* x, long long rows, int W, int C, i
   cudaStream_t st = PE_ST(stream);
 #define PE_BN_BWD(K)                                                                                      \
   do {                                                                                                    \
-    bn_bwd_reduce_kernel<K><<<g1, 256, sm1, st>>>(a, sums, per);                                          \
+    if (!sums_ready) bn_bwd_reduce_kernel<K><<<g1, 256, sm1, st>>>(a, sums, per);                         \
     bn_bwd_params_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, (double)rows * W, scale, mean, rstd, dgamma, dbeta, \
                                                           coef, C);                                       \
     bn_bwd_apply_kernel<K><<<g2, 256, sm2, st>>>(a, coef, (__nv_bfloat16*)dx);                            \

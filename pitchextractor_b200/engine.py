@@ -171,7 +171,11 @@ class Engine:
             self.bn_index[prefix] = len(self.bn_index)
         return self.bn_index[prefix]
 
-    def _bn_prepare(self, prefix, x, rows, C, training):
+    def _bn_fwd_sums(self, prefix, training):
+        """fp64 [2][C] accumulator a producing convolution fills with this BN's batch statistics (training only)."""
+        return self.bn_sums[2 * self._bn_slot(prefix)] if training else None
+
+    def _bn_prepare(self, prefix, x, rows, C, training, stats_fused=False):
         """Batch statistics (training) or running statistics (eval) -> scale / shift / mean / rstd for this BN."""
         i = self._bn_slot(prefix)
         aff = self.bn_aff[i]
@@ -179,7 +183,8 @@ class Engine:
         m = self.model.get_submodule(prefix)
         if training:
             sums = self.bn_sums[2 * i]
-            call("pe_bn_stats", ptr(x), c_ll(rows), c_int(C), ptr(sums), stream())
+            if not stats_fused:
+                call("pe_bn_stats", ptr(x), c_ll(rows), c_int(C), ptr(sums), stream())
             call("pe_bn_finalize", ptr(sums), c_d(float(rows)), ptr(m.weight), ptr(m.bias), c_f(BN_EPS),
                  c_f(BN_MOMENTUM), ptr(sc), ptr(sh), ptr(mu), ptr(rs), ptr(m.running_mean), ptr(m.running_var),
                  ptr(m.num_batches_tracked), c_int(C), stream())
@@ -193,15 +198,24 @@ class Engine:
         call("pe_bn_act_pool_fwd", ptr(x), c_ll(rows), c_int(W), c_int(C), c_int(k), ptr(sc), ptr(sh), c_f(self.slope),
              c_u(drop[0]), c_f(drop[1]), c_ull(seed), ptr(out), c_ll(ld_out), c_int(c_off), ptr(out_seq), stream())
 
+    def _bn_bwd_fused(self, prefix, x):
+        """Epilogue arguments that make a convolution accumulate the first pass of this BN's backward (sum g, sum g*x)
+        while it writes the gradient w.r.t. the BN output (k = 1, no dropout)."""
+        i = self._bn_slot(prefix)
+        aff = self.bn_aff[i]
+        return dict(stats=self.bn_sums[2 * i + 1], stats_mode=2, stats_x=x, stats_scale=aff[0], stats_shift=aff[1],
+                    stats_slope=self.slope)
+
     def _act_pool_bwd(self, prefix, x, rows, W, C, k, dx, dout=None, ld_dout=0, c_off=0, dout_seq=None, drop=(0, 1.0),
-                      seed=0):
+                      seed=0, sums_ready=False):
         i = self._bn_slot(prefix)
         aff = self.bn_aff[i]
         sums = self.bn_sums[2 * i + 1]
         g = self.gview
         call("pe_bn_act_pool_bwd", ptr(x), c_ll(rows), c_int(W), c_int(C), c_int(k), ptr(aff[0]), ptr(aff[1]),
              ptr(aff[2]), ptr(aff[3]), c_f(self.slope), c_u(drop[0]), c_f(drop[1]), c_ull(seed), ptr(dout),
-             c_ll(ld_dout), c_int(c_off), ptr(dout_seq), ptr(sums), ptr(self.bn_coef[i]), ptr(g[prefix + ".weight"]),
+             c_ll(ld_dout), c_int(c_off), ptr(dout_seq), ptr(sums), c_int(int(sums_ready)), ptr(self.bn_coef[i]),
+             ptr(g[prefix + ".weight"]),
              ptr(g[prefix + ".bias"]), ptr(dx), stream())
 
     # ------------------------------------------------------------------ forward
@@ -238,26 +252,28 @@ class Engine:
         Z1 = self.buf("Z1", (B, T, 80, 64))
         self._act_pool(Y1, BT, 80, 64, 1, aff, out=Z1, ld_out=64)
         R = self.buf("R0", (B, T, 80, 64))
-        ops.conv3x3(Z1, self.mat("conv_block.3.weight", 64, 576), R)
+        ops.conv3x3(Z1, self.mat("conv_block.3.weight", 64, 576), R,
+                    stats=self._bn_fwd_sums("res_block1.pre_conv.0", training))
         # ---- residual blocks (model.py:143-175)
         width = 80
         for i, (cin, cout) in enumerate(((64, 128), (128, 192), (192, 256)), 1):
             r = "res_block%d" % i
-            aff = self._bn_prepare(r + ".pre_conv.0", R, BT * width, cin, training)
+            aff = self._bn_prepare(r + ".pre_conv.0", R, BT * width, cin, training, stats_fused=True)
             P = self.buf("P%d" % i, (B, T, width // 2, cin))
             self._act_pool(R, BT, width, cin, 2, aff, out=P, ld_out=cin)
             width //= 2
             U = self.buf("U%d" % i, (B, T, width, cout))
-            ops.conv3x3(P, self.mat(r + ".conv.0.weight", cout, 9 * cin), U)
-            aff = self._bn_prepare(r + ".conv.1", U, BT * width, cout, training)
+            ops.conv3x3(P, self.mat(r + ".conv.0.weight", cout, 9 * cin), U, stats=self._bn_fwd_sums(r + ".conv.1", training))
+            aff = self._bn_prepare(r + ".conv.1", U, BT * width, cout, training, stats_fused=True)
             Vv = self.buf("V%d" % i, (B, T, width, cout))
             self._act_pool(U, BT, width, cout, 1, aff, out=Vv, ld_out=cout)
             R = self.buf("R%d" % i, (B, T, width, cout))
-            ops.conv3x3(Vv, self.wops[r + ".B.fwd"], R, x2=P)
+            nxt = "res_block%d.pre_conv.0" % (i + 1) if i < 3 else "pool_block.0"
+            ops.conv3x3(Vv, self.wops[r + ".B.fwd"], R, x2=P, stats=self._bn_fwd_sums(nxt, training))
         # ---- pool_block + auxiliary max-pools + concat (model.py:36-49,103-108)
         CAT = self.buf("CAT", (B, T, 2, 640))
         SEQC = self.buf("SEQC", (BT, 512))
-        aff = self._bn_prepare("pool_block.0", R, BT * 10, 256, training)
+        aff = self._bn_prepare("pool_block.0", R, BT * 10, 256, training, stats_fused=True)
         self._act_pool(R, BT, 10, 256, 4, aff, out=CAT, ld_out=640, c_off=384, out_seq=SEQC,
                        drop=self._drop(self.p_trunk, training), seed=self._seed(1))
         self._act_pool(self._bufs["R0"], BT, 80, 64, 40, None, out=CAT, ld_out=640, c_off=0)
@@ -265,8 +281,9 @@ class Engine:
         self._act_pool(self._bufs["R2"], BT, 20, 192, 10, None, out=CAT, ld_out=640, c_off=192)
         # ---- detector_conv (model.py:52-57): 1x1 conv == GEMM over the 640 concatenated channels
         DD = self.buf("DD", (BT * 2, 256))
-        ops.gemm(CAT.view(BT * 2, 640), self.mat("detector_conv.0.weight", 256, 640), DD, BT * 2, 256, 640)
-        aff = self._bn_prepare("detector_conv.1", DD, BT * 2, 256, training)
+        ops.gemm(CAT.view(BT * 2, 640), self.mat("detector_conv.0.weight", 256, 640), DD, BT * 2, 256, 640,
+                 stats=self._bn_fwd_sums("detector_conv.1", training))
+        aff = self._bn_prepare("detector_conv.1", DD, BT * 2, 256, training, stats_fused=True)
         SEQD = self.buf("SEQD", (BT, 512))
         self._act_pool(DD, BT, 2, 256, 1, aff, out=None, out_seq=SEQD, drop=self._drop(self.p_trunk, training),
                        seed=self._seed(2))
@@ -311,8 +328,9 @@ class Engine:
                  ptr(stats[2 * l + 1, 1]), stream())
             U = self.buf(t + "U", (M, FF))
             G = self.buf(t + "G", (M, FF))
-            ops.gemm(H1, W16[q + "linear1.weight"], G, M, FF, D, bias=V[q + "linear1.bias"], act=L.PE_ACT_GELU, out2=U,
-                     p_drop=pdrop, seed=self._seed(site + 2))
+            # U receives d G / d(pre-activation) = gelu'(.) * dropout factor: the backward GEMM only multiplies by it
+            ops.gemm(H1, W16[q + "linear1.weight"], G, M, FF, D, bias=V[q + "linear1.bias"],
+                     act=L.PE_ACT_GELU_SAVE_GRAD, out2=U, p_drop=pdrop, seed=self._seed(site + 2))
             S2 = self.buf(t + "S2", (M, D), torch.float32)
             ops.gemm(G, W16[q + "linear2.weight"], S2, M, D, FF, bias=V[q + "linear2.bias"], p_drop=pdrop,
                      seed=self._seed(site + 3), aux=H1, aux_mode=L.PE_AUX_ADD)
@@ -478,8 +496,7 @@ class Engine:
                  c_f(drop[1]), c_ull(self._seed(site + 3)), ptr(g[q + "norm2.weight"]), ptr(g[q + "norm2.bias"]),
                  ptr(g[q + "linear2.bias"]), stream())
             # linear2: dG -> through dropout and GELU' -> dU ; weight gradient
-            ops.gemm(dSm, W16[q + "linear2.weight"], dU, M, FF, D, b_mn=True, p_drop=pdrop, seed=self._seed(site + 2),
-                     aux=U, aux_mode=L.PE_AUX_GELU_GRAD)
+            ops.gemm(dSm, W16[q + "linear2.weight"], dU, M, FF, D, b_mn=True, aux=U, aux_mode=L.PE_AUX_MUL)
             self._wgrad_linear(dSm, G, q + "linear2.weight", D, FF, M)
             # linear1: dH1 = dU W1 + dS (residual) ; weight / bias gradients
             ops.gemm(dU, W16[q + "linear1.weight"], dH1, M, D, FF, b_mn=True, aux=dS, aux_mode=L.PE_AUX_ADD)
@@ -549,11 +566,11 @@ class Engine:
             gA = self.mat(r + ".conv.0.weight", cout, 9 * cin, "grad")
             # conv B + shortcut
             dV = self.buf("dV%d" % i, (B, T, width, cout))
-            ops.conv3x3(dR, self.wops[r + ".B.dgrad"], dV)
+            ops.conv3x3(dR, self.wops[r + ".B.dgrad"], dV, **self._bn_bwd_fused(r + ".conv.1", U))
             ops.conv_wgrad(dR, Vv, gB, taps=9)
             ops.conv_wgrad(dR, P, gS, taps=1)
             dU = self.buf("dU%d" % i, (B, T, width, cout))
-            self._act_pool_bwd(r + ".conv.1", U, BT, width, cout, 1, dU, dout=dV, ld_dout=cout)
+            self._act_pool_bwd(r + ".conv.1", U, BT, width, cout, 1, dU, dout=dV, ld_dout=cout, sums_ready=True)
             # conv A (+ shortcut data gradient fused as extra K columns)
             dP = self.buf("dP%d" % i, (B, T, width, cin))
             ops.conv3x3(dU, self.wops[r + ".A.dgrad"], dP, x2=dR)
@@ -569,10 +586,10 @@ class Engine:
             width *= 2
         # conv_block
         dZ1 = self.buf("dZ1", (B, T, 80, 64))
-        ops.conv3x3(dR, self.wops["conv_block.3.dgrad"], dZ1)
+        ops.conv3x3(dR, self.wops["conv_block.3.dgrad"], dZ1, **self._bn_bwd_fused("conv_block.1", bufs["Y1"]))
         ops.conv_wgrad(dR, bufs["Z1"], self.mat("conv_block.3.weight", 64, 576, "grad"), taps=9)
         dY1 = self.buf("dY1", (B, T, 80, 64))
-        self._act_pool_bwd("conv_block.1", bufs["Y1"], BT, 80, 64, 1, dY1, dout=dZ1, ld_dout=64)
+        self._act_pool_bwd("conv_block.1", bufs["Y1"], BT, 80, 64, 1, dY1, dout=dZ1, ld_dout=64, sums_ready=True)
         x = self._x
         call("pe_stem_conv_wgrad", ptr(x), c_ll(x.stride(0)), c_ll(x.stride(2)), c_ll(x.stride(3)), c_int(B), c_int(T),
              c_int(80), ptr(dY1), ptr(g["conv_block.0.weight"]), stream())

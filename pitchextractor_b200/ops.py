@@ -30,7 +30,8 @@ class _Timed:
 
 
 def make_epilogue(out, out_mode=None, bias=None, act=L.PE_ACT_NONE, out2=None, aux=None, aux_mode=L.PE_AUX_NONE,
-                  p_drop=0.0, seed=0, alpha=1.0, ldc=None):
+                  p_drop=0.0, seed=0, alpha=1.0, ldc=None, stats=None, stats_mode=0, stats_x=None, stats_scale=None,
+                  stats_shift=None, stats_slope=0.01):
     ep = Epilogue()
     ep.out = out.data_ptr()
     ep.ldc = out.stride(-2) if ldc is None else ldc
@@ -49,6 +50,12 @@ def make_epilogue(out, out_mode=None, bias=None, act=L.PE_ACT_NONE, out2=None, a
     ep.drop_thresh, ep.drop_scale = L.drop_thresh(p_drop)
     ep.drop_seed = seed
     ep.alpha = alpha
+    if stats is not None:
+        assert stats.dtype == torch.float64
+        ep.stats, ep.stats_mode = stats.data_ptr(), (stats_mode or 1)
+        if ep.stats_mode == 2:
+            ep.stats_x, ep.stats_scale, ep.stats_shift = stats_x.data_ptr(), stats_scale.data_ptr(), stats_shift.data_ptr()
+            ep.stats_slope = stats_slope
     return ep
 
 

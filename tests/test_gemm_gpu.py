@@ -81,6 +81,20 @@ def test_gemm_epilogues(built_lib):
     x = res.float().requires_grad_()
     torch.nn.functional.gelu(x).sum().backward()
     _close(out32, (a.float() @ b.float().t()) * x.grad)
+    # gelu with saved derivative * dropout factor, and the multiply epilogue that consumes it
+    dact = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, b, out, M, N, K, bias=bias, act=L.PE_ACT_GELU_SAVE_GRAD, out2=dact, p_drop=0.25, seed=99)
+    torch.cuda.synchronize()
+    xr = ref.clone().requires_grad_()
+    torch.nn.functional.gelu(xr).sum().backward()
+    keep = dact != 0
+    assert abs(keep.float().mean().item() - 0.75) < 0.02
+    _close(out.float()[keep], (torch.nn.functional.gelu(ref) / 0.75)[keep])
+    _close(dact.float()[keep], (xr.grad / 0.75)[keep])
+    assert (out[~keep] == 0).all()
+    ops.gemm(a, b, out32, M, N, K, aux=dact, aux_mode=L.PE_AUX_MUL)
+    torch.cuda.synchronize()
+    _close(out32, (a.float() @ b.float().t()) * dact.float())
     # dropout: deterministic in (seed, index); keep-rate and scaling
     ops.gemm(a, b, out32, M, N, K, bias=bias, p_drop=0.25, seed=1234)
     out_b = torch.empty_like(out32)
@@ -126,3 +140,29 @@ def test_conv_wgrad(built_lib, B, H, W, C, Cout, taps):
     y.backward(dy.float().permute(0, 3, 1, 2))
     ref = wt.grad.permute(0, 2, 3, 1).reshape(Cout, taps * C)
     _close(dw, ref)
+
+
+def test_conv_epilogue_column_statistics(built_lib):
+    """BatchNorm statistics / first BatchNorm-backward pass fused into the convolution epilogue."""
+    from pitchextractor_b200 import ops
+    B, H, W, C1, Cout = 2, 192, 40, 64, 128
+    x = _rand((B, H, W, C1), 20)
+    w = _rand((Cout, 9 * C1), 21, 0.05)
+    out = torch.empty(B, H, W, Cout, device="cuda", dtype=torch.bfloat16)
+    sums = torch.zeros(2, Cout, device="cuda", dtype=torch.float64)
+    ops.conv3x3(x, w, out, stats=sums)
+    torch.cuda.synchronize()
+    o = out.double().reshape(-1, Cout)
+    assert torch.allclose(sums[0], o.sum(0), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(sums[1], (o * o).sum(0), rtol=1e-4, atol=1e-2)
+    # mode 2: g = v * lrelu'(xb * scale + shift); sums = (sum g, sum g * xb)
+    xb = _rand((B, H, W, Cout), 22)
+    scale = torch.randn(Cout, device="cuda")
+    shift = torch.randn(Cout, device="cuda") * 0.1
+    sums2 = torch.zeros(2, Cout, device="cuda", dtype=torch.float64)
+    ops.conv3x3(x, w, out, stats=sums2, stats_mode=2, stats_x=xb, stats_scale=scale, stats_shift=shift, stats_slope=0.01)
+    torch.cuda.synchronize()
+    z = xb.float().reshape(-1, Cout) * scale + shift
+    g = out.float().reshape(-1, Cout) * torch.where(z > 0, 1.0, 0.01)
+    assert torch.allclose(sums2[0], g.double().sum(0), rtol=1e-3, atol=1e-2)
+    assert torch.allclose(sums2[1], (g.double() * xb.double().reshape(-1, Cout)).sum(0), rtol=1e-3, atol=1e-2)
