@@ -67,11 +67,23 @@ _LAUNCHES_PER_CALL = {"pe_logmel_f32": 2, "pe_bn_act_pool_bwd": 3, "pe_attn_bwd"
 launch_count = 0
 
 
+# When set to a list, every C-ABI call appends (name, start_event, end_event): per-entry-point GPU time with warm
+# caches (tools/step_breakdown.py).  Adds event records only, no synchronisation.
+TIMING = None
+
+
 def call(name, *args):
     global launch_count
     fn = getattr(lib(), name)
     fn.restype = ctypes.c_int
-    check(fn(*args), name)
+    if TIMING is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(fn(*args), name)
+        e1.record()
+        TIMING.append((name, e0, e1))
+    else:
+        check(fn(*args), name)
     launch_count += _LAUNCHES_PER_CALL.get(name, 1)
 
 

@@ -37,6 +37,25 @@ __device__ __forceinline__ void oper_store32(uint8_t* base, int r, int k0, const
   }
 }
 
+// write 16 consecutive columns [k0, k0+16) of row r (k0 multiple of 16) as bf16
+__device__ __forceinline__ void oper_store16(uint8_t* base, int r, int k0, const float* v) {
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const uint4 pk = make_uint4(pack_bf16(v[8 * u], v[8 * u + 1]), pack_bf16(v[8 * u + 2], v[8 * u + 3]),
+                                pack_bf16(v[8 * u + 4], v[8 * u + 5]), pack_bf16(v[8 * u + 6], v[8 * u + 7]));
+    *reinterpret_cast<uint4*>(base + oper_off(r, k0 + 8 * u)) = pk;
+  }
+}
+__device__ __forceinline__ void store16_bf16(__nv_bfloat16* op, const uint32_t* v) {
+#pragma unroll
+  for (int j = 0; j < 16; j += 8)
+    *reinterpret_cast<uint4*>(op + j) =
+        make_uint4(pack_bf16(__uint_as_float(v[j]), __uint_as_float(v[j + 1])),
+                   pack_bf16(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])),
+                   pack_bf16(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5])),
+                   pack_bf16(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7])));
+}
+
 struct AttnSync {
   uint64_t* bar;
   uint32_t phase;
@@ -190,7 +209,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, int H, unsigned d
 // -------------------------------------------------------------------------------------------------
 // backward: phase A (query-major) -> dQ;  phase B (key-major, S^T recomputed) -> dK, dV
 // -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 1)
+constexpr int ABW_THREADS = 512;  // 16 warps: four per TMEM lane quarter, 48 score columns each
+
+__global__ void __launch_bounds__(ABW_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do, int H,
                    unsigned drop_thresh, float drop_scale, unsigned long long seed,
                    const __nv_bfloat16* __restrict__ ctx, const __nv_bfloat16* __restrict__ dctx,
@@ -257,7 +278,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 
   constexpr uint32_t IDESC_S = umma_idesc(UMMA_BF16, 128, AT, 0, 0);
   constexpr uint32_t IDESC_O = umma_idesc(UMMA_BF16, 128, AD, 0, 1);
-  const int quarter = warp & 3, half = warp >> 2;
+  const int quarter = warp & 3, part = warp >> 2;  // part 0..3: score columns [48*part, 48*part+48)
   const int r = quarter * 32 + lane;
   const uint32_t lane_base = tm + ((uint32_t)(quarter * 32) << 16);
   const float kscale = 0.125f * LOG2E;
@@ -279,21 +300,21 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     const int q = t * 128 + r;
     const int qc = q < AT ? q : AT - 1;
     const float lq = sLse[qc], dq_delta = sDel[qc];
-    for (int c = half * 3; c < half * 3 + 3; ++c) {
-      uint32_t s[32], d[32];
-      tmem_ld32(lane_base + c * 32, s);
-      tmem_ld32(lane_base + AT + c * 32, d);
+    for (int c = part * 3; c < part * 3 + 3; ++c) {  // 16-column chunks
+      uint32_t s[16], d[16];
+      tmem_ld16(lane_base + c * 16, s);
+      tmem_ld16(lane_base + AT + c * 16, d);
       tmem_ld_wait();
-      float ds[32];
+      float ds[16];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
+      for (int j = 0; j < 16; ++j) {
         const float p = ex2(__uint_as_float(s[j]) * kscale - lq);
         float dp = __uint_as_float(d[j]);
         if (drop_thresh)
-          dp = attn_drop_hash(seed, e_bh + (unsigned long long)q * AT + c * 32 + j) < drop_thresh ? dp * drop_scale : 0.f;
+          dp = attn_drop_hash(seed, e_bh + (unsigned long long)q * AT + c * 16 + j) < drop_thresh ? dp * drop_scale : 0.f;
         ds[j] = 0.125f * p * (dp - dq_delta);
       }
-      oper_store32(sA, r, c * 32, ds);
+      oper_store16(sA, r, c * 16, ds);
     }
     attn_handoff();
     if (tid == 0) {
@@ -303,19 +324,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     }
     sync.wait();
     {
-      uint32_t v[32];
-      tmem_ld32(lane_base + 2 * AT + half * 32, v);
+      uint32_t v[16];
+      tmem_ld16(lane_base + 2 * AT + part * 16, v);
       tmem_ld_wait();
-      if (q < AT) {
-        __nv_bfloat16* op = dqkv + ((long long)b * AT + q) * ld3 + h * AD + half * 32;
-#pragma unroll
-        for (int j = 0; j < 32; j += 8)
-          *reinterpret_cast<uint4*>(op + j) =
-              make_uint4(pack_bf16(__uint_as_float(v[j]), __uint_as_float(v[j + 1])),
-                         pack_bf16(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])),
-                         pack_bf16(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5])),
-                         pack_bf16(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7])));
-      }
+      if (q < AT) store16_bf16(dqkv + ((long long)b * AT + q) * ld3 + h * AD + part * 16, v);
     }
     tc_fence_before();
     __syncthreads();
@@ -331,15 +343,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     }
     sync.wait();
     const int jkey = t * 128 + r;
-    for (int c = half * 3; c < half * 3 + 3; ++c) {
-      uint32_t s[32], d[32];
-      tmem_ld32(lane_base + c * 32, s);
-      tmem_ld32(lane_base + AT + c * 32, d);
+    for (int c = part * 3; c < part * 3 + 3; ++c) {
+      uint32_t s[16], d[16];
+      tmem_ld16(lane_base + c * 16, s);
+      tmem_ld16(lane_base + AT + c * 16, d);
       tmem_ld_wait();
-      float pt[32], dst[32];
+      float pt[16], dst[16];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int q = c * 32 + j;
+      for (int j = 0; j < 16; ++j) {
+        const int q = c * 16 + j;
         const float p = ex2(__uint_as_float(s[j]) * kscale - sLse[q]);
         float dp = __uint_as_float(d[j]);
         float pd = p;
@@ -351,8 +363,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         pt[j] = pd;
         dst[j] = 0.125f * p * (dp - sDel[q]);
       }
-      oper_store32(sA, r, c * 32, pt);
-      oper_store32(sB, r, c * 32, dst);
+      oper_store16(sA, r, c * 16, pt);
+      oper_store16(sB, r, c * 16, dst);
     }
     attn_handoff();
     if (tid == 0) {
@@ -364,19 +376,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     sync.wait();
 #pragma unroll
     for (int which = 0; which < 2; ++which) {  // 0: dV, 1: dK
-      uint32_t v[32];
-      tmem_ld32(lane_base + 2 * AT + which * AD + half * 32, v);
+      uint32_t v[16];
+      tmem_ld16(lane_base + 2 * AT + which * AD + part * 16, v);
       tmem_ld_wait();
-      if (jkey < AT) {
-        __nv_bfloat16* op = dqkv + ((long long)b * AT + jkey) * ld3 + (which == 0 ? 2 * D : D) + h * AD + half * 32;
-#pragma unroll
-        for (int j = 0; j < 32; j += 8)
-          *reinterpret_cast<uint4*>(op + j) =
-              make_uint4(pack_bf16(__uint_as_float(v[j]), __uint_as_float(v[j + 1])),
-                         pack_bf16(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])),
-                         pack_bf16(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5])),
-                         pack_bf16(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7])));
-      }
+      if (jkey < AT)
+        store16_bf16(dqkv + ((long long)b * AT + jkey) * ld3 + (which == 0 ? 2 * D : D) + h * AD + part * 16, v);
     }
     tc_fence_before();
     __syncthreads();
@@ -426,7 +430,7 @@ int pe_attn_bwd_tc(const void* qkv, const void* ctx, const void* dctx, const flo
       return PE_ERR_LAUNCH;
     attr = true;
   }
-  pe::attn_bwd_tc_kernel<<<dim3(H, B), 256, smem, stream>>>(tq, td, H, drop_thresh, drop_scale, seed,
+  pe::attn_bwd_tc_kernel<<<dim3(H, B), pe::ABW_THREADS, smem, stream>>>(tq, td, H, drop_thresh, drop_scale, seed,
                                                             (const __nv_bfloat16*)ctx, (const __nv_bfloat16*)dctx, lse,
                                                             (__nv_bfloat16*)dqkv);
   return cudaGetLastError() == cudaSuccess ? PE_OK : PE_ERR_LAUNCH;

@@ -13,7 +13,8 @@ namespace pe {
 
 constexpr int LH = 384;         // hidden size
 constexpr int LG = 4 * LH;      // gate rows per direction
-constexpr int L_THREADS = 192;  // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int L_EPI_WARPS = 8;   // two per TMEM lane quarter: each takes half of the unit chunks
+constexpr int L_THREADS = 64 + 32 * L_EPI_WARPS;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
 struct LstmStepParams {
   int B, T, step, first;
@@ -30,8 +31,9 @@ struct LstmStepParams {
   float* dc[2];                // [B][2*LH] running dL/dc
 };
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
-__device__ __forceinline__ float tanhf_(float x) { return 2.f / (1.f + __expf(-2.f * x)) - 1.f; }
+// sigmoid / tanh through one ex2 + one fast reciprocal each (relative error ~1e-6, far below the bf16 hidden state)
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanhf_(float x) { return fmaf(2.f, __fdividef(1.f, 1.f + __expf(-2.f * x)), -1.f); }
 
 struct LstmMaps {
   CUtensorMap act[2];  // per model: forward: y (dims 2*LH, T, B); backward: dg (dims 2*LG, T, B)
@@ -104,56 +106,53 @@ lstm_step_fwd_kernel(const __grid_constant__ LstmMaps maps, const LstmStepParams
   if (warp >= 2) {
     const int q = warp & 3;
     const int b = b0 + q * 32 + lane;
-    if (!p.first) {
-      mbar_wait(done_bar, 0);
-      tc_fence_after();
-    }
+    const bool row_ok = b < p.B;
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     const long long tok = (long long)b * p.T + t;
     const long long tok_prev = (long long)b * p.T + t_prev;
-    for (int uc = 0; uc < 4; ++uc) {
-      uint32_t acc[4][16];
-      if (!p.first) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) tmem_ld16(trow + g * 64 + uc * 16, acc[g]);
-        tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-#pragma unroll
-          for (int j = 0; j < 16; ++j) acc[g][j] = 0u;
-      }
-      if (b >= p.B) continue;
+    const int pair = (warp - 2) >> 2;
+    float pre[4][16], cprev[16];
+    // input projection + both biases and c_{t-1} of one 16-unit chunk (independent of this step's MMA)
+    auto load_inputs = [&](int uc) {
       const int u = u0 + uc * 16;
-      float* gxp = p.gx[model] + tok * (2 * LG) + dir * LG + u;
-      float pre[4][16];
+      const float* gxp = p.gx[model] + tok * (2 * LG) + dir * LG + u;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const float* bi = p.b_ih[rec] + g * LH + u;
         const float* bh = p.b_hh[rec] + g * LH + u;
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
-          const float4 x = *reinterpret_cast<const float4*>(gxp + g * LH + j);
+          const float4 x = row_ok ? *reinterpret_cast<const float4*>(gxp + g * LH + j) : make_float4(0.f, 0.f, 0.f, 0.f);
           const float4 y1 = __ldg(reinterpret_cast<const float4*>(bi + j));
           const float4 y2 = __ldg(reinterpret_cast<const float4*>(bh + j));
-          pre[g][j] = __uint_as_float(acc[g][j]) + x.x + y1.x + y2.x;
-          pre[g][j + 1] = __uint_as_float(acc[g][j + 1]) + x.y + y1.y + y2.y;
-          pre[g][j + 2] = __uint_as_float(acc[g][j + 2]) + x.z + y1.z + y2.z;
-          pre[g][j + 3] = __uint_as_float(acc[g][j + 3]) + x.w + y1.w + y2.w;
+          pre[g][j] = x.x + y1.x + y2.x;
+          pre[g][j + 1] = x.y + y1.y + y2.y;
+          pre[g][j + 2] = x.z + y1.z + y2.z;
+          pre[g][j + 3] = x.w + y1.w + y2.w;
         }
       }
-      float cprev[16];
-      if (p.first) {
+      const float* cp = p.c[model] + tok_prev * (2 * LH) + dir * LH + u;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) cprev[j] = 0.f;
-      } else {
-        const float* cp = p.c[model] + tok_prev * (2 * LH) + dir * LH + u;
-#pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          const float4 x = *reinterpret_cast<const float4*>(cp + j);
-          cprev[j] = x.x; cprev[j + 1] = x.y; cprev[j + 2] = x.z; cprev[j + 3] = x.w;
-        }
+      for (int j = 0; j < 16; j += 4) {
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!p.first && row_ok) x = *reinterpret_cast<const float4*>(cp + j);
+        cprev[j] = x.x; cprev[j + 1] = x.y; cprev[j + 2] = x.z; cprev[j + 3] = x.w;
       }
+    };
+    // recurrent contribution from TMEM, cell update, stores
+    auto finish = [&](int uc) {
+      if (!p.first) {
+        uint32_t acc[4][16];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) tmem_ld16(trow + g * 64 + uc * 16, acc[g]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pre[g][j] += __uint_as_float(acc[g][j]);
+      }
+      if (!row_ok) return;
+      const int u = u0 + uc * 16;
       float cn[16], hn[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
@@ -162,6 +161,7 @@ lstm_step_fwd_kernel(const __grid_constant__ LstmMaps maps, const LstmStepParams
         cn[j] = fmaf(fg, cprev[j], ig * gg);
         hn[j] = og * tanhf_(cn[j]);
       }
+      float* gxp = p.gx[model] + tok * (2 * LG) + dir * LG + u;
 #pragma unroll
       for (int g = 0; g < 4; ++g)
 #pragma unroll
@@ -175,7 +175,15 @@ lstm_step_fwd_kernel(const __grid_constant__ LstmMaps maps, const LstmStepParams
       for (int j = 0; j < 16; j += 8)
         *reinterpret_cast<uint4*>(yw + j) = make_uint4(pack_bf16(hn[j], hn[j + 1]), pack_bf16(hn[j + 2], hn[j + 3]),
                                                        pack_bf16(hn[j + 4], hn[j + 5]), pack_bf16(hn[j + 6], hn[j + 7]));
+    };
+    load_inputs(2 * pair);  // overlaps the TMA + MMA main loop of this step
+    if (!p.first) {
+      mbar_wait(done_bar, 0);
+      tc_fence_after();
     }
+    finish(2 * pair);
+    load_inputs(2 * pair + 1);
+    finish(2 * pair + 1);
   }
   tc_fence_before();
   __syncthreads();
@@ -248,37 +256,26 @@ lstm_step_bwd_kernel(const __grid_constant__ LstmMaps maps, const LstmStepParams
   if (warp >= 2) {
     const int q = warp & 3;
     const int b = b0 + q * 32 + lane;
-    if (!p.first) {
-      mbar_wait(done_bar, 0);
-      tc_fence_after();
-    }
+    const bool row_ok = b < p.B;
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     const long long tok = (long long)b * p.T + t;
     const long long tok_pf = (long long)b * p.T + t_pf;
-    for (int uc = 0; uc < 4; ++uc) {
-      uint32_t acc[16];
-      if (!p.first) {
-        tmem_ld16(trow + uc * 16, acc);
-        tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = 0u;
-      }
-      if (b >= p.B) continue;
+    const int pair = (warp - 2) >> 2;
+    float dh[16], gate[4][16], ct[16], cp[16], dcs[16];
+    // everything the cell backward needs except the recurrent gradient (independent of this step's MMA)
+    auto load_inputs = [&](int uc) {
       const int u = u0 + uc * 16;
-      float dh[16], gate[4][16], ct[16], cp[16], dcs[16];
-      {
-        const __nv_bfloat16* dyp = p.dy[model] + tok * (2 * LH) + dir * LH + u;
+      const __nv_bfloat16* dyp = p.dy[model] + tok * (2 * LH) + dir * LH + u;
 #pragma unroll
-        for (int j = 0; j < 16; j += 8) {
-          const uint4 raw = *reinterpret_cast<const uint4*>(dyp + j);
-          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+      for (int j = 0; j < 16; j += 8) {
+        uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+        if (row_ok) raw = *reinterpret_cast<const uint4*>(dyp + j);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float2 f = __bfloat1622float2(h2[k]);
-            dh[j + 2 * k] = f.x + __uint_as_float(acc[j + 2 * k]);
-            dh[j + 2 * k + 1] = f.y + __uint_as_float(acc[j + 2 * k + 1]);
-          }
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __bfloat1622float2(h2[k]);
+          dh[j + 2 * k] = f.x;
+          dh[j + 2 * k + 1] = f.y;
         }
       }
       const float* gxp = p.gx[model] + tok * (2 * LG) + dir * LG + u;
@@ -286,22 +283,35 @@ lstm_step_bwd_kernel(const __grid_constant__ LstmMaps maps, const LstmStepParams
       for (int g = 0; g < 4; ++g)
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
-          const float4 x = *reinterpret_cast<const float4*>(gxp + g * LH + j);
+          const float4 x = row_ok ? *reinterpret_cast<const float4*>(gxp + g * LH + j) : make_float4(0.f, 0.f, 0.f, 0.f);
           gate[g][j] = x.x; gate[g][j + 1] = x.y; gate[g][j + 2] = x.z; gate[g][j + 3] = x.w;
         }
       const float* ctp = p.c[model] + tok * (2 * LH) + dir * LH + u;
       const float* cpp = p.c[model] + tok_pf * (2 * LH) + dir * LH + u;
-      float* dcp = p.dc[model] + (long long)b * (2 * LH) + dir * LH + u;
+      const float* dcp = p.dc[model] + (long long)b * (2 * LH) + dir * LH + u;
 #pragma unroll
       for (int j = 0; j < 16; j += 4) {
-        const float4 x = *reinterpret_cast<const float4*>(ctp + j);
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f), y = x, z = x;
+        if (row_ok) {
+          x = *reinterpret_cast<const float4*>(ctp + j);
+          if (has_prev) y = *reinterpret_cast<const float4*>(cpp + j);
+          if (!p.first) z = *reinterpret_cast<const float4*>(dcp + j);
+        }
         ct[j] = x.x; ct[j + 1] = x.y; ct[j + 2] = x.z; ct[j + 3] = x.w;
-        float4 y = make_float4(0.f, 0.f, 0.f, 0.f), z = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (has_prev) y = *reinterpret_cast<const float4*>(cpp + j);
-        if (!p.first) z = *reinterpret_cast<const float4*>(dcp + j);
         cp[j] = y.x; cp[j + 1] = y.y; cp[j + 2] = y.z; cp[j + 3] = y.w;
         dcs[j] = z.x; dcs[j + 1] = z.y; dcs[j + 2] = z.z; dcs[j + 3] = z.w;
       }
+    };
+    auto finish = [&](int uc) {
+      if (!p.first) {
+        uint32_t acc[16];
+        tmem_ld16(trow + uc * 16, acc);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dh[j] += __uint_as_float(acc[j]);
+      }
+      if (!row_ok) return;
+      const int u = u0 + uc * 16;
       float dpre[4][16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
@@ -314,6 +324,7 @@ lstm_step_bwd_kernel(const __grid_constant__ LstmMaps maps, const LstmStepParams
         dpre[3][j] = dh[j] * tc * og * (1.f - og);
         dcs[j] = dc * fg;
       }
+      float* dcp = p.dc[model] + (long long)b * (2 * LH) + dir * LH + u;
 #pragma unroll
       for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dcp + j) = make_float4(dcs[j], dcs[j + 1], dcs[j + 2], dcs[j + 3]);
       __nv_bfloat16* dgp = p.dg[model] + tok * (2 * LG) + dir * LG + u;
@@ -324,7 +335,15 @@ lstm_step_bwd_kernel(const __grid_constant__ LstmMaps maps, const LstmStepParams
           *reinterpret_cast<uint4*>(dgp + g * LH + j) =
               make_uint4(pack_bf16(dpre[g][j], dpre[g][j + 1]), pack_bf16(dpre[g][j + 2], dpre[g][j + 3]),
                          pack_bf16(dpre[g][j + 4], dpre[g][j + 5]), pack_bf16(dpre[g][j + 6], dpre[g][j + 7]));
+    };
+    load_inputs(2 * pair);  // overlaps the TMA + MMA main loop of this step
+    if (!p.first) {
+      mbar_wait(done_bar, 0);
+      tc_fence_after();
     }
+    finish(2 * pair);
+    load_inputs(2 * pair + 1);
+    finish(2 * pair + 1);
   }
   tc_fence_before();
   __syncthreads();
