@@ -110,7 +110,7 @@ def logmel_tables(device, sample_rate=24000, n_fft=1024, win_length=1024, hop_le
             "n_fft": n_fft, "hop": hop_length, "n_mels": n_mels, "sr": sample_rate,
             "basis": windowed_dft_basis(n_fft, win_length).to(device),
             "fb": fb.to(device),
-            "tc": n_fft == 1024 and hop_length % 4 == 0 and n_mels <= 85,
+            "tc": n_fft == 1024 and hop_length % 4 == 0 and n_mels <= 128,
         }
         if tab["tc"]:
             win = np.zeros(n_fft)
@@ -161,7 +161,7 @@ class LogMel:
             crop = crop.to(self.device, torch.int32).contiguous()
         use_tc = self.tables["tc"] if self.impl == "auto" else self.impl == "tc"
         if use_tc and not self.tables["tc"]:
-            raise RuntimeError("the tcgen05 log-mel kernel needs n_fft == 1024, hop % 4 == 0, n_mels <= 85")
+            raise RuntimeError("the tcgen05 log-mel kernel needs n_fft == 1024, hop % 4 == 0, n_mels <= 128")
         if use_tc:
             need = B * ((Lw + 3) // 4 * 4)
         else:
