@@ -119,3 +119,29 @@ def test_synthetic_segments_are_seeded_and_labelled():
     assert 80.0 < voiced.min() and voiced.max() < 340.0
     assert 0.05 < (f1 == 0).mean() < 0.4
     assert np.abs(w1).max() < 1.0
+
+
+def test_metrics_match_reference_definitions():
+    """RMSE-cents / RPA / RCA / VUV / OctaveError vs hand-computed cases and, when present, the reference's own
+    Utils/dynamic_pitch_tools.py."""
+    from pitchextractor_b200 import inference as I
+    rng = np.random.default_rng(0)
+    ref = (100.0 + 200.0 * rng.random(500)).astype(np.float32)
+    ref[rng.random(500) < 0.2] = 0.0
+    pred = ref * (2.0 ** (rng.normal(0.0, 30.0, 500) / 1200.0)).astype(np.float32)
+    pred[::17] *= 2.0          # octave errors
+    pred[ref == 0] = 3.0       # predicted unvoiced
+    m = I.compute_metrics(ref, pred)
+    voiced = ref > 0
+    cents = 1200.0 * np.log2(pred[voiced] / ref[voiced])
+    assert abs(m["RPA"] - np.mean(np.abs(cents) <= 50.0)) < 1e-6
+    assert m["VUV"] == 1.0 and m["RCA"] >= m["RPA"] and 0.03 < m["OctaveError"] < 0.08
+    assert abs(I.rms_cents_error(ref, pred) - np.sqrt(np.mean(cents ** 2))) < 1e-2
+    from oracle import refshim
+    if refshim.available():
+        import importlib, sys
+        sys.path.insert(0, refshim.REF_ROOT)
+        T = importlib.import_module("Utils.dynamic_pitch_tools")
+        assert abs(T.rms_cents_error(ref, pred) - I.rms_cents_error(ref, pred)) < 1e-6
+        np.testing.assert_array_equal(T.hz_to_cents(ref), I.hz_to_cents(ref))
+        np.testing.assert_allclose(T.circular_cents_distance(cents, 0 * cents), I.circular_cents_distance(cents, 0 * cents))

@@ -94,3 +94,25 @@ def test_checkpoint_roundtrip_and_mel_batches(built_lib, tmp_path):
     model.eval()
     ev = model.engine.eval_loss(mel, f0, sil).tolist()
     assert np.isfinite(ev).all()
+
+
+def test_predict_f0_matches_reference_chunking(built_lib):
+    """Batched chunked inference vs the notebook's per-chunk loop restated on the fp32 oracle (eval mode)."""
+    from oracle import jdcnet_torch as J, logmel_np
+    from pitchextractor_b200 import JDCNet, predict_f0
+    sd = GI.model_state_dict("transformer")
+    rng = np.random.default_rng(3)
+    audio = (0.1 * rng.standard_normal(24000 * 4 + 137)).astype(np.float32)  # 321 frames -> chunks at 0, 144, 288
+    mel = torch.from_numpy(logmel_np.log_mel(audio)).float()
+    total, preds = mel.shape[-1], []
+    for start in range(0, total, 144):
+        end = min(start + 192, total)
+        chunk = torch.nn.functional.pad(mel[:, start:end], (0, 192 - (end - start)))[None, None].transpose(-1, -2)
+        cls, _ = J.jdcnet_forward(sd, chunk, J.default_config("transformer"), training=False)
+        preds.append(cls.squeeze().numpy()[:end - start])
+    ref = np.concatenate(preds)
+    model = JDCNet(num_class=1, sequence_model_config=GI.model_config("transformer"))
+    model.load_state_dict(sd)
+    got = predict_f0(model.cuda(), audio)
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() <= 2e-2 * np.abs(ref).max() + 1e-2
