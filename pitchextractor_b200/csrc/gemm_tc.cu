@@ -122,6 +122,27 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         } else {
           m0 = tc.tx * kBlockM;  // Cout tile; tc.ty = tap
         }
+        // Per-tile constants and incremental k-block state: the producer is a single thread, so its address arithmetic
+        // (integer divisions) must stay out of the per-k-block path or it starves the tensor pipe.
+        int c_tap = 0, c_chunk = 0;                    // conv fwd: current tap and 64-channel chunk
+        int pb = 0, ph0 = 0, pw0 = 0;                  // conv wgrad: current 64-pixel patch
+        int box_c[4], box_dh[4], box_dw[4];            // conv wgrad: channel / tap shift of each B box of this tile
+        if (p.mode == 1) {
+          c_tap = kb_begin / p.c1_chunks;              // kb_begin is 0 for convolutions (no split-K), kept general
+          c_chunk = kb_begin - c_tap * p.c1_chunks;
+        } else if (p.mode == 2) {
+          decode_conv_tile(p, kb_begin, pb, ph0, pw0);
+          const int cin = p.c1_chunks * 64;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int col = tc.ty * p.block_n + j * 64;
+            const int tap = col / cin;
+            box_c[j] = tap < p.taps ? col - tap * cin : cin;  // past the last tap: out-of-range channel -> zero fill
+            box_dh[j] = p.taps == 9 ? (tap / 3) - 1 : 0;
+            box_dw[j] = p.taps == 9 ? (tap % 3) - 1 : 0;
+          }
+        }
+        const int main_kb = 9 * p.c1_chunks;
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           const int s = stage;
           const long long c0 = p.dbg ? clock64() : 0;
@@ -149,11 +170,13 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 tma_load_2d(&tma_b, &full_bar[s], sb + j * (elems_per_row * kRowBytes), n0 + j * elems_per_row, k0);
             }
           } else if (p.mode == 1) {
-            const int main_kb = 9 * p.c1_chunks;
             if (kb < main_kb) {
-              const int t = kb / p.c1_chunks;
-              const int c0 = (kb - t * p.c1_chunks) * 64;
-              tma_load_4d(&tma_a, &full_bar[s], sa, c0, w0 + (t % 3) - 1, h0 + (t / 3) - 1, img);
+              const int kh = c_tap >= 6 ? 2 : (c_tap >= 3 ? 1 : 0);
+              tma_load_4d(&tma_a, &full_bar[s], sa, c_chunk * 64, w0 + (c_tap - 3 * kh) - 1, h0 + kh - 1, img);
+              if (++c_chunk == p.c1_chunks) {
+                c_chunk = 0;
+                ++c_tap;
+              }
             } else {
               tma_load_4d(&tma_a2, &full_bar[s], sa, (kb - main_kb) * 64, w0, h0, img);
             }
@@ -161,19 +184,20 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           } else {
             // k-block = one 64-pixel patch; A = dy (Cout-major); B = x shifted by the tap(s) this tile owns: output
             // column n = tap * Cin + ci, 64-wide boxes, several taps per tile when Cin is small (A is loaded once)
-            int pb, ph0, pw0;
-            decode_conv_tile(p, kb, pb, ph0, pw0);
-            const int cin = p.c1_chunks * 64;
             for (int j = 0; j < p.a_boxes; ++j)
               tma_load_4d(&tma_a, &full_bar[s], sa + j * (64 * kRowBytes), m0 + j * 64, pw0, ph0, pb);
-            for (int j = 0; j < p.b_boxes; ++j) {
-              const int col = tc.ty * p.block_n + j * 64;
-              const int tap = col / cin;
-              const int dh = p.taps == 9 ? (tap / 3) - 1 : 0;
-              const int dw = p.taps == 9 ? (tap % 3) - 1 : 0;
-              // columns past the last tap are loaded from beyond the channel extent: TMA zero-fills them
-              tma_load_4d(&tma_b, &full_bar[s], sb + j * (64 * kRowBytes), tap < p.taps ? col - tap * cin : cin,
-                          pw0 + dw, ph0 + dh, pb);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (j < p.b_boxes)
+                tma_load_4d(&tma_b, &full_bar[s], sb + j * (64 * kRowBytes), box_c[j], pw0 + box_dw[j], ph0 + box_dh[j], pb);
+            pw0 += p.tw;  // next patch: row-major over (image, patch row, patch column)
+            if (pw0 >= p.tiles_w * p.tw) {
+              pw0 = 0;
+              ph0 += p.th;
+              if (ph0 >= p.tiles_h * p.th) {
+                ph0 = 0;
+                ++pb;
+              }
             }
           }
         }

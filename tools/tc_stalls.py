@@ -29,3 +29,16 @@ def conv(B, H, W, C1, C2, Cout):
 
 gemm(12288, 1536, 512); gemm(12288, 512, 1536); gemm(12288, 256, 2048)
 conv(64, 192, 80, 64, 0, 64); conv(64, 192, 40, 128, 64, 128); conv(64, 192, 10, 256, 192, 256)
+
+def wgrad(B, H, W, C, Cout, taps=9):
+    x = torch.randn(B, H, W, C, device="cuda").to(torch.bfloat16)
+    dy = torch.randn(B, H, W, Cout, device="cuda").to(torch.bfloat16)
+    dw = torch.zeros(Cout, taps * C, device="cuda")
+    ops.conv_wgrad(dy, x, dw, taps=taps); torch.cuda.synchronize()
+    lib.pe_tc_set_debug(ctypes.c_void_p(dbg.data_ptr())); dbg.zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); ops.conv_wgrad(dy, x, dw, taps=taps); e1.record()
+    show("wgrad W=%d C=%d Cout=%d" % (W, C, Cout)); lib.pe_tc_set_debug(None)
+    print("     %.1f us  %.0f TFLOP/s" % (e0.elapsed_time(e1) * 1e3, 2.0 * B * H * W * C * Cout * taps / e0.elapsed_time(e1) / 1e9))
+
+wgrad(64, 192, 80, 64, 64); wgrad(64, 192, 40, 64, 128); wgrad(64, 192, 40, 128, 128); wgrad(64, 192, 20, 192, 192); wgrad(64, 192, 10, 256, 256)
