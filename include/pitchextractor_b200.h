@@ -36,6 +36,12 @@ typedef struct CUstream_st* pe_stream_t; /* == cudaStream_t */
 int pe_version(void);
 int pe_check_device(void); /* PE_OK iff the current device is sm_100 */
 
+/* Per-step dropout salt: every dropout site (reference model.py:40,56 nn.Dropout, the Transformer / LSTM dropouts of
+ * model.py:306-341) draws its mask from (seed argument + salt).  The salt lives in device memory so that a training
+ * step captured once into a CUDA graph -- whose seed arguments are frozen -- still sees fresh masks on every replay:
+ * the host bumps the salt (stream-ordered, one 1-block kernel) before each replay.  Eager launches keep it at 0. */
+int pe_set_step_salt(unsigned long long salt, pe_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Fused epilogue description shared by the tensor-core GEMM / implicit-GEMM convolution.
  *   v = acc (+ bias[col]);  if act==GELU {out2 = bf16(v); v = gelu(v)};  if drop_thresh {v = keep ? v*drop_scale : 0};

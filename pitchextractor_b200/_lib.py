@@ -65,6 +65,7 @@ def check(rc, what):
 # kernels launched per C-ABI call (for bench.py's gpu_launches count)
 _LAUNCHES_PER_CALL = {"pe_logmel_f32": 2, "pe_bn_act_pool_bwd": 3, "pe_attn_bwd": 2, "pe_heads_loss": 2}
 launch_count = 0
+step_salt = 0  # host mirror of the device-side dropout salt (pe_set_step_salt)
 
 
 # When set to a list, every C-ABI call appends (name, start_event, end_event): per-entry-point GPU time with warm

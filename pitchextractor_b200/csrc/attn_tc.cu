@@ -7,6 +7,8 @@
 #include "common.cuh"
 #include "../../include/pitchextractor_b200.h"
 
+PE_USES_STEP_SALT()
+
 namespace pe {
 
 constexpr int AT = 192;            // sequence length (frames)

@@ -49,10 +49,17 @@ __device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t k
   }
   return make_uint4(c0, c1, c2, c3);
 }
+// Per-step seed salt.  Every dropout site's effective seed is (launch-argument seed + pe_step_salt): an eagerly
+// launched step leaves the salt at 0 and passes fresh seeds as arguments, while a step replayed from a CUDA graph
+// (whose launch arguments are frozen) gets fresh masks by bumping the salt through pe_set_step_salt() between
+// replays.  One copy per translation unit; units that draw dropout masks register theirs with PE_USES_STEP_SALT().
+static __device__ unsigned long long pe_step_salt __attribute__((unused)) = 0ull;
+
 // Dropout keep decisions for the 8 consecutive elements [8q, 8q+8): bit i of the result is set iff 16-bit lane i of
 // one Philox block is below thresh16 (= keep probability * 65536).  Every dropout site indexes elements the same
 // way in its forward and backward kernels, so masks are never stored.
 __device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint64_t q, uint32_t thresh16) {
+  seed += pe_step_salt;
   const uint4 r = philox4x32((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)seed, (uint32_t)(seed >> 32));
   uint32_t m = 0;
   m |= (uint32_t)((r.x & 0xFFFFu) < thresh16) << 0;
@@ -69,6 +76,9 @@ __device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint64_t q, uin
 // attention-probability dropout: keep iff fmix32(seed, element) < thresh.  A counter hash instead of Philox because
 // the attention backward walks the mask in both row- and column-major order.
 __host__ __device__ __forceinline__ uint32_t attn_drop_hash(unsigned long long seed, unsigned long long e) {
+#ifdef __CUDA_ARCH__
+  seed += pe_step_salt;
+#endif
   uint32_t h = (uint32_t)e * 0x9E3779B1u ^ ((uint32_t)(e >> 32) * 0x85EBCA77u) ^ (uint32_t)seed ^
                ((uint32_t)(seed >> 32) * 0xC2B2AE3Du);
   h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
@@ -299,4 +309,20 @@ int encode_tmap(CUtensorMap* map, CUtensorMapDataType dt, int rank, const void* 
 int num_sms();
 int check_arch();  // PE_OK on sm_100, PE_ERR_ARCH otherwise
 
+// Step-salt registry (see pe::pe_step_salt): each translation unit that draws dropout masks registers a getter
+// for the device address of its own copy; pe_set_step_salt() writes all of them with one tiny kernel.
+typedef void* (*salt_addr_fn)();
+void register_salt(salt_addr_fn fn);
+struct SaltRegistrar {
+  explicit SaltRegistrar(salt_addr_fn fn) { register_salt(fn); }
+};
+
 }  // namespace pe_host
+
+#define PE_USES_STEP_SALT()                              \
+  static void* pe_salt_addr_() {                         \
+    void* p = nullptr;                                   \
+    cudaGetSymbolAddress(&p, pe::pe_step_salt);          \
+    return p;                                            \
+  }                                                      \
+  static pe_host::SaltRegistrar pe_salt_registrar_(pe_salt_addr_);

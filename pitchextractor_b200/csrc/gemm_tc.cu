@@ -8,6 +8,8 @@
 #include "../../include/pitchextractor_b200.h"
 #include <cstdlib>
 
+PE_USES_STEP_SALT()
+
 namespace pe {
 
 constexpr int kBlockM = 128;

@@ -61,7 +61,42 @@ int check_arch() {
   return ok;
 }
 
+static salt_addr_fn* salt_table(int** count) {
+  static salt_addr_fn fns[8];
+  static int n = 0;
+  *count = &n;
+  return fns;
+}
+void register_salt(salt_addr_fn fn) {
+  int* n;
+  salt_addr_fn* fns = salt_table(&n);
+  if (*n < 8) fns[(*n)++] = fn;
+}
+
+struct SaltAddrs {
+  unsigned long long* p[8];
+};
+__global__ void set_salt_kernel(SaltAddrs a, int n, unsigned long long salt) {
+  if (threadIdx.x < n) *a.p[threadIdx.x] = salt;
+}
+
 }  // namespace pe_host
+
+extern "C" int pe_set_step_salt(unsigned long long salt, pe_stream_t stream) {
+  static pe_host::SaltAddrs addrs;
+  static int n_addrs = -1;
+  if (n_addrs < 0) {
+    int* n;
+    pe_host::salt_addr_fn* fns = pe_host::salt_table(&n);
+    for (int i = 0; i < *n; ++i) {
+      addrs.p[i] = (unsigned long long*)fns[i]();
+      if (!addrs.p[i]) return PE_ERR_LAUNCH;
+    }
+    n_addrs = *n;
+  }
+  pe_host::set_salt_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(addrs, n_addrs, salt);
+  return cudaGetLastError() == cudaSuccess ? PE_OK : PE_ERR_LAUNCH;
+}
 
 extern "C" int pe_version(void) { return 100; }
 extern "C" int pe_check_device(void) { return pe_host::check_arch(); }

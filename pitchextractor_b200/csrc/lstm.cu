@@ -9,6 +9,8 @@
 #include "common.cuh"
 #include "../../include/pitchextractor_b200.h"
 
+PE_USES_STEP_SALT()
+
 namespace pe {
 
 constexpr int LH = 384;         // hidden size

@@ -5,6 +5,8 @@
 #include "common.cuh"
 #include "../../include/pitchextractor_b200.h"
 
+PE_USES_STEP_SALT()
+
 namespace pe {
 
 __device__ __forceinline__ void ld8b(const __nv_bfloat16* p, float* f) {

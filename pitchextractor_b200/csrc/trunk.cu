@@ -6,6 +6,8 @@
 #include "common.cuh"
 #include "../../include/pitchextractor_b200.h"
 
+PE_USES_STEP_SALT()
+
 namespace pe {
 
 __device__ __forceinline__ void ld8(const __nv_bfloat16* p, float* f) {

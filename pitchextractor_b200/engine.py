@@ -10,6 +10,7 @@ Data layout in HBM
   * dropout masks are never stored: Philox keyed by (site seed, element index) is replayed in the backward kernels.
 """
 import ctypes
+import os
 
 import torch
 
@@ -71,6 +72,11 @@ class Engine:
         self._bufs = {}
         self._fwd_token = 0
         self.on_grads_ready = None  # callback(tag) for the data-parallel gradient reducer
+        self.reducer = None         # GradReducer: begin_step() / ready(tag) / wait() bracket every training step
+        # Training steps are captured into a CUDA graph after two eager warm-up steps and replayed from then on
+        # (~270 launches per step; eagerly the host needs ~10 ms to enqueue them).  PE_CUDA_GRAPH=0 disables it.
+        self.use_graph = os.environ.get("PE_CUDA_GRAPH", "1") != "0"
+        self._graphs = {}
         self._pack()
 
     # ------------------------------------------------------------------ parameter arenas
@@ -534,7 +540,7 @@ class Engine:
         BT = B * T
         training = self._training
         W16, g, bufs = self.bview, self.gview, self._bufs
-        notify = self.on_grads_ready or (lambda tag: None)
+        notify = self.on_grads_ready or (self.reducer.ready if self.reducer is not None else (lambda tag: None))
         if self.seq_type == "transformer":
             dSEQD = self._transformer_bwd("sequence_detector", "d", bufs["SEQD"], dHd, B, T, 64)
             notify("sequence_detector+heads")
@@ -599,13 +605,78 @@ class Engine:
     def train_step(self, mel, f0, sil, lambda_f0=0.1, grad_scale=1.0):
         """mel [B,1,80,T] (reference batch layout) -> fills .grad, returns device tensor [loss, f0, sil]."""
         x = mel.transpose(-1, -2)  # trainer.py:235
+        if self.use_graph and ops.PROFILE is None and L.TIMING is None:
+            return self._train_step_graphed(x, f0, sil, float(lambda_f0), float(grad_scale))
+        self._set_salt(0)
+        return self._train_step_eager(x, f0, sil, lambda_f0, grad_scale)
+
+    def _train_step_eager(self, x, f0, sil, lambda_f0, grad_scale):
+        if self.reducer is not None:
+            self.reducer.begin_step()
         self.zero_grad()
         self.forward_core(x, training=True)
         f0 = f0.to(self.device, torch.float32).contiguous().view(-1)
         sil = sil.to(self.device, torch.float32).contiguous().view(-1)
         dHc, dHd = self._heads(f0, sil, lambda_f0, grad_scale, want_grad=True)
         self.backward_core(dHc, dHd)
+        if self.reducer is not None:
+            self.reducer.wait()  # the current stream waits for the bucket all-reduces (captured as graph edges)
         return self.loss_out
+
+    # ------------------------------------------------------------------ CUDA-graph replay of the training step
+    def _set_salt(self, salt):
+        salt &= 0xFFFFFFFFFFFFFFFF
+        if salt != L.step_salt:  # the salt is device state shared by every engine of this process
+            call("pe_set_step_salt", ctypes.c_ulonglong(salt), stream())
+            L.step_salt = salt
+
+    def _train_step_graphed(self, x, f0, sil, lambda_f0, grad_scale):
+        x, B, T, _ = self._prep_input(x)
+        key = (tuple(x.shape), tuple(x.stride()), lambda_f0, grad_scale, self.dropout_enabled)
+        ent = self._graphs.setdefault(key, {"warm": 0})
+        if ent.get("failed") or ent["warm"] < 2:  # eager warm-up: allocates every buffer, sets kernel attributes
+            ent["warm"] += 1
+            self._set_salt(0)
+            return self._train_step_eager(x, f0, sil, lambda_f0, grad_scale)
+        if "graph" not in ent:
+            self._capture(ent, x, B, T, lambda_f0, grad_scale)
+            if ent.get("failed"):
+                return self._train_step_eager(x, f0, sil, lambda_f0, grad_scale)
+        ent["x"].copy_(x, non_blocking=True)
+        ent["f0"].copy_(f0.reshape(-1), non_blocking=True)
+        ent["sil"].copy_(sil.reshape(-1), non_blocking=True)
+        self._x, self._B, self._T, self._training = ent["x"], B, T, True
+        self._fwd_token += 1
+        self.step_seed += 1
+        # the graph's launch arguments carry the seeds of the capture step; the salt moves them to this step's
+        self._set_salt((self.step_seed - ent["seed"]) << 8)
+        ent["graph"].replay()
+        L.launch_count += ent["launches"]
+        return self.loss_out
+
+    def _capture(self, ent, x, B, T, lambda_f0, grad_scale):
+        ent["x"] = torch.empty_strided(x.shape, x.stride(), device=self.device, dtype=torch.float32)
+        ent["f0"] = torch.zeros(B * T, device=self.device, dtype=torch.float32)
+        ent["sil"] = torch.zeros(B * T, device=self.device, dtype=torch.float32)
+        ent["x"].copy_(x)
+        self._set_salt(0)
+        seed_before, token_before, launches_before = self.step_seed, self._fwd_token, L.launch_count
+        graph = torch.cuda.CUDAGraph()
+        try:
+            with torch.cuda.graph(graph):
+                self._train_step_eager(ent["x"], ent["f0"], ent["sil"], lambda_f0, grad_scale)
+        except Exception as e:  # stay on the eager CUDA path (still no CPU fallback)
+            if os.environ.get("PE_CUDA_GRAPH") == "1":
+                raise
+            import logging
+            logging.getLogger(__name__).warning("CUDA-graph capture of the training step failed (%s); running eagerly", e)
+            ent["failed"] = True
+            self.step_seed, self._fwd_token, L.launch_count = seed_before, token_before, launches_before
+            return
+        ent["graph"] = graph
+        ent["launches"] = L.launch_count - launches_before
+        ent["seed"] = self.step_seed  # baked into the captured launch arguments
+        self.step_seed, self._fwd_token, L.launch_count = seed_before, token_before, launches_before
 
     def eval_loss(self, mel, f0, sil, lambda_f0=0.1):
         self.forward_core(mel.transpose(-1, -2), training=False)
@@ -616,6 +687,7 @@ class Engine:
 
     def autograd_forward(self, x):
         training = self.model.training
+        self._set_salt(0)
         self.forward_core(x, training=training)
         B, T = self._B, self._T
         self._predict_only()
@@ -633,6 +705,7 @@ class Engine:
 
     def backward_from_output_grads(self, dcls, ddet):
         M = self._B * self._T
+        self._set_salt(0)
         gc = dcls.to(torch.float32).contiguous().view(M)
         gd = ddet.to(torch.float32).contiguous().view(M)
         if any(p.grad is None for p in self.params):

@@ -112,7 +112,7 @@ class Trainer(object):
                     dist.broadcast(b, src=0)
             offs = [eng.offset[n] for n in eng.names]
             self._reducer = GradReducer(eng.flat_grad, bucket_ranges(eng.names, offs, eng.total))
-            eng.on_grads_ready = self._reducer.ready
+            eng.reducer = self._reducer  # the engine brackets each step with begin_step() / ready(tag) / wait()
             if hasattr(self.optimizer, "grad_scale"):
                 self.optimizer.grad_scale = 1.0 / self.world
 
@@ -122,13 +122,9 @@ class Trainer(object):
         x, f0, sil = self._mel_from_batch(batch)
         f0 = f0.to(self.device, non_blocking=True)
         sil = sil.to(self.device, non_blocking=True)
-        if self._reducer is not None:
-            self._reducer.begin_step()
         losses = self.model.train_step_loss(x, f0, sil, self.loss_config["lambda_f0"])
-        if self._reducer is not None:
-            self._reducer.wait()
-            if not hasattr(self.optimizer, "grad_scale"):
-                self.model.engine.flat_grad.mul_(1.0 / self.world)
+        if self._reducer is not None and not hasattr(self.optimizer, "grad_scale"):
+            self.model.engine.flat_grad.mul_(1.0 / self.world)
         self.optimizer.step()
         self.scheduler.step()
         self.steps += 1

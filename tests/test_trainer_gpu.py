@@ -116,3 +116,43 @@ def test_predict_f0_matches_reference_chunking(built_lib):
     got = predict_f0(model.cuda(), audio)
     assert got.shape == ref.shape
     assert np.abs(got - ref).max() <= 2e-2 * np.abs(ref).max() + 1e-2
+
+
+@pytest.mark.parametrize("model_type", ["transformer", "bilstm"])
+def test_cuda_graph_replay_matches_eager(built_lib, model_type):
+    """The training step is captured into a CUDA graph after two eager steps.  With dropout ON, graph replay must
+    (a) follow the eagerly launched trajectory step for step (same per-step seeds via the device-side salt) and
+    (b) draw fresh masks on every replay (loss on an identical batch changes from replay to replay)."""
+    from pitchextractor_b200 import JDCNet, Trainer, build_optimizer
+    sd = GI.model_state_dict(model_type)
+    B = 4
+    g = torch.Generator().manual_seed(5)
+    mel = (torch.randn(B, 1, 80, 192, generator=g) * 2 - 4).cuda()
+    f0 = (torch.rand(B, 192, generator=g) * 300 + 80) * (torch.rand(B, 192, generator=g) > 0.3)
+    sil = (f0 == 0).float()
+
+    def trajectory(use_graph, lr):
+        model = JDCNet(num_class=1, sequence_model_config=GI.model_config(model_type))
+        model.load_state_dict(sd)
+        model = model.cuda()
+        opt, sched = build_optimizer({"params": model.parameters(), "optimizer_params": {"lr": lr},
+                                      "scheduler_params": {"max_lr": lr, "epochs": 100, "steps_per_epoch": 1000}})
+        tr = Trainer(model=model, optimizer=opt, scheduler=sched, loss_config={"lambda_f0": 0.1}, device="cuda")
+        model.engine.use_graph = use_graph
+        model.train()
+        out = [tr.run((mel, f0, sil))["loss"] for _ in range(6)]
+        captured = any("graph" in e for e in model.engine._graphs.values())
+        return out, captured, model
+
+    eager, cap_e, _ = trajectory(False, 2e-4)
+    graphed, cap_g, model = trajectory(True, 2e-4)
+    print("eager  ", eager)
+    print("graphed", graphed)
+    assert cap_g and not cap_e
+    for a, b in zip(eager, graphed):  # fp32 atomics reorder sums from run to run; nothing else may differ
+        assert abs(a - b) <= 5e-3 * abs(a), (eager, graphed)
+    assert model.conv_block._modules["1"].num_batches_tracked.item() == 6
+    # frozen weights (lr = 0): any change between replays is the dropout mask alone
+    frozen, _, _ = trajectory(True, 0.0)
+    print("frozen ", frozen)
+    assert len({round(v, 4) for v in frozen[2:]}) == len(frozen[2:]), frozen
