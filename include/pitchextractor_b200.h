@@ -97,8 +97,9 @@ int pe_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long lon
 int pe_conv3x3_nhwc(const void* x, const void* x2, const void* w, int B, int H, int W, int C1, int C2, int Cout,
                     const pe_epilogue* ep, pe_stream_t stream);
 
-/* tuning aid: when buf != NULL the tile engine writes per-CTA cycle counters [grid][4] = {main-loop total, MMA thread
- * waiting for operands, MMA thread waiting for a free accumulator stage, TMA thread waiting for a free smem slot} */
+/* tuning aid: when buf != NULL the tile engine writes per-CTA counters [grid][8] = {main-loop cycles, MMA thread
+ * waiting for operands, MMA thread waiting for a free accumulator stage, TMA thread waiting for a free smem slot,
+ * CTA entry time (globaltimer ns), cycles from entry to: set-up done, MMA loop end, CTA exit} */
 int pe_tc_set_debug(long long* buf);
 
 /* Weight gradient of the convolution above: dw[Cout][taps*C + ...] += sum_pixels dy[p][co] * x[p+tap][ci].

@@ -35,7 +35,8 @@ struct TcParams {
   int H, W, tw, th, tiles_w, tiles_h;
   int c1_chunks, c2_chunks;
   int taps;  // wgrad: 9 or 1
-  long long* dbg;  // optional [gridDim.x][4] cycle counters (tuning): total, mma wait-full, mma wait-tmem, tma wait-empty
+  long long* dbg;  // optional [gridDim.x][8] counters (tuning): mma loop cycles, mma wait-full, mma wait-tmem, tma wait-empty,
+                   // entry globaltimer ns, cycles entry->setup done, entry->mma loop end, entry->CTA end
   pe_epilogue ep;
 };
 
@@ -78,6 +79,12 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const long long t_entry = p.dbg ? clock64() : 0;
+  if (p.dbg && threadIdx.x == 0) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
+    p.dbg[blockIdx.x * 8 + 4] = (long long)ns;
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -102,6 +109,7 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 8 + 5] = clock64() - t_entry;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -204,7 +212,7 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           }
         }
       }
-      if (p.dbg) p.dbg[blockIdx.x * 4 + 3] = w_empty;
+      if (p.dbg) p.dbg[blockIdx.x * 8 + 3] = w_empty;
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
@@ -263,9 +271,10 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         tc_commit(&tmem_full_bar[acc]);
       }
       if (p.dbg) {
-        p.dbg[blockIdx.x * 4 + 0] = clock64() - t_begin;
-        p.dbg[blockIdx.x * 4 + 1] = w_full;
-        p.dbg[blockIdx.x * 4 + 2] = w_tmem;
+        p.dbg[blockIdx.x * 8 + 0] = clock64() - t_begin;
+        p.dbg[blockIdx.x * 8 + 1] = w_full;
+        p.dbg[blockIdx.x * 8 + 2] = w_tmem;
+        p.dbg[blockIdx.x * 8 + 6] = clock64() - t_entry;
       }
     }
   } else {
@@ -504,6 +513,7 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 8 + 7] = clock64() - t_entry;
   if (warp == 2) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 

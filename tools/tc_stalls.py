@@ -2,7 +2,7 @@
 import ctypes, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pitchextractor_b200 import ops, _lib
-dbg = torch.zeros(148, 4, dtype=torch.int64, device="cuda")
+dbg = torch.zeros(148, 8, dtype=torch.int64, device="cuda")
 lib = _lib.lib()
 
 def show(tag):
@@ -10,6 +10,9 @@ def show(tag):
     d = dbg.float().mean(0).tolist()
     print("%-34s main-loop %8.0f cyc | mma waits operands %5.1f%% | mma waits accumulator %5.1f%% | tma waits slot %5.1f%%" % (
         tag, d[0], 100 * d[1] / max(d[0], 1), 100 * d[2] / max(d[0], 1), 100 * d[3] / max(d[0], 1)), flush=True)
+    t0 = dbg[:, 4]
+    print("      CTA entry skew %.2f us | setup %.0f cyc | entry->mma end %.0f cyc | entry->exit %.0f cyc (max %.0f)" % (
+        (t0.max() - t0.min()).item() / 1e3, d[5], d[6], d[7], dbg[:, 7].max().item()), flush=True)
 
 def gemm(M, N, K):
     a = torch.randn(M, K, device="cuda").to(torch.bfloat16); b = torch.randn(N, K, device="cuda").to(torch.bfloat16)
