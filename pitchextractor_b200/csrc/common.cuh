@@ -138,6 +138,15 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
   }
 }
 
+// One lane of a converged warp.  The single-thread instructions (tcgen05.mma / commit, TMA) are issued under this
+// predicate from warp-uniform code, so that their operands stay in uniform registers: under an `if (lane == 0)`
+// branch the compiler cannot prove uniformity and wraps every such instruction in an ELECT / R2UR.BROADCAST loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor) loads, completion on an mbarrier
 // ---------------------------------------------------------------------------------------------
@@ -173,6 +182,40 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint64_t* bar,
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+
+// TMA stores: shared -> global, tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+// same, but the tile is ADDED to global memory (fp32 reduction performed by the L2, like atomicAdd)
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all of this thread's bulk stores have finished READING their shared-memory source (it may be overwritten)
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... all but the most recent group (double-buffered staging)
+__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+// ... and have completed (writes performed)
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
 // tcgen05 / TMEM
@@ -262,27 +305,39 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// single-MUFU reciprocal / 2^x (the IEEE-rounded __frcp_rn carries a range check and a slow-path call per element,
+// which also stops the compiler from interleaving the 32 independent chains of an epilogue chunk)
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 // erf by Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7, far below bf16 resolution): one ex2, one rcp, a few FMAs
 __device__ __forceinline__ float erf_fast(float x) {
   const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  const float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
-  const float e = __expf(-ax * ax);
+  const float e = ex2_approx(-1.4426950408889634f * ax * ax);
   const float r = fmaf(-p * t, e, 1.0f);
   return copysignf(r, x);
 }
 // gelu(x) and gelu'(x) with one exponential: exp(-(x/sqrt2)^2) of the erf approximation is sqrt(2 pi) * pdf(x)
 __device__ __forceinline__ void gelu_erf_both(float x, float& g, float& gp) {
   const float ax = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  const float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
-  const float e = __expf(-ax * ax);
+  const float e = ex2_approx(-1.4426950408889634f * ax * ax);
   const float er = copysignf(fmaf(-p * t, e, 1.0f), x);
   const float cdf = 0.5f * (1.0f + er);
   g = x * cdf;
@@ -291,7 +346,7 @@ __device__ __forceinline__ void gelu_erf_both(float x, float& g, float& gp) {
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float cdf = 0.5f * (1.0f + erf_fast(x * 0.70710678118654752f));
-  const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
+  const float pdf = 0.39894228040143268f * ex2_approx(-0.72134752044448170f * x * x);
   return cdf + x * pdf;
 }
 
@@ -305,7 +360,7 @@ namespace pe_host {
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency, so the
 // library also loads on the GPU-less build host).
 int encode_tmap(CUtensorMap* map, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims,
-                const uint64_t* strides_bytes /* rank-1 entries */, const uint32_t* box);
+                const uint64_t* strides_bytes /* rank-1 entries */, const uint32_t* box, int swizzle_bytes = 128);
 int num_sms();
 int check_arch();  // PE_OK on sm_100, PE_ERR_ARCH otherwise
 

@@ -16,6 +16,7 @@ constexpr int kBlockM = 128;
 constexpr int kRowBytes = 128;                    // one swizzle-128B row: 64 bf16 (or 32 tf32) along the contiguous dim
 constexpr int kATileBytes = kBlockM * kRowBytes;  // 16 KB
 constexpr int kNumEpiWarps = 8;
+constexpr int kStagingBytes = 2 * 32 * 64;  // per epilogue warp: two 32-row x 64-byte blocks (64-byte swizzled)
 constexpr int kNumThreads = 64 + 32 * kNumEpiWarps;  // warp 0 = TMA, warp 1 = MMA, warps 2..9 = epilogue
 
 struct TcParams {
@@ -35,6 +36,8 @@ struct TcParams {
   int H, W, tw, th, tiles_w, tiles_h;
   int c1_chunks, c2_chunks;
   int taps;  // wgrad: 9 or 1
+  int commit_group;  // 1, 2 or 4: k-blocks per tcgen05.commit on the smem ring (p.stages is a multiple of it)
+  int out_tma;  // bit 0 / 1: ep.out / ep.out2 are written with TMA tensor stores from the staging blocks
   long long* dbg;  // optional [gridDim.x][8] counters (tuning): mma loop cycles, mma wait-full, mma wait-tmem, tma wait-empty,
                    // entry globaltimer ns, cycles entry->setup done, entry->mma loop end, entry->CTA end
   pe_epilogue ep;
@@ -65,12 +68,17 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile) {
 // the TMA + MMA main loop of tile i + 1.
 __global__ void __launch_bounds__(kNumThreads, 1)
 tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_a2,
-               const __grid_constant__ CUtensorMap tma_b, const TcParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+               const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_out,
+               const __grid_constant__ CUtensorMap tma_out2, const TcParams p) {
+  // No static shared memory in this kernel: the dynamic window then starts 1024-byte aligned (which the 128-byte
+  // swizzle of the operand tiles needs), and all 227 KB are usable.
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
   const int b_tile_bytes = p.block_n * kRowBytes;
   const int stage_bytes = kATileBytes + b_tile_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  // layout: operand ring | epilogue staging (8 warps x 2 blocks of 32 rows x 64 B) | barriers | TMEM slot | column statistics
+  uint8_t* staging = smem + (size_t)p.stages * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kNumEpiWarps * kStagingBytes);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full_bar = empty_bar + p.stages;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
@@ -83,13 +91,15 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if (p.dbg && threadIdx.x == 0) {
     unsigned long long ns;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
-    p.dbg[blockIdx.x * 8 + 4] = (long long)ns;
+    p.dbg[blockIdx.x * 16 + 4] = (long long)ns;
   }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
     if (p.mode == 1 && p.c2_chunks > 0) tma_prefetch_desc(&tma_a2);
+    if (p.out_tma & 1) tma_prefetch_desc(&tma_out);
+    if (p.out_tma & 2) tma_prefetch_desc(&tma_out2);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -109,11 +119,12 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 8 + 5] = clock64() - t_entry;
+  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 16 + 5] = clock64() - t_entry;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // (whole warp in uniform control flow, one elected lane issues: see elect_one())
+    {
       const int elems_per_row = p.kind == 0 ? 64 : 32;
       int stage = 0;
       uint32_t phase = 0;
@@ -156,7 +167,7 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           const int s = stage;
           const long long c0 = p.dbg ? clock64() : 0;
-          mbar_wait(&empty_bar[s], phase ^ 1u);
+          mbar_wait(&empty_bar[s | (p.commit_group - 1)], phase ^ 1u);  // slots are released per commit group
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
@@ -164,8 +175,11 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           if (p.dbg) w_empty += clock64() - c0;
           uint8_t* sa = smem + (size_t)s * stage_bytes;
           uint8_t* sb = sa + kATileBytes;
-          mbar_arrive_expect_tx(&full_bar[s], (uint32_t)p.tx_bytes);
-          if (p.mode == 0) {
+          const bool leader = elect_one();
+          if (leader) mbar_arrive_expect_tx(&full_bar[s], (uint32_t)p.tx_bytes);
+          if (!leader) {
+            // only the elected lane issues; the others just keep the per-k-block state below in step
+          } else if (p.mode == 0) {
             const int k0 = kb * elems_per_row;
             if (!p.a_mn) {
               tma_load_2d(&tma_a, &full_bar[s], sa, k0, m0);
@@ -183,10 +197,6 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             if (kb < main_kb) {
               const int kh = c_tap >= 6 ? 2 : (c_tap >= 3 ? 1 : 0);
               tma_load_4d(&tma_a, &full_bar[s], sa, c_chunk * 64, w0 + (c_tap - 3 * kh) - 1, h0 + kh - 1, img);
-              if (++c_chunk == p.c1_chunks) {
-                c_chunk = 0;
-                ++c_tap;
-              }
             } else {
               tma_load_4d(&tma_a2, &full_bar[s], sa, (kb - main_kb) * 64, w0, h0, img);
             }
@@ -200,6 +210,15 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             for (int j = 0; j < 4; ++j)
               if (j < p.b_boxes)
                 tma_load_4d(&tma_b, &full_bar[s], sb + j * (64 * kRowBytes), box_c[j], pw0 + box_dw[j], ph0 + box_dh[j], pb);
+          }
+          __syncwarp();
+          // per-k-block state, advanced by every lane
+          if (p.mode == 1) {
+            if (kb < main_kb && ++c_chunk == p.c1_chunks) {
+              c_chunk = 0;
+              ++c_tap;
+            }
+          } else if (p.mode == 2) {
             pw0 += p.tw;  // next patch: row-major over (image, patch row, patch column)
             if (pw0 >= p.tiles_w * p.tw) {
               pw0 = 0;
@@ -212,11 +231,12 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           }
         }
       }
-      if (p.dbg) p.dbg[blockIdx.x * 8 + 3] = w_empty;
+      if (p.dbg && lane == 0) p.dbg[blockIdx.x * 16 + 3] = w_empty;
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // The whole warp walks the loop (uniform control flow), one elected lane issues the tcgen05 instructions.
+    {
       const uint32_t idesc = umma_idesc(p.kind == 0 ? UMMA_BF16 : UMMA_TF32, kBlockM, p.block_n, p.a_mn, p.b_mn);
       const int k_rows = p.kind == 0 ? 16 : 8;  // UMMA_K
       const uint32_t a_step = p.a_mn ? (uint32_t)(k_rows * kRowBytes) : 32u;
@@ -234,6 +254,7 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const uint64_t da0 = umma_desc_sw128(0, a_lbo, 1024), db0 = umma_desc_sw128(0, b_lbo, 1024);
       const uint32_t a_inc = a_step >> 4, b_inc = b_step >> 4;
       const uint32_t smem_base = smem_u32(smem);
+      const int gmask = p.commit_group - 1;  // smem slots are handed back in groups of 1, 2 or 4 k-blocks
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
         const TileCoord tc = decode_tile(p, tile);
         const int kb_begin = tc.tz * p.kb_per_split;
@@ -251,30 +272,35 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           tc_fence_after();
           const uint32_t sa = (smem_base + (uint32_t)stage * (uint32_t)stage_bytes) >> 4;
           const uint32_t sb = sa + (kATileBytes >> 4);
-          if (p.kind == 0) {
+          if (elect_one()) {
+            if (p.kind == 0) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              tc_mma_bf16(d_tmem, da0 | (uint64_t)(sa + k * a_inc), db0 | (uint64_t)(sb + k * b_inc), idesc,
-                          (i > 0 || k > 0) ? 1u : 0u);
-          } else {
+              for (int k = 0; k < 4; ++k)
+                tc_mma_bf16(d_tmem, da0 | (uint64_t)(sa + k * a_inc), db0 | (uint64_t)(sb + k * b_inc), idesc,
+                            (i > 0 || k > 0) ? 1u : 0u);
+            } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              tc_mma_tf32(d_tmem, da0 | (uint64_t)(sa + k * a_inc), db0 | (uint64_t)(sb + k * b_inc), idesc,
-                          (i > 0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < 4; ++k)
+                tc_mma_tf32(d_tmem, da0 | (uint64_t)(sa + k * a_inc), db0 | (uint64_t)(sb + k * b_inc), idesc,
+                            (i > 0 || k > 0) ? 1u : 0u);
+            }
+            // tcgen05.commit costs the issuing thread ~200 cycles: narrow tiles (short MMAs) release their slots in
+            // groups -- the commit on the group's last slot covers every earlier MMA, the producer waits on that slot
+            if ((stage & gmask) == gmask) tc_commit(&empty_bar[stage]);
+            if (i == num_kb - 1) tc_commit(&tmem_full_bar[acc]);
           }
-          tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          __syncwarp();
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        tc_commit(&tmem_full_bar[acc]);
       }
-      if (p.dbg) {
-        p.dbg[blockIdx.x * 8 + 0] = clock64() - t_begin;
-        p.dbg[blockIdx.x * 8 + 1] = w_full;
-        p.dbg[blockIdx.x * 8 + 2] = w_tmem;
-        p.dbg[blockIdx.x * 8 + 6] = clock64() - t_entry;
+      if (p.dbg && lane == 0) {
+        p.dbg[blockIdx.x * 16 + 0] = clock64() - t_begin;
+        p.dbg[blockIdx.x * 16 + 1] = w_full;
+        p.dbg[blockIdx.x * 16 + 2] = w_tmem;
+        p.dbg[blockIdx.x * 16 + 6] = clock64() - t_entry;
       }
     }
   } else {
@@ -284,7 +310,10 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int pair = (warp - 2) >> 2;    // which of the two warps of the quarter: takes chunks c with (c & 1) == pair
     const int r = q * 32 + lane;
     const int nchunks = (p.block_n + 31) / 32;
+    uint8_t* stg = staging + (warp - 2) * kStagingBytes;
+    uint32_t stg_flip = 0;
     uint32_t local = 0;
+    long long e_wait = 0, e_ld = 0, e_work = 0, e_last = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
       const TileCoord tc = decode_tile(p, tile);
       int m0 = 0, n0 = 0, img = 0, h0 = 0, w0 = 0;
@@ -303,21 +332,70 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         grow = m0 + r;
         row_ok = grow < p.M;
       }
+      // 64-byte row blocks -> one of this warp's two staging blocks (each lane its own row; 16-byte units XOR-swizzled
+      // as SWIZZLE_64B expects, which also makes the writes bank-conflict free) -> one TMA tensor store / reduction.
+      // Rows and columns outside the tensor are clipped by the TMA unit, so every lane takes part regardless of row_ok.
+      auto stage_block = [&](const CUtensorMap* map, const uint4 (&w)[4], int col, bool reduce) {
+        uint8_t* buf = stg + stg_flip * (kStagingBytes / 2);
+        stg_flip ^= 1u;
+        if (lane == 0) bulk_wait_read_1();  // the store issued two blocks ago (same buffer) has been read
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(buf + lane * 64 + ((u ^ ((lane >> 1) & 3)) << 4)) = w[u];
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (p.mode == 1) {
+            if (reduce) tma_reduce_add_4d(map, buf, col, w0, h0 + (q * 32) / p.tw, img);
+            else tma_store_4d(map, buf, col, w0, h0 + (q * 32) / p.tw, img);
+          } else {
+            if (reduce) tma_reduce_add_2d(map, buf, col, m0 + q * 32);
+            else tma_store_2d(map, buf, col, m0 + q * 32);
+          }
+          bulk_commit_group();
+        }
+      };
+      auto stage_and_store = [&](const CUtensorMap* map, const float (&vals)[32], int col) {  // bf16 chunk
+        uint4 w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          w[u] = make_uint4(pack_bf16(vals[u * 8], vals[u * 8 + 1]), pack_bf16(vals[u * 8 + 2], vals[u * 8 + 3]),
+                            pack_bf16(vals[u * 8 + 4], vals[u * 8 + 5]), pack_bf16(vals[u * 8 + 6], vals[u * 8 + 7]));
+        stage_block(map, w, col, false);
+      };
+      auto stage_and_store_f32 = [&](const CUtensorMap* map, const float (&vals)[32], int col, bool reduce) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {  // two 16-column halves of 64 bytes per row
+          uint4 w[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            w[u] = make_uint4(__float_as_uint(vals[h * 16 + u * 4]), __float_as_uint(vals[h * 16 + u * 4 + 1]),
+                              __float_as_uint(vals[h * 16 + u * 4 + 2]), __float_as_uint(vals[h * 16 + u * 4 + 3]));
+          stage_block(map, w, col + h * 16, reduce);
+        }
+      };
       const uint32_t acc = local & 1u;
+      const long long e_t0 = p.dbg ? clock64() : 0;
       mbar_wait_relaxed(&tmem_full_bar[acc], (local >> 1) & 1u);
       tc_fence_after();
+      const long long e_t1 = p.dbg ? clock64() : 0;
+      e_wait += e_t1 - e_t0;
       const uint32_t t_row = tmem_base + acc * (uint32_t)p.acc_stride + ((uint32_t)(q * 32) << 16);
       for (int c = pair; c < nchunks; c += 2) {
         uint32_t v[32];
+        const long long e_t2 = p.dbg ? clock64() : 0;
         tmem_ld32(t_row + (uint32_t)(c * 32), v);
         tmem_ld_wait();
-        if (!row_ok && !ep.stats_mode) continue;
+        e_ld += p.dbg ? clock64() - e_t2 : 0;
+        if (!row_ok && !ep.stats_mode && !p.out_tma) continue;  // (warp-uniform paths below need every lane)
         const int col0 = n0 + c * 32;
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * ep.alpha;
         const bool full = (col0 + 32 <= p.N) && (c * 32 + 32 <= p.block_n);
-        if (row_ok) {  // rows outside the tensor only take part in the column-statistics shuffles below
+        // rows outside the tensor only take part in the column-statistics shuffles and (with junk values that the TMA
+        // unit clips) in the staged stores; their global loads / direct stores stay predicated on row_ok
+        if (row_ok || p.out_tma) {
         if (ep.bias) {
           if (full) {
 #pragma unroll
@@ -349,7 +427,10 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
           }
           __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(ep.out2) + grow * ep.ld2 + col0;
-          if (full) {
+          if (p.out_tma & 2) {
+            stage_and_store(&tma_out2, gp, col0);
+          } else if (!row_ok) {
+          } else if (full) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8)
               *reinterpret_cast<uint4*>(o2 + j) = make_uint4(pack_bf16(gp[j], gp[j + 1]), pack_bf16(gp[j + 2], gp[j + 3]),
@@ -362,7 +443,10 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (ep.act == PE_ACT_GELU) {
           if (ep.out2) {
             __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(ep.out2) + grow * ep.ld2 + col0;
-            if (full) {
+            if (p.out_tma & 2) {
+              stage_and_store(&tma_out2, f, col0);
+            } else if (!row_ok) {
+            } else if (full) {
 #pragma unroll
               for (int j = 0; j < 32; j += 8)
                 *reinterpret_cast<uint4*>(o2 + j) = make_uint4(pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]),
@@ -388,7 +472,10 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (ep.aux_mode != PE_AUX_NONE) {
           const __nv_bfloat16* ax = reinterpret_cast<const __nv_bfloat16*>(ep.aux) + grow * ep.ld_aux + col0;
           float a[32];
-          if (full) {
+          if (!row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) a[j] = 0.f;
+          } else if (full) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               const uint4 u = *reinterpret_cast<const uint4*>(ax + j);
@@ -462,9 +549,13 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             atomicAdd(&s_stats[col0 + lane], sa[0]);
             atomicAdd(&s_stats[256 + col0 + lane], sb[0]);
           }
-          if (!row_ok) continue;
         }
-        if (ep.out_mode == PE_OUT_BF16) {
+        if (p.out_tma & 1) {
+          if (ep.out_mode == PE_OUT_BF16) stage_and_store(&tma_out, f, col0);
+          else stage_and_store_f32(&tma_out, f, col0, ep.out_mode == PE_OUT_F32_ATOMIC);
+        } else if (!row_ok) {
+          // nothing to write for rows outside the tensor
+        } else if (ep.out_mode == PE_OUT_BF16) {
           __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + grow * ep.ldc + out_col_off + col0;
           if (full) {
 #pragma unroll
@@ -501,6 +592,14 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (p.dbg) { e_last = clock64() - e_t1; e_work += e_last; }
+    }
+    if (p.out_tma && lane == 0) bulk_wait_all();  // staged stores have landed before the CTA may exit
+    if (p.dbg && warp == 2 && lane == 0) {
+      p.dbg[blockIdx.x * 16 + 8] = e_wait;
+      p.dbg[blockIdx.x * 16 + 9] = e_ld;
+      p.dbg[blockIdx.x * 16 + 10] = e_work;
+      p.dbg[blockIdx.x * 16 + 11] = e_last;
     }
     if (ep.stats_mode) {
       asm volatile("bar.sync 2, 256;" ::: "memory");  // the 8 epilogue warps
@@ -513,7 +612,7 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
-  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 8 + 7] = clock64() - t_entry;
+  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 16 + 7] = clock64() - t_entry;
   if (warp == 2) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
@@ -536,16 +635,45 @@ static int pow2_cols(int n) {
   return c;
 }
 
+// Tensor maps for the epilogue's staged bf16 stores (32-column x 32-row boxes, SWIZZLE_64B).  Returns false when the
+// output cannot be addressed by TMA (pitch / base not 16-byte aligned): the kernel then stores from the lanes directly.
+static bool out_tmap(CUtensorMap* m, const TcParams& p, void* base, long long ld, int conv_B, int elem_bytes) {
+  if (!base || (ld * elem_bytes) % 16 || (reinterpret_cast<uintptr_t>(base) & 15)) return false;
+  const CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const uint32_t bc = 64 / elem_bytes;  // box columns: 64 bytes per row
+  const uint64_t eb = (uint64_t)elem_bytes;
+  if (p.mode == 1) {
+    if (32 % p.tw) return false;
+    uint64_t dims[4] = {(uint64_t)p.N, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)conv_B};
+    uint64_t str[3] = {(uint64_t)ld * eb, (uint64_t)p.W * ld * eb, (uint64_t)p.H * p.W * ld * eb};
+    uint32_t box[4] = {bc, (uint32_t)p.tw, (uint32_t)(32 / p.tw), 1};
+    return pe_host::encode_tmap(m, dt, 4, base, dims, str, box, 64) == PE_OK;
+  }
+  uint64_t dims[2] = {(uint64_t)p.N, (uint64_t)p.M};
+  uint64_t str[1] = {(uint64_t)ld * eb};
+  uint32_t box[2] = {bc, 32};
+  return pe_host::encode_tmap(m, dt, 2, base, dims, str, box, 64) == PE_OK;
+}
+
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, TcParams& p, dim3 tiles,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, int conv_B = 0) {
   const int stage_bytes = pe::kATileBytes + p.block_n * pe::kRowBytes;
-  int stages = (198 * 1024) / stage_bytes;
+  int stages = (192 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;
   if (const char* env = getenv("PE_TC_STAGES")) {  // tuning knob
     const int v = atoi(env);
     if (v >= 2 && v < stages) stages = v;
   }
   if (stages < 2) return PE_ERR_BAD_SHAPE;
+  // narrow tiles: MMAs are short, so the per-k-block commit would dominate the issue thread
+  p.commit_group = 1;
+  if (p.block_n <= 128 && stages >= 4) p.commit_group = 2;
+  if (p.block_n <= 64 && stages >= 8) p.commit_group = 4;
+  if (const char* env = getenv("PE_TC_COMMIT_GROUP")) {  // tuning knob
+    const int v = atoi(env);
+    if ((v == 1 || v == 2 || v == 4) && stages >= 2 * v) p.commit_group = v;
+  }
+  stages -= stages % p.commit_group;
   p.stages = stages;
   p.tmem_cols = pow2_cols(2 * p.block_n);
   p.tx_bytes = p.mode == 2 ? (p.a_boxes + p.b_boxes) * 64 * pe::kRowBytes : stage_bytes;
@@ -561,7 +689,16 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtens
     if (!p.ep.stats || p.N > 256 || (p.N % 32) || p.tiles_y != 1 || p.mode == 2) return PE_ERR_BAD_SHAPE;
     if (p.ep.stats_mode == 2 && (!p.ep.stats_x || !p.ep.stats_scale || !p.ep.stats_shift)) return PE_ERR_BAD_SHAPE;
   }
-  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 4) * sizeof(uint64_t) + 16 + 2048 + 1024;
+  // staged TMA stores for bf16 outputs of the GEMM / conv modes (whole 32-column chunks only)
+  CUtensorMap tout = ta, tout2 = ta;
+  p.out_tma = 0;
+  static const bool tma_store_off = getenv("PE_TC_DIRECT_STORE") != nullptr;  // tuning knob
+  if (!tma_store_off && (p.block_n % 32 == 0 || p.tiles_y == 1)) {
+    if (out_tmap(&tout, p, p.ep.out, p.ep.ldc, conv_B, p.ep.out_mode == PE_OUT_BF16 ? 2 : 4)) p.out_tma |= 1;
+    if (p.ep.out2 && p.ep.act != PE_ACT_NONE && out_tmap(&tout2, p, p.ep.out2, p.ep.ld2, conv_B, 2)) p.out_tma |= 2;
+  }
+  const size_t smem = (size_t)stages * stage_bytes + pe::kNumEpiWarps * pe::kStagingBytes +
+                      (2 * stages + 4) * sizeof(uint64_t) + 16 + 2048;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(pe::tc_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
@@ -570,7 +707,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtens
     attr_set = true;
   }
   const int grid = p.num_tiles < pe_host::num_sms() ? p.num_tiles : pe_host::num_sms();
-  pe::tc_tile_kernel<<<grid, pe::kNumThreads, smem, stream>>>(ta, ta2, tb, p);
+  pe::tc_tile_kernel<<<grid, pe::kNumThreads, smem, stream>>>(ta, ta2, tb, tout, tout2, p);
   return cudaGetLastError() == cudaSuccess ? PE_OK : PE_ERR_LAUNCH;
 }
 
@@ -680,7 +817,7 @@ extern "C" int pe_conv3x3_nhwc(const void* x, const void* x2, const void* w, int
     if (int rc = pe_host::encode_tmap(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w, dims, str, box)) return rc;
   }
   dim3 grid(B * p.tiles_h * p.tiles_w, (Cout + p.block_n - 1) / p.block_n, 1);
-  return launch_tc(ta, ta2, tb, p, grid, reinterpret_cast<cudaStream_t>(stream));
+  return launch_tc(ta, ta2, tb, p, grid, reinterpret_cast<cudaStream_t>(stream), B);
 }
 
 extern "C" int pe_conv_wgrad_nhwc(const void* dy, const void* x, float* dw, long long ldw, int B, int H, int W, int C,

@@ -21,7 +21,7 @@ static void load_encode() {
 }
 
 int encode_tmap(CUtensorMap* map, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims,
-                const uint64_t* strides_bytes, const uint32_t* box) {
+                const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
   std::call_once(g_encode_once, load_encode);
   if (!g_encode) return PE_ERR_DRIVER;
   cuuint64_t gdim[5];
@@ -35,7 +35,8 @@ int encode_tmap(CUtensorMap* map, CUtensorMapDataType dt, int rank, const void* 
     if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
   }
   CUresult r = g_encode(map, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? PE_OK : PE_ERR_DRIVER;
 }

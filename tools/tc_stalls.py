@@ -2,7 +2,7 @@
 import ctypes, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pitchextractor_b200 import ops, _lib
-dbg = torch.zeros(148, 8, dtype=torch.int64, device="cuda")
+dbg = torch.zeros(148, 16, dtype=torch.int64, device="cuda")
 lib = _lib.lib()
 
 def show(tag):
