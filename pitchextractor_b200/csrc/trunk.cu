@@ -4,6 +4,7 @@
 // branch.  All kernels are coalesced 16-byte-vector passes; per-channel reductions use fp32 partials per CTA and
 // fp64 atomics across CTAs.
 #include "common.cuh"
+#include <cstdlib>
 #include "../../include/pitchextractor_b200.h"
 
 PE_USES_STEP_SALT()
@@ -23,6 +24,21 @@ __device__ __forceinline__ void ld8(const __nv_bfloat16* p, float* f) {
 __device__ __forceinline__ void st8(__nv_bfloat16* p, const float* f) {
   *reinterpret_cast<uint4*>(p) =
       make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+}
+
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+__device__ __forceinline__ float bf16_at(const uint4& q, int i) {
+  const uint32_t w = i < 2 ? q.x : i < 4 ? q.y : i < 6 ? q.z : q.w;
+  return (i & 1) ? bf16_hi(w) : bf16_lo(w);
+}
+// streaming 16-byte load: read once, do not keep in L1
+__device__ __forceinline__ uint4 ld_stream(const __nv_bfloat16* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -259,6 +275,78 @@ bn_act_pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, PoolGeom g, const fl
   }
 }
 
+// Same pass for K in {1, 2, 4} with memory-level parallelism: a thread owns one 8-channel group (its BN constants stay
+// in registers) and U windows spaced one grid sweep apart; all U*K 16-byte loads are issued before any arithmetic, so
+// a 256-thread CTA keeps 16 KB in flight instead of 4 KB.  blockDim.x = (C/8) * ry exactly.
+template <int K, int U, bool EXTRA>
+__global__ void __launch_bounds__(256)
+bn_act_pool_fwd_mlp_kernel(const __nv_bfloat16* __restrict__ x, PoolGeom g, const float* __restrict__ scale,
+                           const float* __restrict__ shift, float slope, unsigned drop_thresh, float drop_scale,
+                           unsigned long long seed, __nv_bfloat16* __restrict__ out, long long ld_out, int c_off,
+                           __nv_bfloat16* __restrict__ out_seq) {
+  const int cg = g.C >> 3;
+  const int ry = blockDim.x / cg;
+  const int tx = threadIdx.x % cg, ty = threadIdx.x / cg;
+  const long long nwin = g.rows * g.Wo;
+  const long long stride = (long long)gridDim.x * ry;
+  const long long w_first = (long long)blockIdx.x * ry + ty;
+  float sc[8], sh[8];
+  if (scale) {
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(scale + tx * 8)), a1 = __ldg(reinterpret_cast<const float4*>(scale + tx * 8 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(shift + tx * 8)), b1 = __ldg(reinterpret_cast<const float4*>(shift + tx * 8 + 4));
+    sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
+    sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
+  }
+  uint4 xv[U][K];
+  long long wrow[U];
+  int wwo[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const long long w = w_first + u * stride;
+    const long long row = (long long)((unsigned)w / (unsigned)g.Wo);  // the launcher guarantees nwin < 2^31
+    wrow[u] = w < nwin ? row : -1;
+    wwo[u] = (int)(w - row * g.Wo);
+    if (w < nwin) {
+      const __nv_bfloat16* xp = x + ((row * g.W + (long long)wwo[u] * K) * g.C + tx * 8);
+#pragma unroll
+      for (int j = 0; j < K; ++j) xv[u][j] = ld_stream(xp + (long long)j * g.C);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (wrow[u] < 0) continue;
+    const long long row = wrow[u];
+    const int wo = wwo[u];
+    float best[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float b = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        float z = bf16_at(xv[u][j], i);
+        if (scale) {
+          z = fmaf(z, sc[i], sh[i]);
+          z = z > 0.f ? z : z * slope;
+        }
+        b = fmaxf(b, z);
+      }
+      best[i] = b;
+    }
+    if (EXTRA && drop_thresh) {
+      const unsigned long long e0 = (unsigned long long)((row * g.Wo + wo) * g.C + tx * 8);
+      const uint32_t km = dropout_keep8(seed, e0 >> 3, drop_thresh);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) best[i] = ((km >> i) & 1u) ? best[i] * drop_scale : 0.f;
+    }
+    if (out) st8(out + (row * g.Wo + wo) * ld_out + c_off + tx * 8, best);
+    if (EXTRA && out_seq) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        out_seq[row * ((long long)g.C * g.Wo) + (long long)(tx * 8 + i) * g.Wo + wo] = __float2bfloat16(best[i]);
+    }
+  }
+}
+
 // Backward of y = Dropout(MaxPool(1,K)(LeakyReLU(BN_train(x)))) in two coalesced passes.  For one window (row, wo) and 8
 // channels a thread recomputes z_j = lrelu(x_j*scale + shift), the first arg-max j*, and g* = dout * dropout * lrelu'.
 // Per-channel constants live in shared memory (registers are kept low so that 32+ warps per SM hide HBM latency).
@@ -277,15 +365,9 @@ struct BnBwdArgs {
   const __nv_bfloat16* dout_seq;  // sequence-layout consumer gradient (may be NULL)
 };
 
-__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
-__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
-__device__ __forceinline__ float bf16_at(const uint4& q, int i) {
-  const uint32_t w = i < 2 ? q.x : i < 4 ? q.y : i < 6 ? q.z : q.w;
-  return (i & 1) ? bf16_hi(w) : bf16_lo(w);
-}
 
 // loads the K-window and the consumer gradient, returns per channel: jstar, g*, x at jstar
-template <int K>
+template <int K, bool EXTRA = true>
 __device__ __forceinline__ void bn_bwd_route(const BnBwdArgs& a, const float* s_sc, const float* s_sh, long long row,
                                              int wo, int tx, uint4* xv, int* jstar, float* gstar, float* xstar) {
   const PoolGeom& g = a.g;
@@ -301,12 +383,12 @@ __device__ __forceinline__ void bn_bwd_route(const BnBwdArgs& a, const float* s_
 #pragma unroll
     for (int i = 0; i < 8; ++i) go[i] = 0.f;
   }
-  if (a.dout_seq) {
+  if (EXTRA && a.dout_seq) {
 #pragma unroll
     for (int i = 0; i < 8; ++i)
       go[i] += __bfloat162float(a.dout_seq[row * ((long long)g.C * g.Wo) + (long long)(tx * 8 + i) * g.Wo + wo]);
   }
-  if (a.drop_thresh) {
+  if (EXTRA && a.drop_thresh) {
     const unsigned long long e0 = (unsigned long long)((row * g.Wo + wo) * g.C + tx * 8);
     const uint32_t km = dropout_keep8(a.seed, e0 >> 3, a.drop_thresh);
 #pragma unroll
@@ -339,7 +421,7 @@ __device__ __forceinline__ void bn_bwd_route(const BnBwdArgs& a, const float* s_
 }
 
 // pass 1: sums[0][c] += sum g, sums[1][c] += sum g * x   (raw x; centred / scaled in fp64 by the params kernel)
-template <int K>
+template <int K, bool EXTRA>
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(BnBwdArgs a, double* __restrict__ sums, int windows_per_cta) {
   extern __shared__ __align__(16) float sm[];  // sc[C] | sh[C] | red[2][C]
@@ -371,7 +453,7 @@ bn_bwd_reduce_kernel(BnBwdArgs a, double* __restrict__ sums, int windows_per_cta
       uint4 xv[K];
       int js[8];
       float gs[8], xs[8];
-      bn_bwd_route<K>(a, s_sc, s_sh, row, wo, tx, xv, js, gs, xs);
+      bn_bwd_route<K, EXTRA>(a, s_sc, s_sh, row, wo, tx, xv, js, gs, xs);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         s[i] += gs[i];
@@ -457,6 +539,100 @@ bn_bwd_apply_kernel(BnBwdArgs a, const float* __restrict__ coef, __nv_bfloat16* 
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] = fmaf(-A[i], bf16_at(q, i), Bc[i]);
       st8(dx + base + (long long)j * g.C, o);
+    }
+  }
+}
+
+// pass 2 with memory-level parallelism (see bn_act_pool_fwd_mlp_kernel): U windows per thread, every 16-byte load of
+// x and of the consumer gradient issued before the arithmetic; per-channel constants in registers.
+// EXTRA = false compiles the dropout replay and the sequence-layout gradient gather out (most layers have neither;
+// predicated-off Philox rounds would otherwise still take issue slots and make the pass instruction-bound).
+template <int K, int U, bool EXTRA>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_mlp_kernel(BnBwdArgs a, const float* __restrict__ coef, __nv_bfloat16* __restrict__ dx) {
+  const PoolGeom& g = a.g;
+  const int cg = g.C >> 3;
+  const int ry = blockDim.x / cg;
+  const int tx = threadIdx.x % cg, ty = threadIdx.x / cg;
+  const long long nwin = g.rows * g.Wo;
+  const long long stride = (long long)gridDim.x * ry;
+  const long long w_first = (long long)blockIdx.x * ry + ty;
+  uint4 xv[U][K], dv[U];
+  long long wrow[U];
+  int wwo[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const long long w = w_first + u * stride;
+    const long long row = (long long)((unsigned)w / (unsigned)g.Wo);  // the launcher guarantees nwin < 2^31
+    wrow[u] = w < nwin ? row : -1;
+    wwo[u] = (int)(w - row * g.Wo);
+    dv[u] = make_uint4(0u, 0u, 0u, 0u);
+    if (w < nwin) {
+      const __nv_bfloat16* xp = a.x + ((row * g.W + (long long)wwo[u] * K) * g.C + tx * 8);
+#pragma unroll
+      for (int j = 0; j < K; ++j) xv[u][j] = ld_stream(xp + (long long)j * g.C);
+      if (a.dout) dv[u] = ld_stream(a.dout + w * a.ld_dout + a.c_off + tx * 8);
+    }
+  }
+  float sc[8], sh[8], A[8], Bc[8];
+  {
+    const float4* p4 = reinterpret_cast<const float4*>(a.scale + tx * 8);
+    const float4 v0 = __ldg(p4), v1 = __ldg(p4 + 1);
+    sc[0] = v0.x; sc[1] = v0.y; sc[2] = v0.z; sc[3] = v0.w; sc[4] = v1.x; sc[5] = v1.y; sc[6] = v1.z; sc[7] = v1.w;
+    p4 = reinterpret_cast<const float4*>(a.shift + tx * 8);
+    const float4 s0 = __ldg(p4), s1 = __ldg(p4 + 1);
+    sh[0] = s0.x; sh[1] = s0.y; sh[2] = s0.z; sh[3] = s0.w; sh[4] = s1.x; sh[5] = s1.y; sh[6] = s1.z; sh[7] = s1.w;
+    p4 = reinterpret_cast<const float4*>(coef + tx * 8);
+    const float4 a0 = __ldg(p4), a1 = __ldg(p4 + 1);
+    A[0] = a0.x; A[1] = a0.y; A[2] = a0.z; A[3] = a0.w; A[4] = a1.x; A[5] = a1.y; A[6] = a1.z; A[7] = a1.w;
+    p4 = reinterpret_cast<const float4*>(coef + g.C + tx * 8);
+    const float4 b0 = __ldg(p4), b1 = __ldg(p4 + 1);
+    Bc[0] = b0.x; Bc[1] = b0.y; Bc[2] = b0.z; Bc[3] = b0.w; Bc[4] = b1.x; Bc[5] = b1.y; Bc[6] = b1.z; Bc[7] = b1.w;
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (wrow[u] < 0) continue;
+    const long long row = wrow[u];
+    const int wo = wwo[u];
+    uint32_t km = 0xFFu;
+    if (EXTRA && a.drop_thresh) {
+      const unsigned long long e0 = (unsigned long long)((row * g.Wo + wo) * g.C + tx * 8);
+      km = dropout_keep8(a.seed, e0 >> 3, a.drop_thresh);
+    }
+    const long long base = (row * g.W + (long long)wo * K) * g.C + tx * 8;
+    float o[K][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float go = bf16_at(dv[u], i);
+      if (EXTRA && a.dout_seq)
+        go += __bfloat162float(a.dout_seq[row * ((long long)g.C * g.Wo) + (long long)(tx * 8 + i) * g.Wo + wo]);
+      if (EXTRA && a.drop_thresh) go = ((km >> i) & 1u) ? go * a.drop_scale : 0.f;
+      float best = -INFINITY, pre = 0.f;
+      int js = 0;
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        const float zp = fmaf(bf16_at(xv[u][j], i), sc[i], sh[i]);
+        const float z = zp > 0.f ? zp : zp * a.slope;
+        if (z > best) {
+          best = z;
+          js = j;
+          pre = zp;
+        }
+      }
+      const float sg = sc[i] * go * (pre > 0.f ? 1.f : a.slope);
+#pragma unroll
+      for (int j = 0; j < K; ++j) o[j][i] = fmaf(-A[i], bf16_at(xv[u][j], i), Bc[i]) + (j == js ? sg : 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j) st8(dx + base + (long long)j * g.C, o[j]);
+    if (wo == g.Wo - 1) {
+      for (int j = K; j < g.W - wo * K; ++j) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(a.x + base + (long long)j * g.C));
+        float t[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i] = fmaf(-A[i], bf16_at(q, i), Bc[i]);
+        st8(dx + base + (long long)j * g.C, t);
+      }
     }
   }
 }
@@ -571,6 +747,28 @@ extern "C" int pe_bn_act_pool_fwd(const void* x, long long rows, int W, int C, i
     return PE_ERR_BAD_SHAPE;
   PoolGeom g{rows, W, C, k, W / k};
   const long long total = rows * g.Wo * (C / 8);
+  if ((k == 1 || k == 2 || k == 4) && rows * g.Wo < (1ll << 31) - (1ll << 24)) {
+    const int cg = C / 8, ry = 256 / cg, threads = cg * ry;
+    const long long nwin = rows * g.Wo;
+    const bool extra = drop_thresh != 0 || out_seq != nullptr;
+#define PE_FWD(K, U)                                                                                               \
+  do {                                                                                                             \
+    const unsigned grid = (unsigned)((nwin + (long long)ry * U - 1) / ((long long)ry * U));                        \
+    if (extra)                                                                                                     \
+      bn_act_pool_fwd_mlp_kernel<K, U, true><<<grid, threads, 0, PE_ST(stream)>>>(                                 \
+          (const __nv_bfloat16*)x, g, scale, shift, slope, drop_thresh, drop_scale, seed, (__nv_bfloat16*)out,     \
+          ld_out, c_off, (__nv_bfloat16*)out_seq);                                                                 \
+    else                                                                                                           \
+      bn_act_pool_fwd_mlp_kernel<K, U, false><<<grid, threads, 0, PE_ST(stream)>>>(                                \
+          (const __nv_bfloat16*)x, g, scale, shift, slope, drop_thresh, drop_scale, seed, (__nv_bfloat16*)out,     \
+          ld_out, c_off, (__nv_bfloat16*)out_seq);                                                                 \
+  } while (0)
+    if (k == 1) PE_FWD(1, 4);
+    else if (k == 2) PE_FWD(2, 2);
+    else PE_FWD(4, 1);
+#undef PE_FWD
+    return PE_LAUNCH_RC();
+  }
   bn_act_pool_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, PE_ST(stream)>>>(
       (const __nv_bfloat16*)x, g, scale, shift, slope, drop_thresh, drop_scale, seed, (__nv_bfloat16*)out, ld_out, c_off,
       (__nv_bfloat16*)out_seq);
@@ -585,7 +783,8 @@ extern "C" int pe_bn_act_pool_bwd(const void* x, long long rows, int W, int C, i
                                   void* dx, pe_stream_t stream) {
   if (int rc = pe_host::check_arch()) return rc;
   if (!x || !scale || !shift || !mean || !rstd || !sums || !coef || !dx || rows <= 0 || W <= 0 || !chan_ok(C) ||
-      C / 8 > 256 || (k != 1 && k != 2 && k != 4) || k > W || (!dout && !dout_seq))
+      C / 8 > 256 || (k != 1 && k != 2 && k != 4) || k > W || (!dout && !dout_seq) ||
+      rows * (W / k) >= (1ll << 31) - (1ll << 24))
     return PE_ERR_BAD_SHAPE;
   BnBwdArgs a{};
   a.x = (const __nv_bfloat16*)x;
@@ -601,16 +800,25 @@ extern "C" int pe_bn_act_pool_bwd(const void* x, long long rows, int W, int C, i
   const unsigned g2 = (unsigned)((total + 255) / 256);
   const size_t sm1 = 4 * C * sizeof(float), sm2 = 4 * C * sizeof(float);
   cudaStream_t st = PE_ST(stream);
-#define PE_BN_BWD(K)                                                                                      \
+#define PE_BN_BWD(K, U)                                                                                    \
   do {                                                                                                    \
-    if (!sums_ready) bn_bwd_reduce_kernel<K><<<g1, 256, sm1, st>>>(a, sums, per);                         \
+    if (!sums_ready && extra) bn_bwd_reduce_kernel<K, true><<<g1, 256, sm1, st>>>(a, sums, per);          \
+    else if (!sums_ready) bn_bwd_reduce_kernel<K, false><<<g1, 256, sm1, st>>>(a, sums, per);             \
     bn_bwd_params_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, (double)rows * W, scale, mean, rstd, dgamma, dbeta, \
                                                           coef, C);                                       \
-    bn_bwd_apply_kernel<K><<<g2, 256, sm2, st>>>(a, coef, (__nv_bfloat16*)dx);                            \
+    if (extra)                                                                                            \
+      bn_bwd_apply_mlp_kernel<K, U, true><<<(unsigned)((nwin + (long long)ry * U - 1) / ((long long)ry * U)), cgs * ry, 0, st>>>( \
+          a, coef, (__nv_bfloat16*)dx);                                                                   \
+    else                                                                                                  \
+      bn_bwd_apply_mlp_kernel<K, U, false><<<(unsigned)((nwin + (long long)ry * U - 1) / ((long long)ry * U)), cgs * ry, 0, st>>>( \
+          a, coef, (__nv_bfloat16*)dx);                                                                   \
   } while (0)
-  if (k == 1) PE_BN_BWD(1);
-  else if (k == 2) PE_BN_BWD(2);
-  else PE_BN_BWD(4);
+  const int cgs = C / 8, ry = 256 / cgs;
+  const bool extra = drop_thresh != 0 || dout_seq != nullptr;
+  (void)g2; (void)sm2;
+  if (k == 1) PE_BN_BWD(1, 2);
+  else if (k == 2) PE_BN_BWD(2, 2);
+  else PE_BN_BWD(4, 1);
 #undef PE_BN_BWD
   return PE_LAUNCH_RC();
 }
