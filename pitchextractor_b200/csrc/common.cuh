@@ -59,7 +59,6 @@ static __device__ unsigned long long pe_step_salt __attribute__((unused)) = 0ull
 // one Philox block is below thresh16 (= keep probability * 65536).  Every dropout site indexes elements the same
 // way in its forward and backward kernels, so masks are never stored.
 __device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint64_t q, uint32_t thresh16) {
-  seed += pe_step_salt;
   const uint4 r = philox4x32((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)seed, (uint32_t)(seed >> 32));
   uint32_t m = 0;
   m |= (uint32_t)((r.x & 0xFFFFu) < thresh16) << 0;
@@ -76,9 +75,6 @@ __device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint64_t q, uin
 // attention-probability dropout: keep iff fmix32(seed, element) < thresh.  A counter hash instead of Philox because
 // the attention backward walks the mask in both row- and column-major order.
 __host__ __device__ __forceinline__ uint32_t attn_drop_hash(unsigned long long seed, unsigned long long e) {
-#ifdef __CUDA_ARCH__
-  seed += pe_step_salt;
-#endif
   uint32_t h = (uint32_t)e * 0x9E3779B1u ^ ((uint32_t)(e >> 32) * 0x85EBCA77u) ^ (uint32_t)seed ^
                ((uint32_t)(seed >> 32) * 0xC2B2AE3Du);
   h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;

@@ -306,6 +306,7 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   } else {
     // -------------------------------------------------------------------- epilogue (8 warps, 2 per TMEM lane quarter)
     const pe_epilogue& ep = p.ep;
+    const unsigned long long drop_seed = ep.drop_seed + pe_step_salt;
     const int q = warp & 3;              // TMEM lane quarter this warp may access
     const int pair = (warp - 2) >> 2;    // which of the two warps of the quarter: takes chunks c with (c & 1) == pair
     const int r = q * 32 + lane;
@@ -417,7 +418,7 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             const unsigned long long e0 = (unsigned long long)grow * (unsigned long long)p.N + (unsigned long long)col0;
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
-              const uint32_t km = dropout_keep8(ep.drop_seed, (e0 + j) >> 3, ep.drop_thresh);
+              const uint32_t km = dropout_keep8(drop_seed, (e0 + j) >> 3, ep.drop_thresh);
 #pragma unroll
               for (int t = 0; t < 8; ++t) {
                 const float sc = ((km >> t) & 1u) ? ep.drop_scale : 0.f;
@@ -463,7 +464,7 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           const unsigned long long e0 = (unsigned long long)grow * (unsigned long long)p.N + (unsigned long long)col0;
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
-            const uint32_t km = dropout_keep8(ep.drop_seed, (e0 + j) >> 3, ep.drop_thresh);
+            const uint32_t km = dropout_keep8(drop_seed, (e0 + j) >> 3, ep.drop_thresh);
 #pragma unroll
             for (int t = 0; t < 8; ++t) f[j + t] = ((km >> t) & 1u) ? f[j + t] * ep.drop_scale : 0.f;
           }

@@ -101,6 +101,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ xf
               const float* __restrict__ rstd_in, long long M, int rows_per_cta, __nv_bfloat16* __restrict__ dx,
               __nv_bfloat16* __restrict__ dxm, unsigned drop_thresh, float drop_scale, unsigned long long seed,
               float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias) {
+  seed += pe_step_salt;
   constexpr int D = 256 * NCH;
   __shared__ float red[3][D];
   for (int i = threadIdx.x; i < 3 * D; i += 256) (&red[0][0])[i] = 0.f;
@@ -257,6 +258,7 @@ __device__ __forceinline__ void load_head(const __nv_bfloat16* src, long long ld
 __global__ void __launch_bounds__(256)
 attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int T, int H, float scale, unsigned drop_thresh,
                 float drop_scale, unsigned long long seed, __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse) {
+  seed += pe_step_salt;
   extern __shared__ __align__(16) float sm[];
   float* Ks = sm;
   float* Vs = sm + T * HD;
@@ -323,6 +325,7 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
                    const __nv_bfloat16* __restrict__ dctx, const float* __restrict__ lse, int T, int H, float scale,
                    unsigned drop_thresh, float drop_scale, unsigned long long seed, __nv_bfloat16* __restrict__ dqkv,
                    float* __restrict__ delta) {
+  seed += pe_step_salt;
   extern __shared__ __align__(16) float sm[];
   float* Ks = sm;
   float* Vs = sm + T * HD;
@@ -377,6 +380,7 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
                     const float* __restrict__ lse, const float* __restrict__ delta, int T, int H, float scale,
                     unsigned drop_thresh, float drop_scale, unsigned long long seed,
                     __nv_bfloat16* __restrict__ dqkv) {
+  seed += pe_step_salt;
   extern __shared__ __align__(16) float sm[];
   float* Qs = sm;                 // pre-scaled queries
   float* dOs = sm + T * HD;
