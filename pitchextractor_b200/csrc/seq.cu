@@ -95,7 +95,7 @@ ln_fwd_kernel(const float* __restrict__ xf, const __nv_bfloat16* __restrict__ xb
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma.  Also: dxm = dropout-masked copy of dx (the
 // gradient entering the preceding Linear), dgamma/dbeta and the Linear's bias gradient dbias = colsum(dxm).
 template <int NCH>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ xf, const __nv_bfloat16* __restrict__ xb,
               const float* __restrict__ pe, int T, const float* __restrict__ gamma, const float* __restrict__ mean_in,
               const float* __restrict__ rstd_in, long long M, int rows_per_cta, __nv_bfloat16* __restrict__ dx,
@@ -103,36 +103,45 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ xf
               float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias) {
   seed += pe_step_salt;
   constexpr int D = 256 * NCH;
-  __shared__ float red[3][D];
-  for (int i = threadIdx.x; i < 3 * D; i += 256) (&red[0][0])[i] = 0.f;
-  __syncthreads();
+  // column partial sums (dgamma, dbeta, dbias) live in a private shared-memory slice per warp instead of 48 registers
+  // per thread: that keeps two CTAs (16 rows in flight) resident per SM
+  extern __shared__ __align__(16) float sacc[];  // [8 warps][3][D]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float ag[NCH][8], ab[NCH][8], abias[NCH][8], gm[NCH][8];
+  float* my = sacc + warp * 3 * D;
+  for (int i = lane * 4; i < 3 * D; i += 128) *reinterpret_cast<float4*>(my + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncwarp();
+  float gm[NCH][8];
 #pragma unroll
-  for (int i = 0; i < NCH; ++i) {
-    ld8f(gamma + i * 256 + lane * 8, gm[i]);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) ag[i][j] = ab[i][j] = abias[i][j] = 0.f;
-  }
+  for (int i = 0; i < NCH; ++i) ld8f(gamma + i * 256 + lane * 8, gm[i]);
   const long long m0 = (long long)blockIdx.x * rows_per_cta;
   const long long m1 = min(M, m0 + rows_per_cta);
   for (long long m = m0 + warp; m < m1; m += 8) {
     float v[NCH][8], d[NCH][8];
     ln_load_row<NCH>(xf, xb, pe, T, m, lane, v);
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) ld8b(dy + m * D + i * 256 + lane * 8, d[i]);
     const float mean = mean_in[m], rstd = rstd_in[m];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
-      ld8b(dy + m * D + i * 256 + lane * 8, d[i]);
+      float* pg = my + i * 256 + lane * 8;
+      float4 g0 = *reinterpret_cast<float4*>(pg), g1 = *reinterpret_cast<float4*>(pg + 4);
+      float4 b0 = *reinterpret_cast<float4*>(pg + D), b1 = *reinterpret_cast<float4*>(pg + D + 4);
+      float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      float ba[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         v[i][j] = (v[i][j] - mean) * rstd;  // xhat
         const float g = d[i][j] * gm[i][j];
         s1 += g;
         s2 = fmaf(g, v[i][j], s2);
-        ag[i][j] = fmaf(d[i][j], v[i][j], ag[i][j]);
-        ab[i][j] += d[i][j];
+        ga[j] = fmaf(d[i][j], v[i][j], ga[j]);
+        ba[j] += d[i][j];
       }
+      *reinterpret_cast<float4*>(pg) = make_float4(ga[0], ga[1], ga[2], ga[3]);
+      *reinterpret_cast<float4*>(pg + 4) = make_float4(ga[4], ga[5], ga[6], ga[7]);
+      *reinterpret_cast<float4*>(pg + D) = make_float4(ba[0], ba[1], ba[2], ba[3]);
+      *reinterpret_cast<float4*>(pg + D + 4) = make_float4(ba[4], ba[5], ba[6], ba[7]);
     }
     s1 = warp_sum(s1) * (1.f / D);
     s2 = warp_sum(s2) * (1.f / D);
@@ -153,25 +162,25 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ xf
         st8b(dxm + m * D + c, o);
       }
       if (dbias) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) abias[i][j] += __bfloat162float(__float2bfloat16(o[j]));
+        float* pb = my + 2 * D + c;
+        float4 a0 = *reinterpret_cast<float4*>(pb), a1 = *reinterpret_cast<float4*>(pb + 4);
+        a0.x += __bfloat162float(__float2bfloat16(o[0])); a0.y += __bfloat162float(__float2bfloat16(o[1]));
+        a0.z += __bfloat162float(__float2bfloat16(o[2])); a0.w += __bfloat162float(__float2bfloat16(o[3]));
+        a1.x += __bfloat162float(__float2bfloat16(o[4])); a1.y += __bfloat162float(__float2bfloat16(o[5]));
+        a1.z += __bfloat162float(__float2bfloat16(o[6])); a1.w += __bfloat162float(__float2bfloat16(o[7]));
+        *reinterpret_cast<float4*>(pb) = a0;
+        *reinterpret_cast<float4*>(pb + 4) = a1;
       }
     }
   }
-#pragma unroll
-  for (int i = 0; i < NCH; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = i * 256 + lane * 8 + j;
-      atomicAdd(&red[0][c], ag[i][j]);
-      atomicAdd(&red[1][c], ab[i][j]);
-      if (dbias) atomicAdd(&red[2][c], abias[i][j]);
-    }
   __syncthreads();
-  for (int c = threadIdx.x; c < D; c += 256) {
-    if (dgamma) atomicAdd(dgamma + c, red[0][c]);
-    if (dbeta) atomicAdd(dbeta + c, red[1][c]);
-    if (dbias) atomicAdd(dbias + c, red[2][c]);
+  for (int c = threadIdx.x; c < 3 * D; c += 256) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sacc[w * 3 * D + c];
+    const int which = c / D, col = c - which * D;
+    float* dst = which == 0 ? dgamma : (which == 1 ? dbeta : dbias);
+    if (dst) atomicAdd(dst + col, t);
   }
 }
 
@@ -617,13 +626,24 @@ extern "C" int pe_layernorm_bwd(const void* dy, const float* x_f32, const void* 
   if (int rc = pe_host::check_arch()) return rc;
   if (!dy || (!x_f32 && !x_bf16) || !gamma || !mean || !rstd || !dx || M <= 0 || (pe_table && T <= 0))
     return PE_ERR_BAD_SHAPE;
-  const int per = 64;
+  // two CTAs per SM, one wave
+  long long per_ll = (M + 2LL * pe_host::num_sms() - 1) / (2LL * pe_host::num_sms());
+  if (per_ll < 8) per_ll = 8;
+  const int per = (int)per_ll;
   const unsigned grid = (unsigned)((M + per - 1) / per);
+  const size_t smem = (size_t)8 * 3 * D * sizeof(float);
 #define PE_LN_BWD(N)                                                                                               \
-  ln_bwd_kernel<N><<<grid, 256, 0, PE_ST(stream)>>>((const __nv_bfloat16*)dy, x_f32, (const __nv_bfloat16*)x_bf16,  \
-                                                    pe_table, T, gamma, mean, rstd, M, per, (__nv_bfloat16*)dx,    \
-                                                    (__nv_bfloat16*)dx_masked, drop_thresh, drop_scale, seed,      \
-                                                    dgamma, dbeta, dbias)
+  do {                                                                                                             \
+    static bool attr = false;                                                                                      \
+    if (!attr) {                                                                                                   \
+      cudaFuncSetAttribute(ln_bwd_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 768 * 4);        \
+      attr = true;                                                                                                 \
+    }                                                                                                              \
+    ln_bwd_kernel<N><<<grid, 256, smem, PE_ST(stream)>>>((const __nv_bfloat16*)dy, x_f32, (const __nv_bfloat16*)x_bf16, \
+                                                         pe_table, T, gamma, mean, rstd, M, per, (__nv_bfloat16*)dx, \
+                                                         (__nv_bfloat16*)dx_masked, drop_thresh, drop_scale, seed, \
+                                                         dgamma, dbeta, dbias);                                    \
+  } while (0)
   if (D == 512) PE_LN_BWD(2);
   else if (D == 768) PE_LN_BWD(3);
   else if (D == 256) PE_LN_BWD(1);

@@ -799,7 +799,12 @@ extern "C" int pe_bn_act_pool_bwd(const void* x, long long rows, int W, int C, i
   a.dout = (const __nv_bfloat16*)dout; a.ld_dout = ld_dout; a.c_off = c_off;
   a.dout_seq = (const __nv_bfloat16*)dout_seq;
   const long long nwin = rows * a.g.Wo;
-  const int per = 1024;
+  // pass-1 CTAs: about 8 per SM, at least 8 windows per thread row (the fp64 atomics of a CTA cost ~2*C operations)
+  long long per_ll = (nwin + 8LL * pe_host::num_sms() - 1) / (8LL * pe_host::num_sms());
+  const int ry1 = 256 / (C / 8);
+  if (per_ll < 8 * ry1) per_ll = 8 * ry1;
+  if (per_ll > 4096) per_ll = 4096;
+  const int per = (int)per_ll;
   const unsigned g1 = (unsigned)((nwin + per - 1) / per);
   const long long total = nwin * (C / 8);
   const unsigned g2 = (unsigned)((total + 255) / 256);
