@@ -141,9 +141,10 @@ int pe_logmel_set_debug(long long* buf);
  * Conv trunk, memory-bound passes over NHWC bf16 activations (model.py:23-57,143-175).
  * ------------------------------------------------------------------------------------------------ */
 /* Conv2d(1->64, 3x3, pad 1, no bias) (model.py:24): x[b][t][f] fp32 with element strides (sb, st, sf) -> y bf16
- * [B][T][F][64]; w fp32 [64][9]. */
+ * [B][T][F][64]; w fp32 [64][9].  stats (optional, fp64 [2][64], caller zeroes): the batch statistics of the following
+ * BatchNorm2d (model.py:25) -- sum y, sum y^2 of the bf16-rounded output -- accumulated in the same pass. */
 int pe_stem_conv_fwd(const float* x, long long sb, long long st, long long sf, int B, int T, int F, const float* w,
-                     void* y, pe_stream_t stream);
+                     void* y, double* stats, pe_stream_t stream);
 /* its weight gradient: dw[64][9] += sum_p dy[p][c] x[p+tap] */
 int pe_stem_conv_wgrad(const float* x, long long sb, long long st, long long sf, int B, int T, int F, const void* dy,
                        float* dw, pe_stream_t stream);

@@ -655,8 +655,13 @@ extern "C" int pe_layernorm_bwd(const void* dy, const float* x_f32, const void* 
 extern "C" int pe_colsum_bf16(const void* x, long long M, int N, long long ld, float* out, pe_stream_t stream) {
   if (int rc = pe_host::check_arch()) return rc;
   if (!x || !out || M <= 0 || N <= 0 || (N % 8) || (ld % 8)) return PE_ERR_BAD_SHAPE;
-  const int per = 256;
-  dim3 grid((unsigned)((M + per - 1) / per), (unsigned)((N / 8 + 63) / 64));
+  // ~6 CTAs per SM in flight (each keeps 16 KB of loads outstanding), at least 32 rows each
+  const unsigned gy = (unsigned)((N / 8 + 63) / 64);
+  long long per_ll = (M * gy + 6LL * pe_host::num_sms() - 1) / (6LL * pe_host::num_sms());
+  per_ll = ((per_ll + 15) / 16) * 16;
+  if (per_ll < 32) per_ll = 32;
+  const int per = (int)per_ll;
+  dim3 grid((unsigned)((M + per - 1) / per), gy);
   colsum_kernel<<<grid, 256, 0, PE_ST(stream)>>>((const __nv_bfloat16*)x, M, N, ld, per, out);
   return PE_LAUNCH_RC();
 }

@@ -44,39 +44,103 @@ __device__ __forceinline__ uint4 ld_stream(const __nv_bfloat16* p) {
 // ---------------------------------------------------------------------------------------------
 // stem: Conv2d(1 -> 64, 3x3, pad 1, no bias) on x[b][t][f] (arbitrary strides) -> y[b][t][f][64] bf16
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-stem_conv_fwd_kernel(const float* __restrict__ x, long long sb, long long st, long long sf, int B, int T, int F,
-                     const float* __restrict__ w /*[64][9]*/, __nv_bfloat16* __restrict__ y) {
-  __shared__ float ws[9][64];
-  for (int i = threadIdx.x; i < 576; i += 256) ws[i % 9][i / 9] = w[i];
-  __syncthreads();
-  const int g = threadIdx.x & 7;
-  const long long p = (long long)blockIdx.x * 32 + (threadIdx.x >> 3);
-  const long long P = (long long)B * T * F;
-  if (p >= P) return;
-  const int f = (int)(p % F);
-  const int t = (int)((p / F) % T);
-  const int b = (int)(p / ((long long)F * T));
-  float xv[9];
+// the 3x3 input neighbourhood of pixel (b, t, f), zero padded; branch-free (clamped addresses, selected values)
+__device__ __forceinline__ void stem_taps(const float* __restrict__ x, long long sb, long long st, long long sf, int b,
+                                          int t, int f, int T, int F, float* xv) {
+  const float* xb = x + b * sb;
 #pragma unroll
-  for (int kh = 0; kh < 3; ++kh)
+  for (int kh = 0; kh < 3; ++kh) {
+    const int tt = t + kh - 1;
+    const bool tok = tt >= 0 && tt < T;
+    const float* xr = xb + (long long)min(max(tt, 0), T - 1) * st;
 #pragma unroll
     for (int kw = 0; kw < 3; ++kw) {
-      const int tt = t + kh - 1, ff = f + kw - 1;
-      xv[kh * 3 + kw] = (tt >= 0 && tt < T && ff >= 0 && ff < F) ? __ldg(x + b * sb + tt * st + ff * sf) : 0.f;
+      const int ff = f + kw - 1;
+      const float v = __ldg(xr + (long long)min(max(ff, 0), F - 1) * sf);
+      xv[kh * 3 + kw] = (tok && ff >= 0 && ff < F) ? v : 0.f;
     }
-  float o[8];
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    float a = 0.f;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) a = fmaf(xv[k], ws[k][g * 8 + c], a);
-    o[c] = a;
   }
-  st8(y + p * 64 + g * 8, o);
+}
+// pixel index -> (b, t, f) once, then stepped by 32 pixels per iteration without divisions
+struct StemPos {
+  int b, t, f;
+  __device__ __forceinline__ StemPos(long long p, int T, int F) {
+    f = (int)((unsigned)p % (unsigned)F);
+    const unsigned bt = (unsigned)p / (unsigned)F;
+    t = (int)(bt % (unsigned)T);
+    b = (int)(bt / (unsigned)T);
+  }
+  __device__ __forceinline__ void advance(int n, int T, int F) {
+    f += n;
+    while (f >= F) {
+      f -= F;
+      if (++t == T) {
+        t = 0;
+        ++b;
+      }
+    }
+  }
+};
+
+// A thread owns one 8-channel group (its 72 weights stay in registers) and walks pixels 32 apart; the BatchNorm
+// batch statistics of the bf16-rounded output (model.py:24) are accumulated on the way when `stats` is given.
+__global__ void __launch_bounds__(256)
+stem_conv_fwd_kernel(const float* __restrict__ x, long long sb, long long st, long long sf, int B, int T, int F,
+                     const float* __restrict__ w /*[64][9]*/, __nv_bfloat16* __restrict__ y, int pixels_per_cta,
+                     double* __restrict__ stats /* [2][64] or NULL */) {
+  __shared__ float red[2][64];
+  if (threadIdx.x < 128) (&red[0][0])[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int g = threadIdx.x & 7;
+  const int ty = threadIdx.x >> 3;  // 32 pixel lanes
+  float wr[8][9];
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) wr[c][k] = __ldg(w + (g * 8 + c) * 9 + k);
+  float s1[8], s2[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) s1[c] = s2[c] = 0.f;
+  const long long P = (long long)B * T * F;
+  const long long p0 = (long long)blockIdx.x * pixels_per_cta;
+  const long long p1 = min(P, p0 + pixels_per_cta);
+  StemPos pos(p0 + ty, T, F);
+  for (long long p = p0 + ty; p < p1; p += 32, pos.advance(32, T, F)) {
+    float xv[9];
+    stem_taps(x, sb, st, sf, pos.b, pos.t, pos.f, T, F, xv);
+    float o[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float a = 0.f;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) a = fmaf(xv[k], wr[c][k], a);
+      o[c] = a;
+      const float r = __bfloat162float(__float2bfloat16(a));
+      s1[c] += r;
+      s2[c] = fmaf(r, r, s2[c]);
+    }
+    st8(y + p * 64 + g * 8, o);
+  }
+  if (stats) {
+    // lanes with equal g inside a warp: lane = g + 8*j
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float a = s1[c], q = s2[c];
+      a += __shfl_xor_sync(0xffffffffu, a, 8);
+      a += __shfl_xor_sync(0xffffffffu, a, 16);
+      q += __shfl_xor_sync(0xffffffffu, q, 8);
+      q += __shfl_xor_sync(0xffffffffu, q, 16);
+      if ((threadIdx.x & 31) < 8) {
+        atomicAdd(&red[0][g * 8 + c], a);
+        atomicAdd(&red[1][g * 8 + c], q);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 128) atomicAdd(stats + threadIdx.x, (double)(&red[0][0])[threadIdx.x]);
+  }
 }
 
-// dw[c][tap] += sum_p dy[p][c] * x[p + tap]
+// dw[c][tap] += sum_p dy[p][c] * x[p + tap]; two pixels per thread and iteration in flight
 __global__ void __launch_bounds__(256)
 stem_conv_wgrad_kernel(const float* __restrict__ x, long long sb, long long st, long long sf, int B, int T, int F,
                        const __nv_bfloat16* __restrict__ dy, float* __restrict__ dw, int pixels_per_cta) {
@@ -93,24 +157,26 @@ stem_conv_wgrad_kernel(const float* __restrict__ x, long long sb, long long st, 
   for (int c = 0; c < 8; ++c)
 #pragma unroll
     for (int k = 0; k < 9; ++k) acc[c][k] = 0.f;
-  for (long long p = p0 + ty; p < p1; p += 32) {
-    const int f = (int)(p % F);
-    const int t = (int)((p / F) % T);
-    const int b = (int)(p / ((long long)F * T));
-    float xv[9];
+  StemPos pos(p0 + ty, T, F);
+  for (long long pp = p0 + ty; pp < p1; pp += 64) {
+    uint4 dq[2];
+    float xv[2][9];
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh)
+    for (int u = 0; u < 2; ++u) {
+      const long long p = pp + 32 * u;
+      // (past the end: dy = 0 makes the contribution vanish; the clamped tap addresses stay inside the last image)
+      dq[u] = p < p1 ? ld_stream(dy + p * 64 + g * 8) : make_uint4(0u, 0u, 0u, 0u);
+      stem_taps(x, sb, st, sf, min(pos.b, B - 1), pos.t, pos.f, T, F, xv[u]);
+      pos.advance(32, T, F);
+    }
 #pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const int tt = t + kh - 1, ff = f + kw - 1;
-        xv[kh * 3 + kw] = (tt >= 0 && tt < T && ff >= 0 && ff < F) ? __ldg(x + b * sb + tt * st + ff * sf) : 0.f;
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float d = bf16_at(dq[u], c);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) acc[c][k] = fmaf(d, xv[u][k], acc[c][k]);
       }
-    float d[8];
-    ld8(dy + p * 64 + g * 8, d);
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-#pragma unroll
-      for (int k = 0; k < 9; ++k) acc[c][k] = fmaf(d[c], xv[k], acc[c][k]);
   }
   // lanes with equal g inside a warp: lane = g + 8*j, j = 0..3
 #pragma unroll
@@ -689,13 +755,23 @@ using namespace pe;
 #define PE_ST(s) reinterpret_cast<cudaStream_t>(s)
 #define PE_LAUNCH_RC() (cudaGetLastError() == cudaSuccess ? PE_OK : PE_ERR_LAUNCH)
 
+static int stem_pixels_per_cta(long long P) {
+  // about 8 CTAs per SM, whole multiples of the 64-pixel step of the kernels
+  long long per = (P + 8LL * pe_host::num_sms() - 1) / (8LL * pe_host::num_sms());
+  per = ((per + 63) / 64) * 64;
+  if (per < 256) per = 256;
+  return (int)per;
+}
+
 extern "C" int pe_stem_conv_fwd(const float* x, long long sb, long long st, long long sf, int B, int T, int F,
-                                const float* w, void* y, pe_stream_t stream) {
+                                const float* w, void* y, double* stats, pe_stream_t stream) {
   if (int rc = pe_host::check_arch()) return rc;
   if (!x || !w || !y || B <= 0 || T <= 0 || F <= 0) return PE_ERR_BAD_SHAPE;
   const long long P = (long long)B * T * F;
-  stem_conv_fwd_kernel<<<(unsigned)((P + 31) / 32), 256, 0, PE_ST(stream)>>>(x, sb, st, sf, B, T, F, w,
-                                                                             (__nv_bfloat16*)y);
+  if (P >= (1ll << 31)) return PE_ERR_BAD_SHAPE;
+  const int per = stem_pixels_per_cta(P);
+  stem_conv_fwd_kernel<<<(unsigned)((P + per - 1) / per), 256, 0, PE_ST(stream)>>>(x, sb, st, sf, B, T, F, w,
+                                                                                   (__nv_bfloat16*)y, per, stats);
   return PE_LAUNCH_RC();
 }
 
@@ -704,7 +780,8 @@ extern "C" int pe_stem_conv_wgrad(const float* x, long long sb, long long st, lo
   if (int rc = pe_host::check_arch()) return rc;
   if (!x || !dy || !dw || B <= 0 || T <= 0 || F <= 0) return PE_ERR_BAD_SHAPE;
   const long long P = (long long)B * T * F;
-  const int per = 4096;
+  if (P >= (1ll << 31)) return PE_ERR_BAD_SHAPE;
+  const int per = stem_pixels_per_cta(P);
   stem_conv_wgrad_kernel<<<(unsigned)((P + per - 1) / per), 256, 0, PE_ST(stream)>>>(
       x, sb, st, sf, B, T, F, (const __nv_bfloat16*)dy, dw, per);
   return PE_LAUNCH_RC();

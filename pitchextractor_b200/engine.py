@@ -253,8 +253,8 @@ class Engine:
         # ---- conv_block (model.py:23-28)
         Y1 = self.buf("Y1", (B, T, 80, 64))
         call("pe_stem_conv_fwd", ptr(x), c_ll(x.stride(0)), c_ll(x.stride(2)), c_ll(x.stride(3)), c_int(B), c_int(T),
-             c_int(F), ptr(V["conv_block.0.weight"]), ptr(Y1), st())
-        aff = self._bn_prepare("conv_block.1", Y1, BT * 80, 64, training)
+             c_int(F), ptr(V["conv_block.0.weight"]), ptr(Y1), ptr(self._bn_fwd_sums("conv_block.1", training)), st())
+        aff = self._bn_prepare("conv_block.1", Y1, BT * 80, 64, training, stats_fused=True)
         Z1 = self.buf("Z1", (B, T, 80, 64))
         self._act_pool(Y1, BT, 80, 64, 1, aff, out=Z1, ld_out=64)
         R = self.buf("R0", (B, T, 80, 64))
