@@ -632,13 +632,13 @@ class Engine:
 
     def _train_step_graphed(self, x, f0, sil, lambda_f0, grad_scale):
         x, B, T, _ = self._prep_input(x)
-        key = (tuple(x.shape), tuple(x.stride()), lambda_f0, grad_scale, self.dropout_enabled)
+        key = (tuple(x.shape), tuple(x.stride()), lambda_f0, grad_scale, self.dropout_enabled, self.reducer is not None)
         ent = self._graphs.setdefault(key, {"warm": 0})
         if ent.get("failed") or ent["warm"] < 2:  # eager warm-up: allocates every buffer, sets kernel attributes
             ent["warm"] += 1
             self._set_salt(0)
             return self._train_step_eager(x, f0, sil, lambda_f0, grad_scale)
-        if "graph" not in ent:
+        if "segments" not in ent:
             self._capture(ent, x, B, T, lambda_f0, grad_scale)
             if ent.get("failed"):
                 return self._train_step_eager(x, f0, sil, lambda_f0, grad_scale)
@@ -650,22 +650,79 @@ class Engine:
         self.step_seed += 1
         # the graph's launch arguments carry the seeds of the capture step; the salt moves them to this step's
         self._set_salt((self.step_seed - ent["seed"]) << 8)
-        ent["graph"].replay()
+        if self.reducer is not None:
+            self.reducer.begin_step()
+        for graph, tags in ent["segments"]:
+            graph.replay()
+            for tag in tags:  # gradient buckets completed by this segment: their all-reduces go out from the host
+                self.reducer.ready(tag)
+        if self.reducer is not None:
+            self.reducer.wait()
         L.launch_count += ent["launches"]
         return self.loss_out
 
     def _capture(self, ent, x, B, T, lambda_f0, grad_scale):
+        """Capture the step into CUDA graphs.  Single GPU: one graph.  Data parallel: the capture is cut at every
+        point where the backward pass announces a finished gradient bucket, and the bucket's NCCL all-reduce is launched
+        between the segments at replay time (collectives are not captured)."""
         ent["x"] = torch.empty_strided(x.shape, x.stride(), device=self.device, dtype=torch.float32)
         ent["f0"] = torch.zeros(B * T, device=self.device, dtype=torch.float32)
         ent["sil"] = torch.zeros(B * T, device=self.device, dtype=torch.float32)
         ent["x"].copy_(x)
         self._set_salt(0)
         seed_before, token_before, launches_before = self.step_seed, self._fwd_token, L.launch_count
-        graph = torch.cuda.CUDAGraph()
+        segments, seen, cur = [], set(), {}
+        pool = torch.cuda.graph_pool_handle()
+
+        def begin():
+            cur["g"] = torch.cuda.CUDAGraph()
+            cur["g"].capture_begin(pool=pool, capture_error_mode="thread_local")
+            cur["launches"] = L.launch_count
+
+        def end(tag):
+            cur["g"].capture_end()
+            segments.append((cur.pop("g"), [] if tag is None else [tag]))
+
+        class _Splitter:  # stands in for the gradient reducer while capturing
+            def begin_step(self_):
+                pass
+
+            def ready(self_, tag):
+                if tag in seen:
+                    return
+                seen.add(tag)
+                if segments and L.launch_count == cur["launches"]:
+                    segments[-1][1].append(tag)  # nothing was launched since the last cut: same cut
+                else:
+                    end(tag)
+                    begin()
+
+            def wait(self_):
+                pass
+
+        real = self.reducer
+        side = torch.cuda.Stream(device=self.device)
+        torch.cuda.synchronize()
+        side.wait_stream(torch.cuda.current_stream())
         try:
-            with torch.cuda.graph(graph):
+            with torch.cuda.stream(side):
+                self.reducer = _Splitter() if real is not None else None
+                begin()
                 self._train_step_eager(ent["x"], ent["f0"], ent["sil"], lambda_f0, grad_scale)
+                if segments and L.launch_count == cur["launches"]:  # nothing after the last bucket: drop the empty tail
+                    import warnings
+                    with warnings.catch_warnings():
+                        warnings.simplefilter("ignore")
+                        cur.pop("g").capture_end()
+                else:
+                    end(None)
         except Exception as e:  # stay on the eager CUDA path (still no CPU fallback)
+            self.reducer = real
+            if "g" in cur:
+                try:
+                    cur["g"].capture_end()
+                except Exception:
+                    pass
             if os.environ.get("PE_CUDA_GRAPH") == "1":
                 raise
             import logging
@@ -673,7 +730,10 @@ class Engine:
             ent["failed"] = True
             self.step_seed, self._fwd_token, L.launch_count = seed_before, token_before, launches_before
             return
-        ent["graph"] = graph
+        self.reducer = real
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        ent["segments"] = segments
         ent["launches"] = L.launch_count - launches_before
         ent["seed"] = self.step_seed  # baked into the captured launch arguments
         self.step_seed, self._fwd_token, L.launch_count = seed_before, token_before, launches_before

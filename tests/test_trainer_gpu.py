@@ -141,7 +141,7 @@ def test_cuda_graph_replay_matches_eager(built_lib, model_type):
         model.engine.use_graph = use_graph
         model.train()
         out = [tr.run((mel, f0, sil))["loss"] for _ in range(6)]
-        captured = any("graph" in e for e in model.engine._graphs.values())
+        captured = any("segments" in e for e in model.engine._graphs.values())
         return out, captured, model
 
     eager, cap_e, _ = trajectory(False, 2e-4)
@@ -156,3 +156,50 @@ def test_cuda_graph_replay_matches_eager(built_lib, model_type):
     frozen, _, _ = trajectory(True, 0.0)
     print("frozen ", frozen)
     assert len({round(v, 4) for v in frozen[2:]}) == len(frozen[2:]), frozen
+
+
+def test_cuda_graph_segments_with_reducer(built_lib):
+    """Data parallel replay: the capture is cut where the backward pass announces a finished gradient bucket and the
+    reducer is called from the host between the segments, in bucket order, exactly once per step."""
+    from pitchextractor_b200 import JDCNet, Trainer, build_optimizer
+    sd = GI.model_state_dict("transformer")
+    g = torch.Generator().manual_seed(6)
+    mel = (torch.randn(2, 1, 80, 192, generator=g) * 2 - 4).cuda()
+    f0 = torch.rand(2, 192, generator=g) * 300
+    sil = (f0 < 60).float()
+
+    class Recorder:
+        def __init__(self):
+            self.calls = []
+
+        def begin_step(self):
+            self.calls.append("begin")
+
+        def ready(self, tag):
+            self.calls.append(tag)
+
+        def wait(self):
+            self.calls.append("wait")
+
+    def run(use_graph):
+        model = JDCNet(num_class=1, sequence_model_config=GI.model_config("transformer"))
+        model.load_state_dict(sd)
+        model = model.cuda()
+        opt, sched = build_optimizer({"params": model.parameters(), "optimizer_params": {}, "scheduler_params": {}})
+        tr = Trainer(model=model, optimizer=opt, scheduler=sched, loss_config={"lambda_f0": 0.1}, device="cuda")
+        eng = model.engine
+        eng.use_graph = use_graph
+        eng.dropout_enabled = False
+        eng.reducer = Recorder()
+        model.train()
+        losses = [tr.run((mel, f0, sil))["loss"] for _ in range(5)]
+        return losses, eng
+
+    eager, _ = run(False)
+    graphed, eng = run(True)
+    ent = [e for e in eng._graphs.values() if "segments" in e]
+    assert len(ent) == 1 and len(ent[0]["segments"]) == 3  # one graph per gradient bucket (the trunk's is the last)
+    per_step = ["begin", "sequence_detector+heads", "sequence_classifier", "trunk", "wait"]
+    assert eng.reducer.calls == per_step * 5, eng.reducer.calls
+    for a, b in zip(eager, graphed):
+        assert abs(a - b) <= 5e-3 * abs(a), (eager, graphed)
