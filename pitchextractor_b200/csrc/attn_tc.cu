@@ -91,7 +91,9 @@ __device__ __forceinline__ void mma_k192(uint32_t d, uint32_t a, uint32_t b, uin
 // -------------------------------------------------------------------------------------------------
 // forward
 // -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 1)
+constexpr int AFW_THREADS = 512;  // 16 warps: 8 per query tile (4 TMEM lane quarters x 2 column halves)
+
+__global__ void __launch_bounds__(AFW_THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, int H, unsigned drop_thresh, float drop_scale,
                    unsigned long long seed, __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse) {
   seed += pe_step_salt;
@@ -101,8 +103,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, int H, unsigned d
   uint8_t* sK = smem + TILE_B;
   uint8_t* sV = smem + 2 * TILE_B;
   uint8_t* sP = smem + 3 * TILE_B + 8192;  // two [128 x 192] operands (query tiles 0 and 1)
-  float* red = reinterpret_cast<float*>(sP + 2 * OPER_B);  // [2][128] partial row max / sum exchange
-  uint64_t* bars = reinterpret_cast<uint64_t*>(red + 256);
+  float* red = reinterpret_cast<float*>(sP + 2 * OPER_B);  // [2 tiles][2 halves][128] partial row max / sum exchange
+  uint64_t* bars = reinterpret_cast<uint64_t*>(red + 512);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.x, b = blockIdx.y;
@@ -123,24 +125,33 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, int H, unsigned d
 
   constexpr uint32_t IDESC_S = umma_idesc(UMMA_BF16, 128, AT, 0, 0);
   constexpr uint32_t IDESC_O = umma_idesc(UMMA_BF16, 128, AD, 0, 1);
-  if (tid == 0) {
-    mbar_arrive_expect_tx(&bars[0], 3 * TILE_B);
-    tma_load_2d(&tm_qkv, &bars[0], sQ, h * AD, b * AT);
-    tma_load_2d(&tm_qkv, &bars[0], sK, D + h * AD, b * AT);
-    tma_load_2d(&tm_qkv, &bars[0], sV, 2 * D + h * AD, b * AT);
+  // single-thread instructions are issued by an elected lane of warp 0 from warp-uniform code (see elect_one())
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&bars[0], 3 * TILE_B);
+      tma_load_2d(&tm_qkv, &bars[0], sQ, h * AD, b * AT);
+      tma_load_2d(&tm_qkv, &bars[0], sK, D + h * AD, b * AT);
+      tma_load_2d(&tm_qkv, &bars[0], sV, 2 * D + h * AD, b * AT);
+    }
+    __syncwarp();
     mbar_wait(&bars[0], 0);
     tc_fence_after();
-    mma_k64(tm + 0, smem_u32(sQ), smem_u32(sK), IDESC_S);            // S rows   0..127
-    mma_k64(tm + AT, smem_u32(sQ) + 16384, smem_u32(sK), IDESC_S);   // S rows 128..255 (>= 192 unused)
-    tc_commit(&bars[1]);
+    if (elect_one()) {
+      mma_k64(tm + 0, smem_u32(sQ), smem_u32(sK), IDESC_S);            // S rows   0..127
+      mma_k64(tm + AT, smem_u32(sQ) + 16384, smem_u32(sK), IDESC_S);   // S rows 128..255 (>= 192 unused)
+      tc_commit(&bars[1]);
+    }
+    __syncwarp();
   }
   sync.wait();
 
-  const int quarter = warp & 3, half = warp >> 2;
+  // both query tiles are processed at once: warps 0-7 own rows 0..127, warps 8-15 rows 128..191 (+ unused)
+  const int quarter = warp & 3, half = (warp >> 2) & 1, t = warp >> 3;
   const int r = quarter * 32 + lane;
   const float kscale = 0.125f * LOG2E;
-  float inv_l[2];
-  for (int t = 0; t < 2; ++t) {
+  float* redt = red + t * 256;
+  float inv_l;
+  {
     const int q = t * 128 + r;
     const uint32_t trow = tm + ((uint32_t)(quarter * 32) << 16) + t * AT;
     uint32_t v[32];
@@ -151,9 +162,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, int H, unsigned d
 #pragma unroll
       for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
     }
-    red[half * 128 + r] = mx;
+    redt[half * 128 + r] = mx;
     __syncthreads();
-    mx = fmaxf(red[r], red[128 + r]);
+    mx = fmaxf(redt[r], redt[128 + r]);
     __syncthreads();
     float l = 0.f;
     const unsigned long long e_row = ((unsigned long long)(b * H + h) * AT + q) * (unsigned long long)AT;
@@ -173,22 +184,24 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, int H, unsigned d
       }
       oper_store32(sP + t * OPER_B, r, c * 32, p);
     }
-    red[half * 128 + r] = l;
+    redt[half * 128 + r] = l;
     __syncthreads();
-    l = red[r] + red[128 + r];
-    __syncthreads();
-    inv_l[t] = 1.f / l;
+    l = redt[r] + redt[128 + r];
+    inv_l = 1.f / l;
     if (half == 0 && q < AT) lse[((long long)b * H + h) * AT + q] = mx * 0.125f + __logf(l);
   }
   attn_handoff();
-  if (tid == 0) {
+  if (warp == 0) {
     tc_fence_after();
-    mma_k192(tm + 2 * AT, smem_u32(sP), smem_u32(sV), IDESC_O);
-    mma_k192(tm + 2 * AT + AD, smem_u32(sP) + OPER_B, smem_u32(sV), IDESC_O);
-    tc_commit(&bars[1]);
+    if (elect_one()) {
+      mma_k192(tm + 2 * AT, smem_u32(sP), smem_u32(sV), IDESC_O);
+      mma_k192(tm + 2 * AT + AD, smem_u32(sP) + OPER_B, smem_u32(sV), IDESC_O);
+      tc_commit(&bars[1]);
+    }
+    __syncwarp();
   }
   sync.wait();
-  for (int t = 0; t < 2; ++t) {
+  {
     const int q = t * 128 + r;
     uint32_t v[32];
     tmem_ld32(tm + ((uint32_t)(quarter * 32) << 16) + 2 * AT + t * AD + half * 32, v);
@@ -198,10 +211,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, int H, unsigned d
 #pragma unroll
       for (int j = 0; j < 32; j += 8)
         *reinterpret_cast<uint4*>(op + j) =
-            make_uint4(pack_bf16(__uint_as_float(v[j]) * inv_l[t], __uint_as_float(v[j + 1]) * inv_l[t]),
-                       pack_bf16(__uint_as_float(v[j + 2]) * inv_l[t], __uint_as_float(v[j + 3]) * inv_l[t]),
-                       pack_bf16(__uint_as_float(v[j + 4]) * inv_l[t], __uint_as_float(v[j + 5]) * inv_l[t]),
-                       pack_bf16(__uint_as_float(v[j + 6]) * inv_l[t], __uint_as_float(v[j + 7]) * inv_l[t]));
+            make_uint4(pack_bf16(__uint_as_float(v[j]) * inv_l, __uint_as_float(v[j + 1]) * inv_l),
+                       pack_bf16(__uint_as_float(v[j + 2]) * inv_l, __uint_as_float(v[j + 3]) * inv_l),
+                       pack_bf16(__uint_as_float(v[j + 4]) * inv_l, __uint_as_float(v[j + 5]) * inv_l),
+                       pack_bf16(__uint_as_float(v[j + 6]) * inv_l, __uint_as_float(v[j + 7]) * inv_l));
     }
   }
   tc_fence_before();
@@ -250,12 +263,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   tc_fence_after();
   const uint32_t tm = *tmem_slot;
   AttnSync sync{&bars[1], 0};
-  if (tid == 0) {
-    mbar_arrive_expect_tx(&bars[0], 4 * TILE_B);
-    tma_load_2d(&tm_qkv, &bars[0], sQ, h * AD, b * AT);
-    tma_load_2d(&tm_qkv, &bars[0], sK, D + h * AD, b * AT);
-    tma_load_2d(&tm_qkv, &bars[0], sV, 2 * D + h * AD, b * AT);
-    tma_load_2d(&tm_do, &bars[0], sDO, h * AD, b * AT);
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&bars[0], 4 * TILE_B);
+      tma_load_2d(&tm_qkv, &bars[0], sQ, h * AD, b * AT);
+      tma_load_2d(&tm_qkv, &bars[0], sK, D + h * AD, b * AT);
+      tma_load_2d(&tm_qkv, &bars[0], sV, 2 * D + h * AD, b * AT);
+      tma_load_2d(&tm_do, &bars[0], sDO, h * AD, b * AT);
+    }
+    __syncwarp();
   }
   // delta_q = sum_d dO[q][d] * O[q][d]; lse in log2 units
   if (tid < AT) {
@@ -287,18 +303,21 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   const uint32_t lane_base = tm + ((uint32_t)(quarter * 32) << 16);
   const float kscale = 0.125f * LOG2E;
   const unsigned long long e_bh = (unsigned long long)(b * H + h) * AT * (unsigned long long)AT;
-  if (tid == 0) {
+  if (warp == 0) {
     mbar_wait(&bars[0], 0);
     tc_fence_after();
   }
 
   // ---------------- phase A: per query tile, S and dP in TMEM -> dS operand -> dQ
   for (int t = 0; t < 2; ++t) {
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
-      mma_k64(tm + 0, smem_u32(sQ) + t * 16384, smem_u32(sK), IDESC_S);     // S_t  = Q_t K^T
-      mma_k64(tm + AT, smem_u32(sDO) + t * 16384, smem_u32(sV), IDESC_S);   // dP_t = dO_t V^T
-      tc_commit(&bars[1]);
+      if (elect_one()) {
+        mma_k64(tm + 0, smem_u32(sQ) + t * 16384, smem_u32(sK), IDESC_S);     // S_t  = Q_t K^T
+        mma_k64(tm + AT, smem_u32(sDO) + t * 16384, smem_u32(sV), IDESC_S);   // dP_t = dO_t V^T
+        tc_commit(&bars[1]);
+      }
+      __syncwarp();
     }
     sync.wait();
     const int q = t * 128 + r;
@@ -321,10 +340,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       oper_store16(sA, r, c * 16, ds);
     }
     attn_handoff();
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
-      mma_k192(tm + 2 * AT, smem_u32(sA), smem_u32(sK), IDESC_O);            // dQ_t = dS_t K
-      tc_commit(&bars[1]);
+      if (elect_one()) {
+        mma_k192(tm + 2 * AT, smem_u32(sA), smem_u32(sK), IDESC_O);            // dQ_t = dS_t K
+        tc_commit(&bars[1]);
+      }
+      __syncwarp();
     }
     sync.wait();
     {
@@ -339,11 +361,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 
   // ---------------- phase B: per key tile, S^T and dP^T in TMEM -> P~^T, dS^T operands -> dV, dK
   for (int t = 0; t < 2; ++t) {
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
-      mma_k64(tm + 0, smem_u32(sK) + t * 16384, smem_u32(sQ), IDESC_S);     // S^T_t  = K_t Q^T
-      mma_k64(tm + AT, smem_u32(sV) + t * 16384, smem_u32(sDO), IDESC_S);   // dP^T_t = V_t dO^T
-      tc_commit(&bars[1]);
+      if (elect_one()) {
+        mma_k64(tm + 0, smem_u32(sK) + t * 16384, smem_u32(sQ), IDESC_S);     // S^T_t  = K_t Q^T
+        mma_k64(tm + AT, smem_u32(sV) + t * 16384, smem_u32(sDO), IDESC_S);   // dP^T_t = V_t dO^T
+        tc_commit(&bars[1]);
+      }
+      __syncwarp();
     }
     sync.wait();
     const int jkey = t * 128 + r;
@@ -371,11 +396,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       oper_store16(sB, r, c * 16, dst);
     }
     attn_handoff();
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
-      mma_k192(tm + 2 * AT, smem_u32(sA), smem_u32(sDO), IDESC_O);           // dV_t = P~^T_t dO
-      mma_k192(tm + 2 * AT + AD, smem_u32(sB), smem_u32(sQ), IDESC_O);       // dK_t = dS^T_t Q
-      tc_commit(&bars[1]);
+      if (elect_one()) {
+        mma_k192(tm + 2 * AT, smem_u32(sA), smem_u32(sDO), IDESC_O);           // dV_t = P~^T_t dO
+        mma_k192(tm + 2 * AT + AD, smem_u32(sB), smem_u32(sQ), IDESC_O);       // dK_t = dS^T_t Q
+        tc_commit(&bars[1]);
+      }
+      __syncwarp();
     }
     sync.wait();
 #pragma unroll
@@ -408,7 +436,7 @@ int pe_attn_fwd_tc(const void* qkv, int B, int H, unsigned drop_thresh, float dr
                    void* ctx, float* lse, cudaStream_t stream) {
   CUtensorMap tq;
   if (int rc = token_tmap(&tq, qkv, (long long)B * pe::AT, 3 * H * pe::AD)) return rc;
-  const size_t smem = 3 * pe::TILE_B + 8192 + 2 * pe::OPER_B + 256 * 4 + 64 + 1024;
+  const size_t smem = 3 * pe::TILE_B + 8192 + 2 * pe::OPER_B + 512 * 4 + 64 + 1024;
   static bool attr = false;
   if (!attr) {
     if (cudaFuncSetAttribute(pe::attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
@@ -416,7 +444,7 @@ int pe_attn_fwd_tc(const void* qkv, int B, int H, unsigned drop_thresh, float dr
       return PE_ERR_LAUNCH;
     attr = true;
   }
-  pe::attn_fwd_tc_kernel<<<dim3(H, B), 256, smem, stream>>>(tq, H, drop_thresh, drop_scale, seed,
+  pe::attn_fwd_tc_kernel<<<dim3(H, B), pe::AFW_THREADS, smem, stream>>>(tq, H, drop_thresh, drop_scale, seed,
                                                             (__nv_bfloat16*)ctx, lse);
   return cudaGetLastError() == cudaSuccess ? PE_OK : PE_ERR_LAUNCH;
 }
