@@ -66,6 +66,9 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile) {
 // Persistent, warp-specialised tile engine: every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the smem
 // operand ring and the two TMEM accumulator stages are shared by consecutive tiles, so the epilogue of tile i overlaps
 // the TMA + MMA main loop of tile i + 1.
+// MODE is a compile-time copy of p.mode: the producer / MMA warps are single instruction streams whose per-k-block
+// latency bounds narrow tiles, so their loops must not carry the other modes' branches.
+template <int MODE>
 __global__ void __launch_bounds__(kNumThreads, 1)
 tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_a2,
                const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_out,
@@ -97,7 +100,7 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
-    if (p.mode == 1 && p.c2_chunks > 0) tma_prefetch_desc(&tma_a2);
+    if (MODE == 1 && p.c2_chunks > 0) tma_prefetch_desc(&tma_a2);
     if (p.out_tma & 1) tma_prefetch_desc(&tma_out);
     if (p.out_tma & 2) tma_prefetch_desc(&tma_out2);
   }
@@ -134,10 +137,10 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const int kb_begin = tc.tz * p.kb_per_split;
         const int kb_end = min(p.kb_total, kb_begin + p.kb_per_split);
         int m0 = 0, n0 = 0, img = 0, h0 = 0, w0 = 0;
-        if (p.mode == 0) {
+        if (MODE == 0) {
           m0 = tc.tx * kBlockM;
           n0 = tc.ty * p.block_n;
-        } else if (p.mode == 1) {
+        } else if (MODE == 1) {
           decode_conv_tile(p, tc.tx, img, h0, w0);
           n0 = tc.ty * p.block_n;
         } else {
@@ -148,10 +151,10 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         int c_tap = 0, c_chunk = 0;                    // conv fwd: current tap and 64-channel chunk
         int pb = 0, ph0 = 0, pw0 = 0;                  // conv wgrad: current 64-pixel patch
         int box_c[4], box_dh[4], box_dw[4];            // conv wgrad: channel / tap shift of each B box of this tile
-        if (p.mode == 1) {
+        if (MODE == 1) {
           c_tap = kb_begin / p.c1_chunks;              // kb_begin is 0 for convolutions (no split-K), kept general
           c_chunk = kb_begin - c_tap * p.c1_chunks;
-        } else if (p.mode == 2) {
+        } else if (MODE == 2) {
           decode_conv_tile(p, kb_begin, pb, ph0, pw0);
           const int cin = p.c1_chunks * 64;
 #pragma unroll
@@ -179,7 +182,7 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           if (leader) mbar_arrive_expect_tx(&full_bar[s], (uint32_t)p.tx_bytes);
           if (!leader) {
             // only the elected lane issues; the others just keep the per-k-block state below in step
-          } else if (p.mode == 0) {
+          } else if (MODE == 0) {
             const int k0 = kb * elems_per_row;
             if (!p.a_mn) {
               tma_load_2d(&tma_a, &full_bar[s], sa, k0, m0);
@@ -193,7 +196,7 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               for (int j = 0; j < p.b_boxes; ++j)
                 tma_load_2d(&tma_b, &full_bar[s], sb + j * (elems_per_row * kRowBytes), n0 + j * elems_per_row, k0);
             }
-          } else if (p.mode == 1) {
+          } else if (MODE == 1) {
             if (kb < main_kb) {
               const int kh = c_tap >= 6 ? 2 : (c_tap >= 3 ? 1 : 0);
               tma_load_4d(&tma_a, &full_bar[s], sa, c_chunk * 64, w0 + (c_tap - 3 * kh) - 1, h0 + kh - 1, img);
@@ -213,12 +216,12 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           }
           __syncwarp();
           // per-k-block state, advanced by every lane
-          if (p.mode == 1) {
+          if (MODE == 1) {
             if (kb < main_kb && ++c_chunk == p.c1_chunks) {
               c_chunk = 0;
               ++c_tap;
             }
-          } else if (p.mode == 2) {
+          } else if (MODE == 2) {
             pw0 += p.tw;  // next patch: row-major over (image, patch row, patch column)
             if (pw0 >= p.tiles_w * p.tw) {
               pw0 = 0;
@@ -266,13 +269,15 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.acc_stride;
         for (int i = 0; i < num_kb; ++i) {
-          const long long c2 = p.dbg ? clock64() : 0;
-          mbar_wait(&full_bar[stage], phase);
-          if (p.dbg) w_full += clock64() - c2;
-          tc_fence_after();
           const uint32_t sa = (smem_base + (uint32_t)stage * (uint32_t)stage_bytes) >> 4;
           const uint32_t sb = sa + (kATileBytes >> 4);
+          // Only the elected lane waits: the warp-level loop then has no divergent exit, which lets the compiler keep
+          // stage / phase / descriptor words in uniform registers instead of moving them there (R2UR) every k-block.
           if (elect_one()) {
+            const long long c2 = p.dbg ? clock64() : 0;
+            mbar_wait(&full_bar[stage], phase);
+            if (p.dbg) w_full += clock64() - c2;
+            tc_fence_after();
             if (p.kind == 0) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
@@ -321,7 +326,7 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       long long grow;
       bool row_ok;
       long long out_col_off = 0;
-      if (p.mode == 1) {
+      if (MODE == 1) {
         decode_conv_tile(p, tc.tx, img, h0, w0);
         n0 = tc.ty * p.block_n;
         const int h = h0 + r / p.tw, w = w0 + r % p.tw;
@@ -346,7 +351,7 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          if (p.mode == 1) {
+          if (MODE == 1) {
             if (reduce) tma_reduce_add_4d(map, buf, col, w0, h0 + (q * 32) / p.tw, img);
             else tma_store_4d(map, buf, col, w0, h0 + (q * 32) / p.tw, img);
           } else {
@@ -702,13 +707,16 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtens
                       (2 * stages + 4) * sizeof(uint64_t) + 16 + 2048;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(pe::tc_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
-        cudaSuccess)
+    if (cudaFuncSetAttribute(pe::tc_tile_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(pe::tc_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(pe::tc_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return PE_ERR_LAUNCH;
     attr_set = true;
   }
   const int grid = p.num_tiles < pe_host::num_sms() ? p.num_tiles : pe_host::num_sms();
-  pe::tc_tile_kernel<<<grid, pe::kNumThreads, smem, stream>>>(ta, ta2, tb, tout, tout2, p);
+  if (p.mode == 0) pe::tc_tile_kernel<0><<<grid, pe::kNumThreads, smem, stream>>>(ta, ta2, tb, tout, tout2, p);
+  else if (p.mode == 1) pe::tc_tile_kernel<1><<<grid, pe::kNumThreads, smem, stream>>>(ta, ta2, tb, tout, tout2, p);
+  else pe::tc_tile_kernel<2><<<grid, pe::kNumThreads, smem, stream>>>(ta, ta2, tb, tout, tout2, p);
   return cudaGetLastError() == cudaSuccess ? PE_OK : PE_ERR_LAUNCH;
 }
 
