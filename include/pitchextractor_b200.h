@@ -161,10 +161,11 @@ int pe_bn_eval_params(const float* gamma, const float* beta, const float* runnin
                       float eps, float* scale, float* shift, float* mean, float* rstd, int C, pe_stream_t stream);
 /* y = Dropout(MaxPool2d((1,k))(LeakyReLU(x*scale + shift))) (model.py:36-41,149-153; scale == NULL: pure max-pool,
  * model.py:45-49).  x bf16 [rows][W][C]; output pixel (row, wo) written at out + (row*Wo+wo)*ld_out + c_off, and/or
- * in the sequence layout out_seq[row][c*Wo + wo] (model.py:93,112). */
+ * in the sequence layout out_seq[row][c*Wo + wo] (model.py:93,112).  argmax_out (optional, uint8 [rows][Wo][C], k <= 255):
+ * position of the (first) maximum inside each window, for pe_maxpool_bwd_add. */
 int pe_bn_act_pool_fwd(const void* x, long long rows, int W, int C, int k, const float* scale, const float* shift,
                        float slope, unsigned drop_thresh, float drop_scale, unsigned long long seed, void* out,
-                       long long ld_out, int c_off, void* out_seq, pe_stream_t stream);
+                       long long ld_out, int c_off, void* out_seq, void* argmax_out, pe_stream_t stream);
 /* backward of the block above through dropout, max-pool, LeakyReLU and the BatchNorm batch statistics:
  * dx bf16 [rows][W][C]; dgamma / dbeta accumulated (+=); sums is a zeroed fp64 [2][C] scratch, coef an fp32 [2][C]
  * scratch; k in {1, 2, 4}.  sums_ready != 0: the reduction pass already ran (fused in the producing convolution's
@@ -174,9 +175,10 @@ int pe_bn_act_pool_bwd(const void* x, long long rows, int W, int C, int k, const
                        unsigned long long seed, const void* dout, long long ld_dout, int c_off, const void* dout_seq,
                        double* sums, int sums_ready, float* coef, float* dgamma, float* dbeta, void* dx,
                        pe_stream_t stream);
-/* backward of the auxiliary max-pools: dx[argmax of each window] += dout */
-int pe_maxpool_bwd_add(const void* x, long long rows, int W, int C, int k, const void* dout, long long ld_dout,
-                       int c_off, void* dx, pe_stream_t stream);
+/* backward of the auxiliary max-pools: dx[argmax of each window] += dout.  With argmax (saved by the forward pass) x is
+ * not read; otherwise the arg-max is recomputed from x. */
+int pe_maxpool_bwd_add(const void* x, const void* argmax, long long rows, int W, int C, int k, const void* dout,
+                       long long ld_dout, int c_off, void* dx, pe_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Sequence model passes (model.py:178-256; torch/nn/modules/transformer.py:961-982).

@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(256)
 bn_act_pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, PoolGeom g, const float* __restrict__ scale,
                        const float* __restrict__ shift, float slope, unsigned drop_thresh, float drop_scale,
                        unsigned long long seed, __nv_bfloat16* __restrict__ out, long long ld_out, int c_off,
-                       __nv_bfloat16* __restrict__ out_seq) {
+                       __nv_bfloat16* __restrict__ out_seq, unsigned char* __restrict__ argmax_out) {
   seed += pe_step_salt;
   const int cg = g.C >> 3;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -312,8 +312,12 @@ bn_act_pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, PoolGeom g, const fl
     }
   }
   float best[8];
+  int jbest[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) best[i] = -INFINITY;
+  for (int i = 0; i < 8; ++i) {
+    best[i] = -INFINITY;
+    jbest[i] = 0;
+  }
   const __nv_bfloat16* xp = x + ((row * g.W + (long long)wo * g.k) * g.C + tx * 8);
   for (int j = 0; j < g.k; ++j) {
     float v[8];
@@ -325,8 +329,16 @@ bn_act_pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, PoolGeom g, const fl
         z = fmaf(z, sc[i], sh[i]);
         z = z > 0.f ? z : z * slope;
       }
-      best[i] = fmaxf(best[i], z);
+      if (z > best[i]) {  // first maximum wins, as in the backward routing
+        best[i] = z;
+        jbest[i] = j;
+      }
     }
+  }
+  if (argmax_out) {
+    const uint32_t lo = (uint32_t)jbest[0] | ((uint32_t)jbest[1] << 8) | ((uint32_t)jbest[2] << 16) | ((uint32_t)jbest[3] << 24);
+    const uint32_t hi = (uint32_t)jbest[4] | ((uint32_t)jbest[5] << 8) | ((uint32_t)jbest[6] << 16) | ((uint32_t)jbest[7] << 24);
+    *reinterpret_cast<uint2*>(argmax_out + (row * g.Wo + wo) * g.C + tx * 8) = make_uint2(lo, hi);
   }
   if (drop_thresh) {
     const unsigned long long e0 = (unsigned long long)((row * g.Wo + wo) * g.C + tx * 8);
@@ -746,6 +758,29 @@ maxpool_bwd_add_kernel(const __nv_bfloat16* __restrict__ x, PoolGeom g, const __
   }
 }
 
+// same with the arg-max positions saved by the forward pass (one byte per output element): x is not read again
+__global__ void __launch_bounds__(256)
+maxpool_bwd_idx_kernel(const unsigned char* __restrict__ argmax, PoolGeom g, const __nv_bfloat16* __restrict__ dout,
+                       long long ld_dout, int c_off, __nv_bfloat16* __restrict__ dx) {
+  const int cg = g.C >> 3;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = g.rows * g.Wo * cg;
+  if (idx >= total) return;
+  const int tx = (int)(idx % cg);
+  const int wo = (int)((idx / cg) % g.Wo);
+  const long long row = idx / ((long long)cg * g.Wo);
+  const uint2 jj = *reinterpret_cast<const uint2*>(argmax + (row * g.Wo + wo) * g.C + tx * 8);
+  float d[8];
+  ld8(dout + (row * g.Wo + wo) * ld_dout + c_off + tx * 8, d);
+  const long long base = (row * g.W + (long long)wo * g.k) * g.C + tx * 8;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int j = (int)(((i < 4 ? jj.x : jj.y) >> (8 * (i & 3))) & 0xFFu);
+    __nv_bfloat16* p = dx + base + (long long)j * g.C + i;
+    *p = __float2bfloat16(__bfloat162float(*p) + d[i]);
+  }
+}
+
 }  // namespace pe
 
 // =================================================================================================
@@ -823,13 +858,14 @@ extern "C" int pe_bn_eval_params(const float* gamma, const float* beta, const fl
 extern "C" int pe_bn_act_pool_fwd(const void* x, long long rows, int W, int C, int k, const float* scale,
                                   const float* shift, float slope, unsigned drop_thresh, float drop_scale,
                                   unsigned long long seed, void* out, long long ld_out, int c_off, void* out_seq,
-                                  pe_stream_t stream) {
+                                  void* argmax_out, pe_stream_t stream) {
   if (int rc = pe_host::check_arch()) return rc;
   if (!x || rows <= 0 || W <= 0 || !chan_ok(C) || k <= 0 || k > W || (!out && !out_seq) || ((scale == 0) != (shift == 0)))
     return PE_ERR_BAD_SHAPE;
   PoolGeom g{rows, W, C, k, W / k};
   const long long total = rows * g.Wo * (C / 8);
-  if ((k == 1 || k == 2 || k == 4) && rows * g.Wo < (1ll << 31) - (1ll << 24)) {
+  if (argmax_out && k > 255) return PE_ERR_BAD_SHAPE;
+  if (!argmax_out && (k == 1 || k == 2 || k == 4) && rows * g.Wo < (1ll << 31) - (1ll << 24)) {
     const int cg = C / 8, ry = 256 / cg, threads = cg * ry;
     const long long nwin = rows * g.Wo;
     const bool extra = drop_thresh != 0 || out_seq != nullptr;
@@ -853,7 +889,7 @@ extern "C" int pe_bn_act_pool_fwd(const void* x, long long rows, int W, int C, i
   }
   bn_act_pool_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, PE_ST(stream)>>>(
       (const __nv_bfloat16*)x, g, scale, shift, slope, drop_thresh, drop_scale, seed, (__nv_bfloat16*)out, ld_out, c_off,
-      (__nv_bfloat16*)out_seq);
+      (__nv_bfloat16*)out_seq, (unsigned char*)argmax_out);
   return PE_LAUNCH_RC();
 }
 
@@ -910,12 +946,17 @@ extern "C" int pe_bn_act_pool_bwd(const void* x, long long rows, int W, int C, i
   return PE_LAUNCH_RC();
 }
 
-extern "C" int pe_maxpool_bwd_add(const void* x, long long rows, int W, int C, int k, const void* dout,
-                                  long long ld_dout, int c_off, void* dx, pe_stream_t stream) {
+extern "C" int pe_maxpool_bwd_add(const void* x, const void* argmax, long long rows, int W, int C, int k,
+                                  const void* dout, long long ld_dout, int c_off, void* dx, pe_stream_t stream) {
   if (int rc = pe_host::check_arch()) return rc;
-  if (!x || !dout || !dx || rows <= 0 || W <= 0 || !chan_ok(C) || k <= 0 || k > W) return PE_ERR_BAD_SHAPE;
+  if ((!x && !argmax) || !dout || !dx || rows <= 0 || W <= 0 || !chan_ok(C) || k <= 0 || k > W) return PE_ERR_BAD_SHAPE;
   PoolGeom g{rows, W, C, k, W / k};
   const long long total = rows * g.Wo * (C / 8);
+  if (argmax) {
+    maxpool_bwd_idx_kernel<<<(unsigned)((total + 255) / 256), 256, 0, PE_ST(stream)>>>(
+        (const unsigned char*)argmax, g, (const __nv_bfloat16*)dout, ld_dout, c_off, (__nv_bfloat16*)dx);
+    return PE_LAUNCH_RC();
+  }
   maxpool_bwd_add_kernel<<<(unsigned)((total + 255) / 256), 256, 0, PE_ST(stream)>>>(
       (const __nv_bfloat16*)x, g, (const __nv_bfloat16*)dout, ld_dout, c_off, (__nv_bfloat16*)dx);
   return PE_LAUNCH_RC();

@@ -199,10 +199,12 @@ class Engine:
                  ptr(sc), ptr(sh), ptr(mu), ptr(rs), c_int(C), stream())
         return sc, sh, mu, rs
 
-    def _act_pool(self, x, rows, W, C, k, aff, out=None, ld_out=0, c_off=0, out_seq=None, drop=(0, 1.0), seed=0):
+    def _act_pool(self, x, rows, W, C, k, aff, out=None, ld_out=0, c_off=0, out_seq=None, drop=(0, 1.0), seed=0,
+                  argmax=None):
         sc, sh = (aff[0], aff[1]) if aff is not None else (None, None)
         call("pe_bn_act_pool_fwd", ptr(x), c_ll(rows), c_int(W), c_int(C), c_int(k), ptr(sc), ptr(sh), c_f(self.slope),
-             c_u(drop[0]), c_f(drop[1]), c_ull(seed), ptr(out), c_ll(ld_out), c_int(c_off), ptr(out_seq), stream())
+             c_u(drop[0]), c_f(drop[1]), c_ull(seed), ptr(out), c_ll(ld_out), c_int(c_off), ptr(out_seq), ptr(argmax),
+             stream())
 
     def _bn_bwd_fused(self, prefix, x):
         """Epilogue arguments that make a convolution accumulate the first pass of this BN's backward (sum g, sum g*x)
@@ -282,9 +284,10 @@ class Engine:
         aff = self._bn_prepare("pool_block.0", R, BT * 10, 256, training, stats_fused=True)
         self._act_pool(R, BT, 10, 256, 4, aff, out=CAT, ld_out=640, c_off=384, out_seq=SEQC,
                        drop=self._drop(self.p_trunk, training), seed=self._seed(1))
-        self._act_pool(self._bufs["R0"], BT, 80, 64, 40, None, out=CAT, ld_out=640, c_off=0)
-        self._act_pool(self._bufs["R1"], BT, 40, 128, 20, None, out=CAT, ld_out=640, c_off=64)
-        self._act_pool(self._bufs["R2"], BT, 20, 192, 10, None, out=CAT, ld_out=640, c_off=192)
+        # (the arg-max positions are kept, one byte each, so that the backward pass need not read R_k again)
+        for kk, (Wk, Ck, kw, off) in enumerate(((80, 64, 40, 0), (40, 128, 20, 64), (20, 192, 10, 192))):
+            self._act_pool(self._bufs["R%d" % kk], BT, Wk, Ck, kw, None, out=CAT, ld_out=640, c_off=off,
+                           argmax=self.buf("AUXIDX%d" % kk, (BT, 2, Ck), torch.uint8))
         # ---- detector_conv (model.py:52-57): 1x1 conv == GEMM over the 640 concatenated channels
         DD = self.buf("DD", (BT * 2, 256))
         ops.gemm(CAT.view(BT * 2, 640), self.mat("detector_conv.0.weight", 256, 640), DD, BT * 2, 256, 640,
@@ -586,7 +589,8 @@ class Engine:
             dRin = self.buf("dR%d" % (i - 1), (B, T, width * 2, cin))
             self._act_pool_bwd(r + ".pre_conv.0", Rin, BT, width * 2, cin, 2, dRin, dout=dP, ld_dout=cin)
             k_aux, c_off = aux[i - 1]
-            call("pe_maxpool_bwd_add", ptr(Rin), c_ll(BT), c_int(width * 2), c_int(cin), c_int(k_aux), ptr(dCAT),
+            call("pe_maxpool_bwd_add", None, ptr(bufs["AUXIDX%d" % (i - 1)]), c_ll(BT), c_int(width * 2), c_int(cin),
+                 c_int(k_aux), ptr(dCAT),
                  c_ll(640), c_int(c_off), ptr(dRin), stream())
             dR = dRin
             width *= 2

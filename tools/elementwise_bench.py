@@ -26,7 +26,7 @@ for (W, C, k, drop) in ((80, 64, 1, 0), (80, 64, 2, 0), (40, 128, 1, 0), (40, 12
     dg = torch.zeros(C, device="cuda"); db = torch.zeros(C, device="cuda")
     thr, scl = (32768, 2.0) if drop else (0, 1.0)
     f = lambda i: call("pe_bn_act_pool_fwd", ptr(xs[i]), c_ll(rows), c_int(W), c_int(C), c_int(k), ptr(sc), ptr(sh), c_f(0.01), c_u(thr), c_f(scl),
-                       c_ull(7), ptr(outs[i]), c_ll(C), c_int(0), None, stream())
+                       c_ull(7), ptr(outs[i]), c_ll(C), c_int(0), None, None, stream())
     us_f = timeit(f)
     bytes_f = rows * (W + Wo) * C * 2
     def bwd(i, ready):
