@@ -36,6 +36,7 @@ struct TcParams {
   int H, W, tw, th, tiles_w, tiles_h;
   int c1_chunks, c2_chunks;
   int taps;  // wgrad: 9 or 1
+  int kps;           // 64-wide k-blocks per smem stage (1 or 2): narrow tiles amortise the barrier round trip over two
   int commit_group;  // 1, 2 or 4: k-blocks per tcgen05.commit on the smem ring (p.stages is a multiple of it)
   int out_tma;  // bit 0 / 1: ep.out / ep.out2 are written with TMA tensor stores from the staging blocks
   long long* dbg;  // optional [gridDim.x][8] counters (tuning): mma loop cycles, mma wait-full, mma wait-tmem, tma wait-empty,
@@ -66,9 +67,9 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile) {
 // Persistent, warp-specialised tile engine: every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the smem
 // operand ring and the two TMEM accumulator stages are shared by consecutive tiles, so the epilogue of tile i overlaps
 // the TMA + MMA main loop of tile i + 1.
-// MODE is a compile-time copy of p.mode: the producer / MMA warps are single instruction streams whose per-k-block
+// MODE and KPS are compile-time copies of p.mode and p.kps: the producer / MMA warps are single instruction streams whose per-k-block
 // latency bounds narrow tiles, so their loops must not carry the other modes' branches.
-template <int MODE>
+template <int MODE, int KPS>
 __global__ void __launch_bounds__(kNumThreads, 1)
 tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_a2,
                const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_out,
@@ -78,7 +79,8 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
   const int b_tile_bytes = p.block_n * kRowBytes;
-  const int stage_bytes = kATileBytes + b_tile_bytes;
+  const int sub_bytes = kATileBytes + b_tile_bytes;  // one 64-wide k-block of both operands
+  const int stage_bytes = KPS * sub_bytes;
   // layout: operand ring | epilogue staging (8 warps x 2 blocks of 32 rows x 64 B) | barriers | TMEM slot | column statistics
   uint8_t* staging = smem + (size_t)p.stages * stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kNumEpiWarps * kStagingBytes);
@@ -167,8 +169,9 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           }
         }
         const int main_kb = 9 * p.c1_chunks;
-        for (int kb = kb_begin; kb < kb_end; ++kb) {
+        for (int kb0 = kb_begin; kb0 < kb_end; kb0 += KPS) {
           const int s = stage;
+          const int nsub = min(KPS, kb_end - kb0);
           const long long c0 = p.dbg ? clock64() : 0;
           mbar_wait(&empty_bar[s | (p.commit_group - 1)], phase ^ 1u);  // slots are released per commit group
           if (++stage == p.stages) {
@@ -176,10 +179,12 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             phase ^= 1u;
           }
           if (p.dbg) w_empty += clock64() - c0;
-          uint8_t* sa = smem + (size_t)s * stage_bytes;
-          uint8_t* sb = sa + kATileBytes;
           const bool leader = elect_one();
-          if (leader) mbar_arrive_expect_tx(&full_bar[s], (uint32_t)p.tx_bytes);
+          if (leader) mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(nsub * p.tx_bytes));
+          for (int sub = 0; sub < nsub; ++sub) {
+          const int kb = kb0 + sub;
+          uint8_t* sa = smem + (size_t)s * stage_bytes + (size_t)sub * sub_bytes;
+          uint8_t* sb = sa + kATileBytes;
           if (!leader) {
             // only the elected lane issues; the others just keep the per-k-block state below in step
           } else if (MODE == 0) {
@@ -214,7 +219,6 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               if (j < p.b_boxes)
                 tma_load_4d(&tma_b, &full_bar[s], sb + j * (64 * kRowBytes), box_c[j], pw0 + box_dw[j], ph0 + box_dh[j], pb);
           }
-          __syncwarp();
           // per-k-block state, advanced by every lane
           if (MODE == 1) {
             if (kb < main_kb && ++c_chunk == p.c1_chunks) {
@@ -232,6 +236,8 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               }
             }
           }
+          }  // sub
+          __syncwarp();
         }
       }
       if (p.dbg && lane == 0) p.dbg[blockIdx.x * 16 + 3] = w_empty;
@@ -268,9 +274,9 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (p.dbg) w_tmem += clock64() - c1;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.acc_stride;
-        for (int i = 0; i < num_kb; ++i) {
-          const uint32_t sa = (smem_base + (uint32_t)stage * (uint32_t)stage_bytes) >> 4;
-          const uint32_t sb = sa + (kATileBytes >> 4);
+        for (int i0 = 0; i0 < num_kb; i0 += KPS) {
+          const int nsub = min(KPS, num_kb - i0);
+          const uint32_t s0 = (smem_base + (uint32_t)stage * (uint32_t)stage_bytes) >> 4;
           // Only the elected lane waits: the warp-level loop then has no divergent exit, which lets the compiler keep
           // stage / phase / descriptor words in uniform registers instead of moving them there (R2UR) every k-block.
           if (elect_one()) {
@@ -278,21 +284,26 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             mbar_wait(&full_bar[stage], phase);
             if (p.dbg) w_full += clock64() - c2;
             tc_fence_after();
-            if (p.kind == 0) {
+            for (int sub = 0; sub < nsub; ++sub) {
+              const uint32_t sa = s0 + (uint32_t)sub * ((uint32_t)sub_bytes >> 4);
+              const uint32_t sb = sa + (kATileBytes >> 4);
+              const int i = i0 + sub;
+              if (p.kind == 0) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                tc_mma_bf16(d_tmem, da0 | (uint64_t)(sa + k * a_inc), db0 | (uint64_t)(sb + k * b_inc), idesc,
-                            (i > 0 || k > 0) ? 1u : 0u);
-            } else {
+                for (int k = 0; k < 4; ++k)
+                  tc_mma_bf16(d_tmem, da0 | (uint64_t)(sa + k * a_inc), db0 | (uint64_t)(sb + k * b_inc), idesc,
+                              (i > 0 || k > 0) ? 1u : 0u);
+              } else {
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                tc_mma_tf32(d_tmem, da0 | (uint64_t)(sa + k * a_inc), db0 | (uint64_t)(sb + k * b_inc), idesc,
-                            (i > 0 || k > 0) ? 1u : 0u);
+                for (int k = 0; k < 4; ++k)
+                  tc_mma_tf32(d_tmem, da0 | (uint64_t)(sa + k * a_inc), db0 | (uint64_t)(sb + k * b_inc), idesc,
+                              (i > 0 || k > 0) ? 1u : 0u);
+              }
             }
             // tcgen05.commit costs the issuing thread ~200 cycles: narrow tiles (short MMAs) release their slots in
             // groups -- the commit on the group's last slot covers every earlier MMA, the producer waits on that slot
             if ((stage & gmask) == gmask) tc_commit(&empty_bar[stage]);
-            if (i == num_kb - 1) tc_commit(&tmem_full_bar[acc]);
+            if (i0 + nsub >= num_kb) tc_commit(&tmem_full_bar[acc]);
           }
           __syncwarp();
           if (++stage == p.stages) {
@@ -663,7 +674,15 @@ static bool out_tmap(CUtensorMap* m, const TcParams& p, void* base, long long ld
 
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, TcParams& p, dim3 tiles,
                      cudaStream_t stream, int conv_B = 0) {
-  const int stage_bytes = pe::kATileBytes + p.block_n * pe::kRowBytes;
+  const int sub_bytes = pe::kATileBytes + p.block_n * pe::kRowBytes;
+  // narrow tiles (short MMAs) are bound by the per-stage barrier round trip of the producer / MMA threads: two k-blocks
+  // per stage halve it (wide tiles keep one: two 96 KB stages would not cover the TMA latency)
+  p.kps = (p.block_n <= 128 && p.mode != 2) ? 2 : 1;
+  if (const char* env = getenv("PE_TC_KPS")) {  // tuning knob
+    const int v = atoi(env);
+    if (v == 1 || (v == 2 && 2 * 2 * sub_bytes <= 192 * 1024)) p.kps = v;
+  }
+  const int stage_bytes = p.kps * sub_bytes;
   int stages = (192 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;
   if (const char* env = getenv("PE_TC_STAGES")) {  // tuning knob
@@ -673,8 +692,9 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtens
   if (stages < 2) return PE_ERR_BAD_SHAPE;
   // narrow tiles: MMAs are short, so the per-k-block commit would dominate the issue thread
   p.commit_group = 1;
-  if (p.block_n <= 128 && stages >= 4) p.commit_group = 2;
-  if (p.block_n <= 64 && stages >= 8) p.commit_group = 4;
+  if (p.kps == 1 && p.block_n <= 128 && stages >= 4) p.commit_group = 2;
+  if (p.kps == 1 && p.block_n <= 64 && stages >= 8) p.commit_group = 4;
+  if (p.kps == 2 && p.block_n <= 64 && stages >= 4) p.commit_group = 2;
   if (const char* env = getenv("PE_TC_COMMIT_GROUP")) {  // tuning knob
     const int v = atoi(env);
     if ((v == 1 || v == 2 || v == 4) && stages >= 2 * v) p.commit_group = v;
@@ -682,7 +702,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtens
   stages -= stages % p.commit_group;
   p.stages = stages;
   p.tmem_cols = pow2_cols(2 * p.block_n);
-  p.tx_bytes = p.mode == 2 ? (p.a_boxes + p.b_boxes) * 64 * pe::kRowBytes : stage_bytes;
+  p.tx_bytes = p.mode == 2 ? (p.a_boxes + p.b_boxes) * 64 * pe::kRowBytes : sub_bytes;  // per k-block
   p.acc_stride = p.tmem_cols / 2;
   p.tiles_x = (int)tiles.x;
   p.tiles_y = (int)tiles.y;
@@ -707,16 +727,23 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtens
                       (2 * stages + 4) * sizeof(uint64_t) + 16 + 2048;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(pe::tc_tile_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(pe::tc_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(pe::tc_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+    const int sz = 227 * 1024;
+    if (cudaFuncSetAttribute(pe::tc_tile_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz) != cudaSuccess ||
+        cudaFuncSetAttribute(pe::tc_tile_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz) != cudaSuccess ||
+        cudaFuncSetAttribute(pe::tc_tile_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz) != cudaSuccess ||
+        cudaFuncSetAttribute(pe::tc_tile_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz) != cudaSuccess ||
+        cudaFuncSetAttribute(pe::tc_tile_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz) != cudaSuccess)
       return PE_ERR_LAUNCH;
     attr_set = true;
   }
   const int grid = p.num_tiles < pe_host::num_sms() ? p.num_tiles : pe_host::num_sms();
-  if (p.mode == 0) pe::tc_tile_kernel<0><<<grid, pe::kNumThreads, smem, stream>>>(ta, ta2, tb, tout, tout2, p);
-  else if (p.mode == 1) pe::tc_tile_kernel<1><<<grid, pe::kNumThreads, smem, stream>>>(ta, ta2, tb, tout, tout2, p);
-  else pe::tc_tile_kernel<2><<<grid, pe::kNumThreads, smem, stream>>>(ta, ta2, tb, tout, tout2, p);
+#define PE_TC_LAUNCH(M, K) pe::tc_tile_kernel<M, K><<<grid, pe::kNumThreads, smem, stream>>>(ta, ta2, tb, tout, tout2, p)
+  if (p.mode == 0 && p.kps == 1) PE_TC_LAUNCH(0, 1);
+  else if (p.mode == 0) PE_TC_LAUNCH(0, 2);
+  else if (p.mode == 1 && p.kps == 1) PE_TC_LAUNCH(1, 1);
+  else if (p.mode == 1) PE_TC_LAUNCH(1, 2);
+  else PE_TC_LAUNCH(2, 1);
+#undef PE_TC_LAUNCH
   return cudaGetLastError() == cudaSuccess ? PE_OK : PE_ERR_LAUNCH;
 }
 
