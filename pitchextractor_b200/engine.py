@@ -9,6 +9,7 @@ Data layout in HBM
     checkpointing (reference trainer.py:227-233) unnecessary.
   * dropout masks are never stored: Philox keyed by (site seed, element index) is replayed in the backward kernels.
 """
+import contextlib
 import ctypes
 import os
 
@@ -72,6 +73,7 @@ class Engine:
         self._bufs = {}
         self._fwd_token = 0
         self.on_grads_ready = None  # callback(tag) for the data-parallel gradient reducer
+        self._side_stream = None
         self.reducer = None         # GradReducer: begin_step() / ready(tag) / wait() bracket every training step
         # Training steps are captured into a CUDA graph after two eager warm-up steps and replayed from then on
         # (~270 launches per step; eagerly the host needs ~10 ms to enqueue them).  PE_CUDA_GRAPH=0 disables it.
@@ -298,12 +300,36 @@ class Engine:
                        seed=self._seed(2))
         # ---- sequence models (model.py:94,113)
         if self.seq_type == "transformer":
-            Hc = self._transformer_fwd("sequence_classifier", "c", SEQC, B, T, training, 16)
-            Hd = self._transformer_fwd("sequence_detector", "d", SEQD, B, T, training, 64)
+            # the two encoder stacks are independent: the detector's runs on a second stream, so that the tail of one
+            # stack's kernels (partial last wave, epilogue drain) is filled by the other's
+            with self._forked() as side:
+                with torch.cuda.stream(side):
+                    Hd = self._transformer_fwd("sequence_detector", "d", SEQD, B, T, training, 64)
+                Hc = self._transformer_fwd("sequence_classifier", "c", SEQC, B, T, training, 16)
         else:
             Hc, Hd = self._bilstm_fwd(SEQC, SEQD, B, T, training)
         self._Hc, self._Hd = Hc, Hd
         return Hc, Hd
+
+    @contextlib.contextmanager
+    def _forked(self):
+        """A second stream that starts after everything enqueued so far on the current stream and is joined back on
+        exit (under CUDA-graph capture this becomes a parallel branch of the graph)."""
+        if os.environ.get("PE_TWO_STREAMS", "1") == "0":
+            yield torch.cuda.current_stream()
+            return
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=self.device)
+        main, side = torch.cuda.current_stream(), self._side_stream
+        ev = torch.cuda.Event()
+        ev.record(main)
+        side.wait_event(ev)
+        try:
+            yield side
+        finally:
+            ev2 = torch.cuda.Event()
+            ev2.record(side)
+            main.wait_event(ev2)
 
     def _transformer_fwd(self, prefix, tag, X, B, T, training, site0):
         V, W16 = self.view, self.bview
@@ -545,9 +571,11 @@ class Engine:
         W16, g, bufs = self.bview, self.gview, self._bufs
         notify = self.on_grads_ready or (self.reducer.ready if self.reducer is not None else (lambda tag: None))
         if self.seq_type == "transformer":
-            dSEQD = self._transformer_bwd("sequence_detector", "d", bufs["SEQD"], dHd, B, T, 64)
+            with self._forked() as side:
+                with torch.cuda.stream(side):
+                    dSEQD = self._transformer_bwd("sequence_detector", "d", bufs["SEQD"], dHd, B, T, 64)
+                dSEQC = self._transformer_bwd("sequence_classifier", "c", bufs["SEQC"], dHc, B, T, 16)
             notify("sequence_detector+heads")
-            dSEQC = self._transformer_bwd("sequence_classifier", "c", bufs["SEQC"], dHc, B, T, 16)
             notify("sequence_classifier")
         else:
             dSEQC, dSEQD = self._bilstm_bwd(dHc, dHd, B, T)

@@ -198,7 +198,8 @@ def test_cuda_graph_segments_with_reducer(built_lib):
     eager, _ = run(False)
     graphed, eng = run(True)
     ent = [e for e in eng._graphs.values() if "segments" in e]
-    assert len(ent) == 1 and len(ent[0]["segments"]) == 3  # one graph per gradient bucket (the trunk's is the last)
+    # the two encoder stacks run concurrently, so their buckets complete at the same cut; the trunk's is the last
+    assert len(ent) == 1 and len(ent[0]["segments"]) == 2
     per_step = ["begin", "sequence_detector+heads", "sequence_classifier", "trunk", "wait"]
     assert eng.reducer.calls == per_step * 5, eng.reducer.calls
     for a, b in zip(eager, graphed):
