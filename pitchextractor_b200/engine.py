@@ -74,6 +74,7 @@ class Engine:
         self._fwd_token = 0
         self.on_grads_ready = None  # callback(tag) for the data-parallel gradient reducer
         self._side_stream = None
+        self._side_pending = False
         self.reducer = None         # GradReducer: begin_step() / ready(tag) / wait() bracket every training step
         # Training steps are captured into a CUDA graph after two eager warm-up steps and replayed from then on
         # (~270 launches per step; eagerly the host needs ~10 ms to enqueue them).  PE_CUDA_GRAPH=0 disables it.
@@ -312,9 +313,9 @@ class Engine:
         return Hc, Hd
 
     @contextlib.contextmanager
-    def _forked(self):
-        """A second stream that starts after everything enqueued so far on the current stream and is joined back on
-        exit (under CUDA-graph capture this becomes a parallel branch of the graph)."""
+    def _forked(self, join=True):
+        """A second stream that starts after everything enqueued so far on the current stream; joined back on exit, or
+        (join=False) at the next _join_side().  Under CUDA-graph capture this becomes a parallel branch of the graph."""
         if os.environ.get("PE_TWO_STREAMS", "1") == "0":
             yield torch.cuda.current_stream()
             return
@@ -324,12 +325,19 @@ class Engine:
         ev = torch.cuda.Event()
         ev.record(main)
         side.wait_event(ev)
+        self._side_pending = True
         try:
             yield side
         finally:
-            ev2 = torch.cuda.Event()
-            ev2.record(side)
-            main.wait_event(ev2)
+            if join:
+                self._join_side()
+
+    def _join_side(self):
+        if self._side_pending:
+            ev = torch.cuda.Event()
+            ev.record(self._side_stream)
+            torch.cuda.current_stream().wait_event(ev)
+            self._side_pending = False
 
     def _transformer_fwd(self, prefix, tag, X, B, T, training, site0):
         V, W16 = self.view, self.bview
@@ -603,15 +611,21 @@ class Engine:
             gA = self.mat(r + ".conv.0.weight", cout, 9 * cin, "grad")
             # conv B + shortcut
             dV = self.buf("dV%d" % i, (B, T, width, cout))
+            # weight gradients are off the critical path (nothing reads them before the optimizer): they go to the
+            # second stream and fill the SMs the data-gradient chain leaves idle
+            with self._forked(join=False) as side:
+                with torch.cuda.stream(side):
+                    ops.conv_wgrad(dR, Vv, gB, taps=9)
+                    ops.conv_wgrad(dR, P, gS, taps=1)
             ops.conv3x3(dR, self.wops[r + ".B.dgrad"], dV, **self._bn_bwd_fused(r + ".conv.1", U))
-            ops.conv_wgrad(dR, Vv, gB, taps=9)
-            ops.conv_wgrad(dR, P, gS, taps=1)
             dU = self.buf("dU%d" % i, (B, T, width, cout))
             self._act_pool_bwd(r + ".conv.1", U, BT, width, cout, 1, dU, dout=dV, ld_dout=cout, sums_ready=True)
             # conv A (+ shortcut data gradient fused as extra K columns)
             dP = self.buf("dP%d" % i, (B, T, width, cin))
+            with self._forked(join=False) as side:
+                with torch.cuda.stream(side):
+                    ops.conv_wgrad(dU, P, gA, taps=9)
             ops.conv3x3(dU, self.wops[r + ".A.dgrad"], dP, x2=dR)
-            ops.conv_wgrad(dU, P, gA, taps=9)
             # pre_conv BN/LReLU/pool backward -> gradient of the block input
             Rin = bufs["R%d" % (i - 1)]
             dRin = self.buf("dR%d" % (i - 1), (B, T, width * 2, cin))
@@ -624,13 +638,16 @@ class Engine:
             width *= 2
         # conv_block
         dZ1 = self.buf("dZ1", (B, T, 80, 64))
+        with self._forked(join=False) as side:
+            with torch.cuda.stream(side):
+                ops.conv_wgrad(dR, bufs["Z1"], self.mat("conv_block.3.weight", 64, 576, "grad"), taps=9)
         ops.conv3x3(dR, self.wops["conv_block.3.dgrad"], dZ1, **self._bn_bwd_fused("conv_block.1", bufs["Y1"]))
-        ops.conv_wgrad(dR, bufs["Z1"], self.mat("conv_block.3.weight", 64, 576, "grad"), taps=9)
         dY1 = self.buf("dY1", (B, T, 80, 64))
         self._act_pool_bwd("conv_block.1", bufs["Y1"], BT, 80, 64, 1, dY1, dout=dZ1, ld_dout=64, sums_ready=True)
         x = self._x
         call("pe_stem_conv_wgrad", ptr(x), c_ll(x.stride(0)), c_ll(x.stride(2)), c_ll(x.stride(3)), c_int(B), c_int(T),
              c_int(80), ptr(dY1), ptr(g["conv_block.0.weight"]), stream())
+        self._join_side()
         notify("trunk")
 
     # ------------------------------------------------------------------ public entry points
