@@ -72,7 +72,10 @@ typedef struct pe_epilogue {
   /* optional per-column reductions of the STORED value v over all rows (N <= 256), accumulated atomically in fp64:
    *   stats_mode 1: stats[0][n] += sum v,  stats[1][n] += sum v^2            (BatchNorm batch statistics)
    *   stats_mode 2: g = v * lrelu'(x*scale + shift); stats[0][n] += sum g, stats[1][n] += sum g*x
-   *                 (first pass of the BatchNorm backward; x = stats_x bf16 [M][N], the BN input) */
+   *                 (first pass of the BatchNorm backward; x = stats_x bf16 [M][N], the BN input)
+   *   stats_mode 3: the same through a MaxPool2d((1,2)) between the BN and this gradient (model.py:149-153):
+   *                 x = stats_x bf16 [2M][N]; row m owns x rows 2m, 2m+1 and routes g to the first maximum of
+   *                 lrelu(x*scale + shift) */
   double* stats;
   int stats_mode;
   const void* stats_x;

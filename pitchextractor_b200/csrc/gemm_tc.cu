@@ -532,6 +532,35 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               sa[j] = v;
               sb[j] = v * v;
             }
+          } else if (ep.stats_mode == 3) {
+            // the BatchNorm input is twice as wide as this gradient (MaxPool (1,2) in between): output pixel `grow`
+            // owns input pixels 2*grow and 2*grow+1; the gradient goes to the first maximum of the activated pair
+            const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(ep.stats_x) + grow * 2LL * p.N + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 u0 = make_uint4(0u, 0u, 0u, 0u), u1 = u0;
+              if (row_ok && colok) {
+                u0 = *reinterpret_cast<const uint4*>(xp + j);
+                u1 = *reinterpret_cast<const uint4*>(xp + p.N + j);
+              }
+              const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&u0);
+              const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&u1);
+#pragma unroll
+              for (int t = 0; t < 8; ++t) {
+                const float2 a2 = __bfloat1622float2(h0[t >> 1]), b2 = __bfloat1622float2(h1[t >> 1]);
+                const float x0 = (t & 1) ? a2.y : a2.x, x1 = (t & 1) ? b2.y : b2.x;
+                const float sc = __ldg(ep.stats_scale + min(col0 + j + t, p.N - 1));
+                const float sh = __ldg(ep.stats_shift + min(col0 + j + t, p.N - 1));
+                const float p0 = fmaf(x0, sc, sh), p1 = fmaf(x1, sc, sh);
+                const float z0 = p0 > 0.f ? p0 : p0 * ep.stats_slope, z1 = p1 > 0.f ? p1 : p1 * ep.stats_slope;
+                const bool second = z1 > z0;
+                const float pre = second ? p1 : p0, x = second ? x1 : x0;
+                const float v = (row_ok && colok) ? __bfloat162float(__float2bfloat16(f[j + t])) : 0.f;
+                const float g = v * (pre > 0.f ? 1.f : ep.stats_slope);
+                sa[j + t] = g;
+                sb[j + t] = g * x;
+              }
+            }
           } else {
             const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(ep.stats_x) + grow * (long long)p.N + col0;
 #pragma unroll
@@ -713,7 +742,8 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtens
   if (p.ep.act == PE_ACT_GELU_SAVE_GRAD && !p.ep.out2) return PE_ERR_BAD_SHAPE;
   if (p.ep.stats_mode) {
     if (!p.ep.stats || p.N > 256 || (p.N % 32) || p.tiles_y != 1 || p.mode == 2) return PE_ERR_BAD_SHAPE;
-    if (p.ep.stats_mode == 2 && (!p.ep.stats_x || !p.ep.stats_scale || !p.ep.stats_shift)) return PE_ERR_BAD_SHAPE;
+    if (p.ep.stats_mode < 1 || p.ep.stats_mode > 3) return PE_ERR_BAD_SHAPE;
+    if (p.ep.stats_mode >= 2 && (!p.ep.stats_x || !p.ep.stats_scale || !p.ep.stats_shift)) return PE_ERR_BAD_SHAPE;
   }
   // staged TMA stores for bf16 outputs of the GEMM / conv modes (whole 32-column chunks only)
   CUtensorMap tout = ta, tout2 = ta;

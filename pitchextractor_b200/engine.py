@@ -209,13 +209,13 @@ class Engine:
              c_u(drop[0]), c_f(drop[1]), c_ull(seed), ptr(out), c_ll(ld_out), c_int(c_off), ptr(out_seq), ptr(argmax),
              stream())
 
-    def _bn_bwd_fused(self, prefix, x):
+    def _bn_bwd_fused(self, prefix, x, pooled=False):
         """Epilogue arguments that make a convolution accumulate the first pass of this BN's backward (sum g, sum g*x)
-        while it writes the gradient w.r.t. the BN output (k = 1, no dropout)."""
+        while it writes the gradient w.r.t. the BN output (k = 1) or w.r.t. its MaxPool(1,2) output (pooled); no dropout."""
         i = self._bn_slot(prefix)
         aff = self.bn_aff[i]
-        return dict(stats=self.bn_sums[2 * i + 1], stats_mode=2, stats_x=x, stats_scale=aff[0], stats_shift=aff[1],
-                    stats_slope=self.slope)
+        return dict(stats=self.bn_sums[2 * i + 1], stats_mode=3 if pooled else 2, stats_x=x, stats_scale=aff[0],
+                    stats_shift=aff[1], stats_slope=self.slope)
 
     def _act_pool_bwd(self, prefix, x, rows, W, C, k, dx, dout=None, ld_dout=0, c_off=0, dout_seq=None, drop=(0, 1.0),
                       seed=0, sums_ready=False):
@@ -625,11 +625,11 @@ class Engine:
             with self._forked(join=False) as side:
                 with torch.cuda.stream(side):
                     ops.conv_wgrad(dU, P, gA, taps=9)
-            ops.conv3x3(dU, self.wops[r + ".A.dgrad"], dP, x2=dR)
-            # pre_conv BN/LReLU/pool backward -> gradient of the block input
             Rin = bufs["R%d" % (i - 1)]
+            ops.conv3x3(dU, self.wops[r + ".A.dgrad"], dP, x2=dR, **self._bn_bwd_fused(r + ".pre_conv.0", Rin, pooled=True))
+            # pre_conv BN/LReLU/pool backward -> gradient of the block input
             dRin = self.buf("dR%d" % (i - 1), (B, T, width * 2, cin))
-            self._act_pool_bwd(r + ".pre_conv.0", Rin, BT, width * 2, cin, 2, dRin, dout=dP, ld_dout=cin)
+            self._act_pool_bwd(r + ".pre_conv.0", Rin, BT, width * 2, cin, 2, dRin, dout=dP, ld_dout=cin, sums_ready=True)
             k_aux, c_off = aux[i - 1]
             call("pe_maxpool_bwd_add", None, ptr(bufs["AUXIDX%d" % (i - 1)]), c_ll(BT), c_int(width * 2), c_int(cin),
                  c_int(k_aux), ptr(dCAT),

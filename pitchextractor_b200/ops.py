@@ -53,7 +53,7 @@ def make_epilogue(out, out_mode=None, bias=None, act=L.PE_ACT_NONE, out2=None, a
     if stats is not None:
         assert stats.dtype == torch.float64
         ep.stats, ep.stats_mode = stats.data_ptr(), (stats_mode or 1)
-        if ep.stats_mode == 2:
+        if ep.stats_mode >= 2:
             ep.stats_x, ep.stats_scale, ep.stats_shift = stats_x.data_ptr(), stats_scale.data_ptr(), stats_shift.data_ptr()
             ep.stats_slope = stats_slope
     return ep

@@ -166,3 +166,17 @@ def test_conv_epilogue_column_statistics(built_lib):
     g = out.float().reshape(-1, Cout) * torch.where(z > 0, 1.0, 0.01)
     assert torch.allclose(sums2[0], g.double().sum(0), rtol=1e-3, atol=1e-2)
     assert torch.allclose(sums2[1], (g.double() * xb.double().reshape(-1, Cout)).sum(0), rtol=1e-3, atol=1e-2)
+    # mode 3: the same through MaxPool(1,2): the BN input is twice as wide, g goes to the first maximum of the pair
+    xw = _rand((B, H, 2 * W, Cout), 23)
+    sums3 = torch.zeros(2, Cout, device="cuda", dtype=torch.float64)
+    ops.conv3x3(x, w, out, stats=sums3, stats_mode=3, stats_x=xw, stats_scale=scale, stats_shift=shift, stats_slope=0.01)
+    torch.cuda.synchronize()
+    pair = xw.float().reshape(-1, 2, Cout)
+    pre = pair * scale + shift
+    act = torch.where(pre > 0, pre, 0.01 * pre)
+    second = act[:, 1] > act[:, 0]
+    pre_s = torch.where(second, pre[:, 1], pre[:, 0])
+    x_s = torch.where(second, pair[:, 1], pair[:, 0])
+    g3 = out.float().reshape(-1, Cout) * torch.where(pre_s > 0, 1.0, 0.01)
+    assert torch.allclose(sums3[0], g3.double().sum(0), rtol=1e-3, atol=1e-2)
+    assert torch.allclose(sums3[1], (g3.double() * x_s.double()).sum(0), rtol=1e-3, atol=1e-2)
