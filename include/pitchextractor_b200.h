@@ -172,12 +172,14 @@ int pe_bn_act_pool_fwd(const void* x, long long rows, int W, int C, int k, const
 /* backward of the block above through dropout, max-pool, LeakyReLU and the BatchNorm batch statistics:
  * dx bf16 [rows][W][C]; dgamma / dbeta accumulated (+=); sums is a zeroed fp64 [2][C] scratch, coef an fp32 [2][C]
  * scratch; k in {1, 2, 4}.  sums_ready != 0: the reduction pass already ran (fused in the producing convolution's
- * epilogue, pe_epilogue.stats_mode 2) and is skipped. */
+ * epilogue, pe_epilogue.stats_mode 2 / 3) and is skipped.  aux_argmax != NULL: x also feeds an auxiliary
+ * MaxPool2d((1,aux_k)) (model.py:45-49,103-105) whose arg-max positions pe_bn_act_pool_fwd saved; its gradient
+ * aux_dout (pixel (row, w/aux_k) at aux_dout + (row*(W/aux_k) + w/aux_k)*aux_ld + aux_c_off) is added to dx here. */
 int pe_bn_act_pool_bwd(const void* x, long long rows, int W, int C, int k, const float* scale, const float* shift,
                        const float* mean, const float* rstd, float slope, unsigned drop_thresh, float drop_scale,
                        unsigned long long seed, const void* dout, long long ld_dout, int c_off, const void* dout_seq,
-                       double* sums, int sums_ready, float* coef, float* dgamma, float* dbeta, void* dx,
-                       pe_stream_t stream);
+                       double* sums, int sums_ready, float* coef, float* dgamma, float* dbeta, const void* aux_argmax,
+                       const void* aux_dout, long long aux_ld, int aux_c_off, int aux_k, void* dx, pe_stream_t stream);
 /* backward of the auxiliary max-pools: dx[argmax of each window] += dout.  With argmax (saved by the forward pass) x is
  * not read; otherwise the arg-max is recomputed from x. */
 int pe_maxpool_bwd_add(const void* x, const void* argmax, long long rows, int W, int C, int k, const void* dout,

@@ -443,6 +443,11 @@ struct BnBwdArgs {
   long long ld_dout;
   int c_off;
   const __nv_bfloat16* dout_seq;  // sequence-layout consumer gradient (may be NULL)
+  // auxiliary MaxPool(1, aux_k) of the same tensor (model.py:45-49): its gradient joins at the saved arg-max positions
+  const unsigned char* aux_idx;   // [rows][W / aux_k][C] (may be NULL)
+  const __nv_bfloat16* aux_dout;
+  long long aux_ld;
+  int aux_c_off, aux_k;
 };
 
 
@@ -629,7 +634,7 @@ bn_bwd_apply_kernel(BnBwdArgs a, const float* __restrict__ coef, __nv_bfloat16* 
 // x and of the consumer gradient issued before the arithmetic; per-channel constants in registers.
 // EXTRA = false compiles the dropout replay and the sequence-layout gradient gather out (most layers have neither;
 // predicated-off Philox rounds would otherwise still take issue slots and make the pass instruction-bound).
-template <int K, int U, bool EXTRA>
+template <int K, int U, bool EXTRA, bool AUX>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_mlp_kernel(BnBwdArgs a, const float* __restrict__ coef, __nv_bfloat16* __restrict__ dx) {
   a.seed += pe_step_salt;
@@ -640,7 +645,9 @@ bn_bwd_apply_mlp_kernel(BnBwdArgs a, const float* __restrict__ coef, __nv_bfloat
   const long long nwin = g.rows * g.Wo;
   const long long stride = (long long)gridDim.x * ry;
   const long long w_first = (long long)blockIdx.x * ry + ty;
-  uint4 xv[U][K], dv[U];
+  uint4 xv[U][K], dv[U], adv[AUX ? U : 1];
+  uint2 aidx[AUX ? U : 1];
+  int aj0[AUX ? U : 1];
   long long wrow[U];
   int wwo[U];
 #pragma unroll
@@ -655,6 +662,14 @@ bn_bwd_apply_mlp_kernel(BnBwdArgs a, const float* __restrict__ coef, __nv_bfloat
 #pragma unroll
       for (int j = 0; j < K; ++j) xv[u][j] = ld_stream(xp + (long long)j * g.C);
       if (a.dout) dv[u] = ld_stream(a.dout + w * a.ld_dout + a.c_off + tx * 8);
+      if (AUX) {  // the K input pixels of a window lie in one auxiliary window (the launcher checks aux_k % K == 0)
+        const int w0 = wwo[u] * K;
+        const int aw = w0 / a.aux_k;
+        aj0[u] = w0 - aw * a.aux_k;
+        const long long arow = row * (g.W / a.aux_k) + aw;
+        aidx[u] = __ldg(reinterpret_cast<const uint2*>(a.aux_idx + arow * g.C + tx * 8));
+        adv[u] = __ldg(reinterpret_cast<const uint4*>(a.aux_dout + arow * a.aux_ld + a.aux_c_off + tx * 8));
+      }
     }
   }
   float sc[8], sh[8], A[8], Bc[8];
@@ -705,6 +720,12 @@ bn_bwd_apply_mlp_kernel(BnBwdArgs a, const float* __restrict__ coef, __nv_bfloat
       const float sg = sc[i] * go * (pre > 0.f ? 1.f : a.slope);
 #pragma unroll
       for (int j = 0; j < K; ++j) o[j][i] = fmaf(-A[i], bf16_at(xv[u][j], i), Bc[i]) + (j == js ? sg : 0.f);
+      if (AUX) {
+        const int ja = (int)(((i < 4 ? aidx[u].x : aidx[u].y) >> (8 * (i & 3))) & 0xFFu) - aj0[u];
+        const float da = bf16_at(adv[u], i);
+#pragma unroll
+        for (int j = 0; j < K; ++j) o[j][i] += (j == ja) ? da : 0.f;
+      }
     }
 #pragma unroll
     for (int j = 0; j < K; ++j) st8(dx + base + (long long)j * g.C, o[j]);
@@ -898,7 +919,8 @@ extern "C" int pe_bn_act_pool_bwd(const void* x, long long rows, int W, int C, i
                                   unsigned drop_thresh, float drop_scale, unsigned long long seed, const void* dout,
                                   long long ld_dout, int c_off, const void* dout_seq, double* sums /* [2][C], zeroed */,
                                   int sums_ready, float* coef /* [2][C] scratch */, float* dgamma, float* dbeta,
-                                  void* dx, pe_stream_t stream) {
+                                  const void* aux_argmax, const void* aux_dout, long long aux_ld, int aux_c_off,
+                                  int aux_k, void* dx, pe_stream_t stream) {
   if (int rc = pe_host::check_arch()) return rc;
   if (!x || !scale || !shift || !mean || !rstd || !sums || !coef || !dx || rows <= 0 || W <= 0 || !chan_ok(C) ||
       C / 8 > 256 || (k != 1 && k != 2 && k != 4) || k > W || (!dout && !dout_seq) ||
@@ -911,6 +933,13 @@ extern "C" int pe_bn_act_pool_bwd(const void* x, long long rows, int W, int C, i
   a.slope = slope; a.drop_thresh = drop_thresh; a.drop_scale = drop_scale; a.seed = seed;
   a.dout = (const __nv_bfloat16*)dout; a.ld_dout = ld_dout; a.c_off = c_off;
   a.dout_seq = (const __nv_bfloat16*)dout_seq;
+  const bool aux = aux_argmax != nullptr;
+  if (aux) {  // joins only the plain (no dropout / sequence gradient) layers, whole pool windows inside an aux window
+    if (!aux_dout || aux_k <= 0 || aux_k > 255 || (aux_k % k) || (W % aux_k) || (W % k) || drop_thresh || dout_seq)
+      return PE_ERR_BAD_SHAPE;
+    a.aux_idx = (const unsigned char*)aux_argmax; a.aux_dout = (const __nv_bfloat16*)aux_dout;
+    a.aux_ld = aux_ld; a.aux_c_off = aux_c_off; a.aux_k = aux_k;
+  }
   const long long nwin = rows * a.g.Wo;
   // pass-1 CTAs: about 8 per SM, at least 8 windows per thread row (the fp64 atomics of a CTA cost ~2*C operations)
   long long per_ll = (nwin + 8LL * pe_host::num_sms() - 1) / (8LL * pe_host::num_sms());
@@ -929,12 +958,13 @@ extern "C" int pe_bn_act_pool_bwd(const void* x, long long rows, int W, int C, i
     else if (!sums_ready) bn_bwd_reduce_kernel<K, false><<<g1, 256, sm1, st>>>(a, sums, per);             \
     bn_bwd_params_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, (double)rows * W, scale, mean, rstd, dgamma, dbeta, \
                                                           coef, C);                                       \
-    if (extra)                                                                                            \
-      bn_bwd_apply_mlp_kernel<K, U, true><<<(unsigned)((nwin + (long long)ry * U - 1) / ((long long)ry * U)), cgs * ry, 0, st>>>( \
-          a, coef, (__nv_bfloat16*)dx);                                                                   \
+    const unsigned ga = (unsigned)((nwin + (long long)ry * U - 1) / ((long long)ry * U));                 \
+    if (aux)                                                                                              \
+      bn_bwd_apply_mlp_kernel<K, U, false, true><<<ga, cgs * ry, 0, st>>>(a, coef, (__nv_bfloat16*)dx);   \
+    else if (extra)                                                                                       \
+      bn_bwd_apply_mlp_kernel<K, U, true, false><<<ga, cgs * ry, 0, st>>>(a, coef, (__nv_bfloat16*)dx);   \
     else                                                                                                  \
-      bn_bwd_apply_mlp_kernel<K, U, false><<<(unsigned)((nwin + (long long)ry * U - 1) / ((long long)ry * U)), cgs * ry, 0, st>>>( \
-          a, coef, (__nv_bfloat16*)dx);                                                                   \
+      bn_bwd_apply_mlp_kernel<K, U, false, false><<<ga, cgs * ry, 0, st>>>(a, coef, (__nv_bfloat16*)dx);  \
   } while (0)
   const int cgs = C / 8, ry = 256 / cgs;
   const bool extra = drop_thresh != 0 || dout_seq != nullptr;

@@ -218,7 +218,9 @@ class Engine:
                     stats_shift=aff[1], stats_slope=self.slope)
 
     def _act_pool_bwd(self, prefix, x, rows, W, C, k, dx, dout=None, ld_dout=0, c_off=0, dout_seq=None, drop=(0, 1.0),
-                      seed=0, sums_ready=False):
+                      seed=0, sums_ready=False, aux=None):
+        """aux = (argmax, dout, ld, c_off, k_aux): gradient of the auxiliary max-pool of the same tensor, added here."""
+        aux_idx, aux_dout, aux_ld, aux_off, aux_k = aux if aux is not None else (None, None, 0, 0, 0)
         i = self._bn_slot(prefix)
         aff = self.bn_aff[i]
         sums = self.bn_sums[2 * i + 1]
@@ -226,8 +228,8 @@ class Engine:
         call("pe_bn_act_pool_bwd", ptr(x), c_ll(rows), c_int(W), c_int(C), c_int(k), ptr(aff[0]), ptr(aff[1]),
              ptr(aff[2]), ptr(aff[3]), c_f(self.slope), c_u(drop[0]), c_f(drop[1]), c_ull(seed), ptr(dout),
              c_ll(ld_dout), c_int(c_off), ptr(dout_seq), ptr(sums), c_int(int(sums_ready)), ptr(self.bn_coef[i]),
-             ptr(g[prefix + ".weight"]),
-             ptr(g[prefix + ".bias"]), ptr(dx), stream())
+             ptr(g[prefix + ".weight"]), ptr(g[prefix + ".bias"]), ptr(aux_idx), ptr(aux_dout), c_ll(aux_ld),
+             c_int(aux_off), c_int(aux_k), ptr(dx), stream())
 
     # ------------------------------------------------------------------ forward
     def _prep_input(self, x):
@@ -629,11 +631,9 @@ class Engine:
             ops.conv3x3(dU, self.wops[r + ".A.dgrad"], dP, x2=dR, **self._bn_bwd_fused(r + ".pre_conv.0", Rin, pooled=True))
             # pre_conv BN/LReLU/pool backward -> gradient of the block input
             dRin = self.buf("dR%d" % (i - 1), (B, T, width * 2, cin))
-            self._act_pool_bwd(r + ".pre_conv.0", Rin, BT, width * 2, cin, 2, dRin, dout=dP, ld_dout=cin, sums_ready=True)
-            k_aux, c_off = aux[i - 1]
-            call("pe_maxpool_bwd_add", None, ptr(bufs["AUXIDX%d" % (i - 1)]), c_ll(BT), c_int(width * 2), c_int(cin),
-                 c_int(k_aux), ptr(dCAT),
-                 c_ll(640), c_int(c_off), ptr(dRin), stream())
+            k_aux, c_off = aux[i - 1]  # the auxiliary max-pool of R_{i-1} joins its gradient in the same pass
+            self._act_pool_bwd(r + ".pre_conv.0", Rin, BT, width * 2, cin, 2, dRin, dout=dP, ld_dout=cin, sums_ready=True,
+                               aux=(bufs["AUXIDX%d" % (i - 1)], dCAT, 640, c_off, k_aux))
             dR = dRin
             width *= 2
         # conv_block

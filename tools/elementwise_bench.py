@@ -31,7 +31,7 @@ for (W, C, k, drop) in ((80, 64, 1, 0), (80, 64, 2, 0), (40, 128, 1, 0), (40, 12
     bytes_f = rows * (W + Wo) * C * 2
     def bwd(i, ready):
         call("pe_bn_act_pool_bwd", ptr(xs[i]), c_ll(rows), c_int(W), c_int(C), c_int(k), ptr(sc), ptr(sh), ptr(mu), ptr(rs), c_f(0.01), c_u(thr),
-             c_f(scl), c_ull(7), ptr(outs[i]), c_ll(C), c_int(0), None, ptr(sums), c_int(ready), ptr(coef), ptr(dg), ptr(db), ptr(dxs[i]), stream())
+             c_f(scl), c_ull(7), ptr(outs[i]), c_ll(C), c_int(0), None, ptr(sums), c_int(ready), ptr(coef), ptr(dg), ptr(db), None, None, c_ll(0), c_int(0), c_int(0), ptr(dxs[i]), stream())
     us_b1 = timeit(lambda i: bwd(i, 1))
     us_b0 = timeit(lambda i: bwd(i, 0))
     bytes_b = rows * (2 * W + Wo) * C * 2
