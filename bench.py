@@ -204,9 +204,10 @@ def run_ours(args):
                      "achieved": tc_flops / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else None, "peak": pk["tf_sustained"],
                      "unit": "TFLOP/s",
                      "frac": (tc_flops / (tc_ms / 1e3) / 1e12 / pk["tf_sustained"]) if tc_ms > 0 else None,
-                     # mean dram__bytes_read + write per launch over the seven forward-conv launches of the
-                     # ncu --set full capture in profiles/r01_ncu_full_tc_tile_fwd_convs.csv (B = 64)
-                     "traffic": 164.0e6 if (args.batch == 64 and args.model == "transformer") else None,
+                     # mean dram__bytes_read + write per launch over the first 24 tile-engine launches of a step (7
+                     # forward convs + 17 encoder GEMMs) in the ncu --set full capture
+                     # profiles/r01_ncu_full_tc_tile_24launches.csv (B = 64)
+                     "traffic": 73.0e6 if (args.batch == 64 and args.model == "transformer") else None,
                      "peak_source": pk["src"] + " (sustained bf16)",
                      "launches_per_step": len(prof) // max(1, n_prof_steps), "ms_per_step": tc_ms / max(1, n_prof_steps),
                      "step_frac_of_bf16_peak": seg_s / world * FLOPS_PER_SEGMENT[args.model] / (pk["tf_sustained"] * 1e12)},
