@@ -100,20 +100,21 @@ logmel_tc_kernel(const float* __restrict__ wave, int L, long long ld, int hop, c
 
   if (warp == 0) {
     // ---------------------------------------------------------------- producer: 4 KB bulk copies, one per frame
-    if (lane == 0) {
-      for (int i = 0; i < n_local; ++i) {
-        const int tile = blockIdx.x + i * gridDim.x;
-        const int buf = i % LM_NRAW;
+    // (warp-uniform loop, one elected lane waits and issues: see elect_one())
+    for (int i = 0; i < n_local; ++i) {
+      const int tile = blockIdx.x + i * gridDim.x;
+      const int buf = i % LM_NRAW;
+      const int b = tile / p.tiles_per_item, t0 = (tile - b * p.tiles_per_item) * LM_FR;
+      const int nfr = min(LM_FR, p.T - t0);
+      // interior frames (window fully inside the item) are bulk-copied; the few frames that touch the reflect
+      // padding are gathered by the workers straight from global memory
+      int n_in = 0;
+      for (int j = 0; j < nfr; ++j) {
+        const long long s0 = (long long)(t0 + j) * hop - LM_NFFT / 2;
+        n_in += (s0 >= 0 && s0 + LM_NFFT <= L) ? 1 : 0;
+      }
+      if (elect_one()) {
         mbar_wait(&raw_empty[buf], ((uint32_t)(i / LM_NRAW) & 1u) ^ 1u);
-        const int b = tile / p.tiles_per_item, t0 = (tile - b * p.tiles_per_item) * LM_FR;
-        const int nfr = min(LM_FR, p.T - t0);
-        // interior frames (window fully inside the item) are bulk-copied; the few frames that touch the reflect
-        // padding are gathered by the workers straight from global memory
-        int n_in = 0;
-        for (int j = 0; j < nfr; ++j) {
-          const long long s0 = (long long)(t0 + j) * hop - LM_NFFT / 2;
-          n_in += (s0 >= 0 && s0 + LM_NFFT <= L) ? 1 : 0;
-        }
         mbar_arrive_expect_tx(&raw_full[buf], (uint32_t)n_in * 4096u);
         for (int j = 0; j < nfr; ++j) {
           const long long s0 = (long long)(t0 + j) * hop - LM_NFFT / 2;
@@ -121,34 +122,38 @@ logmel_tc_kernel(const float* __restrict__ wave, int L, long long ld, int hop, c
             bulk_load_1d(s_raw + buf * LM_RAW_B + j * 4096, wave + (long long)b * ld + s0, 4096, &raw_full[buf]);
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer, serving the two worker groups in
     // the order S1(i), S1(i+1), S2(i), S2(i+1): one group's SIMT phases overlap the other group's GEMM stages
-    if (lane == 0) {
+    {
       constexpr uint32_t IDESC1 = umma_idesc(UMMA_F16, 128, 64, 1, 0);  // A MN-major (frames as landed), B K-major
       constexpr uint32_t IDESC2 = umma_idesc(UMMA_F16, 128, 64, 0, 0);
       const uint32_t f = smem_u32(s_f);
       uint32_t ph[2] = {0u, 0u};
       auto stage = [&](int g, int which) {
         const uint32_t ahi = smem_u32(s_a) + g * 2 * LM_OP_B, alo = ahi + LM_OP_B;
-        mbar_wait(&work_ready[g], ph[g]);
-        ph[g] ^= 1u;
-        tc_fence_after();
         const uint32_t d = tm + g * 128 + which * 64;
+        if (elect_one()) {  // warp-uniform loop, one elected lane waits and issues
+          mbar_wait(&work_ready[g], ph[g]);
+          tc_fence_after();
 #pragma unroll
-        for (int prod = 0; prod < 3; ++prod) {
-          const uint32_t a = prod == 2 ? alo : ahi;
-          const uint32_t bm = f + (prod == 0 ? 0 : prod == 1 ? 8192 : 16384);
+          for (int prod = 0; prod < 3; ++prod) {
+            const uint32_t a = prod == 2 ? alo : ahi;
+            const uint32_t bm = f + (prod == 0 ? 0 : prod == 1 ? 8192 : 16384);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // stage 1: A = 2 MN atoms (8 KB apart) x 64 K rows, 16 K rows per MMA; stage 2: A K-major
-            const uint64_t da = which == 0 ? umma_desc_sw128(a + k * 2048, 8192, 1024) : umma_desc_sw128(a + k * 32, 16, 1024);
-            tc_mma_f16(d, da, umma_desc_sw128(bm + k * 32, 16, 1024), which == 0 ? IDESC1 : IDESC2,
-                       (prod > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              // stage 1: A = 2 MN atoms (8 KB apart) x 64 K rows, 16 K rows per MMA; stage 2: A K-major
+              const uint64_t da = which == 0 ? umma_desc_sw128(a + k * 2048, 8192, 1024) : umma_desc_sw128(a + k * 32, 16, 1024);
+              tc_mma_f16(d, da, umma_desc_sw128(bm + k * 32, 16, 1024), which == 0 ? IDESC1 : IDESC2,
+                         (prod > 0 || k > 0) ? 1u : 0u);
+            }
           }
+          tc_commit(&mma_done[g]);
         }
-        tc_commit(&mma_done[g]);
+        __syncwarp();
+        ph[g] ^= 1u;
       };
       for (int i = 0; i < n_local; i += 2) {
         const bool two = i + 1 < n_local;

@@ -79,30 +79,37 @@ lstm_step_fwd_kernel(const __grid_constant__ LstmMaps maps, const LstmStepParams
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (!p.first) {
-    if (warp == 0 && lane == 0) {
+    // warp-uniform loops, one elected lane issues the TMA / tcgen05 instructions (operands stay in uniform registers)
+    if (warp == 0) {
       for (int kb = 0; kb < KB; ++kb) {
         const int s = kb % STAGES;
-        mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
         uint8_t* sa = smem + s * STAGE_B;
         uint8_t* sb = sa + A_B;
-        mbar_arrive_expect_tx(&full_bar[s], STAGE_B);
-        tma_load_3d(&maps.act[model], &full_bar[s], sa, dir * LH + kb * 64, t_prev, b0);
-        for (int g = 0; g < 4; ++g) tma_load_2d(&maps.w[rec], &full_bar[s], sb + g * 8192, kb * 64, g * LH + u0);
+        if (elect_one()) {
+          mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], STAGE_B);
+          tma_load_3d(&maps.act[model], &full_bar[s], sa, dir * LH + kb * 64, t_prev, b0);
+          for (int g = 0; g < 4; ++g) tma_load_2d(&maps.w[rec], &full_bar[s], sb + g * 8192, kb * 64, g * LH + u0);
+        }
+        __syncwarp();
       }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
       constexpr uint32_t IDESC = umma_idesc(UMMA_BF16, 128, 256, 0, 0);
       for (int kb = 0; kb < KB; ++kb) {
         const int s = kb % STAGES;
-        mbar_wait(&full_bar[s], (kb / STAGES) & 1);
-        tc_fence_after();
         const uint32_t sa = smem_u32(smem + s * STAGE_B), sb = sa + A_B;
+        if (elect_one()) {
+          mbar_wait(&full_bar[s], (kb / STAGES) & 1);
+          tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          tc_mma_bf16(tmem_base, umma_desc_sw128(sa + k * 32, 16, 1024), umma_desc_sw128(sb + k * 32, 16, 1024), IDESC,
-                      (kb > 0 || k > 0) ? 1u : 0u);
-        tc_commit(&empty_bar[s]);
+          for (int k = 0; k < 4; ++k)
+            tc_mma_bf16(tmem_base, umma_desc_sw128(sa + k * 32, 16, 1024), umma_desc_sw128(sb + k * 32, 16, 1024), IDESC,
+                        (kb > 0 || k > 0) ? 1u : 0u);
+          tc_commit(&empty_bar[s]);
+          if (kb == KB - 1) tc_commit(done_bar);
+        }
+        __syncwarp();
       }
-      tc_commit(done_bar);
     }
   }
   if (warp >= 2) {
@@ -230,29 +237,36 @@ lstm_step_bwd_kernel(const __grid_constant__ LstmMaps maps, const LstmStepParams
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (!p.first) {
-    if (warp == 0 && lane == 0) {
+    if (warp == 0) {
       for (int kb = 0; kb < KB; ++kb) {
         const int s = kb % STAGES;
-        mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
         uint8_t* sa = smem + s * STAGE_B;
-        mbar_arrive_expect_tx(&full_bar[s], STAGE_B);
-        tma_load_3d(&maps.act[model], &full_bar[s], sa, dir * LG + kb * 64, t_next, b0);
-        tma_load_2d(&maps.w[rec], &full_bar[s], sa + A_B, u0, kb * 64);  // [64 gate rows][64 units]: MN-major B
+        if (elect_one()) {
+          mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], STAGE_B);
+          tma_load_3d(&maps.act[model], &full_bar[s], sa, dir * LG + kb * 64, t_next, b0);
+          tma_load_2d(&maps.w[rec], &full_bar[s], sa + A_B, u0, kb * 64);  // [64 gate rows][64 units]: MN-major B
+        }
+        __syncwarp();
       }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
       constexpr uint32_t IDESC = umma_idesc(UMMA_BF16, 128, 64, 0, 1);
       for (int kb = 0; kb < KB; ++kb) {
         const int s = kb % STAGES;
-        mbar_wait(&full_bar[s], (kb / STAGES) & 1);
-        tc_fence_after();
         const uint32_t sa = smem_u32(smem + s * STAGE_B), sb = sa + A_B;
+        if (elect_one()) {
+          mbar_wait(&full_bar[s], (kb / STAGES) & 1);
+          tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          tc_mma_bf16(tmem_base, umma_desc_sw128(sa + k * 32, 16, 1024), umma_desc_sw128(sb + k * 2048, 8192, 1024),
-                      IDESC, (kb > 0 || k > 0) ? 1u : 0u);
-        tc_commit(&empty_bar[s]);
+          for (int k = 0; k < 4; ++k)
+            tc_mma_bf16(tmem_base, umma_desc_sw128(sa + k * 32, 16, 1024), umma_desc_sw128(sb + k * 2048, 8192, 1024),
+                        IDESC, (kb > 0 || k > 0) ? 1u : 0u);
+          // N = 64 MMAs are short: one commit per two k-blocks would do, but the ring is only STAGES deep
+          tc_commit(&empty_bar[s]);
+          if (kb == KB - 1) tc_commit(done_bar);
+        }
+        __syncwarp();
       }
-      tc_commit(done_bar);
     }
   }
   if (warp >= 2) {
