@@ -75,9 +75,31 @@ def test_forward_backward_parity(built_lib, model_type):
     bad = [(c, r, n) for c, r, n, nrm, ca, ra in worst
            if nrm > 1e-7 and not ((c >= GRAD_COS and r <= GRAD_REL_L2) or r <= 1.25 * ra + 1e-3)]
     assert not bad, bad[:10]
-    return
-    bad = [(c, r, n) for c, r, n, nrm in worst if (c < GRAD_COS or r > GRAD_REL_L2) and nrm > 1e-7]
-    assert not bad, bad[:10]
+
+
+@pytest.mark.parametrize("B", [1, 3, 5])
+def test_ragged_batch_sizes(built_lib, B):
+    """Batches that fill no tile exactly (B * 192 * 80 pixels, B * 192 tokens): partial tiles, TMA clipping and masked
+    epilogues.  B = 1 is the reference's squeeze() corner: the loss is unchanged by it."""
+    from oracle import jdcnet_torch as J
+    mel, f0, sil = _inputs(B, seed=3 + B)
+    m = _model(seed=B)
+    sd = {k: v.detach().clone().float() for k, v in m.state_dict().items()}
+    ref = J.loss_and_grads(sd, mel, f0, sil, J.default_config("transformer"))
+    m = m.cuda()
+    eng = m.engine
+    eng.dropout_enabled = False
+    out = eng.train_step(mel.cuda(), f0.cuda(), sil.cuda(), 0.1).cpu()
+    assert abs(out[0].item() - ref["loss"].item()) <= LOSS_RTOL * abs(ref["loss"].item())
+    assert abs(out[2].item() - ref["sil"].item()) <= LOSS_RTOL * abs(ref["sil"].item()) + 1e-3
+    pred = eng._pred_f0.view(B, 192).cpu()
+    assert (pred - ref["cls"].squeeze(-1)).abs().max().item() <= 5e-2 * ref["cls"].abs().max().item() + 5e-2
+    grads = dict(m.named_parameters())
+    for name in ("classifier.weight", "sequence_classifier.model.layers.3.linear2.weight",
+                 "sequence_detector.model.layers.0.self_attn.in_proj_weight", "detector_conv.0.weight"):
+        gc, gr = grads[name].grad.detach().cpu().float().flatten(), ref["grads"][name].float().flatten()
+        cos = torch.nn.functional.cosine_similarity(gc, gr, dim=0).item()
+        assert cos >= 0.98, (name, cos)
 
 
 @pytest.mark.parametrize("model_type", ["transformer", "bilstm"])
@@ -131,3 +153,42 @@ def test_autograd_path_matches_fused_step(built_lib):
     rel = ((g1 - g2).norm() / g1.norm()).item()
     assert rel_seq < 5e-3, rel_seq
     assert rel < 1e-1, rel
+
+
+def test_full_size_properties(built_lib):
+    """BASELINE configs[1] size (B = 64, where the fp32 oracle is too slow): properties that do not need it.
+    (a) permuting the batch changes neither the losses nor any parameter gradient (BatchNorm statistics, the mean
+        losses and every weight gradient are sums over the batch);
+    (b) the gradients are linear in the loss scale (grad_scale = 4 -> 4x), the loss values are not affected;
+    (c) the log-mel of a waveform delayed by one hop is the log-mel delayed by one frame (interior frames)."""
+    from pitchextractor_b200.mel import LogMel
+    B = 64
+    mel, f0, sil = _inputs(B, seed=11)
+    m = _model(seed=5).cuda()
+    eng = m.engine
+    eng.dropout_enabled = False
+    eng.use_graph = False
+    mel, f0, sil = mel.cuda(), f0.cuda(), sil.cuda()
+    l0 = eng.train_step(mel, f0, sil, 0.1).clone()
+    g0 = eng.flat_grad.clone()
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(1)).cuda()
+    l1 = eng.train_step(mel[perm].contiguous(), f0[perm].contiguous(), sil[perm].contiguous(), 0.1).clone()
+    g1 = eng.flat_grad.clone()
+    assert torch.allclose(l0, l1, rtol=2e-3, atol=1e-4), (l0, l1)
+    cos = torch.nn.functional.cosine_similarity(g0, g1, dim=0).item()
+    rel = ((g0 - g1).norm() / g0.norm()).item()
+    print("permutation: grad cosine %.6f rel %.4g" % (cos, rel))
+    assert cos > 0.999 and rel < 3e-2, (cos, rel)  # bf16 rounding + atomic summation order only
+    l4 = eng.train_step(mel, f0, sil, 0.1, grad_scale=4.0).clone()
+    g4 = eng.flat_grad.clone()
+    assert torch.allclose(l0, l4, rtol=2e-3, atol=1e-4)
+    rel4 = ((g4 - 4.0 * g0).norm() / (4.0 * g0.norm())).item()
+    print("grad_scale linearity rel %.4g" % rel4)
+    assert rel4 < 3e-2, rel4
+    lm = LogMel(torch.device("cuda"))
+    g = torch.Generator(device="cuda").manual_seed(2)
+    w = torch.randn(B, 58624, device="cuda", generator=g) * 0.1
+    a = lm(w, layout="bmt")
+    b = lm(torch.nn.functional.pad(w, (300, 0))[:, :58624].contiguous(), layout="bmt")
+    # frames whose window lies inside both signals and away from the reflected edges
+    assert torch.allclose(a[:, :, 3:180], b[:, :, 4:181], rtol=0, atol=2e-4), (a[:, :, 3:180] - b[:, :, 4:181]).abs().max()
