@@ -43,6 +43,7 @@ class Trainer(object):
         if gradient_checkpointing:
             self.logger.info("gradient_checkpointing ignored: activations stay resident in HBM")
         self._logmel = None
+        self._copy_stream = None
         self._reducer = None
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.sync_every_step = True  # reference semantics: run() returns python floats (3 .item() syncs there, 1 here)
@@ -103,6 +104,42 @@ class Trainer(object):
         x, f0, sil = batch
         return x.to(self.device, non_blocking=True), f0, sil
 
+    # ------------------------------------------------------------------ input pipeline
+    class _DeviceBatch(tuple):
+        """A batch whose tensors were copied to the device on the copy stream; `ready` orders consumers behind it."""
+        ready = None
+
+    def prefetched(self, batches):
+        """Iterate host batches one ahead: the pinned-host -> device copy of batch i+1 is issued on a copy stream before
+        batch i is handed out, so it overlaps batch i's training step (the reference copies synchronously,
+        trainer.py:221-224)."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+
+        def to_device(batch):
+            if batch is None:
+                return None
+            with torch.cuda.stream(self._copy_stream):
+                dev = Trainer._DeviceBatch(t.to(self.device, non_blocking=True) if torch.is_tensor(t) else t for t in batch)
+                dev.ready = torch.cuda.Event()
+                dev.ready.record(self._copy_stream)
+            return dev
+
+        it = iter(batches)
+        nxt = to_device(next(it, None))
+        while nxt is not None:
+            cur, nxt = nxt, to_device(next(it, None))
+            yield cur
+
+    def _await_batch(self, batch):
+        ready = getattr(batch, "ready", None)
+        if ready is not None:
+            cur = torch.cuda.current_stream()
+            cur.wait_event(ready)
+            for t in batch:
+                if torch.is_tensor(t) and t.is_cuda:
+                    t.record_stream(cur)  # allocated on the copy stream, consumed here
+
     def _ensure_parallel(self):
         if self.world > 1 and self._reducer is None:
             eng = self.model.engine
@@ -119,6 +156,7 @@ class Trainer(object):
     def run_async(self, batch):
         """One optimisation step; returns the device tensor [loss, f0, sil] without synchronising."""
         self._ensure_parallel()
+        self._await_batch(batch)
         x, f0, sil = self._mel_from_batch(batch)
         f0 = f0.to(self.device, non_blocking=True)
         sil = sil.to(self.device, non_blocking=True)
@@ -138,7 +176,8 @@ class Trainer(object):
         self.epochs += 1
         train_losses = defaultdict(list)
         self.model.train()
-        for _, batch in enumerate(tqdm(self.train_dataloader, desc="[train]"), 1):
+        for _, batch in enumerate(tqdm(self.prefetched(self.train_dataloader), desc="[train]",
+                                       total=len(self.train_dataloader)), 1):
             for key, value in self.run(batch).items():
                 train_losses["train/%s" % key].append(value)
         train_losses = {key: np.mean(value) for key, value in train_losses.items()}

@@ -204,3 +204,31 @@ def test_cuda_graph_segments_with_reducer(built_lib):
     assert eng.reducer.calls == per_step * 5, eng.reducer.calls
     for a, b in zip(eager, graphed):
         assert abs(a - b) <= 5e-3 * abs(a), (eager, graphed)
+
+
+def test_prefetched_batches_give_the_same_steps(built_lib):
+    """Trainer.prefetched copies batch i+1 on a copy stream while step i runs; the steps themselves are unchanged."""
+    from pitchextractor_b200 import JDCNet, Trainer, build_optimizer
+    sd = GI.model_state_dict("transformer")
+    g = torch.Generator().manual_seed(9)
+    batches = []
+    for _ in range(4):
+        mel = (torch.randn(2, 1, 80, 192, generator=g) * 2 - 4).pin_memory()
+        f0 = (torch.rand(2, 192, generator=g) * 300).pin_memory()
+        batches.append((mel, f0, (f0 < 60).float().pin_memory()))
+
+    def run(prefetch):
+        model = JDCNet(num_class=1, sequence_model_config=GI.model_config("transformer"))
+        model.load_state_dict(sd)
+        model = model.cuda()
+        opt, sched = build_optimizer({"params": model.parameters(), "optimizer_params": {}, "scheduler_params": {}})
+        tr = Trainer(model=model, optimizer=opt, scheduler=sched, loss_config={"lambda_f0": 0.1}, device="cuda")
+        model.engine.dropout_enabled = False
+        model.train()
+        src = tr.prefetched(batches) if prefetch else batches
+        return [tr.run(b)["loss"] for b in src]
+
+    a, b = run(False), run(True)
+    assert len(a) == len(b) == 4
+    for x, y in zip(a, b):
+        assert abs(x - y) <= 5e-3 * abs(x), (a, b)
