@@ -167,7 +167,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, int H, unsigned d
     mx = fmaxf(redt[r], redt[128 + r]);
     __syncthreads();
     float l = 0.f;
-    const unsigned long long e_row = ((unsigned long long)(b * H + h) * AT + q) * (unsigned long long)AT;
+    const uint32_t rkey = attn_row_key(seed, (unsigned long long)(b * H + h) * AT + q);
     for (int c = half * 3; c < half * 3 + 3; ++c) {
       tmem_ld32(trow + c * 32, v);
       tmem_ld_wait();
@@ -180,7 +180,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, int H, unsigned d
       if (drop_thresh) {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          p[j] = attn_drop_hash(seed, e_row + c * 32 + j) < drop_thresh ? p[j] * drop_scale : 0.f;
+          p[j] = attn_drop_hash(rkey, (uint32_t)(c * 32 + j)) < drop_thresh ? p[j] * drop_scale : 0.f;
       }
       oper_store32(sP + t * OPER_B, r, c * 32, p);
     }
@@ -243,7 +243,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   uint8_t* sB = sA + OPER_B;               // dS^T (phase B)
   float* sLse = reinterpret_cast<float*>(sB + OPER_B);  // [192] lse * log2(e)
   float* sDel = sLse + AT;                               // [192] rowsum(dO * O)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDel + AT);
+  uint32_t* sKey = reinterpret_cast<uint32_t*>(sDel + AT);  // [192] dropout row keys (phase B walks the mask by column)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKey + AT);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.x, b = blockIdx.y;
@@ -293,6 +294,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     }
     sDel[tid] = acc;
     sLse[tid] = lse[((long long)b * H + h) * AT + tid] * LOG2E;
+    sKey[tid] = attn_row_key(seed, (unsigned long long)(b * H + h) * AT + tid);
   }
   __syncthreads();
 
@@ -302,7 +304,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   const int r = quarter * 32 + lane;
   const uint32_t lane_base = tm + ((uint32_t)(quarter * 32) << 16);
   const float kscale = 0.125f * LOG2E;
-  const unsigned long long e_bh = (unsigned long long)(b * H + h) * AT * (unsigned long long)AT;
+  const unsigned long long row_bh = (unsigned long long)(b * H + h) * AT;
   if (warp == 0) {
     mbar_wait(&bars[0], 0);
     tc_fence_after();
@@ -323,6 +325,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     const int q = t * 128 + r;
     const int qc = q < AT ? q : AT - 1;
     const float lq = sLse[qc], dq_delta = sDel[qc];
+    const uint32_t rkey = attn_row_key(seed, row_bh + q);
     for (int c = part * 3; c < part * 3 + 3; ++c) {  // 16-column chunks
       uint32_t s[16], d[16];
       tmem_ld16(lane_base + c * 16, s);
@@ -334,7 +337,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         const float p = ex2(__uint_as_float(s[j]) * kscale - lq);
         float dp = __uint_as_float(d[j]);
         if (drop_thresh)
-          dp = attn_drop_hash(seed, e_bh + (unsigned long long)q * AT + c * 16 + j) < drop_thresh ? dp * drop_scale : 0.f;
+          dp = attn_drop_hash(rkey, (uint32_t)(c * 16 + j)) < drop_thresh ? dp * drop_scale : 0.f;
         ds[j] = 0.125f * p * (dp - dq_delta);
       }
       oper_store16(sA, r, c * 16, ds);
@@ -385,7 +388,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         float dp = __uint_as_float(d[j]);
         float pd = p;
         if (drop_thresh) {
-          const bool keep = attn_drop_hash(seed, e_bh + (unsigned long long)q * AT + jkey) < drop_thresh;
+          const bool keep = attn_drop_hash(sKey[q], (uint32_t)jkey) < drop_thresh;
           dp = keep ? dp * drop_scale : 0.f;
           pd = keep ? p * drop_scale : 0.f;
         }
@@ -454,7 +457,7 @@ int pe_attn_bwd_tc(const void* qkv, const void* ctx, const void* dctx, const flo
   CUtensorMap tq, td;
   if (int rc = token_tmap(&tq, qkv, (long long)B * pe::AT, 3 * H * pe::AD)) return rc;
   if (int rc = token_tmap(&td, dctx, (long long)B * pe::AT, H * pe::AD)) return rc;
-  const size_t smem = 4 * pe::TILE_B + 8192 + 2 * pe::OPER_B + 2 * pe::AT * 4 + 64 + 1024;
+  const size_t smem = 4 * pe::TILE_B + 8192 + 2 * pe::OPER_B + 3 * pe::AT * 4 + 64 + 1024;
   static bool attr = false;
   if (!attr) {
     if (cudaFuncSetAttribute(pe::attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=

@@ -72,11 +72,17 @@ __device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint64_t q, uin
   return m;
 }
 
-// attention-probability dropout: keep iff fmix32(seed, element) < thresh.  A counter hash instead of Philox because
-// the attention backward walks the mask in both row- and column-major order.
-__host__ __device__ __forceinline__ uint32_t attn_drop_hash(unsigned long long seed, unsigned long long e) {
-  uint32_t h = (uint32_t)e * 0x9E3779B1u ^ ((uint32_t)(e >> 32) * 0x85EBCA77u) ^ (uint32_t)seed ^
+// attention-probability dropout: keep iff hash(seed, row, column) < thresh.  A counter hash instead of Philox because
+// the attention backward walks the mask in both row- and column-major order.  Split in two so that the per-row part
+// is computed once per query row (row = (item * heads + head) * T + query) and an element costs one add + fmix32.
+__host__ __device__ __forceinline__ uint32_t attn_row_key(unsigned long long seed, unsigned long long row) {
+  uint32_t h = (uint32_t)row * 0x9E3779B1u ^ ((uint32_t)(row >> 32) * 0x85EBCA77u) ^ (uint32_t)seed ^
                ((uint32_t)(seed >> 32) * 0xC2B2AE3Du);
+  h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
+  return h;
+}
+__host__ __device__ __forceinline__ uint32_t attn_drop_hash(uint32_t row_key, uint32_t col) {
+  uint32_t h = row_key + col * 0x9E3779B1u;
   h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
   return h;
 }

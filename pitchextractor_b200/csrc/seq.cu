@@ -292,7 +292,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int T, int H, float scale
     }
   }
   float mx = -INFINITY, l = 0.f;
-  const unsigned long long e_row = ((unsigned long long)(b * H + h) * T + q) * (unsigned long long)T;
+  const uint32_t rkey = attn_row_key(seed, (unsigned long long)(b * H + h) * T + q);
   for (int j0 = 0; j0 < T; j0 += 8) {
     float s[8];
     float bm = mx;
@@ -312,7 +312,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int T, int H, float scale
       const float p = __expf(s[jj] - mx);
       l += p;
       float pd = p;
-      if (drop_thresh) pd = attn_drop_hash(seed, e_row + j0 + jj) < drop_thresh ? p * drop_scale : 0.f;
+      if (drop_thresh) pd = attn_drop_hash(rkey, (uint32_t)(j0 + jj)) < drop_thresh ? p * drop_scale : 0.f;
       axpy64(o, pd, Vs + (j0 + jj) * HD);
     }
   }
@@ -365,11 +365,11 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
     }
   }
   const float L = lse[((long long)b * H + h) * T + q];
-  const unsigned long long e_row = ((unsigned long long)(b * H + h) * T + q) * (unsigned long long)T;
+  const uint32_t rkey = attn_row_key(seed, (unsigned long long)(b * H + h) * T + q);
   for (int j = 0; j < T; ++j) {
     const float p = __expf(dot64(qr, Ks + j * HD) - L);
     float dp = dot64(dor, Vs + j * HD);
-    if (drop_thresh) dp = attn_drop_hash(seed, e_row + j) < drop_thresh ? dp * drop_scale : 0.f;
+    if (drop_thresh) dp = attn_drop_hash(rkey, (uint32_t)j) < drop_thresh ? dp * drop_scale : 0.f;
     axpy64(dq, p * (dp - dl), Ks + j * HD);
   }
   __nv_bfloat16* op = dqkv + row * ld + h * HD;
@@ -419,11 +419,11 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
       acc[c + t] = 0.f;
     }
   }
-  const unsigned long long e_base = (unsigned long long)(b * H + h) * T * (unsigned long long)T + j;
+  const unsigned long long row_bh = (unsigned long long)(b * H + h) * T;
   // pass A: dV_j = sum_q dropout(P)_qj dO_q
   for (int q = 0; q < T; ++q) {
     float p = __expf(dot64(kr, Qs + q * HD) - Ls[q]);
-    if (drop_thresh) p = attn_drop_hash(seed, e_base + (unsigned long long)q * T) < drop_thresh ? p * drop_scale : 0.f;
+    if (drop_thresh) p = attn_drop_hash(attn_row_key(seed, row_bh + q), (uint32_t)j) < drop_thresh ? p * drop_scale : 0.f;
     axpy64(acc, p, dOs + q * HD);
   }
   __nv_bfloat16* ov = dqkv + ((long long)b * T + j) * ld + 2 * D + h * HD;
@@ -444,7 +444,7 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
   for (int q = 0; q < T; ++q) {
     const float p = __expf(dot64(kr, Qs + q * HD) - Ls[q]);
     float dp = dot64(vr, dOs + q * HD);
-    if (drop_thresh) dp = attn_drop_hash(seed, e_base + (unsigned long long)q * T) < drop_thresh ? dp * drop_scale : 0.f;
+    if (drop_thresh) dp = attn_drop_hash(attn_row_key(seed, row_bh + q), (uint32_t)j) < drop_thresh ? dp * drop_scale : 0.f;
     axpy64(acc, p * (dp - Dl[q]), Qs + q * HD);
   }
   __nv_bfloat16* ok = dqkv + ((long long)b * T + j) * ld + D + h * HD;
