@@ -1,9 +1,11 @@
-// tcgen05 / TMEM / TMA tile engine: one warp-specialised kernel that serves
+// tcgen05 / TMEM / TMA tile engine: one persistent warp-specialised kernel (compiled per mode and per k-blocks-per-stage)
 //   mode 0  plain GEMM          D[M,N] = sum_k A(m,k) B(n,k)            (linear fwd / dgrad / wgrad)
 //   mode 1  3x3 conv (+1x1)     implicit GEMM over NHWC pixels, taps walked by shifted 4-D TMA boxes
 //   mode 2  conv weight grad    contraction over pixels, both operands MN-major straight from NHWC
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warps 2..5 = epilogue
-// (TMEM -> registers -> fused bias / GELU / dropout / residual -> global).  Accumulators live in TMEM.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = epilogue (TMEM -> registers ->
+// fused bias / GELU / dropout / residual / column statistics -> swizzled staging block -> TMA store or reduce-add).
+// Producer and MMA warps run warp-uniform loops in which one elected lane issues.  Accumulators live in TMEM (two
+// stages), operands in a 192 KB shared-memory ring shared by consecutive tiles.
 #include "common.cuh"
 #include "../../include/pitchextractor_b200.h"
 #include <cstdlib>
