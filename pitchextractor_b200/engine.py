@@ -162,6 +162,10 @@ class Engine:
     def buf(self, name, shape, dtype=torch.bfloat16):
         t = self._bufs.get(name)
         if t is None or t.shape != torch.Size(shape) or t.dtype != dtype:
+            if t is not None and self._graphs:
+                # a captured step holds the address of the buffer that is about to be released (the batch size changed,
+                # e.g. the short last batch of an epoch): drop the graphs, they are re-captured after two eager steps
+                self._graphs = {}
             t = torch.empty(shape, device=self.device, dtype=dtype)
             self._bufs[name] = t
         return t

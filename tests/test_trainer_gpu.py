@@ -232,3 +232,35 @@ def test_prefetched_batches_give_the_same_steps(built_lib):
     assert len(a) == len(b) == 4
     for x, y in zip(a, b):
         assert abs(x - y) <= 5e-3 * abs(x), (a, b)
+
+
+def test_cuda_graph_survives_a_batch_size_change(built_lib):
+    """The short last batch of an epoch re-allocates the activation buffers a captured step points at: the graphs are
+    dropped and re-captured, and the trajectory equals the eagerly launched one."""
+    from pitchextractor_b200 import JDCNet, Trainer, build_optimizer
+    sd = GI.model_state_dict("transformer")
+    g = torch.Generator().manual_seed(12)
+    sizes = [4, 4, 4, 4, 2, 4, 4, 4, 4]
+    batches = []
+    for B in sizes:
+        mel = (torch.randn(B, 1, 80, 192, generator=g) * 2 - 4).cuda()
+        f0 = (torch.rand(B, 192, generator=g) * 300).cuda()
+        batches.append((mel, f0, (f0 < 60).float()))
+
+    def run(use_graph):
+        model = JDCNet(num_class=1, sequence_model_config=GI.model_config("transformer"))
+        model.load_state_dict(sd)
+        model = model.cuda()
+        opt, sched = build_optimizer({"params": model.parameters(), "optimizer_params": {}, "scheduler_params": {}})
+        tr = Trainer(model=model, optimizer=opt, scheduler=sched, loss_config={"lambda_f0": 0.1}, device="cuda")
+        model.engine.use_graph = use_graph
+        model.engine.dropout_enabled = False
+        model.train()
+        out = [tr.run(b)["loss"] for b in batches]
+        return out, any("segments" in e for e in model.engine._graphs.values())
+
+    eager, _ = run(False)
+    graphed, captured = run(True)
+    assert captured  # re-captured after the size change
+    for a, b in zip(eager, graphed):
+        assert abs(a - b) <= 5e-3 * abs(a), (eager, graphed)
