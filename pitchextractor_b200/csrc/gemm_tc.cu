@@ -20,6 +20,7 @@ constexpr int kATileBytes = kBlockM * kRowBytes;  // 16 KB
 constexpr int kNumEpiWarps = 8;
 constexpr int kStagingBytes = 2 * 32 * 64;  // per epilogue warp: two 32-row x 64-byte blocks (64-byte swizzled)
 constexpr int kNumThreads = 64 + 32 * kNumEpiWarps;  // warp 0 = TMA, warp 1 = MMA, warps 2..9 = epilogue
+constexpr int kNumThreadsWgrad = kNumThreads + 32;   // mode 2: warp 10 = second TMA producer (operand B boxes)
 
 struct TcParams {
   int mode;  // 0 gemm, 1 conv fwd, 2 conv wgrad
@@ -72,7 +73,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile) {
 // MODE and KPS are compile-time copies of p.mode and p.kps: the producer / MMA warps are single instruction streams whose per-k-block
 // latency bounds narrow tiles, so their loops must not carry the other modes' branches.
 template <int MODE, int KPS>
-__global__ void __launch_bounds__(kNumThreads, 1)
+__global__ void __launch_bounds__(kNumThreadsWgrad, 1)
 tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_a2,
                const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_out,
                const __grid_constant__ CUtensorMap tma_out2, const TcParams p) {
@@ -110,7 +111,7 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], MODE == 2 ? 2 : 1);  // mode 2: two producer warps arrive
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -121,16 +122,18 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   }
   if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   if (p.ep.stats_mode)
-    for (int i = threadIdx.x; i < 512; i += kNumThreads) s_stats[i] = 0.f;
+    for (int i = threadIdx.x; i < 512; i += (int)blockDim.x) s_stats[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 16 + 5] = clock64() - t_entry;
 
-  if (warp == 0) {
+  if (warp == 0 || (MODE == 2 && warp == 10)) {
     // ------------------------------------------------------------------ TMA producer
-    // (whole warp in uniform control flow, one elected lane issues: see elect_one())
+    // (whole warp in uniform control flow, one elected lane issues: see elect_one()).  The weight-gradient mode needs
+    // 4-6 boxes per k-block and was bound by this warp's issue rate: there warp 0 loads operand A, warp 10 operand B.
+    const int part = MODE == 2 ? (warp == 0 ? 1 : 2) : 0;  // 0: both operands, 1: A only, 2: B only
     {
       const int elems_per_row = p.kind == 0 ? 64 : 32;
       int stage = 0;
@@ -182,7 +185,11 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           }
           if (p.dbg) w_empty += clock64() - c0;
           const bool leader = elect_one();
-          if (leader) mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(nsub * p.tx_bytes));
+          if (leader) {
+            const int bytes = part == 0 ? p.tx_bytes
+                                        : (part == 1 ? p.a_boxes : p.b_boxes) * 64 * kRowBytes;  // (mode 2: KPS == 1)
+            mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(nsub * bytes));
+          }
           for (int sub = 0; sub < nsub; ++sub) {
           const int kb = kb0 + sub;
           uint8_t* sa = smem + (size_t)s * stage_bytes + (size_t)sub * sub_bytes;
@@ -214,11 +221,12 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           } else {
             // k-block = one 64-pixel patch; A = dy (Cout-major); B = x shifted by the tap(s) this tile owns: output
             // column n = tap * Cin + ci, 64-wide boxes, several taps per tile when Cin is small (A is loaded once)
-            for (int j = 0; j < p.a_boxes; ++j)
-              tma_load_4d(&tma_a, &full_bar[s], sa + j * (64 * kRowBytes), m0 + j * 64, pw0, ph0, pb);
+            if (part != 2)
+              for (int j = 0; j < p.a_boxes; ++j)
+                tma_load_4d(&tma_a, &full_bar[s], sa + j * (64 * kRowBytes), m0 + j * 64, pw0, ph0, pb);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              if (j < p.b_boxes)
+              if (part != 1 && j < p.b_boxes)
                 tma_load_4d(&tma_b, &full_bar[s], sb + j * (64 * kRowBytes), box_c[j], pw0 + box_dw[j], ph0 + box_dh[j], pb);
           }
           // per-k-block state, advanced by every lane
@@ -242,7 +250,7 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           __syncwarp();
         }
       }
-      if (p.dbg && lane == 0) p.dbg[blockIdx.x * 16 + 3] = w_empty;
+      if (p.dbg && lane == 0 && warp == 0) p.dbg[blockIdx.x * 16 + 3] = w_empty;
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
@@ -769,7 +777,9 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtens
     attr_set = true;
   }
   const int grid = p.num_tiles < pe_host::num_sms() ? p.num_tiles : pe_host::num_sms();
-#define PE_TC_LAUNCH(M, K) pe::tc_tile_kernel<M, K><<<grid, pe::kNumThreads, smem, stream>>>(ta, ta2, tb, tout, tout2, p)
+#define PE_TC_LAUNCH(M, K)                                                                                  \
+  pe::tc_tile_kernel<M, K><<<grid, (M) == 2 ? pe::kNumThreadsWgrad : pe::kNumThreads, smem, stream>>>(ta, ta2, tb, tout, \
+                                                                                                     tout2, p)
   if (p.mode == 0 && p.kps == 1) PE_TC_LAUNCH(0, 1);
   else if (p.mode == 0) PE_TC_LAUNCH(0, 2);
   else if (p.mode == 1 && p.kps == 1) PE_TC_LAUNCH(1, 1);
