@@ -479,7 +479,7 @@ class Engine:
                          c_int(192), c_int(G), c_int(0), stream())
                 # input gradient (both directions accumulate into the same tensor)
                 if d == 0:
-                    dX[mi] = self.buf("ldx%d_%d" % (mi, l & 1), (M, In))
+                    dX[mi] = self.buf("ldx%d_%d" % (mi, l), (M, In))
                     ops.gemm(dGd, W16[w_ih], dX[mi], M, In, G, b_mn=True)
                 else:
                     ops.gemm(dGd, W16[w_ih], dX[mi], M, In, G, b_mn=True, aux=dX[mi], aux_mode=L.PE_AUX_ADD)
