@@ -172,13 +172,40 @@ class Trainer(object):
         losses = self.run_async(batch).tolist()  # one device->host read of 3 floats
         return {"loss": losses[0], "f0": losses[1], "sil": losses[2]}
 
+    def run_pipelined(self, batches):
+        """``run`` over an iterable of host batches, yielding the same ``{'loss','f0','sil'}`` floats per batch, but one
+        step behind the GPU: step i+1 (its host->device copies, log-mel, graph replay, optimizer) is enqueued before the
+        host waits for the three loss floats of step i, which travel through a small ring of pinned buffers.  The GPU
+        never idles while Python prepares the next step; every batch is still copied in and every loss read back."""
+        ring = [torch.empty(3, dtype=torch.float32).pin_memory() for _ in range(3)]
+        pending, k = None, 0
+
+        def resolve(item):
+            host, ev = item
+            ev.synchronize()
+            v = host.tolist()
+            return {"loss": v[0], "f0": v[1], "sil": v[2]}
+
+        for batch in self.prefetched(batches):
+            dev_losses = self.run_async(batch)
+            host = ring[k % len(ring)]
+            k += 1
+            host.copy_(dev_losses, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            if pending is not None:
+                yield resolve(pending)
+            pending = (host, ev)
+        if pending is not None:
+            yield resolve(pending)
+
     def _train_epoch(self):
         self.epochs += 1
         train_losses = defaultdict(list)
         self.model.train()
-        for _, batch in enumerate(tqdm(self.prefetched(self.train_dataloader), desc="[train]",
-                                       total=len(self.train_dataloader)), 1):
-            for key, value in self.run(batch).items():
+        for _, losses in enumerate(tqdm(self.run_pipelined(self.train_dataloader), desc="[train]",
+                                        total=len(self.train_dataloader)), 1):
+            for key, value in losses.items():
                 train_losses["train/%s" % key].append(value)
         train_losses = {key: np.mean(value) for key, value in train_losses.items()}
         train_losses["train/learning_rate"] = self._get_lr()

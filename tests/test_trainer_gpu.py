@@ -264,3 +264,31 @@ def test_cuda_graph_survives_a_batch_size_change(built_lib):
     assert captured  # re-captured after the size change
     for a, b in zip(eager, graphed):
         assert abs(a - b) <= 5e-3 * abs(a), (eager, graphed)
+
+
+def test_run_pipelined_yields_every_steps_losses(built_lib):
+    """Trainer.run_pipelined == Trainer.run per batch (same values, same order), one step behind the GPU."""
+    from pitchextractor_b200 import JDCNet, Trainer, build_optimizer
+    sd = GI.model_state_dict("transformer")
+    g = torch.Generator().manual_seed(21)
+    batches = []
+    for _ in range(5):
+        mel = (torch.randn(2, 1, 80, 192, generator=g) * 2 - 4).pin_memory()
+        f0 = (torch.rand(2, 192, generator=g) * 300).pin_memory()
+        batches.append((mel, f0, (f0 < 60).float().pin_memory()))
+
+    def make():
+        model = JDCNet(num_class=1, sequence_model_config=GI.model_config("transformer"))
+        model.load_state_dict(sd)
+        model = model.cuda()
+        opt, sched = build_optimizer({"params": model.parameters(), "optimizer_params": {}, "scheduler_params": {}})
+        tr = Trainer(model=model, optimizer=opt, scheduler=sched, loss_config={"lambda_f0": 0.1}, device="cuda")
+        model.engine.dropout_enabled = False
+        model.train()
+        return tr
+
+    a = [make_out["loss"] for make_out in (lambda tr: [tr.run(b) for b in batches])(make())]
+    b = [o["loss"] for o in make().run_pipelined(batches)]
+    assert len(a) == len(b) == 5
+    for x, y in zip(a, b):
+        assert abs(x - y) <= 5e-3 * abs(x), (a, b)
