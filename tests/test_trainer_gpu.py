@@ -292,3 +292,26 @@ def test_run_pipelined_yields_every_steps_losses(built_lib):
     assert len(a) == len(b) == 5
     for x, y in zip(a, b):
         assert abs(x - y) <= 5e-3 * abs(x), (a, b)
+
+
+def test_train_and_eval_epoch_return_the_reference_keys(built_lib):
+    """Trainer._train_epoch / _eval_epoch (reference trainer.py:254-291) over a list of batches."""
+    from pitchextractor_b200 import JDCNet, Trainer, build_optimizer
+    sd = GI.model_state_dict("transformer")
+    g = torch.Generator().manual_seed(31)
+    batches = []
+    for _ in range(3):
+        mel = torch.randn(2, 1, 80, 192, generator=g) * 2 - 4
+        f0 = torch.rand(2, 192, generator=g) * 300
+        batches.append((mel, f0, (f0 < 60).float()))
+    model = JDCNet(num_class=1, sequence_model_config=GI.model_config("transformer"))
+    model.load_state_dict(sd)
+    model = model.cuda()
+    opt, sched = build_optimizer({"params": model.parameters(), "optimizer_params": {}, "scheduler_params": {}})
+    tr = Trainer(model=model, optimizer=opt, scheduler=sched, loss_config={"lambda_f0": 0.1}, device="cuda",
+                 train_dataloader=batches, val_dataloader=batches)
+    out = tr._train_epoch()
+    assert set(out) == {"train/loss", "train/f0", "train/sil", "train/learning_rate"}
+    assert tr.epochs == 1 and tr.steps == 3 and all(v == v for v in out.values())
+    ev = tr._eval_epoch()
+    assert set(ev) == {"eval/loss", "eval/f0", "eval/sil"} and all(v == v for v in ev.values())
