@@ -203,8 +203,8 @@ class Trainer(object):
         self.epochs += 1
         train_losses = defaultdict(list)
         self.model.train()
-        for _, losses in enumerate(tqdm(self.run_pipelined(self.train_dataloader), desc="[train]",
-                                        total=len(self.train_dataloader)), 1):
+        total = len(self.train_dataloader) if hasattr(self.train_dataloader, "__len__") else None
+        for _, losses in enumerate(tqdm(self.run_pipelined(self.train_dataloader), desc="[train]", total=total), 1):
             for key, value in losses.items():
                 train_losses["train/%s" % key].append(value)
         train_losses = {key: np.mean(value) for key, value in train_losses.items()}
