@@ -232,14 +232,15 @@ def run_ours(args):
                    "frac": frames * 1520.0 / (lm_ms / 1e3) / 1e9 / pk["hbm"]},
         "loss_last": last,
     }
+    if world == 1 and not args.no_torch_gpu_baseline:
+        line["torch_gpu_baseline"] = torch_gpu_baseline(args)
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(sample_batch=args.cpu_sample, steps=1, warmup=1, model=args.model)
+        line["cpu_baseline"] = cpu_baseline(args.batch, model=args.model)
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline(sample_batch, steps, warmup, model="transformer"):
-    """Oracle port of reference Trainer.run on the host cores (fp32; AMP / checkpointing are off on CPU in the
-    reference too, trainer.py:64,103), on a bounded sample of the workload."""
+def _port_cpu(sample_batch, steps, warmup, model):
+    """Fallback when baseline/_ref is not staged: the oracle port of reference Trainer.run on the host cores."""
     from oracle import jdcnet_torch as J, train_step as TS
     from pitchextractor_b200 import synthetic
     from pitchextractor_b200.model import JDCNet
@@ -254,11 +255,38 @@ def cpu_baseline(sample_batch, steps, warmup, model="transformer"):
         ref.step(waves, f0, crops)
     t0 = time.perf_counter()
     for _ in range(steps):
-        ref.step(waves, f0, crops)
+        last = ref.step(waves, f0, crops)
     dt = (time.perf_counter() - t0) / steps
-    return {"value": sample_batch / dt, "unit": "segments/s", "cores": cores, "kind": "port",
-            "sample": "%d step(s) of %d segments (of the 64-segment batch), per-sample CPU log-mel + fp32 fwd/bwd + AdamW"
-                      % (steps, sample_batch), "s_per_step": dt}
+    return {"segments_per_s": sample_batch / dt, "s_per_step": dt, "segments_per_step": sample_batch, "cores": cores,
+            "loss_last": last}
+
+
+def reference_cpu(model, batch, steps, warmup, budget_s):
+    """The reference's own CPU implementation of the step (fp32; the reference itself switches AMP and checkpointing
+    off on CPU, trainer.py:64,103) on all host cores: unmodified code from baseline/_ref when staged (kind "reference"),
+    else the oracle port (kind "port")."""
+    import contextlib
+    from baseline import ref_arm
+    cfg = dict(MODEL_CFG, model_type=model)
+    with contextlib.redirect_stdout(sys.stderr):  # the reference prints from build_optimizer
+        if ref_arm.available():
+            r, kind = ref_arm.time_cpu(cfg, batch, steps, warmup, budget_s=budget_s), "reference"
+        else:
+            n = min(batch, 8)
+            r, kind = _port_cpu(n, steps, warmup, model), "port"
+    r["kind"] = kind
+    what = ("unmodified reference (baseline/_ref): MelDataset._build_training_example per sample (torchaudio, CPU) + "
+            "Collater + Trainer.run fp32 + AdamW/OneCycleLR" if kind == "reference" else
+            "oracle port of Trainer.run: per-sample CPU log-mel + fp32 fwd/bwd + AdamW")
+    r["sample"] = "%d timed step(s) of %d segments (batch of the workload: %d), %s, %d host threads" % (
+        steps, r["segments_per_step"], batch, what, r["cores"])
+    return r
+
+
+def cpu_baseline(batch, model="transformer"):
+    r = reference_cpu(model, batch, steps=1, warmup=1, budget_s=25.0)
+    return {"value": r["segments_per_s"], "unit": "segments/s", "cores": r["cores"], "kind": r["kind"],
+            "sample": r["sample"], "s_per_step": r["s_per_step"]}
 
 
 def run_reference(args):
@@ -266,35 +294,28 @@ def run_reference(args):
     if rank != 0:
         return
     world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
-    from oracle import jdcnet_torch as J, train_step as TS
-    from pitchextractor_b200 import synthetic
-    from pitchextractor_b200.model import JDCNet
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    torch.manual_seed(0)
-    sb = args.cpu_sample
-    sd = JDCNet(num_class=1, sequence_model_config=dict(MODEL_CFG, model_type=args.model)).state_dict()
-    ref = TS.ReferenceStep(sd, J.default_config(args.model))
-    waves, f0 = synthetic.make_batch(sb, seed=4321)
-    crops = np.arange(sb) % 4
-    for _ in range(args.warmup):
-        ref.step(waves, f0, crops)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        last = ref.step(waves, f0, crops)
-    dt = time.perf_counter() - t0
-    v = sb * args.steps / dt
-    sample = ("each step = %d segments (bounded sample of the %d-segment batch): per-sample CPU log-mel + fp32 "
-              "forward/backward + AdamW, %d host threads" % (sb, args.batch, cores))
+    r = reference_cpu(args.model, args.batch, args.steps, max(1, args.warmup), budget_s=240.0)
+    v = r["segments_per_s"]
     print(json.dumps({
         "impl": "reference", "metric": "train_segments_per_s", "value": v, "unit": "segments/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["s_per_step"] * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD[args.model] % args.batch,
-                   "global_batch": args.batch, "parallelism": "cpu"},
-        "cpu_baseline": {"value": v, "unit": "segments/s", "cores": cores, "kind": "port", "sample": sample},
+                   "global_batch": args.batch, "parallelism": "cpu", "segments_per_step": r["segments_per_step"]},
+        "cpu_baseline": {"value": v, "unit": "segments/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
         "e2e": {"value": v, "unit": "segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0, "loss_last": last}), flush=True)
+        "gpu_launches": 0, "loss_last": r["loss_last"]}), flush=True)
+
+
+def torch_gpu_baseline(args):
+    """The unmodified reference model + Trainer.run on this GPU through torch (cuDNN / cuBLAS / SDPA), as shipped (fp16
+    autocast + GradScaler + checkpointing) and in its faster settings -- SURVEY 8d: "that is the real bar"."""
+    import contextlib
+    from baseline import ref_arm
+    if not ref_arm.available():
+        return {"unavailable": "baseline/_ref not staged"}
+    with contextlib.redirect_stdout(sys.stderr):
+        return ref_arm.time_gpu(dict(MODEL_CFG, model_type=args.model), args.batch, steps=5, warmup=4)
 
 
 def main():
@@ -307,8 +328,9 @@ def main():
     ap.add_argument("--model", default="transformer", choices=["transformer", "bilstm"],
                     help="sequence model (default: the configuration the metric is quoted on)")
     ap.add_argument("--pool", type=int, default=3, help="distinct synthetic batches cycled through")
-    ap.add_argument("--cpu-sample", type=int, default=8, help="segments per CPU-baseline step")
+    ap.add_argument("--cpu-sample", type=int, default=8, help="(unused; the CPU sample is sized from a time budget)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-torch-gpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -25,28 +25,34 @@ def fbanks_fp32():
     return torch.max(torch.zeros(1), torch.min((-1.0 * slopes[:, :-2]) / f_diff[:-1], slopes[:, 2:] / f_diff[1:]))
 
 
-_FB = None
+_FB = {}
 
 
 def log_mel_torch(wave):
-    """wave [L] fp32 tensor -> [80, T] fp32, the reference's own arithmetic (torch.stft path)."""
-    global _FB
-    if _FB is None:
-        _FB = fbanks_fp32()
-    spec = torch.stft(wave, 1024, 300, 1024, window=torch.hann_window(1024), center=True, pad_mode="reflect",
+    """wave [L] fp32 tensor -> [80, T] fp32, the reference's own arithmetic (torch.stft path), on wave's device."""
+    dev = wave.device
+    if dev not in _FB:
+        _FB[dev] = (fbanks_fp32().to(dev), torch.hann_window(1024).to(dev))
+    fb, win = _FB[dev]
+    spec = torch.stft(wave, 1024, 300, 1024, window=win, center=True, pad_mode="reflect",
                       normalized=False, onesided=True, return_complex=True)
-    mel = (spec.abs().pow(2.0).transpose(-1, -2) @ _FB).transpose(-1, -2)
+    mel = (spec.abs().pow(2.0).transpose(-1, -2) @ fb).transpose(-1, -2)
     return (torch.log(1e-5 + mel) + 4.0) / 4.0
 
 
 class ReferenceStep:
     """Holds fp32 leaf parameters (reference state_dict layout) + torch AdamW / OneCycleLR and runs CPU steps."""
 
-    def __init__(self, state_dict, cfg, lambda_f0=0.1, max_lr=3e-4, epochs=100, steps_per_epoch=1000):
+    def __init__(self, state_dict, cfg, lambda_f0=0.1, max_lr=3e-4, epochs=100, steps_per_epoch=1000, device="cpu",
+                 autocast_dtype=None):
+        """device: where the fp32 restatement is evaluated (the host for the CPU baseline; a CUDA device lets the tests
+        compare long trajectories in seconds -- TF32 must then be disabled by the caller).  autocast_dtype: run the
+        forward under torch.autocast (yardstick: what torch's own mixed precision does to the same trajectory)."""
         self.cfg, self.lambda_f0 = cfg, lambda_f0
+        self.device, self.autocast_dtype = torch.device(device), autocast_dtype
         self.sd = {}
         for k, v in state_dict.items():
-            t = v.detach().clone().cpu()
+            t = v.detach().clone().to(self.device)
             if t.dtype.is_floating_point:
                 t = t.float().contiguous()
                 if "running" not in k and not k.endswith(".pe"):
@@ -62,16 +68,20 @@ class ReferenceStep:
         """waves [B, L] fp32, f0s [B, T_full] Hz, crops [B] -> dict of python floats (trainer.py:250-252)."""
         items = []
         for w, f0, c in zip(waves, f0s, crops):
-            mel = log_mel_torch(torch.as_tensor(w))
+            mel = log_mel_torch(torch.as_tensor(w).to(self.device))
             f0a = logmel_np.align_length(np.asarray(f0), mel.shape[1])
             c = int(c)
             f0c = f0a[c:c + 192]
-            items.append((mel[:, c:c + 192].numpy(), f0c, (f0c == 0).astype(np.float32)))
-        mels, f0b, silb = (torch.from_numpy(a) for a in logmel_np.collate(items))
+            items.append((mel[:, c:c + 192].cpu().numpy(), f0c, (f0c == 0).astype(np.float32)))
+        mels, f0b, silb = (torch.from_numpy(a).to(self.device) for a in logmel_np.collate(items))
         self.opt.zero_grad(set_to_none=True)
-        cls, det = J.jdcnet_forward(self.sd, mels.transpose(-1, -2), self.cfg, training=True,
-                                    p_scale=1.0 if dropout else 0.0, update_running=True)
-        loss, lf, ls = J.losses(cls, det, f0b, silb, self.lambda_f0)
+        import contextlib
+        ctx = (torch.autocast(self.device.type, dtype=self.autocast_dtype) if self.autocast_dtype is not None
+               else contextlib.nullcontext())
+        with ctx:
+            cls, det = J.jdcnet_forward(self.sd, mels.transpose(-1, -2), self.cfg, training=True,
+                                        p_scale=1.0 if dropout else 0.0, update_running=True)
+            loss, lf, ls = J.losses(cls.float(), det.float(), f0b, silb, self.lambda_f0)
         loss.backward()
         self.opt.step()
         self.sched.step()

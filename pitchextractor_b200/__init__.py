@@ -6,4 +6,5 @@ from .model import JDCNet, ResBlock, SequenceModel, SinusoidalPositionalEncoding
 from .meldataset import MelDataset, Collater, build_dataloader, align_length  # noqa: E402,F401
 from .optimizers import build_optimizer, FusedAdamW  # noqa: E402,F401
 from .trainer import Trainer  # noqa: E402,F401
-from .inference import predict_f0, compute_metrics, rms_cents_error, hz_to_cents  # noqa: E402,F401
+from .inference import (predict_f0, compute_metrics, rms_cents_error, hz_to_cents,  # noqa: E402,F401
+                        estimate_tracking_delay_ms, compute_overshoot_cents)

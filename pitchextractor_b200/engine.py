@@ -68,6 +68,12 @@ class Engine:
         if self.seq_type == "bilstm" and (sc.hidden_size != 384 or not sc.bidirectional):
             raise NotImplementedError("the LSTM recurrence kernels are built for hidden_size 384, bidirectional")
         self.p_lstm = float(getattr(sc, "lstm_dropout", 0.0))
+        # dropout site ids (the low 8 bits of a site's seed): 1, 2 trunk; 8 per encoder layer, the classifier stack from
+        # 16, the detector stack right behind it; LSTM inter-layer dropouts from 128.  SequenceModel bounds num_layers
+        # so that no two sites share an id.
+        self._site_c = 16
+        self._site_d = 16 + 8 * self.num_layers
+        assert self._site_d + 8 * self.num_layers <= 128 or self.seq_type != "transformer"
         self.step_seed = 0x5EED0000
         self.dropout_enabled = True
         self._bufs = {}
@@ -80,6 +86,8 @@ class Engine:
         # (~270 launches per step; eagerly the host needs ~10 ms to enqueue them).  PE_CUDA_GRAPH=0 disables it.
         self.use_graph = os.environ.get("PE_CUDA_GRAPH", "1") != "0"
         self._graphs = {}
+        self.bf16_fresh = False
+        self._capturing = False
         self._pack()
 
     # ------------------------------------------------------------------ parameter arenas
@@ -144,9 +152,20 @@ class Engine:
         self.flat_grad.zero_()
         self.attach_grads()
 
+    def invalidate_bf16(self):
+        """The fp32 master weights were written by something other than FusedAdamW.step (state_dict load, broadcast)."""
+        self.bf16_fresh = False
+
+    def cast_weights(self):
+        """bf16 working copy of the fp32 master weights.  FusedAdamW.step writes it in the optimizer pass itself
+        (``bf16_fresh``); one forward consumes that freshness, so any other writer of the weights (another optimizer,
+        load_state_dict, in-place edits) is picked up by the cast of the following forward."""
+        if not self.bf16_fresh:
+            call("pe_cast_bf16", ptr(self.flat), ptr(self.flat_bf16), c_ll(self.total), stream())
+        self.bf16_fresh = False
+
     def refresh_weights(self):
-        """bf16 working copies of the (possibly just updated) fp32 master weights + conv operand layouts."""
-        call("pe_cast_bf16", ptr(self.flat), ptr(self.flat_bf16), c_ll(self.total), stream())
+        """Tensor-core operand layouts of the convolution weights (from the fp32 master weights)."""
         V = self.view
         prep = lambda w, co, ci, w2, c2, fwd, dgrad: call(
             "pe_conv_weight_prep", ptr(w), c_int(co), c_int(ci), ptr(w2), c_int(c2), ptr(fwd), ptr(dgrad), stream())
@@ -257,6 +276,8 @@ class Engine:
         self.step_seed += 1
         if training:
             self.bn_sums.zero_()
+        if not self._capturing:
+            self.cast_weights()
         self.refresh_weights()
         V, W16 = self.view, self.bview
         BT = B * T
@@ -311,8 +332,8 @@ class Engine:
             # stack's kernels (partial last wave, epilogue drain) is filled by the other's
             with self._forked() as side:
                 with torch.cuda.stream(side):
-                    Hd = self._transformer_fwd("sequence_detector", "d", SEQD, B, T, training, 64)
-                Hc = self._transformer_fwd("sequence_classifier", "c", SEQC, B, T, training, 16)
+                    Hd = self._transformer_fwd("sequence_detector", "d", SEQD, B, T, training, self._site_d)
+                Hc = self._transformer_fwd("sequence_classifier", "c", SEQC, B, T, training, self._site_c)
         else:
             Hc, Hd = self._bilstm_fwd(SEQC, SEQD, B, T, training)
         self._Hc, self._Hd = Hc, Hd
@@ -587,8 +608,8 @@ class Engine:
         if self.seq_type == "transformer":
             with self._forked() as side:
                 with torch.cuda.stream(side):
-                    dSEQD = self._transformer_bwd("sequence_detector", "d", bufs["SEQD"], dHd, B, T, 64)
-                dSEQC = self._transformer_bwd("sequence_classifier", "c", bufs["SEQC"], dHc, B, T, 16)
+                    dSEQD = self._transformer_bwd("sequence_detector", "d", bufs["SEQD"], dHd, B, T, self._site_d)
+                dSEQC = self._transformer_bwd("sequence_classifier", "c", bufs["SEQC"], dHc, B, T, self._site_c)
             notify("sequence_detector+heads")
             notify("sequence_classifier")
         else:
@@ -703,6 +724,7 @@ class Engine:
         self.step_seed += 1
         # the graph's launch arguments carry the seeds of the capture step; the salt moves them to this step's
         self._set_salt((self.step_seed - ent["seed"]) << 8)
+        self.cast_weights()  # not part of the graph: skipped when FusedAdamW.step already wrote the bf16 copy
         if self.reducer is not None:
             self.reducer.begin_step()
         for graph, tags in ent["segments"]:
@@ -755,6 +777,8 @@ class Engine:
 
         real = self.reducer
         side = torch.cuda.Stream(device=self.device)
+        self.cast_weights()
+        self._capturing = True
         torch.cuda.synchronize()
         side.wait_stream(torch.cuda.current_stream())
         try:
@@ -771,6 +795,7 @@ class Engine:
                     end(None)
         except Exception as e:  # stay on the eager CUDA path (still no CPU fallback)
             self.reducer = real
+            self._capturing = False
             if "g" in cur:
                 try:
                     cur["g"].capture_end()
@@ -784,6 +809,7 @@ class Engine:
             self.step_seed, self._fwd_token, L.launch_count = seed_before, token_before, launches_before
             return
         self.reducer = real
+        self._capturing = False
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         ent["segments"] = segments

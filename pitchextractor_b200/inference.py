@@ -93,3 +93,29 @@ def voicing_accuracy(sil_logit, reference_f0):
     """Detector-head accuracy: sigmoid(logit) > 0.5 means silence / unvoiced (label ``f0 == 0``, meldataset.py:659-665)."""
     n = min(sil_logit.shape[0], reference_f0.shape[0])
     return float(np.mean((sil_logit[:n] > 0.0) == (reference_f0[:n] == 0)))
+
+
+def estimate_tracking_delay_ms(reference, prediction, frame_period_ms):
+    """Lag (ms) at which the mean-removed prediction correlates best with the mean-removed reference track
+    (Utils/dynamic_pitch_tools.py:107-124); positive = the prediction trails the reference."""
+    n = min(reference.shape[0], prediction.shape[0])
+    if n == 0:
+        return float("nan")
+    ref = reference[:n] - np.mean(reference[:n])
+    pred = prediction[:n] - np.mean(prediction[:n])
+    if np.allclose(ref, 0) or np.allclose(pred, 0):
+        return float("nan")
+    xc = np.correlate(pred, ref, mode="full")
+    return float((int(np.argmax(xc)) - (n - 1)) * frame_period_ms)
+
+
+def compute_overshoot_cents(reference, prediction):
+    """Peak of the predicted track relative to the reference's final value, in cents
+    (Utils/dynamic_pitch_tools.py:127-136)."""
+    n = min(reference.shape[0], prediction.shape[0])
+    if n == 0:
+        return float("nan")
+    target, peak = reference[:n][-1], np.max(prediction[:n])
+    if target <= 0 or peak <= 0:
+        return float("nan")
+    return float(1200.0 * np.log2(peak / target))

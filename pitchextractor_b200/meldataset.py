@@ -69,7 +69,12 @@ class MelDataset(torch.utils.data.Dataset):
         if self.synthetic_config.get("enabled", False) and not (validation and not self.synthetic_config.get(
                 "apply_to_validation", False)):
             self._synthetic_count = max(1, int(round(self._base_length * float(self.synthetic_config.get("ratio", 0.25)))))
-        self._rng = np.random.RandomState(1)  # the reference seeds np.random with 1 at import (meldataset.py:31)
+        # The reference draws crops / segment starts / the augmentation gain from the process-global numpy / random
+        # generators (seeded with 1 at import, meldataset.py:31-32), which torch re-seeds per DataLoader worker and per
+        # epoch.  A private generator pickled into every worker would repeat the same draws in all of them, so it is
+        # created lazily inside the process that serves the items (see _random()).
+        self._rng = None
+        self._rng_owner = None
         self._logmel = None
         hop = self.mel_params["hop_length"]
         self.segment_samples = int(np.ceil((self.max_mel_length * hop + self.mel_params["n_fft"])))
@@ -77,9 +82,20 @@ class MelDataset(torch.utils.data.Dataset):
     def __len__(self):
         return self._base_length + self._synthetic_count
 
+    def _random(self):
+        """Per-process generator: in a DataLoader worker it is seeded from the worker's torch seed (base_seed +
+        worker_id, fresh every epoch for non-persistent workers), in the main process with 1 as the reference does."""
+        pid = os.getpid()
+        if self._rng is None or self._rng_owner != pid:
+            info = torch.utils.data.get_worker_info()
+            seed = 1 if info is None else int(info.seed) % (2 ** 32)
+            self._rng, self._rng_owner = np.random.RandomState(seed), pid
+        return self._rng
+
     def __getstate__(self):
         state = self.__dict__.copy()
         state["_logmel"] = None  # CUDA tables are rebuilt lazily in the worker / after unpickling
+        state["_rng"] = state["_rng_owner"] = None
         return state
 
     # ---------------------------------------------------------------- item sources
@@ -96,7 +112,7 @@ class MelDataset(torch.utils.data.Dataset):
             f0_path = path[:-4] + "_f0.npy"
             f0 = np.load(f0_path) if os.path.isfile(f0_path) else None
             if wave.shape[0] > self.segment_samples:  # random segment, as meldataset.py:196-201
-                start = int(self._rng.randint(0, wave.shape[0] - self.segment_samples))
+                start = int(self._random().randint(0, wave.shape[0] - self.segment_samples))
                 hop = self.mel_params["hop_length"]
                 if f0 is not None:
                     f0 = f0[start // hop: start // hop + 1 + self.segment_samples // hop + 4]
@@ -107,6 +123,8 @@ class MelDataset(torch.utils.data.Dataset):
 
     def __getitem__(self, idx):
         wave, f0 = self._load_item(idx)
+        if self.data_augmentation:  # random gain in [0.5, 1) (meldataset.py:232-234)
+            wave = (0.5 + 0.5 * self._random().random_sample()) * np.asarray(wave, dtype=np.float32)
         if self.return_wave:
             return self._build_wave_example(wave, f0)
         return self._build_training_example(wave, self.sr, f0)
@@ -116,7 +134,7 @@ class MelDataset(torch.utils.data.Dataset):
         f0 = np.zeros((mel_length,), np.float32) if f0 is None else align_length(f0, mel_length)
         start = 0
         if mel_length > self.max_mel_length:
-            start = int(self._rng.randint(0, mel_length - self.max_mel_length))
+            start = int(self._random().randint(0, mel_length - self.max_mel_length))
             f0 = f0[start:start + self.max_mel_length]
         sil = (f0 == 0).astype(np.float32)
         f0 = np.where(np.isnan(f0), np.float32(self.zero_value), f0).astype(np.float32)

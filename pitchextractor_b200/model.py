@@ -56,9 +56,21 @@ class SequenceModel(nn.Module):
         self.input_size, self.hidden_size, self.num_layers = input_size, hidden_size, num_layers
         self.bidirectional, self.nhead, self.dim_feedforward = bidirectional, nhead, dim_feedforward
         self.dropout = dropout
+        # fail at construction, not at the first step on the GPU, for shapes the sm_100a kernels are not built for
+        if self.model_type == "bilstm" and (hidden_size != 384 or not bidirectional or input_size != 512):
+            raise NotImplementedError("the LSTM kernels are built for input_size 512, hidden_size 384, bidirectional "
+                                      "(reference defaults, model.py:199-210); got input_size=%d hidden_size=%d "
+                                      "bidirectional=%s" % (input_size, hidden_size, bidirectional))
+        if self.model_type == "bilstm" and not 1 <= num_layers <= 16:
+            raise NotImplementedError("1..16 LSTM layers are supported (dropout site ids)")
         if self.model_type == "transformer":  # registered before `model`, as in the reference (state_dict key order)
-            if input_size % nhead or input_size // nhead != 64:
-                raise ValueError("the attention kernels are built for head_dim 64 (d_model / nhead)")
+            if input_size != 512 or input_size % nhead or input_size // nhead != 64:
+                raise NotImplementedError("the attention kernels are built for d_model 512 with head_dim 64 "
+                                          "(d_model / nhead); got d_model=%d nhead=%d" % (input_size, nhead))
+            if not 1 <= num_layers <= 7:
+                raise NotImplementedError("1..7 encoder layers are supported (dropout site ids)")
+            if dim_feedforward % 64:
+                raise NotImplementedError("dim_feedforward must be a multiple of 64")
             self.pos_encoding = SinusoidalPositionalEncoding(input_size, max_len=max_len)
         self.model = _Node()
         if self.model_type == "bilstm":
@@ -193,6 +205,12 @@ class JDCNet(nn.Module):
 
     def forward(self, x):
         return self.engine.autograd_forward(x)
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        if self._engine is not None:
+            self._engine.invalidate_bf16()  # the fp32 master weights changed under the bf16 working copy
+        return out
 
     def train_step_loss(self, mel, f0, sil, lambda_f0=0.1, grad_scale=1.0):
         """Fused forward + losses + backward for Trainer.run: fills ``.grad`` of every parameter and returns a

@@ -62,7 +62,8 @@ class FusedAdamW(Optimizer):
         call("pe_adamw", ptr(eng.flat), ptr(eng.flat_grad), ptr(self.exp_avg), ptr(self.exp_avg_sq),
              ctypes.c_longlong(eng.total), ctypes.c_float(g["lr"]), ctypes.c_float(b1), ctypes.c_float(b2),
              ctypes.c_float(g["eps"]), ctypes.c_float(g["weight_decay"]), ctypes.c_longlong(self._steps),
-             ctypes.c_float(self.grad_scale), None, stream())
+             ctypes.c_float(self.grad_scale), ptr(eng.flat_bf16), stream())
+        eng.bf16_fresh = True  # the same pass wrote the bf16 tensor-core copy of the updated weights
         for st in self.state.values():
             st["step"].fill_(float(self._steps))
 

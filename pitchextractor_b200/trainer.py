@@ -38,6 +38,10 @@ class Trainer(object):
         self.finish_train = False
         if self.device.type != "cuda":
             raise RuntimeError("pitchextractor_b200.Trainer runs on a CUDA (sm_100a) device; there is no CPU fallback")
+        # The fused step computes exactly the criteria train.py:104-106 builds: {'l1': SmoothL1Loss(), 'ce':
+        # BCEWithLogitsLoss()} with default arguments.  Any other criterion dict still trains on the CUDA engine, through
+        # JDCNet.forward + autograd (losses evaluated by the caller's modules on the GPU); anything else is an error.
+        self._fused_losses = self._criterion_is_reference_default(criterion)
         self.use_amp = True  # bf16 tensor-core operands, fp32 accumulation / master weights
         self.gradient_checkpointing = False
         if gradient_checkpointing:
@@ -47,6 +51,21 @@ class Trainer(object):
         self._reducer = None
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.sync_every_step = True  # reference semantics: run() returns python floats (3 .item() syncs there, 1 here)
+
+    @staticmethod
+    def _criterion_is_reference_default(criterion):
+        """True when the fused heads + losses kernel computes exactly this criterion (None = the reference default)."""
+        if criterion is None:
+            return True
+        if not isinstance(criterion, dict) or set(criterion) != {"l1", "ce"}:
+            raise ValueError("criterion must be None or a dict {'l1': <F0 loss>, 'ce': <silence loss>} as built by the "
+                             "reference (train.py:104-106); got %r" % (criterion,))
+        l1, ce = criterion["l1"], criterion["ce"]
+        if not (callable(l1) and callable(ce)):
+            raise ValueError("criterion['l1'] and criterion['ce'] must be callable loss modules")
+        return (type(l1) is torch.nn.SmoothL1Loss and l1.reduction == "mean" and float(l1.beta) == 1.0
+                and type(ce) is torch.nn.BCEWithLogitsLoss and ce.reduction == "mean" and ce.weight is None
+                and ce.pos_weight is None)
 
     # ------------------------------------------------------------------ checkpoints (trainer.py:138-195)
     def save_checkpoint(self, checkpoint_path):
@@ -83,6 +102,8 @@ class Trainer(object):
                 continue
             corner = tuple(slice(0, min(a, b)) for a, b in zip(val.shape, dst.shape))
             dst[corner].copy_(val[corner])
+        if getattr(model, "_engine", None) is not None:
+            model._engine.invalidate_bf16()
 
     @staticmethod
     def get_gradient_norm(model):
@@ -144,6 +165,7 @@ class Trainer(object):
         if self.world > 1 and self._reducer is None:
             eng = self.model.engine
             broadcast_parameters(eng.flat)
+            eng.invalidate_bf16()
             for b in self.model.buffers():
                 if b.dtype.is_floating_point:
                     dist.broadcast(b, src=0)
@@ -160,13 +182,31 @@ class Trainer(object):
         x, f0, sil = self._mel_from_batch(batch)
         f0 = f0.to(self.device, non_blocking=True)
         sil = sil.to(self.device, non_blocking=True)
-        losses = self.model.train_step_loss(x, f0, sil, self.loss_config["lambda_f0"])
+        if self._fused_losses:
+            losses = self.model.train_step_loss(x, f0, sil, self.loss_config["lambda_f0"])
+        else:
+            losses = self._autograd_step(x, f0, sil)
         if self._reducer is not None and not hasattr(self.optimizer, "grad_scale"):
             self.model.engine.flat_grad.mul_(1.0 / self.world)
         self.optimizer.step()
         self.scheduler.step()
         self.steps += 1
         return losses
+
+    def _autograd_step(self, x, f0, sil):
+        """trainer.py:226-246 with a caller-supplied criterion: engine forward, torch losses, engine backward."""
+        eng = self.model.engine
+        if self._reducer is not None:
+            self._reducer.begin_step()
+        eng.zero_grad()
+        f0_pred, sil_pred = self.model(x.transpose(-1, -2))
+        loss_f0 = self.loss_config["lambda_f0"] * self.criterion["l1"](f0_pred.squeeze(), f0)
+        loss_sil = self.criterion["ce"](sil_pred, sil)
+        loss = loss_f0 + loss_sil
+        loss.backward()
+        if self._reducer is not None:
+            self._reducer.wait()
+        return torch.stack([loss.detach(), loss_f0.detach(), loss_sil.detach()]).float()
 
     def run(self, batch):
         losses = self.run_async(batch).tolist()  # one device->host read of 3 floats
@@ -217,7 +257,14 @@ class Trainer(object):
         eval_losses = defaultdict(list)
         for _, batch in enumerate(tqdm(self.val_dataloader, desc="[eval]"), 1):
             x, f0, sil = self._mel_from_batch(batch)
-            out = self.model.engine.eval_loss(x, f0, sil, self.loss_config["lambda_f0"]).tolist()
+            if self._fused_losses:
+                out = self.model.engine.eval_loss(x, f0, sil, self.loss_config["lambda_f0"]).tolist()
+            else:
+                f0_d, sil_d = f0.to(self.device), sil.to(self.device)
+                f0_pred, sil_pred = self.model(x.transpose(-1, -2))
+                lf = self.loss_config["lambda_f0"] * self.criterion["l1"](f0_pred.squeeze(), f0_d)
+                ls = self.criterion["ce"](sil_pred, sil_d)
+                out = [(lf + ls).item(), lf.item(), ls.item()]
             eval_losses["eval/loss"].append(out[0])
             eval_losses["eval/f0"].append(out[1])
             eval_losses["eval/sil"].append(out[2])

@@ -145,3 +145,22 @@ def test_metrics_match_reference_definitions():
         assert abs(T.rms_cents_error(ref, pred) - I.rms_cents_error(ref, pred)) < 1e-6
         np.testing.assert_array_equal(T.hz_to_cents(ref), I.hz_to_cents(ref))
         np.testing.assert_allclose(T.circular_cents_distance(cents, 0 * cents), I.circular_cents_distance(cents, 0 * cents))
+        step = np.concatenate([np.full(40, 220.0), np.full(60, 330.0)])
+        lagged = np.concatenate([np.full(47, 220.0), 330.0 + 25.0 * np.exp(-np.arange(53) / 6.0)])
+        assert T.estimate_tracking_delay_ms(step, lagged, 12.5) == I.estimate_tracking_delay_ms(step, lagged, 12.5)
+        assert T.compute_overshoot_cents(step, lagged) == I.compute_overshoot_cents(step, lagged)
+
+
+def test_lag_and_overshoot_known_answers():
+    """estimate_tracking_delay_ms / compute_overshoot_cents (Utils/dynamic_pitch_tools.py:107-136) on hand cases."""
+    from pitchextractor_b200 import inference as I
+    rng = np.random.default_rng(1)
+    ref = 20.0 * rng.standard_normal(400) + 200.0  # white around 200 Hz: a sharp correlation peak
+    pred = np.concatenate([np.full(5, ref[0]), ref[:-5]])           # the prediction trails by 5 frames
+    assert I.estimate_tracking_delay_ms(ref, pred, 12.5) == 62.5
+    assert I.estimate_tracking_delay_ms(ref, ref, 10.0) == 0.0
+    assert np.isnan(I.estimate_tracking_delay_ms(np.full(10, 3.0), ref[:10], 1.0))
+    assert np.isnan(I.estimate_tracking_delay_ms(ref[:0], ref[:0], 1.0))
+    step = np.concatenate([np.full(10, 220.0), np.full(10, 440.0)])
+    assert abs(I.compute_overshoot_cents(step, step * 2.0 ** (100.0 / 1200.0)) - 100.0) < 1e-9
+    assert np.isnan(I.compute_overshoot_cents(np.zeros(4), np.ones(4)))
