@@ -35,6 +35,10 @@ typedef struct CUstream_st* pe_stream_t; /* == cudaStream_t */
 
 int pe_version(void);
 int pe_check_device(void); /* PE_OK iff the current device is sm_100 */
+/* Bytes of caller-provided workspace entry point `op` (its name, e.g. "pe_lstm_seq_fwd") needs for a batch of B items:
+ * pe_lstm_seq_fwd / _bwd (B, T): arrival counters;  pe_logmel_tc (B, L samples): the re-strided waveform copy;
+ * pe_logmel_f32 (B, T frames, L = n_fft): the power spectrogram.  0 for entry points that need none, -1 on bad arguments. */
+long long pe_workspace_bytes(const char* op, int B, int T, int L);
 
 /* Per-step dropout salt: every dropout site (reference model.py:40,56 nn.Dropout, the Transformer / LSTM dropouts of
  * model.py:306-341) draws its mask from (seed argument + salt).  The salt lives in device memory so that a training
@@ -120,25 +124,27 @@ int pe_conv_wgrad_nhwc(const void* dy, const void* x, float* dw, long long ldw, 
  *   power  : fp32 workspace [B*T][n_fft/2+1]
  *   out_bmt: [B][n_mels][T_out] (reference layout) or NULL;  out_btm: [B][T_out][n_mels] (model layout) or NULL
  *   crop   : int32 [B] first frame kept per item (NULL = 0); T_out frames are written (zero-padded past T).
+ *   lengths: int32 [B] valid samples per item (NULL = L): the reflect padding happens at the item's OWN end and frames
+ *            t >= 1 + lengths[b] / hop are written as 0 (what Collater pads short items with, meldataset.py:804-816).
  * ------------------------------------------------------------------------------------------------ */
 int pe_logmel_f32(const float* wave, int B, int L, int n_fft, int hop, int n_mels, const float* basis,
                   int ld_basis, const float* fb, float* power, size_t power_bytes, float* out_bmt, float* out_btm,
-                  const int* crop, int T_out, pe_stream_t stream);
-/* Same transform on tcgen05 tensor cores for n_fft == 1024: two frames per complex FFT, 32 x 32 four-step
- * factorisation as two [128 x 64] x [64 x 64] fp16-split GEMM stages per 8 frames (fp32-grade accuracy).
+                  const int* crop, const int* lengths, int T_out, pe_stream_t stream);
+/* Same transform on tcgen05 tensor cores for n_fft == 1024, hop % 4 == 0, hop <= 320: two frames per complex FFT,
+ * 32 x 32 four-step factorisation as two [128 x 64] x [64 x 64] fp16-split GEMM stages per 8 frames (fp32-grade
+ * accuracy); every 8-frame slot reads its 1024 + 7*hop samples once.
  *   win [1024] fp32 window;  fmat: 3 x [64][64] fp16 operand images (hi, lo, hi * 2^-11) of the 32-point complex DFT
  *   matrix in the 128-byte-swizzled K-major layout;  tw [2][32][32] fp32 cos / sin of 2 pi k1 n2 / 1024;
- *   mel_start / mel_count / mel_off [n_mels] + mel_w [mel_nnz]: banded filterbank;  xpad: fp32 workspace
- *   [B][round_up(L, 4)], used only when L % 4 != 0 (rows are re-strided to 16 bytes); the reflect padding happens
- *   inside the kernel.  Output frames t with 0 <= t - crop[b] < T_out are
- *   written (the caller zero-fills the outputs when padding rows are possible). */
+ *   mel_w [mel_nnz <= 1536]: the non-zero filterbank weights, band after band;  mel_items int32 [128][4]: the work items
+ *   of the banded mel product, one per worker lane: {filter (-1: idle), first bin, number of bins, offset into mel_w |
+ *   flags << 24}, flags 1 = add the partial sums of lane ^ 1 (a long filter split over two adjacent lanes), 2 = this lane
+ *   writes the filter (n_mels <= 128);
+ *   xpad: fp32 workspace [B][round_up(L, 4)], used only when L % 4 != 0 (rows are re-strided to 16 bytes); the reflect
+ *   padding happens inside the kernel.  Only frames crop[b] .. crop[b] + T_out - 1 are computed; ALL T_out output rows of
+ *   every item are written (zeros past the item's end, see `lengths` above). */
 int pe_logmel_tc(const float* wave, int B, int L, int n_fft, int hop, int n_mels, const float* win, const void* fmat,
-                 const float* tw, const int* mel_start, const int* mel_count, const int* mel_off, const float* mel_w,
-                 int mel_nnz, float* xpad, size_t xpad_bytes, float* out_bmt, float* out_btm, const int* crop,
-                 int T_out, pe_stream_t stream);
-
-/* tuning aid: per-CTA cycle counters of the tcgen05 log-mel worker phases, [grid][8] */
-int pe_logmel_set_debug(long long* buf);
+                 const float* tw, const int* mel_items, const float* mel_w, int mel_nnz, float* xpad, size_t xpad_bytes,
+                 float* out_bmt, float* out_btm, const int* crop, const int* lengths, int T_out, pe_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Conv trunk, memory-bound passes over NHWC bf16 activations (model.py:23-57,143-175).
@@ -235,6 +241,16 @@ int pe_lstm_steps_fwd(int B, int T, int hidden, int step_begin, int step_end, fl
 int pe_lstm_steps_bwd(int B, int T, int hidden, int step_begin, int step_end, const float* const* gates,
                       const float* const* c, const void* const* dy, void* const* dg, float* const* dc,
                       const void* const* w_hh, pe_stream_t stream);
+/* The same recurrences as ONE persistent launch per layer over all T steps (north_star: "persistent kernel with its
+ * weights resident in shared memory"): every CTA keeps its 192 KB slice of W_hh in shared memory, h_t / dgates_t are
+ * exchanged through L2 with a per-step arrival counter.  Same tensors as above; the cell-state gradient is carried in
+ * registers.  workspace: pe_workspace_bytes("pe_lstm_seq_fwd", B, T, 0) bytes of device memory (zeroed by the call). */
+int pe_lstm_seq_fwd(int B, int T, int hidden, float* const* gx, float* const* c, void* const* y,
+                    const void* const* w_hh, const float* const* b_ih, const float* const* b_hh, void* workspace,
+                    size_t workspace_bytes, pe_stream_t stream);
+int pe_lstm_seq_bwd(int B, int T, int hidden, const float* const* gates, const float* const* c, const void* const* dy,
+                    void* const* dg, const void* const* w_hh, void* workspace, size_t workspace_bytes,
+                    pe_stream_t stream);
 /* y = dropout(x) on n bf16 elements (n % 8 == 0); the same call with the same seed back-propagates */
 int pe_dropout_bf16(const void* x, void* y, long long n, unsigned drop_thresh, float drop_scale,
                     unsigned long long seed, pe_stream_t stream);

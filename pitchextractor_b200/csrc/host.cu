@@ -99,5 +99,32 @@ extern "C" int pe_set_step_salt(unsigned long long salt, pe_stream_t stream) {
   return cudaGetLastError() == cudaSuccess ? PE_OK : PE_ERR_LAUNCH;
 }
 
-extern "C" int pe_version(void) { return 100; }
+// Workspace a caller must provide (functions of this library never allocate).  op names the entry point.
+extern "C" long long pe_workspace_bytes(const char* op, int B, int T, int L) {
+  if (!op || B <= 0) return -1;
+  auto is = [&](const char* n) {
+    const char* a = op;
+    while (*a && *n && *a == *n) { ++a; ++n; }
+    return *a == 0 && *n == 0;
+  };
+  if (is("pe_lstm_seq_fwd") || is("pe_lstm_seq_bwd")) {  // per-step arrival counters of the launch's batch tiles
+    if (T <= 0) return -1;
+    const int NB = B <= 16 ? 16 : B <= 32 ? 32 : B <= 64 ? 64 : 128;
+    int nbt = (B + NB - 1) / NB;
+    const int max_bt = pe_host::num_sms() / 24 > 0 ? pe_host::num_sms() / 24 : 6;
+    if (nbt > max_bt) nbt = max_bt;
+    return (long long)4 * nbt * T * (long long)sizeof(int);
+  }
+  if (is("pe_logmel_tc")) {  // re-strided waveform copy, only used when rows are not 16-byte aligned
+    if (L <= 0) return -1;
+    return (long long)B * (((long long)L + 3) / 4 * 4) * (long long)sizeof(float);
+  }
+  if (is("pe_logmel_f32")) {  // power spectrogram [B*T][n_fft/2+1] with T = frames, L = n_fft here
+    if (T <= 0 || L <= 0) return -1;
+    return (long long)B * T * (L / 2 + 1) * (long long)sizeof(float);
+  }
+  return 0;  // every other entry point works in place / in caller-provided outputs
+}
+
+extern "C" int pe_version(void) { return 110; }
 extern "C" int pe_check_device(void) { return pe_host::check_arch(); }

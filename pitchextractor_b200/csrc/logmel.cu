@@ -20,7 +20,8 @@ __device__ __forceinline__ int reflect_idx(int i, int L) {
 // power[f][bin] for f in [0, B*T), bin in [0, n_bins)
 __global__ void __launch_bounds__(256)
 dft_power_kernel(const float* __restrict__ wave, int B, int L, int T, int n_fft, int hop,
-                 const float* __restrict__ basis, int ld_basis, int n_bins, float* __restrict__ power) {
+                 const float* __restrict__ basis, int ld_basis, int n_bins, float* __restrict__ power,
+                 const int* __restrict__ lengths) {
   __shared__ __align__(16) float As[DFT_TK][DFT_TM + 4];
   __shared__ __align__(16) float Bs[DFT_TK][DFT_TN];
   const int tid = threadIdx.x;
@@ -37,6 +38,7 @@ dft_power_kernel(const float* __restrict__ wave, int B, int L, int T, int n_fft,
   const int fb_ = f_ok ? gf / T : 0;
   const int ft = f_ok ? gf - fb_ * T : 0;
   const float* wrow = wave + (size_t)fb_ * L;
+  const int len = lengths ? min(max(lengths[fb_], 1), L) : L;  // reflect at the item's own end
   const int start = ft * hop - half;  // sample index of k = 0
   const int bk = tid >> 4;         // basis row within slice 0..15
   const int bc = (tid & 15) * 4;   // basis col 0..60
@@ -54,12 +56,12 @@ dft_power_kernel(const float* __restrict__ wave, int B, int L, int T, int n_fft,
     const int s = start + k0 + lk;
     if (!f_ok) {
       a4[0] = a4[1] = a4[2] = a4[3] = 0.f;
-    } else if (s >= 0 && s + 3 < L && ((s & 3) == 0) && ((L & 3) == 0)) {
+    } else if (s >= 0 && s + 3 < len && ((s & 3) == 0) && ((L & 3) == 0)) {
       const float4 v = *reinterpret_cast<const float4*>(wrow + s);
       a4[0] = v.x; a4[1] = v.y; a4[2] = v.z; a4[3] = v.w;
     } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) a4[j] = wrow[reflect_idx(s + j, L)];
+      for (int j = 0; j < 4; ++j) a4[j] = wrow[min(max(reflect_idx(s + j, len), 0), len - 1)];
     }
     const float4 b4 = *reinterpret_cast<const float4*>(basis + (size_t)(k0 + bk) * ld_basis + n0 + bc);
     __syncthreads();
@@ -105,15 +107,21 @@ constexpr int MEL_FR = 8;  // frames per CTA
 
 __global__ void __launch_bounds__(128)
 mel_log_kernel(const float* __restrict__ power, int B, int T, int n_bins, int n_mels, const float* __restrict__ fb,
-               float* __restrict__ out_bmt, float* __restrict__ out_btm, const int* __restrict__ crop, int T_out) {
+               float* __restrict__ out_bmt, float* __restrict__ out_btm, const int* __restrict__ crop, int T_out,
+               const int* __restrict__ lengths, int L, int hop, int n_fft) {
   extern __shared__ float ps[];  // [MEL_FR][n_bins]
   const int b = blockIdx.y;
+  int Tb = T;
+  if (lengths) {  // frames of this item: 1 + len / hop (none if the reflect padding would not fit)
+    const int len = min(max(lengths[b], 0), L);
+    Tb = len > n_fft / 2 ? min(T, 1 + len / hop) : 0;
+  }
   const int t0 = blockIdx.x * MEL_FR;
   const int c = crop ? crop[b] : 0;
   for (int i = threadIdx.x; i < MEL_FR * n_bins; i += blockDim.x) {
     const int fr = i / n_bins, k = i - fr * n_bins;
     const int src = c + t0 + fr;
-    ps[i] = (t0 + fr < T_out && src < T) ? power[((size_t)b * T + src) * n_bins + k] : 0.f;
+    ps[i] = (t0 + fr < T_out && src < Tb) ? power[((size_t)b * T + src) * n_bins + k] : 0.f;
   }
   __syncthreads();
   for (int m = threadIdx.x; m < n_mels; m += blockDim.x) {
@@ -131,7 +139,7 @@ mel_log_kernel(const float* __restrict__ power, int B, int T, int n_bins, int n_
     for (int fr = 0; fr < MEL_FR; ++fr) {
       const int t = t0 + fr;
       if (t >= T_out) continue;
-      const bool pad = (c + t) >= T;  // Collater zero padding (meldataset.py:804-816)
+      const bool pad = (c + t) >= Tb;  // Collater zero padding (meldataset.py:804-816)
       const float y = pad ? 0.f : (logf(1e-5f + acc[fr]) + 4.0f) * 0.25f;
       if (out_bmt) out_bmt[((size_t)b * n_mels + m) * T_out + t] = y;
       if (out_btm) out_btm[((size_t)b * T_out + t) * n_mels + m] = y;
@@ -143,7 +151,7 @@ mel_log_kernel(const float* __restrict__ power, int B, int T, int n_bins, int n_
 
 extern "C" int pe_logmel_f32(const float* wave, int B, int L, int n_fft, int hop, int n_mels, const float* basis,
                              int ld_basis, const float* fb, float* power, size_t power_bytes, float* out_bmt,
-                             float* out_btm, const int* crop, int T_out, pe_stream_t stream) {
+                             float* out_btm, const int* crop, const int* lengths, int T_out, pe_stream_t stream) {
   if (int rc = pe_host::check_arch()) return rc;
   if (!wave || !basis || !fb || !power || B <= 0 || L <= 0 || n_fft < 16 || (n_fft % 16) || hop <= 0 || n_mels <= 0)
     return PE_ERR_BAD_SHAPE;
@@ -157,9 +165,10 @@ extern "C" int pe_logmel_f32(const float* wave, int B, int L, int n_fft, int hop
   if (!out_bmt && !out_btm) return PE_ERR_BAD_SHAPE;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   dim3 g1((B * T + pe::DFT_TM - 1) / pe::DFT_TM, ncol_tiles);
-  pe::dft_power_kernel<<<g1, 256, 0, st>>>(wave, B, L, T, n_fft, hop, basis, ld_basis, n_bins, power);
+  pe::dft_power_kernel<<<g1, 256, 0, st>>>(wave, B, L, T, n_fft, hop, basis, ld_basis, n_bins, power, lengths);
   dim3 g2((T_out + pe::MEL_FR - 1) / pe::MEL_FR, B);
   const size_t smem = (size_t)pe::MEL_FR * n_bins * sizeof(float);
-  pe::mel_log_kernel<<<g2, 128, smem, st>>>(power, B, T, n_bins, n_mels, fb, out_bmt, out_btm, crop, T_out);
+  pe::mel_log_kernel<<<g2, 128, smem, st>>>(power, B, T, n_bins, n_mels, fb, out_bmt, out_btm, crop, T_out, lengths, L, hop,
+                                           n_fft);
   return cudaGetLastError() == cudaSuccess ? PE_OK : PE_ERR_LAUNCH;
 }

@@ -3,11 +3,20 @@
 // over 4 frame pairs, with the 1024-th-root twiddles applied between them.  fp32-grade accuracy comes from a two-way
 // fp16 split of both operands (hi*hi + hi*lo + lo*hi, the lo parts pre-scaled by 2^11), accumulated in fp32 in TMEM:
 // 24 tcgen05.mma (kind::f16, 128x64x16) per 8 frames instead of the 6.3 MFLOP/frame of the dense DFT.
-// Frames arrive as 4 KB bulk async copies (cp.async.bulk) straight from the reflect-padded waveform (frame stride =
-// hop), double buffered; windowing + the fp16 split write them in the MN-major operand order stage 1 needs, so no
-// transposition happens before the first GEMM.  Pair unpacking, |.|^2, the banded mel filterbank, log
-// and normalisation run on the TMEM rows in registers / shared memory.  Mirrors torchaudio MelSpectrogram as built at
-// reference meldataset.py:77 and the normalisation at meldataset.py:650.
+//
+// One CTA per SM, persistent.  FOUR independent worker groups (4 warps each) work on four 8-frame slots at a time, so
+// that the SIMT phases of three groups overlap the tensor-core stage and the waits of the fourth:
+//   * every slot's samples are read from HBM ONCE: its 8 overlapping frames span 1024 + 7*hop samples, fetched with one
+//     bulk async copy (cp.async.bulk, 12.5 KB at hop 300) into the group's raw buffer; the reflect padding of the few
+//     frames at the edges of an item is gathered straight from global memory instead.
+//   * pre-pass: window (held in registers) x sample -> fp16 hi / lo' -> MN-major stage-1 operand.
+//   * stage-1 result: twiddle, split, stored as the MN-major stage-2 operand: a thread owns one (pair, n2) accumulator row
+//     and writes 16-byte runs of 8 consecutive k1 -- no transposition through shared memory.
+//   * stage-2 result: pair unpacking by warp shuffles, |.|^2 into the (now free) operand buffer, then the banded mel
+//     filterbank with the 80 filters dealt to 16 threads per frame in a load-balanced order, log, normalise, store.
+// Only the frames that are asked for are computed (crop .. crop + T_out), frames past an item's own end are written as
+// zeros (Collater padding, meldataset.py:804-816).  Mirrors torchaudio MelSpectrogram as built at reference
+// meldataset.py:77 and the normalisation at meldataset.py:650.
 #include "common.cuh"
 #include "../../include/pitchextractor_b200.h"
 #include <cuda_fp16.h>
@@ -15,334 +24,460 @@
 namespace pe {
 
 constexpr int LM_NFFT = 1024;
-constexpr int LM_FR = 8;              // frames per tile (4 pairs)
-constexpr int LM_WORKERS = 256;       // 8 worker warps = two independent groups of 4 (one tile each, ping-pong)
-constexpr int LM_THREADS = 64 + LM_WORKERS;  // warp 0 TMA, warp 1 MMA, warps 2..9 workers
-constexpr int LM_RAW_B = LM_FR * 4096;  // 32 KB of fp32 samples per tile
-constexpr int LM_NRAW = 2;            // raw-sample ring depth (a slot is free again right after the pre-pass)
-constexpr int LM_OP_B = 16384;        // one fp16 [128 x 64] operand
-constexpr int LM_PSTRIDE = 516;
+constexpr int LM_FR = 8;                        // frames per slot (4 pairs)
+constexpr int LM_GROUPS = 4;                    // worker groups == slots in flight
+constexpr int LM_WORKERS = LM_GROUPS * 128;
+constexpr int LM_THREADS = 64 + LM_WORKERS;     // warp 0 producer, warp 1 MMA, warps 2..17 workers
+constexpr int LM_MAX_HOP = 320;
+constexpr int LM_RAW_B = (LM_NFFT + (LM_FR - 1) * LM_MAX_HOP) * 4;   // 13 056 B of fp32 samples per slot
+constexpr int LM_OP_B = 16384;                  // one fp16 [128 x 64] operand
+constexpr int LM_SLOT_B = 2 * LM_OP_B;          // A_hi | A_lo; later the slot's power spectra [513 bins][8 frames]
+constexpr int LM_MEL_W = 1536;                  // banded filter weights held in shared memory
+constexpr int LM_ITEMS = 128;                   // mel work items (one per worker thread of a group)
 
 struct LmParams {
-  int B, T, n_mels, T_out, tiles_per_item, num_tiles;
+  int B, T_out, n_mels, tiles_per_item, num_tiles;
   const float* win;        // [1024]
   const __half* fmat;      // 3 x 8 KB pre-swizzled K-major [64 x 64]: hi, lo, hi * 2^-11
   const float* tw;         // [2][32][32]: cos, sin of 2 pi k1 n2 / 1024, indexed [k1][n2]
-  const int* mel_start;    // [n_mels]
-  const int* mel_count;    // [n_mels]
-  const int* mel_off;      // [n_mels] offset into mel_w
+  const int4* mel_items;   // [128] {filter m (-1: idle), first bin, bins, offset into mel_w | flags << 24}
   const float* mel_w;      // banded filter weights
   int mel_nnz;
   const int* crop;         // [B] or NULL
+  const int* lengths;      // [B] valid samples per item or NULL (= L)
   float* out_bmt;          // [B][n_mels][T_out] or NULL
   float* out_btm;          // [B][T_out][n_mels] or NULL
-  long long* dbg;          // optional per-CTA phase cycle counters (tuning)
 };
+constexpr int LM_ITEM_COMBINE = 1;  // the filter is split over lanes l, l ^ 1: add the partner's partial sums
+constexpr int LM_ITEM_WRITER = 2;   // this lane applies the log and stores the filter's 8 frames
 
 __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
   tc_mma_bf16(tmem_d, da, db, idesc, acc);  // same instruction (kind::f16); operand formats live in idesc
 }
 
-// split x into fp16 hi and fp16 lo' = (x - hi) * 2^11
-__device__ __forceinline__ void split16(float x, __half& hi, __half& lo) {
-  hi = __float2half_rn(x);
-  lo = __float2half_rn((x - __half2float(hi)) * 2048.0f);
+// ---- explicit shared-state-space accesses on 32-bit addresses (the compiler otherwise falls back to generic LD / ST with
+// 64-bit address arithmetic for pointers carved out of the dynamic shared-memory block)
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ int4 lds128i(uint32_t a) {
+  int4 v;
+  asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void sts64f(uint32_t a, float x, float y) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+// wait with a long hardware suspend per probe: the workers wait for whole pipeline phases, and every probe that returns
+// early costs an issue slot the other 17 warps of the SM could use
+__device__ __forceinline__ void mbar_wait_long(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+        : "memory");
+    if (!ok && ++spins > (1u << 22)) mbar_timeout_trap();
+  } while (!ok);
+}
+
+// x0, x1 -> packed fp16 hi pair and packed fp16 lo' pair, lo' = (x - hi) * 2^11
+__device__ __forceinline__ void split16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn((x0 - hf.x) * 2048.0f, (x1 - hf.y) * 2048.0f);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+struct LmSlot {        // where a slot's frames lie (identical arithmetic in the producer and the workers)
+  int b, t_out0, t0, nfr, len;
+  long long s_base;    // sample index of raw[0]
+  long long c_lo, c_hi;  // sample range covered by the bulk copy ([c_lo, c_hi), multiples of 4; empty if c_hi <= c_lo)
+};
+
+__device__ __forceinline__ LmSlot lm_slot(const LmParams& p, int tile, int L, int hop) {
+  LmSlot s;
+  s.b = tile / p.tiles_per_item;
+  s.t_out0 = (tile - s.b * p.tiles_per_item) * LM_FR;
+  s.t0 = (p.crop ? p.crop[s.b] : 0) + s.t_out0;
+  s.len = p.lengths ? min(max(p.lengths[s.b], 0), L) : L;
+  const int T_b = s.len > LM_NFFT / 2 ? 1 + s.len / hop : 0;   // reflect padding needs pad < length (torch.stft)
+  s.nfr = max(0, min(min(LM_FR, p.T_out - s.t_out0), T_b - s.t0));
+  s.s_base = (long long)s.t0 * hop - LM_NFFT / 2;
+  s.c_lo = s.s_base > 0 ? s.s_base : 0;
+  const long long end = s.s_base + LM_NFFT + (long long)(LM_FR - 1) * hop;
+  const long long len4 = s.len & ~3;
+  s.c_hi = s.nfr > 0 ? (end < len4 ? end : len4) : 0;
+  return s;
 }
 
 __global__ void __launch_bounds__(LM_THREADS, 1)
 logmel_tc_kernel(const float* __restrict__ wave, int L, long long ld, int hop, const LmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* s_raw = smem;                                   // LM_NRAW x 32 KB raw samples
-  uint8_t* s_a = smem + LM_NRAW * LM_RAW_B;                // per group: A_hi | A_lo (2 x 16 KB)
-  uint8_t* s_f = s_a + 2 * 2 * LM_OP_B;                    // 24 KB: F_hi | F_lo | F_hi'
-  float* s_tw = reinterpret_cast<float*>(s_f + 3 * 8192);  // 8 KB
-  float* s_win = s_tw + 2048;                              // 4 KB
-  float* s_p = s_win + LM_NFFT;                            // per group [8][516] power spectra
-  float* s_melw = s_p + 2 * LM_FR * LM_PSTRIDE;            // banded mel weights (<= 2048)
-  int* s_meli = reinterpret_cast<int*>(s_melw + 2048);     // start | count | off, 3 x 128
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_meli + 384);
-  uint64_t* raw_full = bars;                  // [LM_NRAW]
-  uint64_t* raw_empty = bars + LM_NRAW;       // [LM_NRAW]
-  uint64_t* work_ready = bars + 2 * LM_NRAW;  // [2] workers of group g -> MMA
-  uint64_t* mma_done = work_ready + 2;        // [2] MMA -> workers of group g
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + 2);
+  // all shared-memory traffic of the workers goes through 32-bit shared-window addresses
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (sbase - smem_u32(smem_raw));
+  const uint32_t a_slots = sbase;                                    // LM_GROUPS x 32 KB operand / power buffers
+  const uint32_t a_f = a_slots + LM_GROUPS * LM_SLOT_B;              // 24 KB: F_hi | F_lo | F_hi'
+  const uint32_t a_raw = a_f + 3 * 8192;                             // LM_GROUPS x raw samples
+  const uint32_t a_tw = a_raw + LM_GROUPS * LM_RAW_B;                // 8 KB twiddles
+  const uint32_t a_melw = a_tw + 2048 * 4;                           // banded mel weights
+  const uint32_t a_items = a_melw + LM_MEL_W * 4;                    // [128] int4
+  const uint32_t a_bars = a_items + LM_ITEMS * 16;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (a_bars - sbase));
+  uint64_t* raw_full = bars;                      // [G] producer -> workers
+  uint64_t* raw_empty = bars + LM_GROUPS;         // [G] workers -> producer
+  uint64_t* work_ready = bars + 2 * LM_GROUPS;    // [G] workers of group g -> MMA
+  uint64_t* mma_done = bars + 3 * LM_GROUPS;      // [G] MMA -> workers of group g
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * LM_GROUPS);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < 3 * 8192 / 16; i += LM_THREADS)
-    reinterpret_cast<uint4*>(s_f)[i] = __ldg(reinterpret_cast<const uint4*>(p.fmat) + i);
-  for (int i = tid; i < 2048; i += LM_THREADS) s_tw[i] = p.tw[i];
-  for (int i = tid; i < LM_NFFT; i += LM_THREADS) s_win[i] = p.win[i];
-  for (int i = tid; i < p.mel_nnz; i += LM_THREADS) s_melw[i] = p.mel_w[i];
-  for (int i = tid; i < p.n_mels; i += LM_THREADS) {
-    s_meli[i] = p.mel_start[i];
-    s_meli[128 + i] = p.mel_count[i];
-    s_meli[256 + i] = p.mel_off[i];
+  {
+    uint4* df = reinterpret_cast<uint4*>(smem + (a_f - sbase));
+    for (int i = tid; i < 3 * 8192 / 16; i += LM_THREADS) df[i] = __ldg(reinterpret_cast<const uint4*>(p.fmat) + i);
+    float* dt = reinterpret_cast<float*>(smem + (a_tw - sbase));
+    for (int i = tid; i < 2048; i += LM_THREADS) dt[i] = p.tw[i];
+    float* dw = reinterpret_cast<float*>(smem + (a_melw - sbase));
+    for (int i = tid; i < p.mel_nnz; i += LM_THREADS) dw[i] = p.mel_w[i];
+    int4* di = reinterpret_cast<int4*>(smem + (a_items - sbase));
+    for (int i = tid; i < LM_ITEMS; i += LM_THREADS) di[i] = p.mel_items[i];
   }
   if (tid == 0) {
-    for (int i = 0; i < LM_NRAW; ++i) {
-      mbar_init(&raw_full[i], 1);
-      mbar_init(&raw_empty[i], 4);
-    }
-    for (int g = 0; g < 2; ++g) {
+    for (int g = 0; g < LM_GROUPS; ++g) {
+      mbar_init(&raw_full[g], 1);
+      mbar_init(&raw_empty[g], 4);
       mbar_init(&work_ready[g], 4);
       mbar_init(&mma_done[g], 1);
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, 256);
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tm = *tmem_slot;
-  const int n_local = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles of this CTA
+  const int n_local = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // slots of this CTA
 
   if (warp == 0) {
-    // ---------------------------------------------------------------- producer: 4 KB bulk copies, one per frame
-    // (warp-uniform loop, one elected lane waits and issues: see elect_one())
+    // ---------------------------------------------------------------- producer: one bulk copy per slot
     for (int i = 0; i < n_local; ++i) {
-      const int tile = blockIdx.x + i * gridDim.x;
-      const int buf = i % LM_NRAW;
-      const int b = tile / p.tiles_per_item, t0 = (tile - b * p.tiles_per_item) * LM_FR;
-      const int nfr = min(LM_FR, p.T - t0);
-      // interior frames (window fully inside the item) are bulk-copied; the few frames that touch the reflect
-      // padding are gathered by the workers straight from global memory
-      int n_in = 0;
-      for (int j = 0; j < nfr; ++j) {
-        const long long s0 = (long long)(t0 + j) * hop - LM_NFFT / 2;
-        n_in += (s0 >= 0 && s0 + LM_NFFT <= L) ? 1 : 0;
-      }
+      const int g = i & (LM_GROUPS - 1);
+      const LmSlot s = lm_slot(p, blockIdx.x + i * gridDim.x, L, hop);
       if (elect_one()) {
-        mbar_wait(&raw_empty[buf], ((uint32_t)(i / LM_NRAW) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(&raw_full[buf], (uint32_t)n_in * 4096u);
-        for (int j = 0; j < nfr; ++j) {
-          const long long s0 = (long long)(t0 + j) * hop - LM_NFFT / 2;
-          if (s0 >= 0 && s0 + LM_NFFT <= L)
-            bulk_load_1d(s_raw + buf * LM_RAW_B + j * 4096, wave + (long long)b * ld + s0, 4096, &raw_full[buf]);
+        mbar_wait_long(&raw_empty[g], ((uint32_t)(i / LM_GROUPS) & 1u) ^ 1u);
+        if (s.c_hi > s.c_lo) {
+          const uint32_t bytes = (uint32_t)(s.c_hi - s.c_lo) * 4u;
+          mbar_arrive_expect_tx(&raw_full[g], bytes);
+          bulk_load_1d(smem + (a_raw - sbase) + g * LM_RAW_B + (s.c_lo - s.s_base) * 4,
+                       wave + (long long)s.b * ld + s.c_lo, bytes, &raw_full[g]);
+        } else {
+          mbar_arrive(&raw_full[g]);
         }
       }
       __syncwarp();
     }
   } else if (warp == 1) {
-    // ---------------------------------------------------------------- MMA issuer, serving the two worker groups in
-    // the order S1(i), S1(i+1), S2(i), S2(i+1): one group's SIMT phases overlap the other group's GEMM stages
-    {
-      constexpr uint32_t IDESC1 = umma_idesc(UMMA_F16, 128, 64, 1, 0);  // A MN-major (frames as landed), B K-major
-      constexpr uint32_t IDESC2 = umma_idesc(UMMA_F16, 128, 64, 0, 0);
-      const uint32_t f = smem_u32(s_f);
-      uint32_t ph[2] = {0u, 0u};
-      auto stage = [&](int g, int which) {
-        const uint32_t ahi = smem_u32(s_a) + g * 2 * LM_OP_B, alo = ahi + LM_OP_B;
-        const uint32_t d = tm + g * 128 + which * 64;
-        if (elect_one()) {  // warp-uniform loop, one elected lane waits and issues
-          mbar_wait(&work_ready[g], ph[g]);
-          tc_fence_after();
+    // ---------------------------------------------------------------- MMA issuer: round-robin over the groups, stage 1
+    // of every slot of a round first, then stage 2 (the groups are naturally staggered by then)
+    constexpr uint32_t IDESC = umma_idesc(UMMA_F16, 128, 64, 1, 0);  // A MN-major, B K-major, both stages
+    uint32_t ph[LM_GROUPS] = {0u, 0u, 0u, 0u};
+    auto stage = [&](int g, int which) {
+      const uint32_t ahi = a_slots + g * LM_SLOT_B, alo = ahi + LM_OP_B;
+      const uint32_t d = tm + g * 128 + which * 64;
+      if (elect_one()) {  // warp-uniform loop, one elected lane waits and issues
+        mbar_wait(&work_ready[g], ph[g]);
+        tc_fence_after();
 #pragma unroll
-          for (int prod = 0; prod < 3; ++prod) {
-            const uint32_t a = prod == 2 ? alo : ahi;
-            const uint32_t bm = f + (prod == 0 ? 0 : prod == 1 ? 8192 : 16384);
+        for (int prod = 0; prod < 3; ++prod) {
+          const uint32_t a = prod == 2 ? alo : ahi;
+          const uint32_t bm = a_f + (prod == 0 ? 0 : prod == 1 ? 8192 : 16384);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              // stage 1: A = 2 MN atoms (8 KB apart) x 64 K rows, 16 K rows per MMA; stage 2: A K-major
-              const uint64_t da = which == 0 ? umma_desc_sw128(a + k * 2048, 8192, 1024) : umma_desc_sw128(a + k * 32, 16, 1024);
-              tc_mma_f16(d, da, umma_desc_sw128(bm + k * 32, 16, 1024), which == 0 ? IDESC1 : IDESC2,
-                         (prod > 0 || k > 0) ? 1u : 0u);
-            }
-          }
-          tc_commit(&mma_done[g]);
+          for (int k = 0; k < 4; ++k)  // A: 2 MN atoms (8 KB apart) x 64 K rows, 16 K rows per MMA
+            tc_mma_f16(d, umma_desc_sw128(a + k * 2048, 8192, 1024), umma_desc_sw128(bm + k * 32, 16, 1024), IDESC,
+                       (prod > 0 || k > 0) ? 1u : 0u);
         }
-        __syncwarp();
-        ph[g] ^= 1u;
-      };
-      for (int i = 0; i < n_local; i += 2) {
-        const bool two = i + 1 < n_local;
-        stage(0, 0);
-        if (two) stage(1, 0);
-        stage(0, 1);
-        if (two) stage(1, 1);
+        tc_commit(&mma_done[g]);
       }
+      __syncwarp();
+      ph[g] ^= 1u;
+    };
+    for (int i = 0; i < n_local; i += LM_GROUPS) {
+      const int n = n_local - i;
+#pragma unroll
+      for (int g = 0; g < LM_GROUPS; ++g)
+        if (g < n) stage(g, 0);
+#pragma unroll
+      for (int g = 0; g < LM_GROUPS; ++g)
+        if (g < n) stage(g, 1);
     }
   } else {
-    // ---------------------------------------------------------------- workers: two groups of 4 warps (128 threads)
-    const int g = (warp - 2) >> 2;         // group: handles this CTA's tiles g, g + 2, g + 4, ...
+    // ---------------------------------------------------------------- workers: LM_GROUPS groups of 4 warps
+    const int g = (warp - 2) >> 2;         // group: handles this CTA's slots g, g + 4, g + 8, ...
     const int q = warp & 3;                // TMEM lane quarter == frame pair handled in the TMEM phases
     const int wt = ((warp - 2) & 3) * 32 + lane;  // 0..127 inside the group
-    uint8_t* s_ahi = s_a + g * 2 * LM_OP_B;
-    uint8_t* s_alo = s_ahi + LM_OP_B;
-    float* s_pg = s_p + g * LM_FR * LM_PSTRIDE;
+    const uint32_t a_hi = a_slots + g * LM_SLOT_B, a_lo = a_hi + LM_OP_B;
+    const uint32_t a_p = a_hi;             // power spectra [513][8] reuse the operand buffer after stage 2
+    const uint32_t a_rawg = a_raw + g * LM_RAW_B;
     const uint32_t trow = tm + ((uint32_t)(q * 32) << 16) + g * 128;
     const uint32_t bar_id = 1 + g;
     uint32_t dph = 0;
-    long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    long long tc0 = clock64();
-#define LM_TICK(k) do { if (p.dbg) { const long long c_ = clock64(); tph[k] += c_ - tc0; tc0 = c_; } } while (0)
-    for (int i = g; i < n_local; i += 2) {
-      const int tile = blockIdx.x + i * gridDim.x;
-      const int buf = i % LM_NRAW;
-      const int b = tile / p.tiles_per_item, t0 = (tile - b * p.tiles_per_item) * LM_FR;
-      // ---- pre-pass: window, split, lay out as the stage-1 A operand (MN-major fp16)
-      mbar_wait(&raw_full[buf], (uint32_t)(i / LM_NRAW) & 1u);
-      LM_TICK(0);
-      const uint8_t* raw = s_raw + buf * LM_RAW_B;
-#pragma unroll 4
-      for (int it = 0; it < 16; ++it) {
-        const int u = wt + 128 * it;              // 16-byte unit of the raw tile: [frame][n1][n2 / 4]
-        const int fr = u >> 8, n1 = (u >> 3) & 31, n2 = (u & 7) << 2;
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);     // frames past the end of the item contribute zeros
-        if (t0 + fr < p.T) {
-          const long long s0 = (long long)(t0 + fr) * hop - LM_NFFT / 2;
-          if (s0 >= 0 && s0 + LM_NFFT <= L) {
-            x = *reinterpret_cast<const float4*>(raw + u * 16);
-          } else {  // reflect padding (torch.stft center=True, pad_mode="reflect")
-            const float* wb = wave + (long long)b * ld;
-            float e[4];
+    // this thread's two window positions (16-byte units wt and wt + 128 of a frame): fixed for every frame
+    float4 wreg[2];
+    uint32_t spos[2];      // byte offset of the position inside a frame
+    uint32_t soff[2][2];   // operand byte offset for (frame parity, position) without the pair terms
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              long long si = s0 + n1 * 32 + n2 + j;
-              if (si < 0) si = -si;
-              if (si >= L) si = 2LL * (L - 1) - si;
-              e[j] = __ldg(wb + si);
+    for (int h = 0; h < 2; ++h) {
+      const int u = wt + 128 * h, n1 = u >> 3, n2 = (u & 7) << 2;
+      wreg[h] = __ldg(reinterpret_cast<const float4*>(p.win + n1 * 32 + n2));
+      spos[h] = (uint32_t)(n1 * 32 + n2) * 4u;
+#pragma unroll
+      for (int par = 0; par < 2; ++par) {
+        const int kk = par * 32 + n1;
+        soff[par][h] = (uint32_t)(kk * 128 + (n2 & 7) * 2) | ((uint32_t)((n2 >> 3) ^ (kk & 7)) << 16);  // row | unit-xor
+      }
+    }
+    const int4 item = lds128i(a_items + wt * 16);
+    for (int i = g; i < n_local; i += LM_GROUPS) {
+      const LmSlot s = lm_slot(p, blockIdx.x + i * gridDim.x, L, hop);
+      const long long span_end = s.s_base + LM_NFFT + (long long)(LM_FR - 1) * hop;
+      const bool all_fast = s.nfr == LM_FR && s.s_base >= s.c_lo && span_end <= s.c_hi;   // slot interior to the item
+      // ---- pre-pass: window, split, lay out as the stage-1 A operand (MN-major fp16)
+      mbar_wait_long(&raw_full[g], (uint32_t)(i / LM_GROUPS) & 1u);
+      auto emit = [&](int fr, int h, const float4 x) {
+        uint32_t h01, l01, h23, l23;
+        split16x2(x.x * wreg[h].x, x.y * wreg[h].y, h01, l01);
+        split16x2(x.z * wreg[h].z, x.w * wreg[h].w, h23, l23);
+        const int pr = fr >> 1;
+        const uint32_t so = soff[fr & 1][h];
+        // unit = (pr & 1) * 4 + (n2 >> 3), xor (kk & 7): the pair bit only flips bit 2 of the 16-byte unit index
+        const uint32_t off = (uint32_t)((pr >> 1) * 8192) + (so & 0xFFFFu) + ((((so >> 16) ^ (uint32_t)((pr & 1) * 4))) << 4);
+        sts64(a_hi + off, h01, h23);
+        sts64(a_lo + off, l01, l23);
+      };
+      if (all_fast) {
+        uint32_t fo = 0;
+#pragma unroll
+        for (int fr = 0; fr < LM_FR; ++fr) {
+          const float4 x0 = lds128(a_rawg + fo + spos[0]);
+          const float4 x1 = lds128(a_rawg + fo + spos[1]);
+          emit(fr, 0, x0);
+          emit(fr, 1, x1);
+          fo += (uint32_t)hop * 4u;
+        }
+      } else {
+#pragma unroll 1
+        for (int fr = 0; fr < LM_FR; ++fr) {
+          const long long s0 = s.s_base + (long long)fr * hop;
+          const bool live = fr < s.nfr;
+          const bool fast = live && s0 >= s.c_lo && s0 + LM_NFFT <= s.c_hi;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);     // frames past the end of the item contribute zeros
+            if (fast) {
+              x = lds128(a_rawg + (uint32_t)(fr * hop) * 4u + spos[h]);
+            } else if (live) {  // reflect padding (torch.stft center=True, pad_mode="reflect") at the item's own ends
+              const float* wb = wave + (long long)s.b * ld;
+              float e[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                long long si = s0 + (spos[h] >> 2) + j;
+                if (si < 0) si = -si;
+                if (si >= s.len) si = 2LL * (s.len - 1) - si;
+                si = si < 0 ? 0 : (si >= s.len ? s.len - 1 : si);
+                e[j] = __ldg(wb + si);
+              }
+              x = make_float4(e[0], e[1], e[2], e[3]);
             }
-            x = make_float4(e[0], e[1], e[2], e[3]);
+            emit(fr, h, x);
           }
         }
-        const float4 w = *reinterpret_cast<const float4*>(s_win + n1 * 32 + n2);
-        __half h[4], l[4];
-        split16(x.x * w.x, h[0], l[0]);
-        split16(x.y * w.y, h[1], l[1]);
-        split16(x.z * w.z, h[2], l[2]);
-        split16(x.w * w.w, h[3], l[3]);
-        const int pr = fr >> 1, kk = (fr & 1) * 32 + n1;
-        const int unit = (pr & 1) * 4 + (n2 >> 3);
-        const uint32_t off = (uint32_t)((pr >> 1) * 8192 + kk * 128 + ((unit ^ (kk & 7)) << 4) + (n2 & 7) * 2);
-        *reinterpret_cast<uint2*>(s_ahi + off) = make_uint2(*reinterpret_cast<uint32_t*>(&h[0]), *reinterpret_cast<uint32_t*>(&h[2]));
-        *reinterpret_cast<uint2*>(s_alo + off) = make_uint2(*reinterpret_cast<uint32_t*>(&l[0]), *reinterpret_cast<uint32_t*>(&l[2]));
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(&raw_empty[buf]);
+        mbar_arrive(&raw_empty[g]);
         mbar_arrive(&work_ready[g]);
       }
-      LM_TICK(1);
-      // ---- stage-1 result: twiddle, split, transpose into the stage-2 A operand (K-major fp16)
-      mbar_wait(&mma_done[g], dph);
+      // ---- stage-1 result: twiddle, split, store as the stage-2 A operand (MN-major: K row = (re/im, n2), this
+      // thread's 32 k1 values of a row are 64 contiguous bytes)
+      mbar_wait_long(&mma_done[g], dph);
       dph ^= 1u;
       tc_fence_after();
-      LM_TICK(2);
       {
-        uint32_t vr[32], vi[32];
-        tmem_ld32(trow, vr);
-        tmem_ld32(trow + 32, vi);
-        tmem_ld_wait();
         const int n2 = lane;
+        const uint32_t atom = (uint32_t)(q >> 1) * 8192u;
+        const uint32_t row_re = atom + (uint32_t)n2 * 128u, row_im = row_re + 32u * 128u;
+        const uint32_t sw = (uint32_t)(n2 & 7);      // (32 + n2) & 7 == n2 & 7
+        const uint32_t a_twl = a_tw + (uint32_t)n2 * 4u;
 #pragma unroll
-        for (int k1 = 0; k1 < 32; ++k1) {
-          const float ct = s_tw[k1 * 32 + n2], st = s_tw[1024 + k1 * 32 + n2];
-          const float re = __uint_as_float(vr[k1]), im = __uint_as_float(vi[k1]);
-          const float yr = fmaf(re, ct, im * st), yi = fmaf(im, ct, -re * st);
-          __half hr, lr, hi_, li;
-          split16(yr, hr, lr);
-          split16(yi, hi_, li);
-          const int m2 = q * 32 + k1;
-          const uint32_t row = (uint32_t)(m2 * 128);
-          const uint32_t o_re = row + ((((n2 >> 3)) ^ (m2 & 7)) << 4) + (n2 & 7) * 2;
-          const uint32_t o_im = row + ((((32 + n2) >> 3) ^ (m2 & 7)) << 4) + (n2 & 7) * 2;
-          *reinterpret_cast<__half*>(s_ahi + o_re) = hr;
-          *reinterpret_cast<__half*>(s_alo + o_re) = lr;
-          *reinterpret_cast<__half*>(s_ahi + o_im) = hi_;
-          *reinterpret_cast<__half*>(s_alo + o_im) = li;
+        for (int c8 = 0; c8 < 4; ++c8) {
+          uint32_t vr[8], vi[8];
+          tmem_ld8(trow + c8 * 8, vr);
+          tmem_ld8(trow + 32 + c8 * 8, vi);
+          tmem_ld_wait();
+          uint32_t rh[4], rl[4], ih[4], il[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float yr[2], yi[2];
+#pragma unroll
+            for (int d = 0; d < 2; ++d) {
+              const int k1 = c8 * 8 + e * 2 + d;
+              const float ct = lds32(a_twl + k1 * 128), st = lds32(a_twl + 4096 + k1 * 128);
+              const float re = __uint_as_float(vr[e * 2 + d]), im = __uint_as_float(vi[e * 2 + d]);
+              yr[d] = fmaf(re, ct, im * st);
+              yi[d] = fmaf(im, ct, -re * st);
+            }
+            split16x2(yr[0], yr[1], rh[e], rl[e]);
+            split16x2(yi[0], yi[1], ih[e], il[e]);
+          }
+          const uint32_t o = (((uint32_t)((q & 1) * 4 + c8)) ^ sw) << 4;
+          sts128(a_hi + row_re + o, rh[0], rh[1], rh[2], rh[3]);
+          sts128(a_lo + row_re + o, rl[0], rl[1], rl[2], rl[3]);
+          sts128(a_hi + row_im + o, ih[0], ih[1], ih[2], ih[3]);
+          sts128(a_lo + row_im + o, il[0], il[1], il[2], il[3]);
         }
       }
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&work_ready[g]);
-      LM_TICK(3);
-      // ---- stage-2 result: unpack the two real spectra of the pair, power
-      mbar_wait(&mma_done[g], dph);
+      // ---- stage-2 result: unpack the two real spectra of the pair, power -> P[bin][frame] in the free operand buffer.
+      // Bin k = k1 + 32 k2 (k1 = lane) pairs with N - k = (32 - k1) % 32 + 32 (31 - k2 [+1 if k1 == 0]): own columns ascend,
+      // the partner's descend, so the accumulator row is read in two halves of 16 + 16 columns
+      mbar_wait_long(&mma_done[g], dph);
       dph ^= 1u;
       tc_fence_after();
-      LM_TICK(4);
       {
-        uint32_t ur[32], ui[32];
-        tmem_ld32(trow + 64, ur);
-        tmem_ld32(trow + 96, ui);
-        tmem_ld_wait();
         const int src = (32 - lane) & 31;
-        float* pa = s_pg + (2 * q) * LM_PSTRIDE;
-        float* pb = pa + LM_PSTRIDE;
-#pragma unroll
-        for (int k2 = 0; k2 <= 16; ++k2) {
-          const int c_self = (32 - k2) & 31, c_other = 31 - k2;
-          const float sr = lane == 0 ? __uint_as_float(ur[c_self]) : __uint_as_float(ur[c_other & 31]);
-          const float si = lane == 0 ? __uint_as_float(ui[c_self]) : __uint_as_float(ui[c_other & 31]);
+        const uint32_t a_pk = a_p + (uint32_t)lane * 32u + (uint32_t)q * 8u;   // + k2 * 1024
+        auto unpack = [&](int k2, float zr, float zi, float sr, float si) {
           const float pr_ = __shfl_sync(0xffffffffu, sr, src);
           const float pi_ = __shfl_sync(0xffffffffu, si, src);
           if (k2 < 16 || lane == 0) {
-            const float zr = __uint_as_float(ur[k2 & 31]), zi = __uint_as_float(ui[k2 & 31]);
             const float ar = zr + pr_, ai = zi - pi_, br = zi + pi_, bi = pr_ - zr;
-            pa[lane + 32 * k2] = 0.25f * fmaf(ar, ar, ai * ai);
-            pb[lane + 32 * k2] = 0.25f * fmaf(br, br, bi * bi);
+            sts64f(a_pk + (uint32_t)k2 * 1024u, 0.25f * fmaf(ar, ar, ai * ai), 0.25f * fmaf(br, br, bi * bi));
+          }
+        };
+        {  // k2 = 0..7: own columns 0..7; partner columns 31..24 (lane 0: 0, 31..25)
+          uint32_t ur[8], ui[8], tr[8], ti[8];
+          tmem_ld8(trow + 64, ur);
+          tmem_ld8(trow + 96, ui);
+          tmem_ld8(trow + 64 + 24, tr);
+          tmem_ld8(trow + 96 + 24, ti);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k2 = 0; k2 < 8; ++k2) {
+            // lane 0 sends column (32 - k2) & 31, the others 31 - k2
+            const uint32_t o_r = tr[7 - k2], o_i = ti[7 - k2];
+            const uint32_t s_r = k2 == 0 ? ur[0] : tr[8 - k2 > 7 ? 7 : 8 - k2], s_i = k2 == 0 ? ui[0] : ti[8 - k2 > 7 ? 7 : 8 - k2];
+            unpack(k2, __uint_as_float(ur[k2]), __uint_as_float(ui[k2]),
+                   __uint_as_float(lane == 0 ? s_r : o_r), __uint_as_float(lane == 0 ? s_i : o_i));
+          }
+        }
+        {  // k2 = 8..16: own columns 8..16; partner columns 23..15 (lane 0: 24..16)
+          uint32_t ur[16], ui[16], t24r[8], t24i[8];
+          tmem_ld16(trow + 64 + 8, ur);    // columns 8..23
+          tmem_ld16(trow + 96 + 8, ui);
+          tmem_ld8(trow + 64 + 24, t24r);  // column 24 (lane 0, k2 = 8)
+          tmem_ld8(trow + 96 + 24, t24i);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k2 = 8; k2 <= 16; ++k2) {
+            const int co = 31 - k2 - 8, cs = 32 - k2 - 8;  // indices into ur / ui (columns 8..23)
+            const uint32_t o_r = ur[co < 0 ? 0 : co], o_i = ui[co < 0 ? 0 : co];
+            const uint32_t s_r = cs > 15 ? t24r[0] : ur[cs], s_i = cs > 15 ? t24i[0] : ui[cs];
+            unpack(k2, __uint_as_float(ur[k2 - 8]), __uint_as_float(ui[k2 - 8]),
+                   __uint_as_float(lane == 0 ? s_r : o_r), __uint_as_float(lane == 0 ? s_i : o_i));
           }
         }
       }
       tc_fence_before();
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-      LM_TICK(5);
-      // ---- banded mel filterbank, log, normalise, store: one work item per (mel filter, group of 3 frames)
-      const int crop = p.crop ? p.crop[b] : 0;
-      for (int o = wt; o < 3 * p.n_mels; o += 128) {
-        const int g3 = o / p.n_mels, m = o - g3 * p.n_mels;
-        const int f0 = 3 * g3, nf = min(3, LM_FR - f0);
-        const float* pp = s_pg + f0 * LM_PSTRIDE + s_meli[m];
-        const float* ww = s_melw + s_meli[256 + m];
-        const int cnt = s_meli[128 + m];
-        float acc[3] = {0.f, 0.f, 0.f};
-        for (int j = 0; j < cnt; ++j) {
-          const float w = ww[j];
-          acc[0] = fmaf(pp[j], w, acc[0]);
-          acc[1] = fmaf(pp[LM_PSTRIDE + j], w, acc[1]);
-          if (nf > 2) acc[2] = fmaf(pp[2 * LM_PSTRIDE + j], w, acc[2]);
+      // ---- banded mel filterbank: thread = one work item (a filter or half of a long one) x the slot's 8 frames;
+      // log, normalise, store
+      {
+        const int m = item.x, cnt = item.z;
+        const uint32_t flags = (uint32_t)item.w >> 24;
+        float acc[LM_FR];
+#pragma unroll
+        for (int f = 0; f < LM_FR; ++f) acc[f] = 0.f;
+        uint32_t ap = a_p + (uint32_t)item.y * 32u;
+        uint32_t aw = a_melw + ((uint32_t)item.w & 0xFFFFFFu) * 4u;
+#pragma unroll 2
+        for (int c = 0; c < cnt; ++c) {
+          const float w = lds32(aw);
+          const float4 p0 = lds128(ap), p1 = lds128(ap + 16);
+          acc[0] = fmaf(p0.x, w, acc[0]); acc[1] = fmaf(p0.y, w, acc[1]);
+          acc[2] = fmaf(p0.z, w, acc[2]); acc[3] = fmaf(p0.w, w, acc[3]);
+          acc[4] = fmaf(p1.x, w, acc[4]); acc[5] = fmaf(p1.y, w, acc[5]);
+          acc[6] = fmaf(p1.z, w, acc[6]); acc[7] = fmaf(p1.w, w, acc[7]);
+          ap += 32;
+          aw += 4;
         }
 #pragma unroll
-        for (int fi = 0; fi < 3; ++fi) {
-          const int t = t0 + f0 + fi, t_out = t - crop;
-          if (fi >= nf || t >= p.T || t_out < 0 || t_out >= p.T_out) continue;
-          const float y = (__logf(1e-5f + acc[fi]) + 4.0f) * 0.25f;
-          if (p.out_bmt) p.out_bmt[((size_t)b * p.n_mels + m) * p.T_out + t_out] = y;
-          if (p.out_btm) p.out_btm[((size_t)b * p.T_out + t_out) * p.n_mels + m] = y;
+        for (int f = 0; f < LM_FR; ++f) {
+          const float o = __shfl_xor_sync(0xffffffffu, acc[f], 1);
+          if (flags & LM_ITEM_COMBINE) acc[f] += o;
+        }
+        if ((flags & LM_ITEM_WRITER) && m >= 0) {
+#pragma unroll
+          for (int f = 0; f < LM_FR; ++f) {
+            const int t_out = s.t_out0 + f;
+            if (t_out < p.T_out) {
+              const float y = f < s.nfr ? (__logf(1e-5f + acc[f]) + 4.0f) * 0.25f : 0.f;
+              if (p.out_bmt) p.out_bmt[((size_t)s.b * p.n_mels + m) * p.T_out + t_out] = y;
+              if (p.out_btm) p.out_btm[((size_t)s.b * p.T_out + t_out) * p.n_mels + m] = y;
+            }
+          }
         }
       }
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-      LM_TICK(6);
     }
-    if (p.dbg && wt == 0 && g == 0)
-      for (int k = 0; k < 7; ++k) p.dbg[blockIdx.x * 8 + k] = tph[k];
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tm, 256);
+  if (warp == 2) tmem_dealloc(tm, 512);
 }
+
+constexpr size_t LM_SMEM = (size_t)LM_GROUPS * LM_SLOT_B + 3 * 8192 + (size_t)LM_GROUPS * LM_RAW_B +
+                           (2048 + LM_MEL_W) * 4 + LM_ITEMS * 16 + (4 * LM_GROUPS + 2) * 8 + 1024;
 
 }  // namespace pe
 
-static long long* g_lm_dbg = nullptr;
-extern "C" int pe_logmel_set_debug(long long* buf) {
-  g_lm_dbg = buf;
-  return PE_OK;
-}
-
 extern "C" int pe_logmel_tc(const float* wave, int B, int L, int n_fft, int hop, int n_mels, const float* win,
-                            const void* fmat, const float* tw, const int* mel_start, const int* mel_count,
-                            const int* mel_off, const float* mel_w, int mel_nnz, float* xpad, size_t xpad_bytes,
-                            float* out_bmt, float* out_btm, const int* crop, int T_out, pe_stream_t stream) {
+                            const void* fmat, const float* tw, const int* mel_items, const float* mel_w, int mel_nnz,
+                            float* xpad, size_t xpad_bytes, float* out_bmt, float* out_btm, const int* crop,
+                            const int* lengths, int T_out, pe_stream_t stream) {
   using namespace pe;
   if (int rc = pe_host::check_arch()) return rc;
-  if (!wave || !win || !fmat || !tw || !mel_start || !mel_count || !mel_off || !mel_w || B <= 0)
+  if (!wave || !win || !fmat || !tw || !mel_items || !mel_w || B <= 0)
     return PE_ERR_BAD_SHAPE;
-  if (n_fft != LM_NFFT || hop <= 0 || (hop % 4) || n_mels <= 0 || n_mels > 128 || mel_nnz <= 0 || mel_nnz > 2048)
+  if (n_fft != LM_NFFT || hop <= 0 || (hop % 4) || hop > LM_MAX_HOP || n_mels <= 0 || n_mels > 128 || mel_nnz <= 0 ||
+      mel_nnz > LM_MEL_W)
     return PE_ERR_BAD_SHAPE;
   if (L <= n_fft / 2 || (!out_bmt && !out_btm)) return PE_ERR_BAD_SHAPE;
   const int T = 1 + L / hop;
@@ -361,22 +496,20 @@ extern "C" int pe_logmel_tc(const float* wave, int B, int L, int n_fft, int hop,
     src = xpad;
   }
   LmParams p{};
-  p.B = B; p.T = T; p.n_mels = n_mels; p.T_out = T_out;
-  p.tiles_per_item = (T + LM_FR - 1) / LM_FR;
+  p.B = B; p.n_mels = n_mels; p.T_out = T_out;
+  p.tiles_per_item = (T_out + LM_FR - 1) / LM_FR;
   p.num_tiles = B * p.tiles_per_item;
   p.win = win; p.fmat = (const __half*)fmat; p.tw = tw;
-  p.mel_start = mel_start; p.mel_count = mel_count; p.mel_off = mel_off; p.mel_w = mel_w; p.mel_nnz = mel_nnz;
-  p.crop = crop; p.out_bmt = out_bmt; p.out_btm = out_btm;
-  p.dbg = g_lm_dbg;
-  const size_t smem = LM_NRAW * LM_RAW_B + 4 * LM_OP_B + 3 * 8192 + (2048 + LM_NFFT + 2 * LM_FR * LM_PSTRIDE + 2048) * 4 +
-                      384 * 4 + 16 * 8 + 1024;
+  p.mel_items = reinterpret_cast<const int4*>(mel_items); p.mel_w = mel_w; p.mel_nnz = mel_nnz;
+  p.crop = crop; p.lengths = lengths; p.out_bmt = out_bmt; p.out_btm = out_btm;
   static bool attr = false;
   if (!attr) {
-    if (cudaFuncSetAttribute(logmel_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(logmel_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LM_SMEM) != cudaSuccess)
       return PE_ERR_LAUNCH;
     attr = true;
   }
-  const int grid = p.num_tiles < pe_host::num_sms() ? p.num_tiles : pe_host::num_sms();
-  logmel_tc_kernel<<<grid, LM_THREADS, smem, st>>>(src, L, ld, hop, p);
+  const int want = (p.num_tiles + LM_GROUPS - 1) / LM_GROUPS;   // every CTA should have a slot for each of its groups
+  const int grid = want < pe_host::num_sms() ? want : pe_host::num_sms();
+  logmel_tc_kernel<<<grid, LM_THREADS, LM_SMEM, st>>>(src, L, ld, hop, p);
   return cudaGetLastError() == cudaSuccess ? PE_OK : PE_ERR_LAUNCH;
 }

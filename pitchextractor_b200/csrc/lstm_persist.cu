@@ -1,0 +1,530 @@
+// Persistent BiLSTM recurrence (reference model.py:218-228 -> torch.nn.LSTM, gate order i,f,g,o): ONE launch runs all T
+// time steps of the four independent recurrences of a layer (2 sequence models x 2 directions).
+//
+// Work split: CTA (unit tile of 64, batch tile of NB, recurrence).  The CTA's slice of W_hh -- forward: the 4 x 64 gate
+// rows of its units (192 KB bf16); backward: the 64 unit columns of all 1536 gate rows (192 KB) -- is loaded into shared
+// memory ONCE and stays there for every time step; only h_{t-1} (forward) / dgates_{t+1} (backward), 12 - 96 KB per step,
+// streams through a small TMA ring.  The MMA is "transposed": weights are the A operand (gate rows / units on the 128 TMEM
+// lanes), the batch is the N dimension, so that a batch of 16 keeps all 128 lanes of the epilogue busy.
+//   forward  D[(gate, unit), b] = W_hh[(gate, unit), :] . h_{t-1}[b, :]          (K = 384)
+//            lanes of a TMEM quarter = 4 gates x 8 units; each lane adds its input projection + biases, applies ITS gate's
+//            activation (tanh(x) = 2 sigmoid(2x) - 1: one formula, per-lane constants), stores the activated gate (kept for
+//            the backward pass); a 4 x 4 register transpose over the four gate lanes of a unit (two rounds of warp shuffles)
+//            then gives every lane all four gates of one batch column: c_t (kept in registers across the steps), h_t.
+//   backward D[unit, b] = sum_j W_hh[j, unit] dgates_{t+1}[b, j]                  (K = 1536; A = W_hh^T, MN-major)
+//            M = 64 units are presented twice (the two 64-row atoms of the A descriptor alias each other), so lanes 64-127
+//            hold a copy and the second half of the epilogue warps takes the second half of the batch columns; dc is
+//            carried in registers.
+// The six unit-tile CTAs of a (recurrence, batch tile) exchange h_t / dgates_t through global memory (L2) and a per-step
+// arrival counter: writers store, fence, barrier, one release-add; the loader thread of every CTA acquire-polls the
+// counter before it issues the TMA loads of the next step.  All CTAs must be co-resident: the launch is cooperative and
+// the grid is at most one CTA per SM.
+#include "common.cuh"
+#include "../../include/pitchextractor_b200.h"
+
+namespace pe {
+
+constexpr int PH = 384;          // hidden size
+constexpr int PG = 4 * PH;       // gate rows per direction
+constexpr int P_EPI_WARPS = 8;
+constexpr int P_THREADS = 64 + 32 * P_EPI_WARPS;   // warp 0 loader, warp 1 MMA, warps 2..9 epilogue
+constexpr int P_W_BYTES = 6 * 32768;               // resident weight slice (both directions of use: 192 KB)
+constexpr int P_RING_BYTES = 32768;
+// backward: the M = 128 MMA sees the CTA's 64 units twice (A descriptor atom stride 0), so that TMEM lanes 64..127 hold a
+// copy for the second half of the epilogue warps.  0: the upper lanes read the next k-block instead and are ignored.
+#ifndef P_BWD_DUP
+#define P_BWD_DUP 1
+#endif
+
+struct LstmSeqParams {
+  int B, T, nbt, b_first;      // batch rows b_first .. b_first + nbt * NB - 1 are handled by this launch
+  float* gx[2];                // per model: [B][T][2*PG] fp32: input projection in, activated gates out
+  float* c[2];                 // [B][T][2*PH] fp32 cell state
+  __nv_bfloat16* y[2];         // [B][T][2*PH] bf16 hidden state
+  const float* b_ih[4];        // per recurrence r = model * 2 + dir
+  const float* b_hh[4];
+  const __nv_bfloat16* dy[2];  // backward: [B][T][2*PH] gradient w.r.t. y from above
+  __nv_bfloat16* dg[2];        // backward: [B][T][2*PG] pre-activation gate gradients
+  int* flags;                  // [4][nbt][T] arrival counters (zeroed before the launch)
+};
+
+struct LstmSeqMaps {
+  CUtensorMap act[2];  // per model: forward y (dims 2*PH, T, B); backward dg (dims 2*PG, T, B); box {64, 1, NB}
+  CUtensorMap w[4];    // per recurrence W_hh: forward 3-D view (k, unit, gate) box {64, 8, 4}; backward 2-D box {64, 64}
+};
+
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
+// bounded acquire-poll of an arrival counter (a protocol bug must end in a trap, not in a hung GPU)
+__device__ __forceinline__ void wait_counter(const int* p, int target) {
+  uint32_t spins = 0;
+  while (ld_acquire_gpu(p) < target) {
+    __nanosleep(32);
+    if (++spins > (1u << 24)) mbar_timeout_trap();
+  }
+}
+
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return fmaf(2.f, __fdividef(1.f, 1.f + __expf(-2.f * x)), -1.f); }
+
+template <int NB>
+struct PlCfg {
+  static constexpr int STAGE_B = NB * 128;                                  // one [NB x 64] bf16 k-block
+  static constexpr int STAGES = (P_RING_BYTES / STAGE_B) > 12 ? 12 : (P_RING_BYTES / STAGE_B);
+  static constexpr size_t SMEM = (size_t)P_W_BYTES + (size_t)STAGES * STAGE_B + (2 * STAGES + 4) * 8 + 16 + 1024;
+};
+
+// =================================================================================================================
+// forward
+// =================================================================================================================
+template <int NB>
+__global__ void __launch_bounds__(P_THREADS, 1)
+lstm_seq_fwd_kernel(const __grid_constant__ LstmSeqMaps maps, const LstmSeqParams p) {
+  using C = PlCfg<NB>;
+  constexpr int KB = PH / 64;  // 6 k-blocks per step
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* s_w = smem;                        // [KB][2 M-tiles][128 rows x 128 B]
+  uint8_t* s_ring = smem + P_W_BYTES;         // [STAGES][NB rows x 128 B]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_ring + C::STAGES * C::STAGE_B);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* w_bar = empty_bar + C::STAGES;
+  uint64_t* done_bar = w_bar + 1;
+  uint64_t* free_bar = done_bar + 1;          // accumulator drained by the epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(free_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u0 = blockIdx.x * 64, bt = blockIdx.y, rec = blockIdx.z;
+  const int b0 = p.b_first + bt * NB;
+  const int model = rec >> 1, dir = rec & 1;
+  int* flags = p.flags + ((size_t)rec * p.nbt + bt) * p.T;
+  constexpr uint32_t TCOLS = 2 * NB < 32 ? 32 : 2 * NB;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(w_bar, 1);
+    mbar_init(done_bar, 1);
+    mbar_init(free_bar, P_EPI_WARPS);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, TCOLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ loader: weights once, then h_{t-1} per step
+    if (elect_one()) {
+      mbar_arrive_expect_tx(w_bar, P_W_BYTES);
+      for (int kb = 0; kb < KB; ++kb)
+        for (int mq = 0; mq < 8; ++mq)
+          tma_load_3d(&maps.w[rec], w_bar, s_w + kb * 32768 + mq * 4096, kb * 64, u0 + mq * 8, 0);
+    }
+    __syncwarp();
+    if (elect_one()) {
+      uint32_t it = 0;
+      for (int step = 1; step < p.T; ++step) {
+        const int t_prev = dir ? p.T - step : step - 1;
+        wait_counter(flags + (step - 1), 6);   // h_{t-1} of all six unit tiles is in global memory
+        fence_proxy_async_global();
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const uint32_t s = it % C::STAGES;
+          mbar_wait(&empty_bar[s], ((it / C::STAGES) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[s], C::STAGE_B);
+          tma_load_3d(&maps.act[model], &full_bar[s], s_ring + s * C::STAGE_B, dir * PH + kb * 64, t_prev, b0);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    constexpr uint32_t IDESC = umma_idesc(UMMA_BF16, 128, NB, 0, 0);
+    if (elect_one()) mbar_wait(w_bar, 0);
+    __syncwarp();
+    uint32_t it = 0;
+    for (int step = 1; step < p.T; ++step) {
+      if (elect_one()) {
+        mbar_wait(free_bar, (uint32_t)(step - 1) & 1u);   // the epilogue of step - 1 has drained the accumulator
+        tc_fence_after();
+        for (int kb = 0; kb < KB; ++kb) {
+          const uint32_t s = (it + kb) % C::STAGES;
+          mbar_wait(&full_bar[s], ((it + kb) / C::STAGES) & 1u);
+          tc_fence_after();
+          const uint32_t sb = smem_u32(s_ring + s * C::STAGE_B), sa = smem_u32(s_w + kb * 32768);
+#pragma unroll
+          for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc_mma_bf16(tm + m * NB, umma_desc_sw128(sa + m * 16384 + k * 32, 16, 1024),
+                          umma_desc_sw128(sb + k * 32, 16, 1024), IDESC, (kb > 0 || k > 0) ? 1u : 0u);
+          tc_commit(&empty_bar[s]);
+        }
+        tc_commit(done_bar);
+      }
+      __syncwarp();
+      it += KB;
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue: 8 warps = 2 M-tiles x 4 lane quarters
+    const int q = warp & 3, m = (warp - 2) >> 2;
+    const int gl = lane >> 3, ul = lane & 7;             // this lane's gate and unit inside the quarter
+    const int u = u0 + (m * 4 + q) * 8 + ul;
+    const uint32_t trow = tm + ((uint32_t)(q * 32) << 16) + m * NB;
+    const float bias = __ldg(p.b_ih[rec] + gl * PH + u) + __ldg(p.b_hh[rec] + gl * PH + u);
+    const float a_s = gl == 2 ? 2.f : 1.f, a_o = gl == 2 ? -1.f : 0.f;   // act(x) = a_s * sigmoid(a_s * x) + a_o
+    const bool hi1 = (gl & 2) != 0, hi0 = (gl & 1) != 0;
+    float cst[NB / 4];
+#pragma unroll
+    for (int j = 0; j < NB / 4; ++j) cst[j] = 0.f;
+    float* gxm = p.gx[model] + dir * PG + gl * PH + u;
+    float* cm = p.c[model] + dir * PH + u;
+    __nv_bfloat16* ym = p.y[model] + dir * PH + u;
+    for (int step = 0; step < p.T; ++step) {
+      const int t = dir ? p.T - 1 - step : step;
+      // input projection of this lane's gate for 4 batch columns at a time (prefetched one group ahead)
+      float zin[4], znext[4];
+      auto load_group = [&](int j, float* z) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int b = b0 + 4 * j + e;
+          z[e] = b < p.B ? gxm[((long long)b * p.T + t) * (2 * PG)] : 0.f;
+        }
+      };
+      load_group(0, zin);
+      if (step > 0) {
+        mbar_wait(done_bar, (uint32_t)(step - 1) & 1u);
+        tc_fence_after();
+      }
+#pragma unroll
+      for (int j = 0; j < NB / 4; ++j) {
+        if (j + 1 < NB / 4) load_group(j + 1, znext);
+        uint32_t acc[4] = {0u, 0u, 0u, 0u};
+        if (step > 0) {
+          tmem_ld4(trow + 4 * j, acc);
+          tmem_ld_wait();
+        }
+        float a[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float z = zin[e] + bias + __uint_as_float(acc[e]);
+          a[e] = fmaf(a_s, sigmoid_fast(a_s * z), a_o);
+          const int b = b0 + 4 * j + e;
+          if (b < p.B) gxm[((long long)b * p.T + t) * (2 * PG)] = a[e];   // activated gate, kept for the backward pass
+        }
+        // 4 x 4 transpose over the lanes (gate 0..3, same unit): afterwards this lane holds i, f, g, o of column 4j + gl
+        {
+          const float s0 = hi1 ? a[0] : a[2], s1 = hi1 ? a[1] : a[3];
+          const float r0 = __shfl_xor_sync(0xffffffffu, s0, 16), r1 = __shfl_xor_sync(0xffffffffu, s1, 16);
+          // rows (gates) {gl & 1, (gl & 1) + 2} x columns {2 * (gl >> 1), + 1}
+          const float b00 = hi1 ? r0 : a[0], b01 = hi1 ? r1 : a[1];   // gate (gl & 1)      columns 2*hi1, 2*hi1 + 1
+          const float b10 = hi1 ? a[2] : r0, b11 = hi1 ? a[3] : r1;   // gate (gl & 1) + 2
+          const float t0 = hi0 ? b00 : b01, t1 = hi0 ? b10 : b11;     // what the partner (gate ^ 1) needs from here
+          const float x0 = __shfl_xor_sync(0xffffffffu, t0, 8), x1 = __shfl_xor_sync(0xffffffffu, t1, 8);
+          // column 2 * hi1 + hi0 == gl: gates 0..3
+          const float g0 = hi0 ? x0 : b00, g1 = hi0 ? b01 : x0, g2 = hi0 ? x1 : b10, g3 = hi0 ? b11 : x1;
+          const int b = b0 + 4 * j + gl;
+          const float cn = fmaf(g1, cst[j], g0 * g2);
+          cst[j] = cn;
+          const float hn = g3 * tanh_fast(cn);
+          if (b < p.B) {
+            const long long tok = (long long)b * p.T + t;
+            cm[tok * (2 * PH)] = cn;
+            ym[tok * (2 * PH)] = __float2bfloat16(hn);
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) zin[e] = znext[e];
+      }
+      // publish h_t: every writer makes its stores visible to the async proxy, then one release-add per CTA
+      fence_proxy_async_global();
+      tc_fence_before();
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * P_EPI_WARPS) : "memory");
+      if (threadIdx.x == 64) {
+        __threadfence();
+        red_release_gpu_add(flags + step, 1);
+      }
+      if (lane == 0) mbar_arrive(free_bar);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tm, TCOLS);
+}
+
+// =================================================================================================================
+// backward
+// =================================================================================================================
+template <int NB>
+__global__ void __launch_bounds__(P_THREADS, 1)
+lstm_seq_bwd_kernel(const __grid_constant__ LstmSeqMaps maps, const LstmSeqParams p) {
+  using C = PlCfg<NB>;
+  constexpr int KB = PG / 64;  // 24 k-blocks (gate rows) per step
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* s_w = smem;                        // [KB][64 gate rows x 128 B (64 units)]
+  uint8_t* s_ring = smem + P_W_BYTES;         // [STAGES][NB rows x 128 B]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_ring + C::STAGES * C::STAGE_B);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* w_bar = empty_bar + C::STAGES;
+  uint64_t* done_bar = w_bar + 1;
+  uint64_t* free_bar = done_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(free_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u0 = blockIdx.x * 64, bt = blockIdx.y, rec = blockIdx.z;
+  const int b0 = p.b_first + bt * NB;
+  const int model = rec >> 1, dir = rec & 1;
+  int* flags = p.flags + ((size_t)rec * p.nbt + bt) * p.T;
+  constexpr uint32_t TCOLS = NB < 32 ? 32 : NB;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(w_bar, 1);
+    mbar_init(done_bar, 1);
+    mbar_init(free_bar, P_EPI_WARPS);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, TCOLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(w_bar, P_W_BYTES);
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(&maps.w[rec], w_bar, s_w + kb * 8192, u0, kb * 64);
+    }
+    __syncwarp();
+    if (elect_one()) {
+      uint32_t it = 0;
+      for (int step = 1; step < p.T; ++step) {
+        // the backward pass walks each direction's own time order in reverse; t_next was processed one step earlier
+        const int t = dir ? step : p.T - 1 - step;
+        const int t_next = dir ? t - 1 : t + 1;
+        wait_counter(flags + (step - 1), 6);
+        fence_proxy_async_global();
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const uint32_t s = it % C::STAGES;
+          mbar_wait(&empty_bar[s], ((it / C::STAGES) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[s], C::STAGE_B);
+          tma_load_3d(&maps.act[model], &full_bar[s], s_ring + s * C::STAGE_B, dir * PG + kb * 64, t_next, b0);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // A = W_hh^T slice, MN-major: 64 units per K row; both 64-row atoms of the M = 128 operand alias the same rows
+    constexpr uint32_t IDESC = umma_idesc(UMMA_BF16, 128, NB, 1, 0);
+    constexpr uint32_t A_LBO = P_BWD_DUP ? 0u : 8192u;
+    if (elect_one()) mbar_wait(w_bar, 0);
+    __syncwarp();
+    uint32_t it = 0;
+    for (int step = 1; step < p.T; ++step) {
+      if (elect_one()) {
+        mbar_wait(free_bar, (uint32_t)(step - 1) & 1u);
+        tc_fence_after();
+        for (int kb = 0; kb < KB; ++kb) {
+          const uint32_t s = (it + kb) % C::STAGES;
+          mbar_wait(&full_bar[s], ((it + kb) / C::STAGES) & 1u);
+          tc_fence_after();
+          const uint32_t sb = smem_u32(s_ring + s * C::STAGE_B), sa = smem_u32(s_w + kb * 8192);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc_mma_bf16(tm, umma_desc_sw128(sa + k * 2048, A_LBO, 1024), umma_desc_sw128(sb + k * 32, 16, 1024), IDESC,
+                        (kb > 0 || k > 0) ? 1u : 0u);
+          tc_commit(&empty_bar[s]);
+        }
+        tc_commit(done_bar);
+      }
+      __syncwarp();
+      it += KB;
+    }
+  } else {
+    // epilogue: lane quarter q -> units (q & 1) * 32 + lane (quarters 2, 3 hold the copy); the 4 (copy, warp-half)
+    // combinations split the NB batch columns
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int u = u0 + (q & 1) * 32 + lane;
+    constexpr int NC = P_BWD_DUP ? NB / 4 : NB / 2;       // columns per thread
+    const int col0 = P_BWD_DUP ? ((q >> 1) * 2 + half) * NC : half * NC;
+    const bool lanes_valid = P_BWD_DUP || q < 2;
+    const uint32_t trow = tm + ((uint32_t)(q * 32) << 16) + col0;
+    float dcs[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) dcs[j] = 0.f;
+    const float* gxm = p.gx[model] + dir * PG + u;
+    const float* cm = p.c[model] + dir * PH + u;
+    const __nv_bfloat16* dym = p.dy[model] + dir * PH + u;
+    __nv_bfloat16* dgm = p.dg[model] + dir * PG + u;
+    for (int step = 0; step < p.T; ++step) {
+      const int t = dir ? step : p.T - 1 - step;
+      const int t_pf = dir ? t + 1 : t - 1;     // forward-order predecessor (c_{t-1})
+      const bool has_prev = dir ? (t < p.T - 1) : (t > 0);
+      if (step > 0) {
+        mbar_wait(done_bar, (uint32_t)(step - 1) & 1u);
+        tc_fence_after();
+      }
+#pragma unroll
+      for (int j4 = 0; j4 < NC; j4 += 4) {
+        uint32_t acc[4] = {0u, 0u, 0u, 0u};
+        if (step > 0) {
+          tmem_ld4(trow + j4, acc);
+          tmem_ld_wait();
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = j4 + e;
+          const int b = b0 + col0 + j;
+          if (b < p.B && lanes_valid) {
+            const long long tok = (long long)b * p.T + t;
+            const float* gp = gxm + tok * (2 * PG);
+            const float ig = gp[0], fg = gp[PH], gg = gp[2 * PH], og = gp[3 * PH];
+            const float ct = cm[tok * (2 * PH)];
+            const float cp = has_prev ? cm[((long long)b * p.T + t_pf) * (2 * PH)] : 0.f;
+            const float dh = __bfloat162float(dym[tok * (2 * PH)]) + __uint_as_float(acc[e]);
+            const float tc = tanh_fast(ct);
+            const float dc = dcs[j] + dh * og * (1.f - tc * tc);
+            dcs[j] = dc * fg;
+            __nv_bfloat16* dp = dgm + tok * (2 * PG);
+            dp[0] = __float2bfloat16(dc * gg * ig * (1.f - ig));
+            dp[PH] = __float2bfloat16(dc * cp * fg * (1.f - fg));
+            dp[2 * PH] = __float2bfloat16(dc * ig * (1.f - gg * gg));
+            dp[3 * PH] = __float2bfloat16(dh * tc * og * (1.f - og));
+          }
+        }
+      }
+      fence_proxy_async_global();
+      tc_fence_before();
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * P_EPI_WARPS) : "memory");
+      if (threadIdx.x == 64) {
+        __threadfence();
+        red_release_gpu_add(flags + step, 1);
+      }
+      if (lane == 0) mbar_arrive(free_bar);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tm, TCOLS);
+}
+
+}  // namespace pe
+
+// =================================================================================================================
+// C-ABI
+// =================================================================================================================
+using namespace pe;
+
+static int seq_maps(LstmSeqMaps* m, const void* const* act, int act_cols, int B, int T, int NB, const void* const* w_hh,
+                    bool backward) {
+  for (int i = 0; i < 2; ++i) {
+    uint64_t dims[3] = {(uint64_t)act_cols, (uint64_t)T, (uint64_t)B};
+    uint64_t str[2] = {(uint64_t)act_cols * 2, (uint64_t)T * act_cols * 2};
+    uint32_t box[3] = {64, 1, (uint32_t)NB};
+    if (int rc = pe_host::encode_tmap(&m->act[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, act[i], dims, str, box)) return rc;
+  }
+  for (int r = 0; r < 4; ++r) {
+    if (backward) {
+      uint64_t dims[2] = {(uint64_t)PH, (uint64_t)PG};
+      uint64_t str[1] = {(uint64_t)PH * 2};
+      uint32_t box[2] = {64, 64};
+      if (int rc = pe_host::encode_tmap(&m->w[r], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w_hh[r], dims, str, box)) return rc;
+    } else {  // [gate][unit][k]: a box of 8 units x 4 gates fills one 32-lane TMEM quarter
+      uint64_t dims[3] = {(uint64_t)PH, (uint64_t)PH, 4};
+      uint64_t str[2] = {(uint64_t)PH * 2, (uint64_t)PH * PH * 2};
+      uint32_t box[3] = {64, 8, 4};
+      if (int rc = pe_host::encode_tmap(&m->w[r], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, w_hh[r], dims, str, box)) return rc;
+    }
+  }
+  return PE_OK;
+}
+
+template <int NB>
+static int launch_seq(bool backward, const LstmSeqMaps& maps, LstmSeqParams p, cudaStream_t st) {
+  const void* fn = backward ? (const void*)lstm_seq_bwd_kernel<NB> : (const void*)lstm_seq_fwd_kernel<NB>;
+  const size_t smem = PlCfg<NB>::SMEM;
+  if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PE_ERR_LAUNCH;
+  void* args[2] = {(void*)&maps, (void*)&p};
+  dim3 grid(PH / 64, p.nbt, 4);
+  if (cudaLaunchCooperativeKernel(fn, grid, dim3(P_THREADS), args, smem, st) != cudaSuccess) return PE_ERR_LAUNCH;
+  return PE_OK;
+}
+
+static int run_seq(bool backward, LstmSeqParams p, const void* const* act, int act_cols, const void* const* w_hh,
+                   int* flags, size_t flags_bytes, cudaStream_t st) {
+  const int B = p.B, T = p.T;
+  const int NB = B <= 16 ? 16 : B <= 32 ? 32 : B <= 64 ? 64 : 128;
+  const int max_bt = pe_host::num_sms() / 24;   // 6 unit tiles x 4 recurrences per batch tile, one CTA per SM
+  if (max_bt < 1) return PE_ERR_ARCH;
+  const int nbt_total = (B + NB - 1) / NB;
+  const int nbt_launch = nbt_total < max_bt ? nbt_total : max_bt;
+  if (!flags || flags_bytes < (size_t)4 * nbt_launch * T * sizeof(int)) return PE_ERR_WORKSPACE;
+  LstmSeqMaps maps;
+  if (int rc = seq_maps(&maps, act, act_cols, B, T, NB, w_hh, backward)) return rc;
+  for (int bt0 = 0; bt0 < nbt_total; bt0 += nbt_launch) {   // batch tiles are independent: chunk them if B is huge
+    p.nbt = nbt_total - bt0 < nbt_launch ? nbt_total - bt0 : nbt_launch;
+    p.b_first = bt0 * NB;
+    p.flags = flags;
+    if (cudaMemsetAsync(flags, 0, (size_t)4 * p.nbt * T * sizeof(int), st) != cudaSuccess) return PE_ERR_LAUNCH;
+    int rc;
+    switch (NB) {
+      case 16: rc = launch_seq<16>(backward, maps, p, st); break;
+      case 32: rc = launch_seq<32>(backward, maps, p, st); break;
+      case 64: rc = launch_seq<64>(backward, maps, p, st); break;
+      default: rc = launch_seq<128>(backward, maps, p, st); break;
+    }
+    if (rc) return rc;
+  }
+  return cudaGetLastError() == cudaSuccess ? PE_OK : PE_ERR_LAUNCH;
+}
+
+extern "C" int pe_lstm_seq_fwd(int B, int T, int hidden, float* const* gx, float* const* c, void* const* y,
+                               const void* const* w_hh, const float* const* b_ih, const float* const* b_hh,
+                               void* workspace, size_t workspace_bytes, pe_stream_t stream) {
+  if (int rc = pe_host::check_arch()) return rc;
+  if (hidden != PH || B <= 0 || T <= 0 || !gx || !c || !y || !w_hh || !b_ih || !b_hh) return PE_ERR_BAD_SHAPE;
+  LstmSeqParams p{};
+  p.B = B; p.T = T;
+  for (int i = 0; i < 2; ++i) {
+    p.gx[i] = gx[i]; p.c[i] = c[i]; p.y[i] = (__nv_bfloat16*)y[i];
+  }
+  for (int r = 0; r < 4; ++r) {
+    p.b_ih[r] = b_ih[r]; p.b_hh[r] = b_hh[r];
+  }
+  const void* act[2] = {y[0], y[1]};
+  return run_seq(false, p, act, 2 * PH, w_hh, (int*)workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int pe_lstm_seq_bwd(int B, int T, int hidden, const float* const* gates, const float* const* c,
+                               const void* const* dy, void* const* dg, const void* const* w_hh, void* workspace,
+                               size_t workspace_bytes, pe_stream_t stream) {
+  if (int rc = pe_host::check_arch()) return rc;
+  if (hidden != PH || B <= 0 || T <= 0 || !gates || !c || !dy || !dg || !w_hh) return PE_ERR_BAD_SHAPE;
+  LstmSeqParams p{};
+  p.B = B; p.T = T;
+  for (int i = 0; i < 2; ++i) {
+    p.gx[i] = const_cast<float*>(gates[i]); p.c[i] = const_cast<float*>(c[i]);
+    p.dy[i] = (const __nv_bfloat16*)dy[i]; p.dg[i] = (__nv_bfloat16*)dg[i];
+  }
+  const void* act[2] = {dg[0], dg[1]};
+  return run_seq(true, p, act, 2 * PG, w_hh, (int*)workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}

@@ -85,6 +85,8 @@ class Engine:
         # Training steps are captured into a CUDA graph after two eager warm-up steps and replayed from then on
         # (~270 launches per step; eagerly the host needs ~10 ms to enqueue them).  PE_CUDA_GRAPH=0 disables it.
         self.use_graph = os.environ.get("PE_CUDA_GRAPH", "1") != "0"
+        # BiLSTM recurrences: persistent kernel (default) or one launch per time step (PE_LSTM_STEPWISE=1)
+        self.lstm_persistent = os.environ.get("PE_LSTM_STEPWISE", "0") != "1"
         self._graphs = {}
         self.bf16_fresh = False
         self._capturing = False
@@ -426,6 +428,12 @@ class Engine:
                 out.append((prefix, "l%d%s" % (layer, sfx)))
         return out  # index = model * 2 + direction
 
+    def _lstm_workspace(self, B, T):
+        fn = L.lib().pe_workspace_bytes
+        fn.restype = ctypes.c_longlong
+        need = int(fn(b"pe_lstm_seq_fwd", c_int(B), c_int(T), c_int(0)))
+        return self.buf("lstm_flags", (max(need, 4) // 4,), torch.int32)
+
     def _bilstm_fwd(self, Xc, Xd, B, T, training):
         V, W16 = self.view, self.bview
         M, Hh, G = B * T, 384, 1536
@@ -455,9 +463,14 @@ class Engine:
             whh = self._ptrs([W16["%s.model.weight_hh_%s" % n] for n in names])
             bih = self._ptrs([V["%s.model.bias_ih_%s" % n] for n in names])
             bhh = self._ptrs([V["%s.model.bias_hh_%s" % n] for n in names])
-            call("pe_lstm_steps_fwd", c_int(B), c_int(T), c_int(Hh), c_int(0), c_int(T), gx_a, c_a, y_a, whh, bih, bhh,
-                 stream())
-            L.launch_count += T - 1
+            if self.lstm_persistent:  # one persistent launch per layer, W_hh resident in shared memory
+                ws = self._lstm_workspace(B, T)
+                call("pe_lstm_seq_fwd", c_int(B), c_int(T), c_int(Hh), gx_a, c_a, y_a, whh, bih, bhh, ptr(ws),
+                     ctypes.c_size_t(ws.numel() * 4), stream())
+            else:                     # one dependent launch per time step (kept as the cross-check)
+                call("pe_lstm_steps_fwd", c_int(B), c_int(T), c_int(Hh), c_int(0), c_int(T), gx_a, c_a, y_a, whh, bih,
+                     bhh, stream())
+                L.launch_count += T - 1
         return Y[0], Y[1]
 
     def _bilstm_bwd(self, dHc, dHd, B, T):
@@ -476,9 +489,14 @@ class Engine:
             dc = [self.buf("ldc%d" % mi, (B, 2 * Hh), torch.float32) for mi in range(2)]
             gx_a, c_a, dy_a, dg_a, dc_a = (self._ptrs(GX), self._ptrs(C), self._ptrs(dY), self._ptrs(dG), self._ptrs(dc))
             whh = self._ptrs([W16["%s.model.weight_hh_%s" % n] for n in names])
-            call("pe_lstm_steps_bwd", c_int(B), c_int(T), c_int(Hh), c_int(0), c_int(T), gx_a, c_a, dy_a, dg_a, dc_a, whh,
-                 stream())
-            L.launch_count += T - 1
+            if self.lstm_persistent:
+                ws = self._lstm_workspace(B, T)
+                call("pe_lstm_seq_bwd", c_int(B), c_int(T), c_int(Hh), gx_a, c_a, dy_a, dg_a, whh, ptr(ws),
+                     ctypes.c_size_t(ws.numel() * 4), stream())
+            else:
+                call("pe_lstm_steps_bwd", c_int(B), c_int(T), c_int(Hh), c_int(0), c_int(T), gx_a, c_a, dy_a, dg_a, dc_a,
+                     whh, stream())
+                L.launch_count += T - 1
             dX = [None, None]
             for r, (prefix, sfx) in enumerate(names):
                 mi, d = r >> 1, r & 1

@@ -98,6 +98,35 @@ def banded_filterbank(fb):
     return to_i(starts), to_i(counts), to_i(offs), torch.tensor(weights, dtype=torch.float32)
 
 
+ITEM_COMBINE, ITEM_WRITER = 1, 2
+
+
+def mel_work_items(starts, counts, offsets, lanes=128):
+    """Work items of the banded mel product for the tcgen05 log-mel kernel, one per worker lane: int32 [lanes][4] =
+    {filter (-1: idle), first bin, number of bins, offset into the weight array | flags << 24}.  The longest filters are
+    split in two halves that sit on adjacent lanes (l, l ^ 1; flag ITEM_COMBINE on both, ITEM_WRITER on the even one)
+    until every lane has work; items are ordered longest first so that the lanes of a warp run similar trip counts."""
+    n = len(counts)
+    if n > lanes:
+        raise ValueError("the tcgen05 log-mel kernel handles at most %d mel filters" % lanes)
+    order = sorted(range(n), key=lambda m: -int(counts[m]))
+    n_split = min(lanes - n, sum(1 for m in order if counts[m] >= 2))
+    pairs, singles = [], []
+    for rank, m in enumerate(order):
+        st, c, off = int(starts[m]), int(counts[m]), int(offsets[m])
+        if rank < n_split:
+            c0 = (c + 1) // 2
+            pairs.append(((m, st, c0, off, ITEM_COMBINE | ITEM_WRITER), (m, st + c0, c - c0, off + c0, ITEM_COMBINE)))
+        else:
+            singles.append((m, st, c, off, ITEM_WRITER))
+    items = [it for pr in pairs for it in pr] + singles
+    out = np.full((lanes, 4), 0, dtype=np.int64)
+    out[:, 0] = -1
+    for i, (m, st, c, off, fl) in enumerate(items):
+        out[i] = (m, st, c, off | (fl << 24))
+    return torch.from_numpy(out.astype(np.int32))
+
+
 _TABLE_CACHE = {}
 
 
@@ -110,7 +139,7 @@ def logmel_tables(device, sample_rate=24000, n_fft=1024, win_length=1024, hop_le
             "n_fft": n_fft, "hop": hop_length, "n_mels": n_mels, "sr": sample_rate,
             "basis": windowed_dft_basis(n_fft, win_length).to(device),
             "fb": fb.to(device),
-            "tc": n_fft == 1024 and hop_length % 4 == 0 and n_mels <= 128,
+            "tc": n_fft == 1024 and hop_length % 4 == 0 and hop_length <= 320 and n_mels <= 128,
         }
         if tab["tc"]:
             win = np.zeros(n_fft)
@@ -119,8 +148,9 @@ def logmel_tables(device, sample_rate=24000, n_fft=1024, win_length=1024, hop_le
             st, cnt, off, w = banded_filterbank(fb)
             tab.update(win=torch.from_numpy(win.astype(np.float32)).to(device), fmat=dft32_operand_images().to(device),
                        tw=four_step_twiddles().to(device), mel_start=st.to(device), mel_count=cnt.to(device),
-                       mel_off=off.to(device), mel_w=w.to(device), mel_nnz=int(w.numel()))
-            tab["tc"] = tab["mel_nnz"] <= 2048
+                       mel_off=off.to(device), mel_w=w.to(device), mel_nnz=int(w.numel()),
+                       mel_items=mel_work_items(st.tolist(), cnt.tolist(), off.tolist()).to(device))
+            tab["tc"] = tab["mel_nnz"] <= 1536
         _TABLE_CACHE[key] = tab
     return _TABLE_CACHE[key]
 
@@ -147,7 +177,10 @@ class LogMel:
     def num_frames(self, num_samples):
         return 1 + num_samples // self.params["hop_length"]
 
-    def __call__(self, wave, crop=None, T_out=0, layout="bmt"):
+    def __call__(self, wave, crop=None, T_out=0, layout="bmt", lengths=None):
+        """lengths: int32 [B] valid samples per item of a zero-padded mixed-length batch (None = all L): each item is
+        reflect-padded at its own end and its frames t >= 1 + length // hop are 0.0, exactly what the reference's
+        per-item mel + Collater give (meldataset.py:644,804-816)."""
         if wave.dim() == 1:
             wave = wave[None]
         wave = wave.to(self.device, torch.float32).contiguous()
@@ -159,19 +192,20 @@ class LogMel:
         out = torch.empty(shape, device=self.device, dtype=torch.float32)
         if crop is not None:
             crop = crop.to(self.device, torch.int32).contiguous()
+        if lengths is not None:
+            lengths = lengths.to(self.device, torch.int32).contiguous()
         use_tc = self.tables["tc"] if self.impl == "auto" else self.impl == "tc"
         if use_tc and not self.tables["tc"]:
-            raise RuntimeError("the tcgen05 log-mel kernel needs n_fft == 1024, hop % 4 == 0, n_mels <= 128")
+            raise RuntimeError("the tcgen05 log-mel kernel needs n_fft == 1024, hop % 4 == 0, hop <= 320, n_mels <= 128")
         if use_tc:
             need = B * ((Lw + 3) // 4 * 4)
         else:
             need = B * T * (self.params["n_fft"] // 2 + 1)
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, device=self.device, dtype=torch.float32)
-        kw = dict(out_bmt=out if layout == "bmt" else None, out_btm=out if layout == "btm" else None, crop=crop, T_out=To)
-        if use_tc:
-            if crop is not None or To != T:
-                out.zero_()  # rows past the end of an item stay zero (Collater padding, meldataset.py:804-816)
+        kw = dict(out_bmt=out if layout == "bmt" else None, out_btm=out if layout == "btm" else None, crop=crop, T_out=To,
+                  lengths=lengths)
+        if use_tc:  # writes every output row itself (zeros past the end of an item: Collater padding)
             ops.logmel_tc(wave, self.tables, ws=self._ws, **kw)
         else:
             ops.logmel(wave, self.tables, power_ws=self._ws, **kw)

@@ -165,7 +165,9 @@ class MelDataset(torch.utils.data.Dataset):
 
 class Collater(object):
     """Zero-pad to 192 frames and stack (meldataset.py:790-826).  With ``return_wave=True`` the batch carries raw
-    waveforms and crop offsets instead of mels: ``(waves [B, L], f0s [B, 192], is_silences [B, 192], crops [B])``."""
+    waveforms instead of mels: ``(waves [B, L], f0s [B, 192], is_silences [B, 192], crops [B], lengths [B])`` -- crop
+    offsets in frames and every item's own sample count, so that the batched GPU log-mel reflect-pads each item at its
+    own end and zero-fills the frames past it, exactly like the per-item mel + zero padding of the reference."""
 
     def __init__(self, return_wave=False):
         self.return_wave = return_wave
@@ -179,12 +181,14 @@ class Collater(object):
             L = max(item[0].shape[0] for item in batch)
             waves = torch.zeros((B, L)).float()
             crops = torch.zeros((B,), dtype=torch.int32)
+            lengths = torch.zeros((B,), dtype=torch.int32)
             for i, (wave, f0, sil, start) in enumerate(batch):
                 waves[i, :wave.shape[0]] = wave
                 f0s[i, :f0.shape[0]] = f0
                 sils[i, :sil.shape[0]] = sil
                 crops[i] = start
-            return waves, f0s, sils, crops
+                lengths[i] = wave.shape[0]
+            return waves, f0s, sils, crops, lengths
         nmels = batch[0][0].size(0)
         mels = torch.zeros((B, nmels, self.max_mel_length), device=batch[0][0].device).float()
         for i, (mel, f0, sil) in enumerate(batch):

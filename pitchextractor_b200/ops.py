@@ -93,7 +93,7 @@ def conv_wgrad(dy, x, dw, taps=9, splits=0, col_offset=0):
     return dw
 
 
-def logmel(wave, tables, out_bmt=None, out_btm=None, crop=None, T_out=0, power_ws=None):
+def logmel(wave, tables, out_bmt=None, out_btm=None, crop=None, T_out=0, power_ws=None, lengths=None):
     """wave [B,L] fp32 cuda -> normalised log-mel; tables from ``logmel_tables``."""
     B, Lw = wave.shape
     n_fft, hop, n_mels = tables["n_fft"], tables["hop"], tables["n_mels"]
@@ -103,7 +103,7 @@ def logmel(wave, tables, out_bmt=None, out_btm=None, crop=None, T_out=0, power_w
         power_ws = torch.empty(B * T * n_bins, device=wave.device, dtype=torch.float32)
     call("pe_logmel_f32", ptr(wave), c_int(B), c_int(Lw), c_int(n_fft), c_int(hop), c_int(n_mels),
          ptr(tables["basis"]), c_int(tables["basis"].stride(0)), ptr(tables["fb"]), ptr(power_ws),
-         c_size(power_ws.numel() * 4), ptr(out_bmt), ptr(out_btm), ptr(crop), c_int(T_out), stream())
+         c_size(power_ws.numel() * 4), ptr(out_bmt), ptr(out_btm), ptr(crop), ptr(lengths), c_int(T_out), stream())
     return power_ws
 
 
@@ -124,11 +124,10 @@ def colsum(x, out):
     call("pe_colsum_bf16", ptr(x), c_ll(M), c_int(N), c_ll(x.stride(0)), ptr(out), stream())
 
 
-def logmel_tc(wave, tables, ws, out_bmt=None, out_btm=None, crop=None, T_out=0):
+def logmel_tc(wave, tables, ws, out_bmt=None, out_btm=None, crop=None, T_out=0, lengths=None):
     """tcgen05 four-step log-mel (n_fft 1024); ws: fp32 workspace for the reflect-padded waveform."""
     B, Lw = wave.shape
     t = tables
     call("pe_logmel_tc", ptr(wave), c_int(B), c_int(Lw), c_int(t["n_fft"]), c_int(t["hop"]), c_int(t["n_mels"]),
-         ptr(t["win"]), ptr(t["fmat"]), ptr(t["tw"]), ptr(t["mel_start"]), ptr(t["mel_count"]), ptr(t["mel_off"]),
-         ptr(t["mel_w"]), c_int(t["mel_nnz"]), ptr(ws), c_size(ws.numel() * 4), ptr(out_bmt), ptr(out_btm), ptr(crop),
-         c_int(T_out), stream())
+         ptr(t["win"]), ptr(t["fmat"]), ptr(t["tw"]), ptr(t["mel_items"]), ptr(t["mel_w"]), c_int(t["mel_nnz"]), ptr(ws),
+         c_size(ws.numel() * 4), ptr(out_bmt), ptr(out_btm), ptr(crop), ptr(lengths), c_int(T_out), stream())

@@ -114,13 +114,14 @@ class Trainer(object):
 
     # ------------------------------------------------------------------ one step (trainer.py:219-252)
     def _mel_from_batch(self, batch):
-        """-> (mel-like model input, f0, sil).  batch = (mels [B,1,80,192], f0, sil) or (waves, f0, sil, crops)."""
-        if len(batch) == 4:
-            waves, f0, sil, crops = batch
+        """-> (mel-like model input, f0, sil).  batch = (mels [B,1,80,192], f0, sil) or (waves, f0, sil, crops[, lengths])."""
+        if len(batch) >= 4:
+            waves, f0, sil, crops = batch[:4]
+            lengths = batch[4].to(self.device, non_blocking=True) if len(batch) > 4 else None
             if self._logmel is None:
                 self._logmel = LogMel(self.device)
             x = self._logmel(waves.to(self.device, non_blocking=True), crop=crops.to(self.device, non_blocking=True),
-                             T_out=192, layout="btm")  # [B, 192, 80] == the transposed model input
+                             T_out=192, layout="btm", lengths=lengths)  # [B, 192, 80] == the transposed model input
             return x[:, None].transpose(-1, -2), f0, sil  # present it as the reference's [B,1,80,192] view
         x, f0, sil = batch
         return x.to(self.device, non_blocking=True), f0, sil

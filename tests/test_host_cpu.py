@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_cabi_exports_every_declared_symbol(built_lib):
     hdr = open(os.path.join(ROOT, "include", "pitchextractor_b200.h")).read()
-    declared = set(re.findall(r"^int (pe_[a-z0-9_]+)\(", hdr, flags=re.M))
+    declared = set(re.findall(r"^(?:int|long long) (pe_[a-z0-9_]+)\(", hdr, flags=re.M))
     assert len(declared) >= 20
     lib = ctypes.CDLL(built_lib)
     for sym in declared:
@@ -23,6 +23,11 @@ def test_cabi_exports_every_declared_symbol(built_lib):
     exported = set(re.findall(r" T (pe_[a-z0-9_]+)", out))
     assert exported == declared, (exported ^ declared)
     assert lib.pe_version() >= 100
+    lib.pe_workspace_bytes.restype = ctypes.c_longlong
+    ws = lambda op, B, T, L: lib.pe_workspace_bytes(op.encode(), B, T, L)
+    assert ws("pe_logmel_tc", 3, 0, 58625) == 3 * 58628 * 4
+    assert ws("pe_logmel_f32", 2, 196, 1024) == 2 * 196 * 513 * 4
+    assert ws("pe_adamw", 1, 0, 0) == 0 and ws("pe_logmel_tc", 0, 0, 0) == -1
 
 
 def test_no_cpu_fallback():
@@ -105,8 +110,9 @@ def test_dataset_wave_items_and_collate():
     wave, f0, sil, start = items[0]
     assert wave.shape == (58624,) and f0.shape == (192,) and sil.shape == (192,) and 0 <= start < 4
     assert torch.equal(sil, (f0 == 0).float())
-    waves, f0s, sils, crops = Collater(return_wave=True)(items)
+    waves, f0s, sils, crops, lengths = Collater(return_wave=True)(items)
     assert waves.shape == (3, 58624) and f0s.shape == (3, 192) and sils.shape == (3, 192) and crops.dtype == torch.int32
+    assert lengths.tolist() == [58624] * 3
 
 
 def test_synthetic_segments_are_seeded_and_labelled():

@@ -83,3 +83,27 @@ def test_logmel_zero_padding_past_the_end(built_lib, impl):
         ref = logmel_np.log_mel(w[b])
         assert np.abs(y[b, :, :81] - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max())
         assert (y[b, :, 81:] == 0).all()
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_logmel_mixed_length_batch_matches_per_item_mel_and_collate(built_lib, impl):
+    """A zero-padded batch of items of different lengths (Collater(return_wave=True)) must give what the reference's
+    per-item path gives: every item's mel computed on its own samples -- reflect padding at ITS end -- cropped, then
+    zero-padded to 192 frames by the Collater (meldataset.py:644-677,804-816)."""
+    from oracle import logmel_np
+    from pitchextractor_b200.mel import LogMel
+    rng = np.random.default_rng(23)
+    lens = [58624, 24000, 40000, 58624, 30001 // 4 * 4, 1200]
+    crops = [3, 0, 0, 1, 0, 0]
+    L = max(lens)
+    w = np.zeros((len(lens), L), np.float32)
+    for i, n in enumerate(lens):
+        w[i, :n] = 0.1 * rng.standard_normal(n)
+    y = LogMel("cuda", impl=impl)(torch.from_numpy(w).cuda(), crop=torch.tensor(crops, dtype=torch.int32), T_out=192,
+                                  layout="bmt", lengths=torch.tensor(lens, dtype=torch.int32)).cpu().numpy()
+    assert y.shape == (len(lens), 80, 192)
+    for i, n in enumerate(lens):
+        ref = logmel_np.log_mel(w[i, :n])[:, crops[i]:crops[i] + 192]
+        k = ref.shape[1]
+        assert np.abs(y[i, :, :k] - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max()), (i, np.abs(y[i, :, :k] - ref).max())
+        assert (y[i, :, k:] == 0).all(), i

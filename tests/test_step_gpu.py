@@ -192,3 +192,30 @@ def test_full_size_properties(built_lib):
     b = lm(torch.nn.functional.pad(w, (300, 0))[:, :58624].contiguous(), layout="bmt")
     # frames whose window lies inside both signals and away from the reflected edges
     assert torch.allclose(a[:, :, 3:180], b[:, :, 4:181], rtol=0, atol=2e-4), (a[:, :, 3:180] - b[:, :, 4:181]).abs().max()
+
+
+@pytest.mark.parametrize("B", [3, 16, 40, 130])
+def test_lstm_persistent_kernel_matches_stepwise_launches(built_lib, B):
+    """The persistent recurrence (W_hh resident in shared memory, one launch per layer) against the one-launch-per-step
+    kernels on the same weights and inputs, across every batch-tile width (16 / 32 / 64 / 128 columns) and a partial
+    second batch tile: losses, hidden states and all gradients."""
+    mel, f0, sil = _inputs(B, seed=21 + B)
+    out, grads, hid = {}, {}, {}
+    for mode in ("stepwise", "persistent"):
+        m = _model(seed=7, model_type="bilstm").cuda()
+        eng = m.engine
+        eng.dropout_enabled = False
+        eng.use_graph = False
+        eng.lstm_persistent = mode == "persistent"
+        out[mode] = eng.train_step(mel.cuda(), f0.cuda(), sil.cuda(), 0.1).clone()
+        grads[mode] = eng.flat_grad.clone()
+        hid[mode] = eng._Hc.float().clone()
+        torch.cuda.synchronize()
+    print(B, out)
+    assert torch.allclose(out["stepwise"], out["persistent"], rtol=2e-3, atol=1e-4), out
+    rel_h = ((hid["stepwise"] - hid["persistent"]).norm() / hid["stepwise"].norm()).item()
+    assert rel_h < 1e-2, rel_h
+    cos = torch.nn.functional.cosine_similarity(grads["stepwise"], grads["persistent"], dim=0).item()
+    rel = ((grads["stepwise"] - grads["persistent"]).norm() / grads["stepwise"].norm()).item()
+    print("B=%d persistent vs stepwise: grad cosine %.6f rel %.4g hidden rel %.3g" % (B, cos, rel, rel_h))
+    assert cos > 0.999 and rel < 5e-2, (cos, rel)
