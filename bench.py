@@ -79,6 +79,16 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def measured_traffic(model, batch):
+    """Mean DRAM bytes per tile-engine launch from the ncu capture of this (model, batch), if one is committed."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get("%s_b%d" % (model, batch), {}).get("bytes_per_launch")
+    except Exception:
+        return None
+
+
 def make_pool(batch, n_batches, rank):
     """Host (pinned) pool of synthetic batches: waves, f0 [B,192], sil [B,192], crops."""
     from pitchextractor_b200 import synthetic
@@ -183,20 +193,30 @@ def run_ours(args):
     tc_ms = sum(a.elapsed_time(b) for _, a, b, _ in prof)
     tc_flops = sum(f for _, _, _, f in prof)
     n_prof_steps = min(3, args.steps)
-    # log-mel alone (second headline metric)
+    # log-mel alone (second headline metric): (a) as it runs inside the step -- the step's batch, 192 of 196 frames per
+    # segment; (b) the largest segment-shaped cell of the BASELINE configs[4] sweep (batch 1024), where the launch
+    # and pipeline-fill overheads of a 40-microsecond kernel no longer dominate
     from pitchextractor_b200.mel import LogMel
     lm = LogMel(dev)
-    w = dpool[0][0]
-    for _ in range(3):
-        lm(w, T_out=FRAMES, layout="btm")
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(10):
-        lm(w, T_out=FRAMES, layout="btm")
-    e1.record()
-    torch.cuda.synchronize()
-    lm_ms = e0.elapsed_time(e1) / 10
+
+    def time_logmel(w, crop, n):
+        for _ in range(3):
+            lm(w, crop=crop, T_out=FRAMES, layout="btm")
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            lm(w, crop=crop, T_out=FRAMES, layout="btm")
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    lm_ms = time_logmel(dpool[0][0], dpool[0][3], 20)
+    LM_BIG = 1024
+    gen = torch.Generator(device=dev).manual_seed(7)
+    wbig = torch.randn(LM_BIG, SEG, device=dev, generator=gen) * 0.1     # 240 MB: larger than the 126 MB L2
+    lm_big_ms = time_logmel(wbig, None, 10)
+    del wbig
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -204,7 +224,6 @@ def run_ours(args):
         return
     pk = peaks()
     seg_s = world * B * args.steps / (ms / 1e3)
-    frames = B * (1 + SEG // 300)
     line = {
         "metric": "train_segments_per_s", "value": seg_s, "unit": "segments/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -220,16 +239,21 @@ def run_ours(args):
                      "achieved": tc_flops / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else None, "peak": pk["tf_sustained"],
                      "unit": "TFLOP/s",
                      "frac": (tc_flops / (tc_ms / 1e3) / 1e12 / pk["tf_sustained"]) if tc_ms > 0 else None,
-                     # mean dram__bytes_read + write per launch over the first 24 tile-engine launches of a step (7
-                     # forward convs + 17 encoder GEMMs) in the ncu --set full capture
-                     # profiles/r01_ncu_full_tc_tile_24launches.csv (B = 64)
-                     "traffic": 73.0e6 if (args.batch == 64 and args.model == "transformer") else None,
+                     # dram__bytes_read + write per launch from the committed ncu --set full capture of this
+                     # configuration (profiles/traffic.json names the capture); null when there is none
+                     "traffic": measured_traffic(args.model, args.batch),
                      "peak_source": pk["src"] + " (sustained bf16)",
                      "launches_per_step": len(prof) // max(1, n_prof_steps), "ms_per_step": tc_ms / max(1, n_prof_steps),
                      "step_frac_of_bf16_peak": seg_s / world * FLOPS_PER_SEGMENT[args.model] / (pk["tf_sustained"] * 1e12)},
-        "logmel": {"frames_per_s": frames / (lm_ms / 1e3), "ms": lm_ms, "bound": "hbm",
-                   "achieved_gbs": frames * 1520.0 / (lm_ms / 1e3) / 1e9, "peak_gbs": pk["hbm"],
-                   "frac": frames * 1520.0 / (lm_ms / 1e3) / 1e9 / pk["hbm"]},
+        # algorithmic bytes per frame: hop * 4 B of waveform read once + 80 * 4 B written = 1520 B
+        "logmel": {"workload": "log-mel of %d segments x 58624 samples -> %d frames each (BASELINE configs[4] cell)"
+                               % (LM_BIG, FRAMES),
+                   "frames_per_s": LM_BIG * FRAMES / (lm_big_ms / 1e3), "ms": lm_big_ms, "bound": "hbm",
+                   "achieved_gbs": LM_BIG * FRAMES * 1520.0 / (lm_big_ms / 1e3) / 1e9, "peak_gbs": pk["hbm"],
+                   "frac": LM_BIG * FRAMES * 1520.0 / (lm_big_ms / 1e3) / 1e9 / pk["hbm"],
+                   "in_step": {"workload": "the step's own batch: %d segments -> %d frames each" % (B, FRAMES),
+                               "frames_per_s": B * FRAMES / (lm_ms / 1e3), "ms": lm_ms,
+                               "frac": B * FRAMES * 1520.0 / (lm_ms / 1e3) / 1e9 / pk["hbm"]}},
         "loss_last": last,
     }
     if world == 1 and not args.no_torch_gpu_baseline:

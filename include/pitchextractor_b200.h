@@ -133,9 +133,10 @@ int pe_logmel_f32(const float* wave, int B, int L, int n_fft, int hop, int n_mel
 /* Same transform on tcgen05 tensor cores for n_fft == 1024, hop % 4 == 0, hop <= 320: two frames per complex FFT,
  * 32 x 32 four-step factorisation as two [128 x 64] x [64 x 64] fp16-split GEMM stages per 8 frames (fp32-grade
  * accuracy); every 8-frame slot reads its 1024 + 7*hop samples once.
- *   win [1024] fp32 window;  fmat: 3 x [64][64] fp16 operand images (hi, lo, hi * 2^-11) of the 32-point complex DFT
- *   matrix in the 128-byte-swizzled K-major layout;  tw [2][32][32] fp32 cos / sin of 2 pi k1 n2 / 1024;
- *   mel_w [mel_nnz <= 1536]: the non-zero filterbank weights, band after band;  mel_items int32 [128][4]: the work items
+ *   win [1024] fp32 window x 2^11;  fmat: 2 x [64][64] fp16 operand images (hi, lo) of the 32-point complex DFT matrix
+ *   in the 128-byte-swizzled K-major layout;  tw [2][32][32] fp32 cos / sin of 2 pi k1 n2 / 1024, x 2^-5;
+ *   mel_w [mel_nnz <= 1536]: the non-zero filterbank weights x 2^-14, band after band (the power-of-two scales keep
+ *   the fp16 split of the data in range and cancel exactly);  mel_items int32 [128][4]: the work items
  *   of the banded mel product, one per worker lane: {filter (-1: idle), first bin, number of bins, offset into mel_w |
  *   flags << 24}, flags 1 = add the partial sums of lane ^ 1 (a long filter split over two adjacent lanes), 2 = this lane
  *   writes the filter (n_mels <= 128);
@@ -145,6 +146,14 @@ int pe_logmel_f32(const float* wave, int B, int L, int n_fft, int hop, int n_mel
 int pe_logmel_tc(const float* wave, int B, int L, int n_fft, int hop, int n_mels, const float* win, const void* fmat,
                  const float* tw, const int* mel_items, const float* mel_w, int mel_nnz, float* xpad, size_t xpad_bytes,
                  float* out_bmt, float* out_btm, const int* crop, const int* lengths, int T_out, pe_stream_t stream);
+
+/* Polyphase windowed-sinc resampling (torchaudio.functional.resample, called per file at meldataset.py:621-627):
+ * y[b][j*up + p] = sum_k xpad[b][j*down + k] * h[p][k], xpad = x zero-padded by (width, width + down); h fp32
+ * [up][2*width + down] is the filter bank of torchaudio's _get_sinc_resample_kernel for the reduced rates
+ * up = new/gcd, down = orig/gcd.  x [B][ldx], y [B][ldy] with L_out = ceil(L*up/down) samples written per item;
+ * lengths (optional int32 [B]): samples at or past an item's length count as zeros. */
+int pe_resample_f32(const float* x, long long ldx, const int* lengths, int B, int L, const float* h, int up, int down,
+                    int width, float* y, long long ldy, int L_out, pe_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Conv trunk, memory-bound passes over NHWC bf16 activations (model.py:23-57,143-175).

@@ -1,8 +1,11 @@
 // log-mel front-end on tcgen05 tensor cores (n_fft = 1024): the 1024-point real DFT of TWO frames is one complex FFT
 // (z = x_a + i x_b), factorised 32 x 32 (four-step): two 32-point DFT stages, each a [128 x 64] x [64 x 64] real GEMM
 // over 4 frame pairs, with the 1024-th-root twiddles applied between them.  fp32-grade accuracy comes from a two-way
-// fp16 split of both operands (hi*hi + hi*lo + lo*hi, the lo parts pre-scaled by 2^11), accumulated in fp32 in TMEM:
-// 24 tcgen05.mma (kind::f16, 128x64x16) per 8 frames instead of the 6.3 MFLOP/frame of the dense DFT.
+// fp16 split of both operands (hi*hi + hi*lo + lo*hi), accumulated in fp32 in TMEM: 24 tcgen05.mma (kind::f16, 128x64x16)
+// per 8 frames instead of the 6.3 MFLOP/frame of the dense DFT.  The data split is conversion-light (the conversion pipe is
+// the scarcest one here): hi = the value with its low 13 mantissa bits cleared (exactly representable in fp16), lo = the
+// exact fp32 remainder; the data are pre-scaled by powers of two (window x 2^11, twiddles x 2^-5, undone in the mel
+// weights) so that the remainders stay in fp16's normal range without a per-element rescale.
 //
 // One CTA per SM, persistent.  FOUR independent worker groups (4 warps each) work on four 8-frame slots at a time, so
 // that the SIMT phases of three groups overlap the tensor-core stage and the waits of the fourth:
@@ -32,16 +35,17 @@ constexpr int LM_MAX_HOP = 320;
 constexpr int LM_RAW_B = (LM_NFFT + (LM_FR - 1) * LM_MAX_HOP) * 4;   // 13 056 B of fp32 samples per slot
 constexpr int LM_OP_B = 16384;                  // one fp16 [128 x 64] operand
 constexpr int LM_SLOT_B = 2 * LM_OP_B;          // A_hi | A_lo; later the slot's power spectra [513 bins][8 frames]
+constexpr int LM_PROW_B = 48;                   // bytes per power-spectrum row (8 frames + pad: 3 x 16 B spreads the banks)
 constexpr int LM_MEL_W = 1536;                  // banded filter weights held in shared memory
 constexpr int LM_ITEMS = 128;                   // mel work items (one per worker thread of a group)
 
 struct LmParams {
   int B, T_out, n_mels, tiles_per_item, num_tiles;
-  const float* win;        // [1024]
-  const __half* fmat;      // 3 x 8 KB pre-swizzled K-major [64 x 64]: hi, lo, hi * 2^-11
-  const float* tw;         // [2][32][32]: cos, sin of 2 pi k1 n2 / 1024, indexed [k1][n2]
+  const float* win;        // [1024], x 2^11
+  const __half* fmat;      // 2 x 8 KB pre-swizzled K-major [64 x 64]: hi, lo
+  const float* tw;         // [2][32][32]: cos, sin of 2 pi k1 n2 / 1024, indexed [k1][n2], x 2^-5
   const int4* mel_items;   // [128] {filter m (-1: idle), first bin, bins, offset into mel_w | flags << 24}
-  const float* mel_w;      // banded filter weights
+  const float* mel_w;      // banded filter weights, x 2^-14 (the power spectra carry (2 * 2^6)^2)
   int mel_nnz;
   const int* crop;         // [B] or NULL
   const int* lengths;      // [B] valid samples per item or NULL (= L)
@@ -103,11 +107,13 @@ __device__ __forceinline__ void mbar_wait_long(uint64_t* bar, uint32_t parity) {
   } while (!ok);
 }
 
-// x0, x1 -> packed fp16 hi pair and packed fp16 lo' pair, lo' = (x - hi) * 2^11
+// x0, x1 -> packed fp16 hi pair (mantissa truncated to fp16's 10 bits: the conversion is exact) and packed fp16 lo pair
+// (the exact remainder x - hi, rounded to fp16): x = hi + lo to ~2^-21 relative
 __device__ __forceinline__ void split16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-  const __half2 h = __floats2half2_rn(x0, x1);
-  const float2 hf = __half22float2(h);
-  const __half2 l = __floats2half2_rn((x0 - hf.x) * 2048.0f, (x1 - hf.y) * 2048.0f);
+  const float h0 = __uint_as_float(__float_as_uint(x0) & 0xFFFFE000u);
+  const float h1 = __uint_as_float(__float_as_uint(x1) & 0xFFFFE000u);
+  const __half2 h = __floats2half2_rn(h0, h1);
+  const __half2 l = __floats2half2_rn(x0 - h0, x1 - h1);
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
@@ -141,8 +147,8 @@ logmel_tc_kernel(const float* __restrict__ wave, int L, long long ld, int hop, c
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (sbase - smem_u32(smem_raw));
   const uint32_t a_slots = sbase;                                    // LM_GROUPS x 32 KB operand / power buffers
-  const uint32_t a_f = a_slots + LM_GROUPS * LM_SLOT_B;              // 24 KB: F_hi | F_lo | F_hi'
-  const uint32_t a_raw = a_f + 3 * 8192;                             // LM_GROUPS x raw samples
+  const uint32_t a_f = a_slots + LM_GROUPS * LM_SLOT_B;              // 16 KB: F_hi | F_lo
+  const uint32_t a_raw = a_f + 2 * 8192;                             // LM_GROUPS x raw samples
   const uint32_t a_tw = a_raw + LM_GROUPS * LM_RAW_B;                // 8 KB twiddles
   const uint32_t a_melw = a_tw + 2048 * 4;                           // banded mel weights
   const uint32_t a_items = a_melw + LM_MEL_W * 4;                    // [128] int4
@@ -157,7 +163,7 @@ logmel_tc_kernel(const float* __restrict__ wave, int L, long long ld, int hop, c
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   {
     uint4* df = reinterpret_cast<uint4*>(smem + (a_f - sbase));
-    for (int i = tid; i < 3 * 8192 / 16; i += LM_THREADS) df[i] = __ldg(reinterpret_cast<const uint4*>(p.fmat) + i);
+    for (int i = tid; i < 2 * 8192 / 16; i += LM_THREADS) df[i] = __ldg(reinterpret_cast<const uint4*>(p.fmat) + i);
     float* dt = reinterpret_cast<float*>(smem + (a_tw - sbase));
     for (int i = tid; i < 2048; i += LM_THREADS) dt[i] = p.tw[i];
     float* dw = reinterpret_cast<float*>(smem + (a_melw - sbase));
@@ -201,39 +207,51 @@ logmel_tc_kernel(const float* __restrict__ wave, int L, long long ld, int hop, c
       __syncwarp();
     }
   } else if (warp == 1) {
-    // ---------------------------------------------------------------- MMA issuer: round-robin over the groups, stage 1
-    // of every slot of a round first, then stage 2 (the groups are naturally staggered by then)
+    // ---------------------------------------------------------------- MMA issuer: serves whichever group has an operand
+    // ready (each group alternates stage 1 / stage 2 of its slots): a fixed order would couple the four groups and make
+    // each wait for the slowest one twice per slot
     constexpr uint32_t IDESC = umma_idesc(UMMA_F16, 128, 64, 1, 0);  // A MN-major, B K-major, both stages
-    uint32_t ph[LM_GROUPS] = {0u, 0u, 0u, 0u};
-    auto stage = [&](int g, int which) {
-      const uint32_t ahi = a_slots + g * LM_SLOT_B, alo = ahi + LM_OP_B;
-      const uint32_t d = tm + g * 128 + which * 64;
-      if (elect_one()) {  // warp-uniform loop, one elected lane waits and issues
-        mbar_wait(&work_ready[g], ph[g]);
-        tc_fence_after();
+    if (lane == 0) {
+      uint32_t ph = 0;        // bit g: parity of group g's next work_ready phase
+      uint32_t which = 0;     // bit g: next stage of group g
+      int left[LM_GROUPS];    // stages still to issue for group g
+      int total = 0;
 #pragma unroll
-        for (int prod = 0; prod < 3; ++prod) {
-          const uint32_t a = prod == 2 ? alo : ahi;
-          const uint32_t bm = a_f + (prod == 0 ? 0 : prod == 1 ? 8192 : 16384);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)  // A: 2 MN atoms (8 KB apart) x 64 K rows, 16 K rows per MMA
-            tc_mma_f16(d, umma_desc_sw128(a + k * 2048, 8192, 1024), umma_desc_sw128(bm + k * 32, 16, 1024), IDESC,
-                       (prod > 0 || k > 0) ? 1u : 0u);
-        }
-        tc_commit(&mma_done[g]);
+      for (int g = 0; g < LM_GROUPS; ++g) {
+        left[g] = 2 * ((n_local - g + LM_GROUPS - 1) / LM_GROUPS);
+        total += left[g];
       }
-      __syncwarp();
-      ph[g] ^= 1u;
-    };
-    for (int i = 0; i < n_local; i += LM_GROUPS) {
-      const int n = n_local - i;
+      uint32_t idle = 0;
+      while (total > 0) {
+        bool any = false;
 #pragma unroll
-      for (int g = 0; g < LM_GROUPS; ++g)
-        if (g < n) stage(g, 0);
+        for (int g = 0; g < LM_GROUPS; ++g) {
+          if (left[g] > 0 && mbar_try_wait(&work_ready[g], (ph >> g) & 1u)) {
+            tc_fence_after();
+            const uint32_t ahi = a_slots + g * LM_SLOT_B, alo = ahi + LM_OP_B;
+            const uint32_t d = tm + g * 128 + ((which >> g) & 1u) * 64;
 #pragma unroll
-      for (int g = 0; g < LM_GROUPS; ++g)
-        if (g < n) stage(g, 1);
+            for (int prod = 0; prod < 3; ++prod) {
+              const uint32_t a = prod == 2 ? alo : ahi;
+              const uint32_t bm = a_f + (prod == 1 ? 8192 : 0);   // hi*hi, hi*lo, lo*hi
+#pragma unroll
+              for (int k = 0; k < 4; ++k)  // A: 2 MN atoms (8 KB apart) x 64 K rows, 16 K rows per MMA
+                tc_mma_f16(d, umma_desc_sw128(a + k * 2048, 8192, 1024), umma_desc_sw128(bm + k * 32, 16, 1024), IDESC,
+                           (prod > 0 || k > 0) ? 1u : 0u);
+            }
+            tc_commit(&mma_done[g]);
+            ph ^= 1u << g;
+            which ^= 1u << g;
+            --left[g];
+            --total;
+            any = true;
+          }
+        }
+        if (any) idle = 0;
+        else if (++idle > (1u << 24)) mbar_timeout_trap();
+      }
     }
+    __syncwarp();
   } else {
     // ---------------------------------------------------------------- workers: LM_GROUPS groups of 4 warps
     const int g = (warp - 2) >> 2;         // group: handles this CTA's slots g, g + 4, g + 8, ...
@@ -324,7 +342,7 @@ logmel_tc_kernel(const float* __restrict__ wave, int L, long long ld, int hop, c
       }
       // ---- stage-1 result: twiddle, split, store as the stage-2 A operand (MN-major: K row = (re/im, n2), this
       // thread's 32 k1 values of a row are 64 contiguous bytes)
-      mbar_wait_long(&mma_done[g], dph);
+      mbar_wait(&mma_done[g], dph);
       dph ^= 1u;
       tc_fence_after();
       {
@@ -368,18 +386,18 @@ logmel_tc_kernel(const float* __restrict__ wave, int L, long long ld, int hop, c
       // ---- stage-2 result: unpack the two real spectra of the pair, power -> P[bin][frame] in the free operand buffer.
       // Bin k = k1 + 32 k2 (k1 = lane) pairs with N - k = (32 - k1) % 32 + 32 (31 - k2 [+1 if k1 == 0]): own columns ascend,
       // the partner's descend, so the accumulator row is read in two halves of 16 + 16 columns
-      mbar_wait_long(&mma_done[g], dph);
+      mbar_wait(&mma_done[g], dph);
       dph ^= 1u;
       tc_fence_after();
       {
         const int src = (32 - lane) & 31;
-        const uint32_t a_pk = a_p + (uint32_t)lane * 32u + (uint32_t)q * 8u;   // + k2 * 1024
+        const uint32_t a_pk = a_p + (uint32_t)lane * LM_PROW_B + (uint32_t)q * 8u;   // + k2 * 32 rows
         auto unpack = [&](int k2, float zr, float zi, float sr, float si) {
           const float pr_ = __shfl_sync(0xffffffffu, sr, src);
           const float pi_ = __shfl_sync(0xffffffffu, si, src);
           if (k2 < 16 || lane == 0) {
             const float ar = zr + pr_, ai = zi - pi_, br = zi + pi_, bi = pr_ - zr;
-            sts64f(a_pk + (uint32_t)k2 * 1024u, 0.25f * fmaf(ar, ar, ai * ai), 0.25f * fmaf(br, br, bi * bi));
+            sts64f(a_pk + (uint32_t)k2 * (32u * LM_PROW_B), fmaf(ar, ar, ai * ai), fmaf(br, br, bi * bi));
           }
         };
         {  // k2 = 0..7: own columns 0..7; partner columns 31..24 (lane 0: 0, 31..25)
@@ -425,7 +443,7 @@ logmel_tc_kernel(const float* __restrict__ wave, int L, long long ld, int hop, c
         float acc[LM_FR];
 #pragma unroll
         for (int f = 0; f < LM_FR; ++f) acc[f] = 0.f;
-        uint32_t ap = a_p + (uint32_t)item.y * 32u;
+        uint32_t ap = a_p + (uint32_t)item.y * LM_PROW_B;
         uint32_t aw = a_melw + ((uint32_t)item.w & 0xFFFFFFu) * 4u;
 #pragma unroll 2
         for (int c = 0; c < cnt; ++c) {
@@ -435,7 +453,7 @@ logmel_tc_kernel(const float* __restrict__ wave, int L, long long ld, int hop, c
           acc[2] = fmaf(p0.z, w, acc[2]); acc[3] = fmaf(p0.w, w, acc[3]);
           acc[4] = fmaf(p1.x, w, acc[4]); acc[5] = fmaf(p1.y, w, acc[5]);
           acc[6] = fmaf(p1.z, w, acc[6]); acc[7] = fmaf(p1.w, w, acc[7]);
-          ap += 32;
+          ap += LM_PROW_B;
           aw += 4;
         }
 #pragma unroll
@@ -444,14 +462,26 @@ logmel_tc_kernel(const float* __restrict__ wave, int L, long long ld, int hop, c
           if (flags & LM_ITEM_COMBINE) acc[f] += o;
         }
         if ((flags & LM_ITEM_WRITER) && m >= 0) {
+          float y[LM_FR];
 #pragma unroll
-          for (int f = 0; f < LM_FR; ++f) {
-            const int t_out = s.t_out0 + f;
-            if (t_out < p.T_out) {
-              const float y = f < s.nfr ? (__logf(1e-5f + acc[f]) + 4.0f) * 0.25f : 0.f;
-              if (p.out_bmt) p.out_bmt[((size_t)s.b * p.n_mels + m) * p.T_out + t_out] = y;
-              if (p.out_btm) p.out_btm[((size_t)s.b * p.T_out + t_out) * p.n_mels + m] = y;
+          for (int f = 0; f < LM_FR; ++f) y[f] = f < s.nfr ? fmaf(__logf(1e-5f + acc[f]), 0.25f, 1.0f) : 0.f;
+          const int nw = min(LM_FR, p.T_out - s.t_out0);   // frames of this slot that exist in the output
+          if (p.out_bmt) {
+            float* o = p.out_bmt + ((size_t)s.b * p.n_mels + m) * p.T_out + s.t_out0;
+            if (nw == LM_FR && (p.T_out & 3) == 0) {       // 8 consecutive frames of one filter: two 16-byte stores
+              reinterpret_cast<float4*>(o)[0] = make_float4(y[0], y[1], y[2], y[3]);
+              reinterpret_cast<float4*>(o)[1] = make_float4(y[4], y[5], y[6], y[7]);
+            } else {
+#pragma unroll
+              for (int f = 0; f < LM_FR; ++f)
+                if (f < nw) o[f] = y[f];
             }
+          }
+          if (p.out_btm) {
+            float* o = p.out_btm + ((size_t)s.b * p.T_out + s.t_out0) * p.n_mels + m;
+#pragma unroll
+            for (int f = 0; f < LM_FR; ++f)
+              if (f < nw) o[(size_t)f * p.n_mels] = y[f];
           }
         }
       }
@@ -463,7 +493,7 @@ logmel_tc_kernel(const float* __restrict__ wave, int L, long long ld, int hop, c
   if (warp == 2) tmem_dealloc(tm, 512);
 }
 
-constexpr size_t LM_SMEM = (size_t)LM_GROUPS * LM_SLOT_B + 3 * 8192 + (size_t)LM_GROUPS * LM_RAW_B +
+constexpr size_t LM_SMEM = (size_t)LM_GROUPS * LM_SLOT_B + 2 * 8192 + (size_t)LM_GROUPS * LM_RAW_B +
                            (2048 + LM_MEL_W) * 4 + LM_ITEMS * 16 + (4 * LM_GROUPS + 2) * 8 + 1024;
 
 }  // namespace pe

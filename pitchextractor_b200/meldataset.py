@@ -55,6 +55,9 @@ class MelDataset(torch.utils.data.Dataset):
         self.sr = sr if sr is not None else self.mel_params["sample_rate"]
         self.mel_params["sample_rate"] = self.sr
         self.f0_params = f0_params or {}
+        # the reference's F0Extractor.cache_identifier ("-" + "_".join(backend keys), f0_backends.py:756-757) names the
+        # cache files; label generation itself is out of scope, so the identifier is configuration here
+        self.f0_cache_identifier = str(self.f0_params.get("cache_identifier", ""))
         self.zero_value = float(self.f0_params.get("zero_fill_value", 0.0))
         self.mean, self.std = -4, 4
         self.max_mel_length = MAX_MEL_LENGTH
@@ -107,19 +110,90 @@ class MelDataset(torch.utils.data.Dataset):
         if path.startswith("synthetic:"):
             return synthetic.make_segment(np.random.default_rng([int(path.split(":")[1]), idx]), self.segment_samples,
                                           self.sr, self.mel_params["hop_length"])
+        return self.path_to_wave_and_label(path)
+
+    # ---------------------------------------------------------------- real audio (meldataset.py:178-245)
+    def _audio_metadata(self, path):
+        """-> {'sample_rate', 'frames', 'channels'} of a PCM ``.wav`` (stdlib ``wave``) or a ``.npy`` waveform (shape
+        [n] or [n, channels]; its rate is read from ``<path>.sr`` if present, else the dataset rate)."""
         if path.endswith(".npy"):
-            wave = np.load(path).astype(np.float32)
-            f0_path = path[:-4] + "_f0.npy"
-            f0 = np.load(f0_path) if os.path.isfile(f0_path) else None
-            if wave.shape[0] > self.segment_samples:  # random segment, as meldataset.py:196-201
-                start = int(self._random().randint(0, wave.shape[0] - self.segment_samples))
-                hop = self.mel_params["hop_length"]
-                if f0 is not None:
-                    f0 = f0[start // hop: start // hop + 1 + self.segment_samples // hop + 4]
-                wave = wave[start:start + self.segment_samples]
-            return wave, f0
-        raise IndexError("audio decoding is outside the accelerated path; provide .npy waveforms or synthetic: items "
-                         "(got %r)" % path)
+            arr = np.load(path, mmap_mode="r")
+            sr_file = path + ".sr"
+            sr = int(open(sr_file).read().strip()) if os.path.isfile(sr_file) else self.sr
+            return {"sample_rate": sr, "frames": int(arr.shape[0]), "channels": int(arr.shape[1]) if arr.ndim > 1 else 1}
+        if path.lower().endswith(".wav"):
+            import wave as _wave
+            with _wave.open(path, "rb") as w:
+                return {"sample_rate": w.getframerate(), "frames": w.getnframes(), "channels": w.getnchannels()}
+        raise IndexError("unsupported audio container %r: this path reads PCM .wav (stdlib) and .npy waveforms; other "
+                         "formats need the reference's soundfile/librosa loaders, which are out of scope" % path)
+
+    def _read_audio(self, path, start_frame=0, num_frames=None):
+        """-> (float32 [n] or [n, channels] in [-1, 1), sample_rate); ``num_frames`` None reads to the end."""
+        if path.endswith(".npy"):
+            arr = np.load(path, mmap_mode="r")
+            end = arr.shape[0] if num_frames is None else min(arr.shape[0], start_frame + num_frames)
+            return np.asarray(arr[start_frame:end], dtype=np.float32), self._audio_metadata(path)["sample_rate"]
+        import wave as _wave
+        with _wave.open(path, "rb") as w:
+            sr, ch, width, total = w.getframerate(), w.getnchannels(), w.getsampwidth(), w.getnframes()
+            w.setpos(min(start_frame, total))
+            raw = w.readframes(total - start_frame if num_frames is None else num_frames)
+        if width == 2:
+            data = np.frombuffer(raw, dtype="<i2").astype(np.float32) / 32768.0
+        elif width == 4:
+            data = np.frombuffer(raw, dtype="<i4").astype(np.float32) / 2147483648.0
+        elif width == 1:
+            data = (np.frombuffer(raw, dtype=np.uint8).astype(np.float32) - 128.0) / 128.0
+        elif width == 3:
+            b = np.frombuffer(raw, dtype=np.uint8).reshape(-1, 3).astype(np.int32)
+            v = b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16)
+            data = (v - ((v & 0x800000) << 1)).astype(np.float32) / 8388608.0
+        else:
+            raise IndexError("unsupported PCM sample width %d in %r" % (width, path))
+        return (data.reshape(-1, ch) if ch > 1 else data), sr
+
+    def path_to_wave_and_label(self, path):
+        """Random training segment of a file + its cached F0 labels, as ``path_to_mel_and_label`` does up to the mel
+        (meldataset.py:178-230): the segment is requested in SOURCE samples, mixed down to mono, resampled (on the GPU,
+        ``resample.py``) when the file's rate differs from the dataset's, and the whole-file F0 cache is sliced at the
+        segment's position.  -> (wave float32 [n] at self.sr, f0 or None)"""
+        from . import cache
+        meta = self._audio_metadata(path)
+        source_sr, total = meta["sample_rate"], meta["frames"]
+        hop = int(self.mel_params["hop_length"])
+        window = int(self.mel_params.get("win_length") or self.mel_params.get("n_fft", hop))
+        requested = (self.max_mel_length * hop) / float(self.sr) + max(window, hop) / float(self.sr)
+        segment = int(np.ceil(requested * float(source_sr)))
+        start, use_full = 0, True
+        if 0 < segment < total:
+            start = int(self._random().randint(0, total - segment + 1))   # random.randint(0, max_start), inclusive
+            use_full = False
+        wave, wave_sr = self._read_audio(path, start, None if use_full else segment)
+        if wave.ndim > 1:
+            wave = wave.mean(axis=-1)
+        wave = wave.astype(np.float32)
+        if wave_sr != self.sr:
+            wave = self._resample(wave, wave_sr)
+        start_resampled = 0 if use_full else int(round(start / float(source_sr) * self.sr))
+        expected = None if use_full else int(np.ceil(len(wave) / max(hop, 1))) + 2
+        f0 = cache.load_cached_f0(path, self.f0_cache_identifier, self.sr, hop)
+        if f0 is None:
+            if not self.f0_params.get("allow_missing_f0", False):
+                raise RuntimeError("no cached F0 for %r (expected %s): F0 extraction (pyworld / CREPE / ...) is outside "
+                                   "this path -- prepare the caches with the reference, or pass f0_params="
+                                   "{'allow_missing_f0': True} to train the voicing of unlabeled audio as silence"
+                                   % (path, cache.f0_cache_paths(path, self.f0_cache_identifier)[0]))
+        else:
+            f0 = cache.slice_cached_f0(f0, start_resampled, expected, hop)
+        return wave, f0
+
+    def _resample(self, wave, source_sr):
+        from .resample import resample
+        dev = torch.device(self.device)
+        if dev.type != "cuda":
+            raise RuntimeError("resampling runs on the GPU: construct the dataset with device='cuda'")
+        return resample(torch.from_numpy(np.ascontiguousarray(wave)).to(dev), int(source_sr), int(self.sr)).cpu().numpy()
 
     def __getitem__(self, idx):
         wave, f0 = self._load_item(idx)
@@ -152,13 +226,28 @@ class MelDataset(torch.utils.data.Dataset):
     def _build_training_example(self, waveform, sr, f0, cache_key=None, allow_cache=True):
         """Reference contract (meldataset.py:629-677): -> (mel [80, <=192], f0 [<=192], is_silence [<=192]); the mel is
         computed by the CUDA log-mel kernels."""
-        if sr != self.sr:
-            raise ValueError("resampling is outside the accelerated path (sr %d != %d)" % (sr, self.sr))
+        waveform = np.asarray(waveform)
+        if waveform.ndim > 1:
+            waveform = waveform.mean(axis=-1)
+        if sr != self.sr:  # meldataset.py:621-627, on the GPU
+            waveform = self._resample(waveform.astype(np.float32), sr)
         wave, f0_t, sil, start = self._build_wave_example(waveform, f0)
         if self._logmel is None:
             self._logmel = LogMel(self.device, **self.mel_params)
         T = self._logmel.num_frames(wave.shape[0])
         T_out = min(T, self.max_mel_length)
+        if cache_key is not None and allow_cache and not self.data_augmentation:
+            # whole-file mel POWER cache in the reference's format (meldataset.py:638-648,679-786)
+            from . import cache
+            meta = cache.mel_metadata(wave.shape[0], 1, self.sr, self.sr, self.mel_params)
+            power = cache.load_cached_mel(cache_key, meta)
+            if power is None:
+                full = self._logmel(wave[None].to(self.device))[0]
+                cache.save_mel_cache(cache_key, torch.clamp(torch.exp(4.0 * full - 4.0) - 1e-5, min=0.0).cpu().numpy(), meta)
+                mel = full[:, start:start + T_out]
+            else:
+                mel = ((torch.log(1e-5 + torch.from_numpy(power).to(self.device)) + 4.0) / 4.0)[:, start:start + T_out]
+            return mel.contiguous(), f0_t, sil
         mel = self._logmel(wave[None].to(self.device), crop=torch.tensor([start], dtype=torch.int32), T_out=T_out)[0]
         return mel, f0_t, sil
 

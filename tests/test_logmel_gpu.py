@@ -39,6 +39,7 @@ def test_logmel_segment_parity(built_lib, impl):
         # tolerance: 1e-4 * max(1,|y|) on broadband input; tonal inputs: no worse than 2x what
         # torchaudio-fp32 itself is off the fp64 oracle (1.6e-4 measured on a pure tone)
         tol = 1e-4 if n in ("noise", "silence", "harm3") else 3.2e-4
+        print("%s %-8s max |err| %.3g (tolerance %.3g)" % (impl, n, err.max(), tol * max(1.0, np.abs(ref).max())))
         assert err.max() <= tol * max(1.0, np.abs(ref).max()), (n, err.max())
 
 
@@ -107,3 +108,21 @@ def test_logmel_mixed_length_batch_matches_per_item_mel_and_collate(built_lib, i
         k = ref.shape[1]
         assert np.abs(y[i, :, :k] - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max()), (i, np.abs(y[i, :, :k] - ref).max())
         assert (y[i, :, k:] == 0).all(), i
+
+
+def test_logmel_quiet_and_loud_inputs(built_lib):
+    """Dynamic range of the fp16-split pipeline: the same noise at -80 dBFS .. +18 dBFS (|x| up to ~8) stays within the
+    broadband tolerance -- the power-of-two pre-scales keep the split remainders normal for quiet input and the stage-2
+    operand inside fp16's range for loud input."""
+    from oracle import logmel_np
+    from pitchextractor_b200.mel import LogMel
+    rng = np.random.default_rng(3)
+    base = rng.standard_normal(24000).astype(np.float32)
+    gains = [1e-4, 1e-3, 1e-2, 1.0, 2.0]
+    w = np.stack([(g * 0.25 * base).astype(np.float32) for g in gains])
+    y = LogMel("cuda", impl="tc")(torch.from_numpy(w).cuda()).cpu().numpy()
+    for i, g in enumerate(gains):
+        ref = logmel_np.log_mel(w[i])
+        err = np.abs(y[i] - ref).max()
+        print("gain %g: max |err| %.3g" % (g, err))
+        assert err <= 1e-4 * max(1.0, np.abs(ref).max()), (g, err)
