@@ -196,25 +196,40 @@ lstm_seq_fwd_kernel(const __grid_constant__ LstmSeqMaps maps, const LstmSeqParam
     float* gxm = p.gx[model] + dir * PG + gl * PH + u;
     float* cm = p.c[model] + dir * PH + u;
     __nv_bfloat16* ym = p.y[model] + dir * PH + u;
+    // Input projections stream through a register FIFO PF groups (of 4 batch columns) deep, filled across step
+    // boundaries: the loads of a step's first groups are in flight while the previous step finishes, so neither the DRAM
+    // latency of the strided [b][t] rows nor the MMA wait is exposed per group.
+    constexpr int NGRP = NB / 4;
+    constexpr int PF = NGRP < 8 ? NGRP : 8;
+    float zq[PF][4];
+    auto load_group = [&](int tt, int j, float* z) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int b = b0 + 4 * j + e;
+        z[e] = b < p.B ? gxm[((long long)b * p.T + tt) * (2 * PG)] : 0.f;
+      }
+    };
+    {
+      const int t_first = dir ? p.T - 1 : 0;
+#pragma unroll
+      for (int j = 0; j < PF; ++j) load_group(t_first, j, zq[j]);
+    }
     for (int step = 0; step < p.T; ++step) {
       const int t = dir ? p.T - 1 - step : step;
-      // input projection of this lane's gate for 4 batch columns at a time (prefetched one group ahead)
-      float zin[4], znext[4];
-      auto load_group = [&](int j, float* z) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int b = b0 + 4 * j + e;
-          z[e] = b < p.B ? gxm[((long long)b * p.T + t) * (2 * PG)] : 0.f;
-        }
-      };
-      load_group(0, zin);
+      const int t_nxt = dir ? t - 1 : t + 1;
+      const bool more = step + 1 < p.T;
       if (step > 0) {
         mbar_wait(done_bar, (uint32_t)(step - 1) & 1u);
         tc_fence_after();
       }
 #pragma unroll
-      for (int j = 0; j < NB / 4; ++j) {
-        if (j + 1 < NB / 4) load_group(j + 1, znext);
+      for (int j = 0; j < NGRP; ++j) {
+        float zin[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) zin[e] = zq[j % PF][e];
+        // refill this FIFO slot: a later group of this step, or an early group of the next step
+        if (j + PF < NGRP) load_group(t, j + PF, zq[j % PF]);
+        else if (more) load_group(t_nxt, j + PF - NGRP, zq[j % PF]);
         uint32_t acc[4] = {0u, 0u, 0u, 0u};
         if (step > 0) {
           tmem_ld4(trow + 4 * j, acc);
@@ -249,8 +264,6 @@ lstm_seq_fwd_kernel(const __grid_constant__ LstmSeqMaps maps, const LstmSeqParam
             ym[tok * (2 * PH)] = __float2bfloat16(hn);
           }
         }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) zin[e] = znext[e];
       }
       // publish h_t: every writer makes its stores visible to the async proxy, then one release-add per CTA
       fence_proxy_async_global();
@@ -375,40 +388,70 @@ lstm_seq_bwd_kernel(const __grid_constant__ LstmSeqMaps maps, const LstmSeqParam
     const float* cm = p.c[model] + dir * PH + u;
     const __nv_bfloat16* dym = p.dy[model] + dir * PH + u;
     __nv_bfloat16* dgm = p.dg[model] + dir * PG + u;
+    // Everything the cell backward needs except the recurrent gradient streams through a register FIFO two groups (of 4
+    // batch columns) deep, filled across step boundaries (7 loads per cell: dy, the four gates, c_t, c_{t-1}).
+    constexpr int NG4 = NC / 4;                  // groups of 4 columns per thread
+    constexpr int PF = NG4 < 2 ? NG4 : 2;
+    struct Cell { float dy, ig, fg, gg, og, ct, cp; };
+    Cell cq[PF][4];
+    auto load_group = [&](int tt, int g4, Cell* cc) {
+      const int t_pf = dir ? tt + 1 : tt - 1;     // forward-order predecessor (c_{t-1})
+      const bool has_prev = dir ? (tt < p.T - 1) : (tt > 0);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int b = b0 + col0 + 4 * g4 + e;
+        Cell c{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (b < p.B && lanes_valid) {
+          const long long tok = (long long)b * p.T + tt;
+          const float* gp = gxm + tok * (2 * PG);
+          c.ig = gp[0]; c.fg = gp[PH]; c.gg = gp[2 * PH]; c.og = gp[3 * PH];
+          c.ct = cm[tok * (2 * PH)];
+          c.cp = has_prev ? cm[((long long)b * p.T + t_pf) * (2 * PH)] : 0.f;
+          c.dy = __bfloat162float(dym[tok * (2 * PH)]);
+        }
+        cc[e] = c;
+      }
+    };
+    {
+      const int t_first = dir ? 0 : p.T - 1;
+#pragma unroll
+      for (int g4 = 0; g4 < PF; ++g4) load_group(t_first, g4, cq[g4]);
+    }
     for (int step = 0; step < p.T; ++step) {
       const int t = dir ? step : p.T - 1 - step;
-      const int t_pf = dir ? t + 1 : t - 1;     // forward-order predecessor (c_{t-1})
-      const bool has_prev = dir ? (t < p.T - 1) : (t > 0);
+      const int t_nxt = dir ? t + 1 : t - 1;
+      const bool more = step + 1 < p.T;
       if (step > 0) {
         mbar_wait(done_bar, (uint32_t)(step - 1) & 1u);
         tc_fence_after();
       }
 #pragma unroll
-      for (int j4 = 0; j4 < NC; j4 += 4) {
+      for (int g4 = 0; g4 < NG4; ++g4) {
+        Cell cur[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) cur[e] = cq[g4 % PF][e];
+        if (g4 + PF < NG4) load_group(t, g4 + PF, cq[g4 % PF]);
+        else if (more) load_group(t_nxt, g4 + PF - NG4, cq[g4 % PF]);
         uint32_t acc[4] = {0u, 0u, 0u, 0u};
         if (step > 0) {
-          tmem_ld4(trow + j4, acc);
+          tmem_ld4(trow + 4 * g4, acc);
           tmem_ld_wait();
         }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const int j = j4 + e;
+          const int j = 4 * g4 + e;
           const int b = b0 + col0 + j;
           if (b < p.B && lanes_valid) {
-            const long long tok = (long long)b * p.T + t;
-            const float* gp = gxm + tok * (2 * PG);
-            const float ig = gp[0], fg = gp[PH], gg = gp[2 * PH], og = gp[3 * PH];
-            const float ct = cm[tok * (2 * PH)];
-            const float cp = has_prev ? cm[((long long)b * p.T + t_pf) * (2 * PH)] : 0.f;
-            const float dh = __bfloat162float(dym[tok * (2 * PH)]) + __uint_as_float(acc[e]);
-            const float tc = tanh_fast(ct);
-            const float dc = dcs[j] + dh * og * (1.f - tc * tc);
-            dcs[j] = dc * fg;
-            __nv_bfloat16* dp = dgm + tok * (2 * PG);
-            dp[0] = __float2bfloat16(dc * gg * ig * (1.f - ig));
-            dp[PH] = __float2bfloat16(dc * cp * fg * (1.f - fg));
-            dp[2 * PH] = __float2bfloat16(dc * ig * (1.f - gg * gg));
-            dp[3 * PH] = __float2bfloat16(dh * tc * og * (1.f - og));
+            const Cell c = cur[e];
+            const float dh = c.dy + __uint_as_float(acc[e]);
+            const float tc = tanh_fast(c.ct);
+            const float dc = dcs[j] + dh * c.og * (1.f - tc * tc);
+            dcs[j] = dc * c.fg;
+            __nv_bfloat16* dp = dgm + ((long long)b * p.T + t) * (2 * PG);
+            dp[0] = __float2bfloat16(dc * c.gg * c.ig * (1.f - c.ig));
+            dp[PH] = __float2bfloat16(dc * c.cp * c.fg * (1.f - c.fg));
+            dp[2 * PH] = __float2bfloat16(dc * c.ig * (1.f - c.gg * c.gg));
+            dp[3 * PH] = __float2bfloat16(dh * tc * c.og * (1.f - c.og));
           }
         }
       }

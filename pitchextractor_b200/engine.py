@@ -489,7 +489,9 @@ class Engine:
             dc = [self.buf("ldc%d" % mi, (B, 2 * Hh), torch.float32) for mi in range(2)]
             gx_a, c_a, dy_a, dg_a, dc_a = (self._ptrs(GX), self._ptrs(C), self._ptrs(dY), self._ptrs(dG), self._ptrs(dc))
             whh = self._ptrs([W16["%s.model.weight_hh_%s" % n] for n in names])
-            if self.lstm_persistent:
+            # measured on a B200 (profiles/r02_lstm_breakdown.txt): the persistent backward wins while the batch tile is
+            # narrow (its epilogue is then latency-bound); at 128-column tiles the per-step launches are faster
+            if self.lstm_persistent and B <= 64:
                 ws = self._lstm_workspace(B, T)
                 call("pe_lstm_seq_bwd", c_int(B), c_int(T), c_int(Hh), gx_a, c_a, dy_a, dg_a, whh, ptr(ws),
                      ctypes.c_size_t(ws.numel() * 4), stream())
