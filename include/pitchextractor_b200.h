@@ -41,10 +41,12 @@ int pe_check_device(void); /* PE_OK iff the current device is sm_100 */
 long long pe_workspace_bytes(const char* op, int B, int T, int L);
 
 /* Per-step dropout salt: every dropout site (reference model.py:40,56 nn.Dropout, the Transformer / LSTM dropouts of
- * model.py:306-341) draws its mask from (seed argument + salt).  The salt lives in device memory so that a training
- * step captured once into a CUDA graph -- whose seed arguments are frozen -- still sees fresh masks on every replay:
- * the host bumps the salt (stream-ordered, one 1-block kernel) before each replay.  Eager launches keep it at 0. */
-int pe_set_step_salt(unsigned long long salt, pe_stream_t stream);
+ * model.py:306-341) draws its mask from (seed argument + salt[slot]), slot = the top 8 bits of the seed argument.  The
+ * salt lives in device memory so that a training step captured once into a CUDA graph -- whose seed arguments are
+ * frozen -- still sees fresh masks on every replay: the host bumps the salt of ITS slot (stream-ordered, one 1-block
+ * kernel) before each replay.  Every model instance uses its own slot (0..255), so the library holds no state that two
+ * callers share; eager launches keep their slot at 0. */
+int pe_set_step_salt(int slot, unsigned long long salt, pe_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused epilogue description shared by the tensor-core GEMM / implicit-GEMM convolution.
@@ -86,6 +88,10 @@ typedef struct pe_epilogue {
   const float* stats_scale;
   const float* stats_shift;
   float stats_slope;
+  /* tuning aid (NULL in production): per-CTA counters [grid][16] = {main-loop cycles, MMA thread waiting for operands,
+   * MMA thread waiting for a free accumulator stage, TMA thread waiting for a free smem slot, CTA entry time
+   * (globaltimer ns), cycles from entry to: set-up done, MMA loop end, CTA exit, ...} */
+  long long* debug;
 } pe_epilogue;
 
 /* D[M,N] = sum_k A(m,k) * B(n,k), bf16 operands, fp32 accumulation in TMEM (tcgen05.mma kind::f16).
@@ -103,11 +109,6 @@ int pe_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long lon
  * computes the data gradient when given the flipped / transposed weights. */
 int pe_conv3x3_nhwc(const void* x, const void* x2, const void* w, int B, int H, int W, int C1, int C2, int Cout,
                     const pe_epilogue* ep, pe_stream_t stream);
-
-/* tuning aid: when buf != NULL the tile engine writes per-CTA counters [grid][8] = {main-loop cycles, MMA thread
- * waiting for operands, MMA thread waiting for a free accumulator stage, TMA thread waiting for a free smem slot,
- * CTA entry time (globaltimer ns), cycles from entry to: set-up done, MMA loop end, CTA exit} */
-int pe_tc_set_debug(long long* buf);
 
 /* Weight gradient of the convolution above: dw[Cout][taps*C + ...] += sum_pixels dy[p][co] * x[p+tap][ci].
  * dy: [B][H][W][Cout] bf16, x: [B][H][W][C] bf16, dw: fp32 [Cout][ldw] at column offset tap*C (3x3, taps=9) or
@@ -218,13 +219,13 @@ int pe_layernorm_bwd(const void* dy, const float* x_f32, const void* x_bf16, con
 int pe_colsum_bf16(const void* x, long long M, int N, long long ld, float* out, pe_stream_t stream);
 /* multi-head softmax attention with dropout on the probabilities (nn.MultiheadAttention inside
  * nn.TransformerEncoderLayer, model.py:231-239): qkv bf16 [B*T][3*H*64] -> ctx bf16 [B*T][H*64], lse fp32 [B][H][T] */
+/* T == 192 runs on the tcgen05 kernels, other lengths on the fp32 SIMT kernels; force_simt != 0 selects the SIMT kernels
+ * at T == 192 too (cross-checks). */
 int pe_attn_fwd(const void* qkv, int B, int T, int H, int head_dim, unsigned drop_thresh, float drop_scale,
-                unsigned long long seed, void* ctx, float* lse, pe_stream_t stream);
+                unsigned long long seed, void* ctx, float* lse, int force_simt, pe_stream_t stream);
 int pe_attn_bwd(const void* qkv, const void* ctx, const void* dctx, const float* lse, int B, int T, int H,
                 int head_dim, unsigned drop_thresh, float drop_scale, unsigned long long seed, void* dqkv, float* delta,
-                pe_stream_t stream);
-/* T == 192 runs on the tcgen05 kernels, other lengths on the fp32 SIMT kernels; on != 0 forces SIMT (cross-checks) */
-int pe_attn_set_simt(int on);
+                int force_simt, pe_stream_t stream);
 /* heads (num_class == 1) + losses (model.py:96-98,115-117; train.py:104-106; trainer.py:237-239):
  * f0 = hc.wc + bc, logit = hd.(wd[0]+wd[1]) + bd[0]+bd[1]; loss_out = {total, lambda*SmoothL1, BCE}.
  * When dhc != NULL also writes dL/dhc, dL/dhd (bf16) and accumulates the head parameter gradients; with gc_ext /

@@ -27,7 +27,7 @@ class Epilogue(ctypes.Structure):
         ("drop_thresh", ctypes.c_uint), ("drop_scale", ctypes.c_float), ("drop_seed", ctypes.c_ulonglong),
         ("alpha", ctypes.c_float), ("stats", ctypes.c_void_p), ("stats_mode", ctypes.c_int),
         ("stats_x", ctypes.c_void_p), ("stats_scale", ctypes.c_void_p), ("stats_shift", ctypes.c_void_p),
-        ("stats_slope", ctypes.c_float),
+        ("stats_slope", ctypes.c_float), ("debug", ctypes.c_void_p),
     ]
 
 
@@ -65,7 +65,15 @@ def check(rc, what):
 # kernels launched per C-ABI call (for bench.py's gpu_launches count)
 _LAUNCHES_PER_CALL = {"pe_logmel_f32": 2, "pe_bn_act_pool_bwd": 3, "pe_attn_bwd": 2, "pe_heads_loss": 2}
 launch_count = 0
-step_salt = 0  # host mirror of the device-side dropout salt (pe_set_step_salt)
+_next_salt_slot = 0
+
+
+def new_salt_slot():
+    """A dropout-salt slot (0..255) for one engine: its seeds carry the slot in their top 8 bits (pe_set_step_salt)."""
+    global _next_salt_slot
+    slot = _next_salt_slot % 256
+    _next_salt_slot += 1
+    return slot
 
 
 # When set to a list, every C-ABI call appends (name, start_event, end_event): per-entry-point GPU time with warm

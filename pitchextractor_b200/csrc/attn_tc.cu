@@ -96,7 +96,7 @@ constexpr int AFW_THREADS = 512;  // 16 warps: 8 per query tile (4 TMEM lane qua
 __global__ void __launch_bounds__(AFW_THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, int H, unsigned drop_thresh, float drop_scale,
                    unsigned long long seed, __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse) {
-  seed += pe_step_salt;
+  seed = pe_salted(seed);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                 // Q | K | V tiles, contiguous: rows past 192 of a tile read the next tile
@@ -232,7 +232,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
                    unsigned drop_thresh, float drop_scale, unsigned long long seed,
                    const __nv_bfloat16* __restrict__ ctx, const __nv_bfloat16* __restrict__ dctx,
                    const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv) {
-  seed += pe_step_salt;
+  seed = pe_salted(seed);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;

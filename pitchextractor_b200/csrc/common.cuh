@@ -49,11 +49,16 @@ __device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t k
   }
   return make_uint4(c0, c1, c2, c3);
 }
-// Per-step seed salt.  Every dropout site's effective seed is (launch-argument seed + pe_step_salt): an eagerly
-// launched step leaves the salt at 0 and passes fresh seeds as arguments, while a step replayed from a CUDA graph
-// (whose launch arguments are frozen) gets fresh masks by bumping the salt through pe_set_step_salt() between
-// replays.  One copy per translation unit; units that draw dropout masks register theirs with PE_USES_STEP_SALT().
-static __device__ unsigned long long pe_step_salt __attribute__((unused)) = 0ull;
+// Per-step seed salt.  Every dropout site's effective seed is (launch-argument seed + salt): an eagerly launched step
+// leaves the salt at 0 and passes fresh seeds as arguments, while a step replayed from a CUDA graph (whose launch
+// arguments are frozen) gets fresh masks by bumping the salt through pe_set_step_salt() between replays.  The salt is
+// per CALLER: the top 8 bits of every seed argument name one of 256 salt slots, and each engine (model instance) owns a
+// slot, so two models training in one process never see each other's salt.  One table per translation unit; units that
+// draw dropout masks register theirs with PE_USES_STEP_SALT().
+static __device__ unsigned long long pe_step_salt[256] __attribute__((unused));
+__device__ __forceinline__ unsigned long long pe_salted(unsigned long long seed) {
+  return seed + pe_step_salt[(unsigned)(seed >> 56)];
+}
 
 // Dropout keep decisions for the 8 consecutive elements [8q, 8q+8): bit i of the result is set iff 16-bit lane i of
 // one Philox block is below thresh16 (= keep probability * 65536).  Every dropout site indexes elements the same

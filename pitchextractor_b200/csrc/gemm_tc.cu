@@ -332,7 +332,7 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   } else {
     // -------------------------------------------------------------------- epilogue (8 warps, 2 per TMEM lane quarter)
     const pe_epilogue& ep = p.ep;
-    const unsigned long long drop_seed = ep.drop_seed + pe_step_salt;
+    const unsigned long long drop_seed = pe_salted(ep.drop_seed);
     const int q = warp & 3;              // TMEM lane quarter this warp may access
     const int pair = (warp - 2) >> 2;    // which of the two warps of the quarter: takes chunks c with (c & 1) == pair
     const int r = q * 32 + lane;
@@ -679,12 +679,6 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 // =================================================================================================
 using pe::TcParams;
 
-static long long* g_tc_dbg = nullptr;
-extern "C" int pe_tc_set_debug(long long* buf) {
-  g_tc_dbg = buf;
-  return PE_OK;
-}
-
 static int pow2_cols(int n) {
   int c = 32;
   while (c < n) c <<= 1;
@@ -747,7 +741,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtens
   p.tiles_y = (int)tiles.y;
   p.tiles_z = (int)tiles.z;
   p.num_tiles = p.tiles_x * p.tiles_y * p.tiles_z;
-  p.dbg = g_tc_dbg;
+  p.dbg = p.ep.debug;
   if (p.ep.drop_thresh && (p.N % 8)) return PE_ERR_BAD_SHAPE;
   if (p.ep.act == PE_ACT_GELU_SAVE_GRAD && !p.ep.out2) return PE_ERR_BAD_SHAPE;
   if (p.ep.stats_mode) {

@@ -77,13 +77,14 @@ void register_salt(salt_addr_fn fn) {
 struct SaltAddrs {
   unsigned long long* p[8];
 };
-__global__ void set_salt_kernel(SaltAddrs a, int n, unsigned long long salt) {
-  if (threadIdx.x < n) *a.p[threadIdx.x] = salt;
+__global__ void set_salt_kernel(SaltAddrs a, int n, int slot, unsigned long long salt) {
+  if (threadIdx.x < n) a.p[threadIdx.x][slot] = salt;
 }
 
 }  // namespace pe_host
 
-extern "C" int pe_set_step_salt(unsigned long long salt, pe_stream_t stream) {
+extern "C" int pe_set_step_salt(int slot, unsigned long long salt, pe_stream_t stream) {
+  if (slot < 0 || slot > 255) return PE_ERR_BAD_SHAPE;
   static pe_host::SaltAddrs addrs;
   static int n_addrs = -1;
   if (n_addrs < 0) {
@@ -95,7 +96,7 @@ extern "C" int pe_set_step_salt(unsigned long long salt, pe_stream_t stream) {
     }
     n_addrs = *n;
   }
-  pe_host::set_salt_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(addrs, n_addrs, salt);
+  pe_host::set_salt_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(addrs, n_addrs, slot, salt);
   return cudaGetLastError() == cudaSuccess ? PE_OK : PE_ERR_LAUNCH;
 }
 

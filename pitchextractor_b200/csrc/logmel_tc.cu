@@ -91,6 +91,19 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
                : "r"(taddr)
                : "memory");
 }
+// non-blocking probe (mbarrier.try_wait suspends the thread for a hardware time slice when the phase is not complete:
+// useless for a poller that watches several barriers)
+__device__ __forceinline__ uint32_t mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
 // wait with a long hardware suspend per probe: the workers wait for whole pipeline phases, and every probe that returns
 // early costs an issue slot the other 17 warps of the SM could use
 __device__ __forceinline__ void mbar_wait_long(uint64_t* bar, uint32_t parity) {
@@ -226,7 +239,7 @@ logmel_tc_kernel(const float* __restrict__ wave, int L, long long ld, int hop, c
         bool any = false;
 #pragma unroll
         for (int g = 0; g < LM_GROUPS; ++g) {
-          if (left[g] > 0 && mbar_try_wait(&work_ready[g], (ph >> g) & 1u)) {
+          if (left[g] > 0 && mbar_test(&work_ready[g], (ph >> g) & 1u)) {
             tc_fence_after();
             const uint32_t ahi = a_slots + g * LM_SLOT_B, alo = ahi + LM_OP_B;
             const uint32_t d = tm + g * 128 + ((which >> g) & 1u) * 64;

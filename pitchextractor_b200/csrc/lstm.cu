@@ -370,7 +370,7 @@ lstm_step_bwd_kernel(const __grid_constant__ LstmMaps maps, const LstmStepParams
 __global__ void __launch_bounds__(256)
 dropout_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n8,
                     unsigned thresh, float scale, unsigned long long seed) {
-  seed += pe_step_salt;
+  seed = pe_salted(seed);
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n8) return;
   const uint4 raw = *reinterpret_cast<const uint4*>(x + i * 8);

@@ -101,7 +101,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ xf
               const float* __restrict__ rstd_in, long long M, int rows_per_cta, __nv_bfloat16* __restrict__ dx,
               __nv_bfloat16* __restrict__ dxm, unsigned drop_thresh, float drop_scale, unsigned long long seed,
               float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias) {
-  seed += pe_step_salt;
+  seed = pe_salted(seed);
   constexpr int D = 256 * NCH;
   // column partial sums (dgamma, dbeta, dbias) live in a private shared-memory slice per warp instead of 48 registers
   // per thread: that keeps two CTAs (16 rows in flight) resident per SM
@@ -267,7 +267,7 @@ __device__ __forceinline__ void load_head(const __nv_bfloat16* src, long long ld
 __global__ void __launch_bounds__(256)
 attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int T, int H, float scale, unsigned drop_thresh,
                 float drop_scale, unsigned long long seed, __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse) {
-  seed += pe_step_salt;
+  seed = pe_salted(seed);
   extern __shared__ __align__(16) float sm[];
   float* Ks = sm;
   float* Vs = sm + T * HD;
@@ -334,7 +334,7 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
                    const __nv_bfloat16* __restrict__ dctx, const float* __restrict__ lse, int T, int H, float scale,
                    unsigned drop_thresh, float drop_scale, unsigned long long seed, __nv_bfloat16* __restrict__ dqkv,
                    float* __restrict__ delta) {
-  seed += pe_step_salt;
+  seed = pe_salted(seed);
   extern __shared__ __align__(16) float sm[];
   float* Ks = sm;
   float* Vs = sm + T * HD;
@@ -389,7 +389,7 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
                     const float* __restrict__ lse, const float* __restrict__ delta, int T, int H, float scale,
                     unsigned drop_thresh, float drop_scale, unsigned long long seed,
                     __nv_bfloat16* __restrict__ dqkv) {
-  seed += pe_step_salt;
+  seed = pe_salted(seed);
   extern __shared__ __align__(16) float sm[];
   float* Qs = sm;                 // pre-scaled queries
   float* dOs = sm + T * HD;
@@ -673,17 +673,11 @@ int pe_attn_fwd_tc(const void* qkv, int B, int H, unsigned drop_thresh, float dr
                    void* ctx, float* lse, cudaStream_t stream);
 int pe_attn_bwd_tc(const void* qkv, const void* ctx, const void* dctx, const float* lse, int B, int H,
                    unsigned drop_thresh, float drop_scale, unsigned long long seed, void* dqkv, cudaStream_t stream);
-static bool g_attn_force_simt = false;
-extern "C" int pe_attn_set_simt(int on) {
-  g_attn_force_simt = on != 0;
-  return PE_OK;
-}
-
 extern "C" int pe_attn_fwd(const void* qkv, int B, int T, int H, int head_dim, unsigned drop_thresh, float drop_scale,
-                           unsigned long long seed, void* ctx, float* lse, pe_stream_t stream) {
+                           unsigned long long seed, void* ctx, float* lse, int force_simt, pe_stream_t stream) {
   if (int rc = pe_host::check_arch()) return rc;
   if (!qkv || !ctx || !lse || B <= 0 || T <= 0 || T > 256 || H <= 0 || head_dim != HD) return PE_ERR_BAD_SHAPE;
-  if (T == 192 && !g_attn_force_simt)
+  if (T == 192 && !force_simt)
     return pe_attn_fwd_tc(qkv, B, H, drop_thresh, drop_scale, seed, ctx, lse, PE_ST(stream));
   const size_t smem = 2ull * T * HD * sizeof(float);
   static bool attr = false;
@@ -699,11 +693,11 @@ extern "C" int pe_attn_fwd(const void* qkv, int B, int T, int H, int head_dim, u
 
 extern "C" int pe_attn_bwd(const void* qkv, const void* ctx, const void* dctx, const float* lse, int B, int T, int H,
                            int head_dim, unsigned drop_thresh, float drop_scale, unsigned long long seed, void* dqkv,
-                           float* delta, pe_stream_t stream) {
+                           float* delta, int force_simt, pe_stream_t stream) {
   if (int rc = pe_host::check_arch()) return rc;
   if (!qkv || !ctx || !dctx || !lse || !dqkv || !delta || B <= 0 || T <= 0 || T > 256 || H <= 0 || head_dim != HD)
     return PE_ERR_BAD_SHAPE;
-  if (T == 192 && !g_attn_force_simt)
+  if (T == 192 && !force_simt)
     return pe_attn_bwd_tc(qkv, ctx, dctx, lse, B, H, drop_thresh, drop_scale, seed, dqkv, PE_ST(stream));
   static bool attr = false;
   if (!attr) {

@@ -295,7 +295,7 @@ bn_act_pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, PoolGeom g, const fl
                        const float* __restrict__ shift, float slope, unsigned drop_thresh, float drop_scale,
                        unsigned long long seed, __nv_bfloat16* __restrict__ out, long long ld_out, int c_off,
                        __nv_bfloat16* __restrict__ out_seq, unsigned char* __restrict__ argmax_out) {
-  seed += pe_step_salt;
+  seed = pe_salted(seed);
   const int cg = g.C >> 3;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = g.rows * g.Wo * cg;
@@ -363,7 +363,7 @@ bn_act_pool_fwd_mlp_kernel(const __nv_bfloat16* __restrict__ x, PoolGeom g, cons
                            const float* __restrict__ shift, float slope, unsigned drop_thresh, float drop_scale,
                            unsigned long long seed, __nv_bfloat16* __restrict__ out, long long ld_out, int c_off,
                            __nv_bfloat16* __restrict__ out_seq) {
-  seed += pe_step_salt;
+  seed = pe_salted(seed);
   const int cg = g.C >> 3;
   const int ry = blockDim.x / cg;
   const int tx = threadIdx.x % cg, ty = threadIdx.x / cg;
@@ -509,7 +509,7 @@ __device__ __forceinline__ void bn_bwd_route(const BnBwdArgs& a, const float* s_
 template <int K, bool EXTRA>
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(BnBwdArgs a, double* __restrict__ sums, int windows_per_cta) {
-  a.seed += pe_step_salt;
+  a.seed = pe_salted(a.seed);
   extern __shared__ __align__(16) float sm[];  // sc[C] | sh[C] | red[2][C]
   const PoolGeom& g = a.g;
   float* s_sc = sm;
@@ -579,7 +579,7 @@ __global__ void bn_bwd_params_kernel(const double* __restrict__ sums, double cou
 template <int K>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(BnBwdArgs a, const float* __restrict__ coef, __nv_bfloat16* __restrict__ dx) {
-  a.seed += pe_step_salt;
+  a.seed = pe_salted(a.seed);
   extern __shared__ __align__(16) float sm[];  // sc | sh | A | B
   const PoolGeom& g = a.g;
   float* s_sc = sm;
@@ -637,7 +637,7 @@ bn_bwd_apply_kernel(BnBwdArgs a, const float* __restrict__ coef, __nv_bfloat16* 
 template <int K, int U, bool EXTRA, bool AUX>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_mlp_kernel(BnBwdArgs a, const float* __restrict__ coef, __nv_bfloat16* __restrict__ dx) {
-  a.seed += pe_step_salt;
+  a.seed = pe_salted(a.seed);
   const PoolGeom& g = a.g;
   const int cg = g.C >> 3;
   const int ry = blockDim.x / cg;

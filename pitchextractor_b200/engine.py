@@ -75,6 +75,7 @@ class Engine:
         self._site_d = 16 + 8 * self.num_layers
         assert self._site_d + 8 * self.num_layers <= 128 or self.seq_type != "transformer"
         self.step_seed = 0x5EED0000
+        self.salt_slot, self._salt = L.new_salt_slot(), 0
         self.dropout_enabled = True
         self._bufs = {}
         self._fwd_token = 0
@@ -192,7 +193,7 @@ class Engine:
         return t
 
     def _seed(self, site):
-        return (self.step_seed << 8) + site
+        return (self.salt_slot << 56) | (((self.step_seed << 8) + site) & ((1 << 56) - 1))
 
     def _drop(self, p, training):
         if not training or not self.dropout_enabled or p <= 0.0:
@@ -390,7 +391,7 @@ class Engine:
             CTX = self.buf(t + "CTX", (M, D))
             LSE = self.buf(t + "LSE", (B, H, T), torch.float32)
             call("pe_attn_fwd", ptr(QKV), c_int(B), c_int(T), c_int(H), c_int(64), c_u(adrop[0]), c_f(adrop[1]),
-                 c_ull(self._seed(site + 0)), ptr(CTX), ptr(LSE), stream())
+                 c_ull(self._seed(site + 0)), ptr(CTX), ptr(LSE), c_int(0), stream())
             S1 = self.buf(t + "S1", (M, D), torch.float32)
             ops.gemm(CTX, W16[q + "self_attn.out_proj.weight"], S1, M, D, D, bias=V[q + "self_attn.out_proj.bias"],
                      p_drop=pdrop, seed=self._seed(site + 1), aux=Hcur, aux_mode=L.PE_AUX_ADD)
@@ -602,7 +603,7 @@ class Engine:
             self._wgrad_linear(dSm, CTX, q + "self_attn.out_proj.weight", D, D, M)
             # attention
             call("pe_attn_bwd", ptr(QKV), ptr(CTX), ptr(dCTX), ptr(LSE), c_int(B), c_int(T), c_int(H), c_int(64),
-                 c_u(adrop[0]), c_f(adrop[1]), c_ull(self._seed(site + 0)), ptr(dQKV), ptr(delta), stream())
+                 c_u(adrop[0]), c_f(adrop[1]), c_ull(self._seed(site + 0)), ptr(dQKV), ptr(delta), c_int(0), stream())
             # in_proj: dH = dQKV Wqkv + dS (residual)
             dHn = self.buf(tag + "dHin%d" % (l & 1), (M, D))
             ops.gemm(dQKV, W16[q + "self_attn.in_proj_weight"], dHn, M, D, 3 * D, b_mn=True, aux=dS,
@@ -719,10 +720,10 @@ class Engine:
 
     # ------------------------------------------------------------------ CUDA-graph replay of the training step
     def _set_salt(self, salt):
-        salt &= 0xFFFFFFFFFFFFFFFF
-        if salt != L.step_salt:  # the salt is device state shared by every engine of this process
-            call("pe_set_step_salt", ctypes.c_ulonglong(salt), stream())
-            L.step_salt = salt
+        salt &= (1 << 56) - 1
+        if salt != self._salt:  # this engine's own slot of the device-side salt table
+            call("pe_set_step_salt", c_int(self.salt_slot), ctypes.c_ulonglong(salt), stream())
+            self._salt = salt
 
     def _train_step_graphed(self, x, f0, sil, lambda_f0, grad_scale):
         x, B, T, _ = self._prep_input(x)

@@ -29,10 +29,15 @@ class _Timed:
             PROFILE.append((self.tag, self.e0, self.e1, self.flops))
 
 
+DEBUG_BUFFER = None  # tuning aid: int64 [grid][16] tensor the next tile-engine launches fill with per-CTA counters
+
+
 def make_epilogue(out, out_mode=None, bias=None, act=L.PE_ACT_NONE, out2=None, aux=None, aux_mode=L.PE_AUX_NONE,
                   p_drop=0.0, seed=0, alpha=1.0, ldc=None, stats=None, stats_mode=0, stats_x=None, stats_scale=None,
                   stats_shift=None, stats_slope=0.01):
     ep = Epilogue()
+    if DEBUG_BUFFER is not None:
+        ep.debug = DEBUG_BUFFER.data_ptr()
     ep.out = out.data_ptr()
     ep.ldc = out.stride(-2) if ldc is None else ldc
     if out_mode is None:
@@ -107,16 +112,17 @@ def logmel(wave, tables, out_bmt=None, out_btm=None, crop=None, T_out=0, power_w
     return power_ws
 
 
-def attn_fwd(qkv, B, T, H, ctx, lse, p_drop=0.0, seed=0):
+def attn_fwd(qkv, B, T, H, ctx, lse, p_drop=0.0, seed=0, force_simt=False):
     th, sc = L.attn_drop_thresh(p_drop)
     call("pe_attn_fwd", ptr(qkv), c_int(B), c_int(T), c_int(H), c_int(64), ctypes.c_uint(th), ctypes.c_float(sc),
-         ctypes.c_ulonglong(seed), ptr(ctx), ptr(lse), stream())
+         ctypes.c_ulonglong(seed), ptr(ctx), ptr(lse), c_int(int(force_simt)), stream())
 
 
-def attn_bwd(qkv, ctx, dctx, lse, B, T, H, dqkv, delta, p_drop=0.0, seed=0):
+def attn_bwd(qkv, ctx, dctx, lse, B, T, H, dqkv, delta, p_drop=0.0, seed=0, force_simt=False):
     th, sc = L.attn_drop_thresh(p_drop)
     call("pe_attn_bwd", ptr(qkv), ptr(ctx), ptr(dctx), ptr(lse), c_int(B), c_int(T), c_int(H), c_int(64),
-         ctypes.c_uint(th), ctypes.c_float(sc), ctypes.c_ulonglong(seed), ptr(dqkv), ptr(delta), stream())
+         ctypes.c_uint(th), ctypes.c_float(sc), ctypes.c_ulonglong(seed), ptr(dqkv), ptr(delta), c_int(int(force_simt)),
+         stream())
 
 
 def colsum(x, out):

@@ -22,17 +22,15 @@ def _ref(qkv, B, T, dctx=None):
 
 
 def _run(qkv, B, T, dctx, p_drop=0.0, seed=0, simt=False):
-    from pitchextractor_b200 import ops, _lib
-    _lib.lib().pe_attn_set_simt(ctypes.c_int(int(simt)))
+    from pitchextractor_b200 import ops
     D = H * HD
     ctx = torch.empty(B * T, D, device="cuda", dtype=torch.bfloat16)
     lse = torch.empty(B, H, T, device="cuda", dtype=torch.float32)
     dqkv = torch.zeros(B * T, 3 * D, device="cuda", dtype=torch.bfloat16)
     delta = torch.empty(B, H, T, device="cuda", dtype=torch.float32)
-    ops.attn_fwd(qkv, B, T, H, ctx, lse, p_drop, seed)
-    ops.attn_bwd(qkv, ctx, dctx, lse, B, T, H, dqkv, delta, p_drop, seed)
+    ops.attn_fwd(qkv, B, T, H, ctx, lse, p_drop, seed, force_simt=simt)
+    ops.attn_bwd(qkv, ctx, dctx, lse, B, T, H, dqkv, delta, p_drop, seed, force_simt=simt)
     torch.cuda.synchronize()
-    _lib.lib().pe_attn_set_simt(ctypes.c_int(0))
     return ctx, lse, dqkv
 
 

@@ -14,8 +14,8 @@ def conv(B, H, W, C1, C2, Cout, reps=10):
     for _ in range(reps): ops.conv3x3(x, w, out, x2=x2)
     e1.record(); torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / reps * 1e3
-    lib.pe_tc_set_debug(ctypes.c_void_p(dbg.data_ptr())); dbg.zero_()
-    ops.conv3x3(x, w, out, x2=x2); torch.cuda.synchronize(); lib.pe_tc_set_debug(None)
+    ops.DEBUG_BUFFER = dbg; dbg.zero_()
+    ops.conv3x3(x, w, out, x2=x2); torch.cuda.synchronize(); ops.DEBUG_BUFFER = None
     d = dbg.float().mean(0).tolist()
     tiles = B * H * W / 128 / min(148, B * H * W / 128)
     kb = tiles * (9 * C1 // 64 + C2 // 64)

@@ -12,8 +12,8 @@ def rep(tag, M, N, K, out_dtype=torch.bfloat16, **kw):
     e0.record()
     for _ in range(20): ops.gemm(a, b, out, M, N, K, **kw)
     e1.record(); torch.cuda.synchronize()
-    lib.pe_tc_set_debug(ctypes.c_void_p(dbg.data_ptr())); dbg.zero_()
-    ops.gemm(a, b, out, M, N, K, **kw); torch.cuda.synchronize(); lib.pe_tc_set_debug(None)
+    ops.DEBUG_BUFFER = dbg; dbg.zero_()
+    ops.gemm(a, b, out, M, N, K, **kw); torch.cuda.synchronize(); ops.DEBUG_BUFFER = None
     d = dbg.float().mean(0).tolist()
     tiles = (M // 128) * ((N + 255) // 256) / 148
     print("%-34s %5.1f us | %.1f tiles/CTA | mma loop %6.0f (wait opnd %5.0f, acc %5.0f) | exit %6.0f | epi: wait %6.0f ld %6.0f work %6.0f last %6.0f" % (

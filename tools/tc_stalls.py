@@ -18,8 +18,8 @@ def gemm(M, N, K):
     a = torch.randn(M, K, device="cuda").to(torch.bfloat16); b = torch.randn(N, K, device="cuda").to(torch.bfloat16)
     out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
     ops.gemm(a, b, out, M, N, K); torch.cuda.synchronize()
-    lib.pe_tc_set_debug(ctypes.c_void_p(dbg.data_ptr())); dbg.zero_()
-    ops.gemm(a, b, out, M, N, K); show("gemm M=%d N=%d K=%d" % (M, N, K)); lib.pe_tc_set_debug(None)
+    ops.DEBUG_BUFFER = dbg; dbg.zero_()
+    ops.gemm(a, b, out, M, N, K); show("gemm M=%d N=%d K=%d" % (M, N, K)); ops.DEBUG_BUFFER = None
 
 def conv(B, H, W, C1, C2, Cout):
     x = torch.randn(B, H, W, C1, device="cuda").to(torch.bfloat16)
@@ -27,8 +27,8 @@ def conv(B, H, W, C1, C2, Cout):
     w = torch.randn(Cout, 9 * C1 + C2, device="cuda").to(torch.bfloat16)
     out = torch.empty(B, H, W, Cout, device="cuda", dtype=torch.bfloat16)
     ops.conv3x3(x, w, out, x2=x2); torch.cuda.synchronize()
-    lib.pe_tc_set_debug(ctypes.c_void_p(dbg.data_ptr())); dbg.zero_()
-    ops.conv3x3(x, w, out, x2=x2); show("conv W=%d C=%d->%d" % (W, C1, Cout)); lib.pe_tc_set_debug(None)
+    ops.DEBUG_BUFFER = dbg; dbg.zero_()
+    ops.conv3x3(x, w, out, x2=x2); show("conv W=%d C=%d->%d" % (W, C1, Cout)); ops.DEBUG_BUFFER = None
 
 gemm(12288, 1536, 512); gemm(12288, 512, 1536); gemm(12288, 256, 2048)
 conv(64, 192, 80, 64, 0, 64); conv(64, 192, 40, 128, 64, 128); conv(64, 192, 10, 256, 192, 256)
@@ -38,10 +38,10 @@ def wgrad(B, H, W, C, Cout, taps=9):
     dy = torch.randn(B, H, W, Cout, device="cuda").to(torch.bfloat16)
     dw = torch.zeros(Cout, taps * C, device="cuda")
     ops.conv_wgrad(dy, x, dw, taps=taps); torch.cuda.synchronize()
-    lib.pe_tc_set_debug(ctypes.c_void_p(dbg.data_ptr())); dbg.zero_()
+    ops.DEBUG_BUFFER = dbg; dbg.zero_()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); ops.conv_wgrad(dy, x, dw, taps=taps); e1.record()
-    show("wgrad W=%d C=%d Cout=%d" % (W, C, Cout)); lib.pe_tc_set_debug(None)
+    show("wgrad W=%d C=%d Cout=%d" % (W, C, Cout)); ops.DEBUG_BUFFER = None
     print("     %.1f us  %.0f TFLOP/s" % (e0.elapsed_time(e1) * 1e3, 2.0 * B * H * W * C * Cout * taps / e0.elapsed_time(e1) / 1e9))
 
 wgrad(64, 192, 80, 64, 64); wgrad(64, 192, 40, 64, 128); wgrad(64, 192, 40, 128, 128); wgrad(64, 192, 20, 192, 192); wgrad(64, 192, 10, 256, 256)
