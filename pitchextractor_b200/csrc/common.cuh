@@ -57,7 +57,9 @@ __device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t k
 // draw dropout masks register theirs with PE_USES_STEP_SALT().
 static __device__ unsigned long long pe_step_salt[256] __attribute__((unused));
 __device__ __forceinline__ unsigned long long pe_salted(unsigned long long seed) {
-  return seed + pe_step_salt[(unsigned)(seed >> 56)];
+  // the slot bits select the salt and are then dropped: the masks depend on (seed, salt) only, not on which slot an
+  // engine happens to own
+  return (seed & 0x00FFFFFFFFFFFFFFull) + pe_step_salt[(unsigned)(seed >> 56)];
 }
 
 // Dropout keep decisions for the 8 consecutive elements [8q, 8q+8): bit i of the result is set iff 16-bit lane i of

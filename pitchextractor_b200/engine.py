@@ -63,8 +63,10 @@ class Engine:
         self.ff = sc.dim_feedforward
         self.p_seq = float(sc.dropout)
         self.p_trunk = 0.5  # nn.Dropout(p=0.5) in pool_block / detector_conv (model.py:40,56)
-        if model.num_class != 1:
-            raise NotImplementedError("the fused heads kernel implements num_class == 1 (Configs/config.yml:17)")
+        # num_class == 1 (Configs/config.yml:17, the only value the reference's Trainer can train): fused heads + losses
+        # kernel.  num_class > 1 (the reference constructor's default 722): the classifier head is a tile-engine GEMM,
+        # available through forward() / autograd; the fused training step needs the scalar regression head.
+        self.num_class = int(model.num_class)
         if self.seq_type == "bilstm" and (sc.hidden_size != 384 or not sc.bidirectional):
             raise NotImplementedError("the LSTM recurrence kernels are built for hidden_size 384, bidirectional")
         self.p_lstm = float(getattr(sc, "lstm_dropout", 0.0))
@@ -542,6 +544,10 @@ class Engine:
         dHd = self.buf("dHd", (M, D)) if want_grad else None
         self.loss_acc.zero_()
         gw = lambda n: ptr(g[n]) if want_grad else None
+        if self.num_class > 1:  # the scalar classifier slot of the fused kernel is unused: row 0 in, scratch gradients out
+            scratch = self.buf("cls_scalar_scratch", (D + 64,), torch.float32)
+            gw_c = {"classifier.weight": ptr(scratch), "classifier.bias": ctypes.c_void_p(scratch.data_ptr() + 4 * D)}
+            gw = lambda n, _gw=gw: (gw_c[n] if n in gw_c and want_grad else _gw(n))
         call("pe_heads_loss", ptr(self._Hc), ptr(self._Hd), c_ll(M), c_int(D), ptr(V["classifier.weight"]),
              ptr(V["classifier.bias"]), ptr(V["detector.weight"]), ptr(V["detector.bias"]), ptr(f0), ptr(sil),
              c_f(lambda_f0), c_f(grad_scale), ptr(self._pred_f0), ptr(self._pred_sil),
@@ -699,6 +705,10 @@ class Engine:
     # ------------------------------------------------------------------ public entry points
     def train_step(self, mel, f0, sil, lambda_f0=0.1, grad_scale=1.0):
         """mel [B,1,80,T] (reference batch layout) -> fills .grad, returns device tensor [loss, f0, sil]."""
+        if self.num_class != 1:
+            raise ValueError("the fused training step regresses F0 with num_class == 1 (Configs/config.yml:17; the "
+                             "reference's Trainer.run cannot train num_class > 1 either: SmoothL1 of [B,T,C] against "
+                             "[B,T]); use model(x) + your own loss + backward() for a classification head")
         x = mel.transpose(-1, -2)  # trainer.py:235
         if self.use_graph and ops.PROFILE is None and L.TIMING is None:
             return self._train_step_graphed(x, f0, sil, float(lambda_f0), float(grad_scale))
@@ -839,6 +849,8 @@ class Engine:
         self.step_seed, self._fwd_token, L.launch_count = seed_before, token_before, launches_before
 
     def eval_loss(self, mel, f0, sil, lambda_f0=0.1):
+        if self.num_class != 1:
+            raise ValueError("eval_loss needs the scalar regression head (num_class == 1); use model(x)")
         self.forward_core(mel.transpose(-1, -2), training=False)
         f0 = f0.to(self.device, torch.float32).contiguous().view(-1)
         sil = sil.to(self.device, torch.float32).contiguous().view(-1)
@@ -851,7 +863,10 @@ class Engine:
         self.forward_core(x, training=training)
         B, T = self._B, self._T
         self._predict_only()
-        self._out_cls = self._pred_f0.view(B, T, 1)
+        if self.num_class > 1:
+            self._out_cls = self._cls_logits[:, :self.num_class].reshape(B, T, self.num_class)
+        else:
+            self._out_cls = self._pred_f0.view(B, T, 1)
         self._out_det = self._pred_sil.view(B, T)
         if torch.is_grad_enabled() and training:
             return _OutputGrad.apply(self, self._fwd_token, *self.params)
@@ -862,14 +877,64 @@ class Engine:
         zeros = self.buf("zero_targets", (M,), torch.float32)
         zeros.zero_()
         self._heads(zeros, zeros, 0.0, 1.0, want_grad=False)
+        if self.num_class > 1:
+            self._classifier_fwd()
+
+    # ------------------------------------------------------------------ classification head (num_class > 1)
+    def _classifier_pad(self):
+        """Zero-padded (to a multiple of 64 classes) bf16 weight / fp32 bias operands of Linear(D -> num_class)."""
+        nc, D = self.num_class, self.seq_dim
+        npad = _align(nc, 64)
+        W = self.buf("cls_wpad", (npad, D))
+        b = self.buf("cls_bpad", (npad,), torch.float32)
+        if not getattr(self, "_cls_pad_zeroed", False):
+            W.zero_()
+            b.zero_()
+            self._cls_pad_zeroed = True
+        W[:nc].copy_(self.bview["classifier.weight"])
+        b[:nc].copy_(self.view["classifier.bias"])
+        return W, b, npad
+
+    def _classifier_fwd(self):
+        """model.py:96-98 with num_class > 1: logits [M, num_class] = Hc W^T + b on the tile engine."""
+        M, D = self._B * self._T, self.seq_dim
+        W, b, npad = self._classifier_pad()
+        out = self.buf("cls_logits", (M, npad), torch.float32)
+        ops.gemm(self._Hc, W, out, M, npad, D, bias=b)
+        self._cls_logits = out
+
+    def _classifier_bwd(self, dcls, dHc):
+        """dHc = dcls W (overwrites the zero the scalar path left there); dW += dcls^T Hc; db += column sums."""
+        M, D, nc = self._B * self._T, self.seq_dim, self.num_class
+        W, _, npad = self._classifier_pad()
+        g = self.buf("cls_gpad", (M, npad))
+        g.zero_()
+        g[:, :nc].copy_(dcls.reshape(M, nc))
+        ops.gemm(g, W, dHc, M, D, npad, b_mn=True)
+        dW = self.buf("cls_dw", (npad, D), torch.float32)
+        db = self.buf("cls_db", (npad,), torch.float32)
+        dW.zero_()
+        db.zero_()
+        tiles = ((npad + 127) // 128) * ((D + 255) // 256)
+        splits = max(1, min((M + 63) // 64, 148 // tiles))
+        ops.gemm(g, self._Hc, dW, npad, D, M, a_mn=True, b_mn=True, splits=splits, out_mode=L.PE_OUT_F32_ATOMIC)
+        ops.colsum(g, db)
+        self.gview["classifier.weight"].add_(dW[:nc])
+        self.gview["classifier.bias"].add_(db[:nc])
 
     def backward_from_output_grads(self, dcls, ddet):
         M = self._B * self._T
         self._set_salt(0)
-        gc = dcls.to(torch.float32).contiguous().view(M)
         gd = ddet.to(torch.float32).contiguous().view(M)
         if any(p.grad is None for p in self.params):
             self.flat_grad.zero_()  # grads were dropped by zero_grad(set_to_none=True): start from zero
         self.attach_grads()
-        dHc, dHd = self._heads(None, None, 0.0, 1.0, want_grad=True, gc_ext=gc, gd_ext=gd)
+        if self.num_class > 1:
+            zero = self.buf("zero_targets", (M,), torch.float32)
+            zero.zero_()
+            dHc, dHd = self._heads(None, None, 0.0, 1.0, want_grad=True, gc_ext=zero, gd_ext=gd)
+            self._classifier_bwd(dcls.to(torch.float32), dHc)
+        else:
+            gc = dcls.to(torch.float32).contiguous().view(M)
+            dHc, dHd = self._heads(None, None, 0.0, 1.0, want_grad=True, gc_ext=gc, gd_ext=gd)
         self.backward_core(dHc, dHd)

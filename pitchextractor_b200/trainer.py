@@ -177,7 +177,9 @@ class Trainer(object):
                 self.optimizer.grad_scale = 1.0 / self.world
 
     def run_async(self, batch):
-        """One optimisation step; returns the device tensor [loss, f0, sil] without synchronising."""
+        """One optimisation step; returns the device tensor [loss, f0, sil] without synchronising.  The tensor is the
+        engine's persistent loss buffer: the next step overwrites it, so ``.clone()`` (or copy to the host, as ``run`` and
+        ``run_pipelined`` do) anything that must outlive the step."""
         self._ensure_parallel()
         self._await_batch(batch)
         x, f0, sil = self._mel_from_batch(batch)

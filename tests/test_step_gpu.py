@@ -219,3 +219,45 @@ def test_lstm_persistent_kernel_matches_stepwise_launches(built_lib, B):
     rel = ((grads["stepwise"] - grads["persistent"]).norm() / grads["stepwise"].norm()).item()
     print("B=%d persistent vs stepwise: grad cosine %.6f rel %.4g hidden rel %.3g" % (B, cos, rel, rel_h))
     assert cos > 0.999 and rel < 5e-2, (cos, rel)
+
+
+def test_classification_head_forward_and_backward(built_lib):
+    """JDCNet(num_class=722), the reference constructor's default (model.py:17): forward logits and the gradients of a
+    cross-entropy loss through autograd against the fp32 oracle."""
+    from oracle import jdcnet_torch as J
+    from pitchextractor_b200.model import JDCNet
+    B, NC = 3, 722
+    torch.manual_seed(4)
+    cfg = dict(model_type="transformer", num_layers=4, dropout=0.1, nhead=8, dim_feedforward=1536, max_len=2048)
+    m = JDCNet(num_class=NC, sequence_model_config=cfg)
+    sd = {k: v.detach().clone().float() for k, v in m.state_dict().items()}
+    mel, _, sil = _inputs(B, seed=9)
+    target = torch.randint(0, NC, (B, 192), generator=torch.Generator().manual_seed(1))
+    params = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "running" not in k and not k.endswith(".pe"))
+              for k, v in sd.items()}
+    cls, det = J.jdcnet_forward(params, mel.transpose(-1, -2), J.default_config("transformer"), training=True)
+    loss = torch.nn.functional.cross_entropy(cls.reshape(-1, NC), target.reshape(-1)) + \
+        torch.nn.functional.binary_cross_entropy_with_logits(det, sil)
+    names = ["classifier.weight", "classifier.bias", "sequence_classifier.model.layers.3.linear2.weight",
+             "detector.weight", "detector_conv.0.weight"]
+    ref = dict(zip(names, torch.autograd.grad(loss, [params[n] for n in names])))
+    m = m.cuda()
+    m.engine.dropout_enabled = False
+    m.train()
+    c2, d2 = m(mel.cuda().transpose(-1, -2))
+    assert c2.shape == (B, 192, NC) and d2.shape == (B, 192)
+    assert (c2.cpu() - cls.detach()).abs().max().item() <= 3e-2 * cls.abs().max().item() + 2e-2
+    l2 = torch.nn.functional.cross_entropy(c2.reshape(-1, NC), target.cuda().reshape(-1)) + \
+        torch.nn.functional.binary_cross_entropy_with_logits(d2, sil.cuda())
+    assert abs(l2.item() - loss.item()) <= 2e-2 * abs(loss.item())
+    for p in m.parameters():
+        p.grad = None
+    l2.backward()
+    got = dict(m.named_parameters())
+    for n in names:
+        a, b = got[n].grad.detach().cpu().float().flatten(), ref[n].flatten()
+        cos = torch.nn.functional.cosine_similarity(a, b, dim=0).item()
+        print("%-55s cosine %.5f" % (n, cos))
+        assert cos >= 0.98, (n, cos)
+    with pytest.raises(ValueError):
+        m.engine.train_step(mel.cuda(), sil.cuda(), sil.cuda(), 0.1)

@@ -90,7 +90,19 @@ def test_checkpoint_roundtrip_and_mel_batches(built_lib, tmp_path):
     model2.engine.dropout_enabled = False
     o1 = tr.run((mel.cpu(), f0, sil))
     o2 = tr2.run((mel.cpu(), f0, sil))
-    assert abs(o1["loss"] - o2["loss"]) <= 1e-3 * abs(o1["loss"]), (o1, o2)  # optimizer moments restored too
+    assert abs(o1["loss"] - o2["loss"]) <= 1e-3 * abs(o1["loss"]), (o1, o2)
+    # the restored optimizer state itself: moments, step count and schedule position equal the originals' after the
+    # extra step both trainers just made (a broken restore of exp_avg / exp_avg_sq / step would show here, not in a loss
+    # that is computed before the update)
+    assert opt2._steps == opt._steps == 2 and sched2.last_epoch == sched.last_epoch
+    for key in ("exp_avg", "exp_avg_sq"):
+        a, b = getattr(opt, key), getattr(opt2, key)
+        # (the two trainers' second-step gradients differ by atomic-summation order, amplified by BatchNorm at batch 2)
+        assert (a - b).abs().max().item() <= 2e-2 * a.abs().max().item() + 1e-12, key
+    upd = (model.engine.flat - model2.engine.flat).norm().item() / model.engine.flat.norm().item()
+    assert upd <= 2e-4, upd
+    o1b, o2b = tr.run((mel.cpu(), f0, sil)), tr2.run((mel.cpu(), f0, sil))
+    assert abs(o1b["loss"] - o2b["loss"]) <= 2e-3 * abs(o1b["loss"]), (o1b, o2b)
     model.eval()
     ev = model.engine.eval_loss(mel, f0, sil).tolist()
     assert np.isfinite(ev).all()
@@ -155,7 +167,7 @@ def test_cuda_graph_replay_matches_eager(built_lib, model_type):
     # frozen weights (lr = 0): any change between replays is the dropout mask alone
     frozen, _, _ = trajectory(True, 0.0)
     print("frozen ", frozen)
-    assert len({round(v, 4) for v in frozen[2:]}) == len(frozen[2:]), frozen
+    assert len(set(frozen[2:])) == len(frozen[2:]), frozen  # every replay draws its own masks
 
 
 def test_cuda_graph_segments_with_reducer(built_lib):
