@@ -276,13 +276,17 @@ logmel_tc_kernel(const float* __restrict__ wave, int L, long long ld, int hop, c
     const uint32_t trow = tm + ((uint32_t)(q * 32) << 16) + g * 128;
     const uint32_t bar_id = 1 + g;
     uint32_t dph = 0;
-    // this thread's two window positions (16-byte units wt and wt + 128 of a frame): fixed for every frame
+    // this thread's two window positions (two 16-byte units of a frame): fixed for every frame
     float4 wreg[2];
     uint32_t spos[2];      // byte offset of the position inside a frame
     uint32_t soff[2][2];   // operand byte offset for (frame parity, position) without the pair terms
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const int u = wt + 128 * h, n1 = u >> 3, n2 = (u & 7) << 2;
+      // (n1, n2) of the thread's 16-byte unit.  The four n1 rows of a warp are {b, b+1, b+4, b+5}: their operand rows
+      // then split 2 + 2 over the two 64-byte halves of the swizzled 128-byte row, the minimum for a 256-byte store
+      // (four consecutive rows would all land in the same half: 4-way bank conflicts)
+      const int r4 = (wt >> 3) & 3, w4 = wt >> 5;
+      const int n1 = (r4 & 1) + 4 * (r4 >> 1) + 2 * (w4 & 1) + 8 * ((w4 >> 1) + 2 * h), n2 = (wt & 7) << 2;
       wreg[h] = __ldg(reinterpret_cast<const float4*>(p.win + n1 * 32 + n2));
       spos[h] = (uint32_t)(n1 * 32 + n2) * 4u;
 #pragma unroll

@@ -104,25 +104,64 @@ def mel_work_items(starts, counts, offsets, lanes=128):
     """Work items of the banded mel product for the tcgen05 log-mel kernel, one per worker lane: int32 [lanes][4] =
     {filter (-1: idle), first bin, number of bins, offset into the weight array | flags << 24}.  The longest filters are
     split in two halves that sit on adjacent lanes (l, l ^ 1; flag ITEM_COMBINE on both, ITEM_WRITER on the even one)
-    until every lane has work; items are ordered longest first so that the lanes of a warp run similar trip counts."""
+    until every lane has work.  Items are packed into groups of 8 lanes (the lanes one shared-memory wavefront of a
+    16-byte load serves) such that (a) the 8 first bins are distinct modulo 8 -- the power-spectrum rows are 48 bytes
+    apart, so rows k that differ modulo 8 lie in different 16-byte bank groups and the loads of a group never
+    conflict while it walks its bands in lockstep -- and (b) lengths are similar, longest groups first, so the lanes of a
+    warp run similar trip counts."""
     n = len(counts)
     if n > lanes:
         raise ValueError("the tcgen05 log-mel kernel handles at most %d mel filters" % lanes)
     order = sorted(range(n), key=lambda m: -int(counts[m]))
     n_split = min(lanes - n, sum(1 for m in order if counts[m] >= 2))
-    pairs, singles = [], []
+    units = []  # (length, [items]) -- a split filter is one unit of two adjacent items
     for rank, m in enumerate(order):
         st, c, off = int(starts[m]), int(counts[m]), int(offsets[m])
         if rank < n_split:
             c0 = (c + 1) // 2
-            pairs.append(((m, st, c0, off, ITEM_COMBINE | ITEM_WRITER), (m, st + c0, c - c0, off + c0, ITEM_COMBINE)))
+            if c0 % 8 == 0 and c - c0 > 1:
+                c0 += 1  # keep the two halves' first bins distinct modulo 8
+            units.append((c0, [(m, st, c0, off, ITEM_COMBINE | ITEM_WRITER), (m, st + c0, c - c0, off + c0, ITEM_COMBINE)]))
         else:
-            singles.append((m, st, c, off, ITEM_WRITER))
-    items = [it for pr in pairs for it in pr] + singles
+            units.append((c, [(m, st, c, off, ITEM_WRITER)]))
+    units.sort(key=lambda u: -u[0])
+    groups, remaining = [], units
+    while remaining:
+        used, group, rest = set(), [], []
+        for length, items in remaining:
+            res = [it[1] % 8 for it in items]
+            fits = len(group) + len(items) <= 8 and len(set(res)) == len(res) and not (set(res) & used)
+            if fits:
+                group.extend(items)
+                used.update(res)
+            else:
+                rest.append((length, items))
+        if len(group) < 8:  # residues could not all be distinct: fill up with the longest leftovers
+            keep = []
+            for length, items in rest:
+                if len(group) + len(items) <= 8 and (len(group) % 2 == 0 or len(items) == 1):
+                    group.extend(items)
+                else:
+                    keep.append((length, items))
+            rest = keep
+        groups.append(group)
+        remaining = rest
+    items = []
+    for g in groups:
+        assert len(g) <= 8
+        items.extend(g + [(-1, 0, 0, 0, 0)] * ((8 - len(g)) if len(items) + 8 <= lanes else 0))
+    items = items[:lanes] if len(items) <= lanes else None
+    if items is None:  # could not pack into 8-lane groups within the lane budget: plain longest-first order
+        items = [it for _, its in units for it in its]
     out = np.full((lanes, 4), 0, dtype=np.int64)
     out[:, 0] = -1
     for i, (m, st, c, off, fl) in enumerate(items):
         out[i] = (m, st, c, off | (fl << 24))
+    # split pairs must sit on lanes (l, l ^ 1)
+    for i in range(0, lanes, 2):
+        a, b = out[i], out[i + 1]
+        if ((a[3] >> 24) & ITEM_COMBINE) or ((b[3] >> 24) & ITEM_COMBINE):
+            assert a[0] == b[0] and ((a[3] >> 24) & ITEM_COMBINE) and ((b[3] >> 24) & ITEM_COMBINE), (i, a, b)
     return torch.from_numpy(out.astype(np.int32))
 
 

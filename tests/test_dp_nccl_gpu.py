@@ -40,12 +40,16 @@ def make():
 sp = {"max_lr": 3e-4, "pct_start": 0.0, "epochs": 100, "steps_per_epoch": 1000}
 # ---- every rank alone: gradients of each rank's first batch, and the AdamW step on their mean
 alone = make()
-grads = []
+grads, again = [], []
 for r in range(world):
     alone.engine.use_graph = False
     alone.engine.train_step(*batch(r, 0), 0.1)
     grads.append(alone.engine.flat_grad.clone())
+for r in range(world):   # the same gradients a second time: the run-to-run noise of fp32 atomics / split-K order, which
+    alone.engine.train_step(*batch(r, 0), 0.1)   # train-mode BatchNorm at batch 4 amplifies, is the yardstick
+    again.append(alone.engine.flat_grad.clone())
 expect_sum = sum(grads)
+noise = ((sum(again) - expect_sum).norm() / expect_sum.norm()).item()
 opt_a, sch_a = build_optimizer({"params": alone.parameters(), "optimizer_params": {}, "scheduler_params": sp})
 alone.engine.flat_grad.copy_(expect_sum / world)
 init_params = alone.engine.flat.clone()
@@ -61,8 +65,8 @@ out = tr.run(batch(rank, 0))
 eng = model.engine
 rel_g = ((eng.flat_grad - expect_sum).norm() / expect_sum.norm()).item()
 # AdamW's first update is sign-like (lr * g / (|g| + eps)): elements whose gradient is ~0 may flip under a different
-# summation order, so compare the update vectors in norm
-rel_p = ((eng.flat - expect_params).norm() / (expect_params - init_params).norm()).item()
+# summation order, so compare the directions of the update vectors
+rel_p = 1.0 - torch.nn.functional.cosine_similarity(eng.flat - init_params, expect_params - init_params, dim=0).item()
 # further steps: eager warm-up, capture (segments cut at the buckets), replay
 losses = [out["loss"]] + [tr.run(batch(rank, s))["loss"] for s in range(1, 6)]
 captured = any("segments" in e for e in eng._graphs.values())
@@ -72,7 +76,7 @@ same = all(torch.equal(gathered[0], g) for g in gathered)
 bn = model.conv_block._modules["1"].running_mean.clone()
 bns = [torch.empty_like(bn) for _ in range(world)]
 dist.all_gather(bns, bn)
-res = dict(rank=rank, rel_grad_vs_sum_of_alone=rel_g, rel_param_vs_adamw_on_mean=rel_p, params_identical=same,
+res = dict(rank=rank, run_to_run_noise=noise, rel_grad_vs_sum_of_alone=rel_g, rel_param_vs_adamw_on_mean=rel_p, params_identical=same,
            captured=captured, losses=losses, bn_running_stats_per_rank_differ=not torch.equal(bns[0], bns[-1]))
 print("RESULT " + json.dumps(res), flush=True)
 dist.barrier()
@@ -104,8 +108,8 @@ def test_two_rank_gradients_equal_sum_of_single_rank_runs(built_lib, tmp_path):
     for r in results:
         print(r)
         # fp32 atomics / split-K order differ between runs; nothing else may
-        assert r["rel_grad_vs_sum_of_alone"] < 2e-3, r
-        assert r["rel_param_vs_adamw_on_mean"] < 5e-2, r
+        assert r["rel_grad_vs_sum_of_alone"] <= 3.0 * r["run_to_run_noise"] + 1e-3, r
+        assert r["rel_param_vs_adamw_on_mean"] < 2e-2, r   # 1 - cosine of the two update vectors
         assert r["params_identical"] and r["captured"], r
         assert r["bn_running_stats_per_rank_differ"], r  # BatchNorm statistics stay per rank (reference semantics)
         assert all(v == v for v in r["losses"])
