@@ -239,15 +239,17 @@ int pe_heads_loss(const void* hc, const void* hd, long long M, int D, const floa
 /* ------------------------------------------------------------------------------------------------
  * BiLSTM sequence model (model.py:218-228 -> torch.nn.LSTM; gates i,f,g,o, torch/nn/modules/rnn.py:842-847).
  * One call advances the four recurrences of a layer (2 sequence models x 2 directions) through time steps
- * [step_begin, step_end) (one dependent launch per step); hidden size 384.  Arrays indexed [model] (2 entries) or [model*2 + direction] (4 entries); all pointers device memory.
- *   gx : fp32 [B][T][2*1536]  input projection x W_ih^T on entry, activated gates (kept for the backward) on exit
- *   c  : fp32 [B][T][2*384]   cell state;   y : bf16 [B][T][2*384] hidden state (direction d at columns d*384)
+ * [step_begin, step_end) (one dependent launch per step); hidden size 384.  Arrays indexed [model] (2 entries) or
+ * [model*2 + direction] (4 entries); all pointers device memory.  Token tensors are TIME-MAJOR (row = t * B + b): a
+ * time step then touches one contiguous slab of B rows.
+ *   gx : fp32 [T][B][2*1536]  input projection x W_ih^T on entry, activated gates (kept for the backward) on exit
+ *   c  : fp32 [T][B][2*384]   cell state;   y : bf16 [T][B][2*384] hidden state (direction d at columns d*384)
  * ------------------------------------------------------------------------------------------------ */
 int pe_lstm_steps_fwd(int B, int T, int hidden, int step_begin, int step_end, float* const* gx, float* const* c,
                       void* const* y, const void* const* w_hh /* bf16 [1536][384] */, const float* const* b_ih,
                       const float* const* b_hh, pe_stream_t stream);
-/* backward steps (step 0 = the last forward step of each direction): dg bf16 [B][T][2*1536] receives the
- * pre-activation gate gradients, dc fp32 [B][2*384] carries dL/dc between calls, dy bf16 [B][T][2*384] is dL/dy. */
+/* backward steps (step 0 = the last forward step of each direction): dg bf16 [T][B][2*1536] receives the
+ * pre-activation gate gradients, dc fp32 [B][2*384] carries dL/dc between calls, dy bf16 [T][B][2*384] is dL/dy. */
 int pe_lstm_steps_bwd(int B, int T, int hidden, int step_begin, int step_end, const float* const* gates,
                       const float* const* c, const void* const* dy, void* const* dg, float* const* dc,
                       const void* const* w_hh, pe_stream_t stream);

@@ -21,15 +21,15 @@ constexpr int L_THREADS = 64 + 32 * L_EPI_WARPS;  // warp 0 TMA, warp 1 MMA, war
 struct LstmStepParams {
   int B, T, step, first;
   // per model (0 = classifier, 1 = detector)
-  float* gx[2];              // [B][T][2*LG] fp32: input projection in, activated gates out
-  float* c[2];               // [B][T][2*LH] fp32 cell state
-  __nv_bfloat16* y[2];       // [B][T][2*LH] bf16 hidden state
+  float* gx[2];              // [T][B][2*LG] fp32 (time-major): input projection in, activated gates out
+  float* c[2];               // [T][B][2*LH] fp32 cell state
+  __nv_bfloat16* y[2];       // [T][B][2*LH] bf16 hidden state
   // per recurrence r = model*2 + dir
   const float* b_ih[4];
   const float* b_hh[4];
   // backward only
-  const __nv_bfloat16* dy[2];  // [B][T][2*LH] gradient w.r.t. y from above
-  __nv_bfloat16* dg[2];        // [B][T][2*LG] pre-activation gate gradients
+  const __nv_bfloat16* dy[2];  // [T][B][2*LH] gradient w.r.t. y from above
+  __nv_bfloat16* dg[2];        // [T][B][2*LG] pre-activation gate gradients
   float* dc[2];                // [B][2*LH] running dL/dc
 };
 
@@ -38,7 +38,7 @@ __device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f
 __device__ __forceinline__ float tanhf_(float x) { return fmaf(2.f, __fdividef(1.f, 1.f + __expf(-2.f * x)), -1.f); }
 
 struct LstmMaps {
-  CUtensorMap act[2];  // per model: forward: y (dims 2*LH, T, B); backward: dg (dims 2*LG, T, B)
+  CUtensorMap act[2];  // per model: forward: y (dims 2*LH, B, T); backward: dg (dims 2*LG, B, T)
   CUtensorMap w[4];    // per recurrence: W_hh [LG][LH] bf16
 };
 
@@ -88,7 +88,7 @@ lstm_step_fwd_kernel(const __grid_constant__ LstmMaps maps, const LstmStepParams
         if (elect_one()) {
           mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
           mbar_arrive_expect_tx(&full_bar[s], STAGE_B);
-          tma_load_3d(&maps.act[model], &full_bar[s], sa, dir * LH + kb * 64, t_prev, b0);
+          tma_load_3d(&maps.act[model], &full_bar[s], sa, dir * LH + kb * 64, b0, t_prev);
           for (int g = 0; g < 4; ++g) tma_load_2d(&maps.w[rec], &full_bar[s], sb + g * 8192, kb * 64, g * LH + u0);
         }
         __syncwarp();
@@ -117,8 +117,8 @@ lstm_step_fwd_kernel(const __grid_constant__ LstmMaps maps, const LstmStepParams
     const int b = b0 + q * 32 + lane;
     const bool row_ok = b < p.B;
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    const long long tok = (long long)b * p.T + t;
-    const long long tok_prev = (long long)b * p.T + t_prev;
+    const long long tok = (long long)t * p.B + b;            // time-major tokens: row = t * B + b
+    const long long tok_prev = (long long)t_prev * p.B + b;
     const int pair = (warp - 2) >> 2;
     float pre[4][16], cprev[16];
     // input projection + both biases and c_{t-1} of one 16-unit chunk (independent of this step's MMA)
@@ -244,7 +244,7 @@ lstm_step_bwd_kernel(const __grid_constant__ LstmMaps maps, const LstmStepParams
         if (elect_one()) {
           mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
           mbar_arrive_expect_tx(&full_bar[s], STAGE_B);
-          tma_load_3d(&maps.act[model], &full_bar[s], sa, dir * LG + kb * 64, t_next, b0);
+          tma_load_3d(&maps.act[model], &full_bar[s], sa, dir * LG + kb * 64, b0, t_next);
           tma_load_2d(&maps.w[rec], &full_bar[s], sa + A_B, u0, kb * 64);  // [64 gate rows][64 units]: MN-major B
         }
         __syncwarp();
@@ -274,8 +274,8 @@ lstm_step_bwd_kernel(const __grid_constant__ LstmMaps maps, const LstmStepParams
     const int b = b0 + q * 32 + lane;
     const bool row_ok = b < p.B;
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    const long long tok = (long long)b * p.T + t;
-    const long long tok_pf = (long long)b * p.T + t_pf;
+    const long long tok = (long long)t * p.B + b;            // time-major tokens: row = t * B + b
+    const long long tok_pf = (long long)t_pf * p.B + b;
     const int pair = (warp - 2) >> 2;
     float dh[16], gate[4][16], ct[16], cp[16], dcs[16];
     // everything the cell backward needs except the recurrent gradient (independent of this step's MMA)
@@ -397,9 +397,9 @@ using namespace pe;
 static int lstm_maps(LstmMaps* m, const void* const* act, int act_cols, int B, int T, const void* const* w_hh,
                      bool w_mn) {
   for (int i = 0; i < 2; ++i) {
-    uint64_t dims[3] = {(uint64_t)act_cols, (uint64_t)T, (uint64_t)B};
-    uint64_t str[2] = {(uint64_t)act_cols * 2, (uint64_t)T * act_cols * 2};
-    uint32_t box[3] = {64, 1, 128};
+    uint64_t dims[3] = {(uint64_t)act_cols, (uint64_t)B, (uint64_t)T};   // time-major: [T][B][cols]
+    uint64_t str[2] = {(uint64_t)act_cols * 2, (uint64_t)B * act_cols * 2};
+    uint32_t box[3] = {64, 128, 1};
     if (int rc = pe_host::encode_tmap(&m->act[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, act[i], dims, str, box))
       return rc;
   }

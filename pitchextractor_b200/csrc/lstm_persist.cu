@@ -26,8 +26,8 @@ namespace pe {
 
 constexpr int PH = 384;          // hidden size
 constexpr int PG = 4 * PH;       // gate rows per direction
-constexpr int P_EPI_WARPS = 8;
-constexpr int P_THREADS = 64 + 32 * P_EPI_WARPS;   // warp 0 loader, warp 1 MMA, warps 2..9 epilogue
+constexpr int PF_EPI_WARPS = 16;                   // forward: 2 M-tiles x 4 lane quarters x 2 column halves
+constexpr int PF_THREADS = 64 + 32 * PF_EPI_WARPS;
 constexpr int P_W_BYTES = 6 * 32768;               // resident weight slice (both directions of use: 192 KB)
 constexpr int P_RING_BYTES = 32768;
 // backward: the M = 128 MMA sees the CTA's 64 units twice (A descriptor atom stride 0), so that TMEM lanes 64..127 hold a
@@ -38,18 +38,18 @@ constexpr int P_RING_BYTES = 32768;
 
 struct LstmSeqParams {
   int B, T, nbt, b_first;      // batch rows b_first .. b_first + nbt * NB - 1 are handled by this launch
-  float* gx[2];                // per model: [B][T][2*PG] fp32: input projection in, activated gates out
-  float* c[2];                 // [B][T][2*PH] fp32 cell state
-  __nv_bfloat16* y[2];         // [B][T][2*PH] bf16 hidden state
+  float* gx[2];                // per model: [T][B][2*PG] fp32 (time-major): input projection in, activated gates out
+  float* c[2];                 // [T][B][2*PH] fp32 cell state
+  __nv_bfloat16* y[2];         // [T][B][2*PH] bf16 hidden state
   const float* b_ih[4];        // per recurrence r = model * 2 + dir
   const float* b_hh[4];
-  const __nv_bfloat16* dy[2];  // backward: [B][T][2*PH] gradient w.r.t. y from above
-  __nv_bfloat16* dg[2];        // backward: [B][T][2*PG] pre-activation gate gradients
+  const __nv_bfloat16* dy[2];  // backward: [T][B][2*PH] gradient w.r.t. y from above
+  __nv_bfloat16* dg[2];        // backward: [T][B][2*PG] pre-activation gate gradients
   int* flags;                  // [4][nbt][T] arrival counters (zeroed before the launch)
 };
 
 struct LstmSeqMaps {
-  CUtensorMap act[2];  // per model: forward y (dims 2*PH, T, B); backward dg (dims 2*PG, T, B); box {64, 1, NB}
+  CUtensorMap act[2];  // per model: forward y (dims 2*PH, B, T); backward dg (dims 2*PG, B, T); box {64, NB, 1}
   CUtensorMap w[4];    // per recurrence W_hh: forward 3-D view (k, unit, gate) box {64, 8, 4}; backward 2-D box {64, 64}
 };
 
@@ -85,6 +85,8 @@ template <int NB>
 struct PlCfg {
   static constexpr int STAGE_B = NB * 128;                                  // one [NB x 64] bf16 k-block
   static constexpr int STAGES = (P_RING_BYTES / STAGE_B) > 12 ? 12 : (P_RING_BYTES / STAGE_B);
+  static constexpr int BWD_EPI_WARPS = NB >= 64 ? 16 : 8;                   // backward epilogue warps
+  static constexpr int BWD_THREADS = 64 + 32 * BWD_EPI_WARPS;
   static constexpr size_t SMEM = (size_t)P_W_BYTES + (size_t)STAGES * STAGE_B + (2 * STAGES + 4) * 8 + 16 + 1024;
 };
 
@@ -92,7 +94,7 @@ struct PlCfg {
 // forward
 // =================================================================================================================
 template <int NB>
-__global__ void __launch_bounds__(P_THREADS, 1)
+__global__ void __launch_bounds__(PF_THREADS, 1)
 lstm_seq_fwd_kernel(const __grid_constant__ LstmSeqMaps maps, const LstmSeqParams p) {
   using C = PlCfg<NB>;
   constexpr int KB = PH / 64;  // 6 k-blocks per step
@@ -120,7 +122,7 @@ lstm_seq_fwd_kernel(const __grid_constant__ LstmSeqMaps maps, const LstmSeqParam
     }
     mbar_init(w_bar, 1);
     mbar_init(done_bar, 1);
-    mbar_init(free_bar, P_EPI_WARPS);
+    mbar_init(free_bar, PF_EPI_WARPS);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, TCOLS);
@@ -148,7 +150,7 @@ lstm_seq_fwd_kernel(const __grid_constant__ LstmSeqMaps maps, const LstmSeqParam
           const uint32_t s = it % C::STAGES;
           mbar_wait(&empty_bar[s], ((it / C::STAGES) & 1u) ^ 1u);
           mbar_arrive_expect_tx(&full_bar[s], C::STAGE_B);
-          tma_load_3d(&maps.act[model], &full_bar[s], s_ring + s * C::STAGE_B, dir * PH + kb * 64, t_prev, b0);
+          tma_load_3d(&maps.act[model], &full_bar[s], s_ring + s * C::STAGE_B, dir * PH + kb * 64, b0, t_prev);
         }
       }
     }
@@ -182,42 +184,52 @@ lstm_seq_fwd_kernel(const __grid_constant__ LstmSeqMaps maps, const LstmSeqParam
       it += KB;
     }
   } else {
-    // ------------------------------------------------------------ epilogue: 8 warps = 2 M-tiles x 4 lane quarters
-    const int q = warp & 3, m = (warp - 2) >> 2;
+    // ------------------------------------------------------------ epilogue: 16 warps = 2 M-tiles x 4 lane quarters x
+    // 2 column halves (the epilogue is the longest part of a step at wide batch tiles: twice the warps hide its latencies)
+    const int ew = warp - 2;
+    const int q = warp & 3, m = (ew >> 2) & 1, ch = ew >> 3;
     const int gl = lane >> 3, ul = lane & 7;             // this lane's gate and unit inside the quarter
     const int u = u0 + (m * 4 + q) * 8 + ul;
-    const uint32_t trow = tm + ((uint32_t)(q * 32) << 16) + m * NB;
+    constexpr int NGRP = NB / 8;                         // groups of 4 batch columns handled by this warp
+    const int colw = ch * (NB / 2);                      // its first column
+    const uint32_t trow = tm + ((uint32_t)(q * 32) << 16) + m * NB + colw;
     const float bias = __ldg(p.b_ih[rec] + gl * PH + u) + __ldg(p.b_hh[rec] + gl * PH + u);
     const float a_s = gl == 2 ? 2.f : 1.f, a_o = gl == 2 ? -1.f : 0.f;   // act(x) = a_s * sigmoid(a_s * x) + a_o
     const bool hi1 = (gl & 2) != 0, hi0 = (gl & 1) != 0;
-    float cst[NB / 4];
+    float cst[NGRP];
 #pragma unroll
-    for (int j = 0; j < NB / 4; ++j) cst[j] = 0.f;
-    float* gxm = p.gx[model] + dir * PG + gl * PH + u;
-    float* cm = p.c[model] + dir * PH + u;
-    __nv_bfloat16* ym = p.y[model] + dir * PH + u;
+    for (int j = 0; j < NGRP; ++j) cst[j] = 0.f;
+    // Time-major tensors ([T][B][...]): a step touches one contiguous slab of B rows (DRAM pages stay open), a batch
+    // column is one row (12 KB / 3 KB / 1.5 KB) further: per-step base pointer + small constant byte offsets
+    const int nvalid = min(NB, p.B - b0) - colw;         // valid columns of this warp's range (may be <= 0)
+    constexpr uint32_t sg = 2u * PG * 4u, sc = 2u * PH * 4u, sy = sc / 2u;
+    const size_t tg = (size_t)p.B * sg, tc = (size_t)p.B * sc, ty = (size_t)p.B * sy;   // bytes per time step
+    char* gx0 = reinterpret_cast<char*>(p.gx[model] + (long long)(b0 + colw) * (2 * PG) + dir * PG + gl * PH + u);
+    char* c0p = reinterpret_cast<char*>(p.c[model] + (long long)(b0 + colw + gl) * (2 * PH) + dir * PH + u);
+    char* y0p = reinterpret_cast<char*>(p.y[model] + (long long)(b0 + colw + gl) * (2 * PH) + dir * PH + u);
     // Input projections stream through a register FIFO PF groups (of 4 batch columns) deep, filled across step
     // boundaries: the loads of a step's first groups are in flight while the previous step finishes, so neither the DRAM
     // latency of the strided [b][t] rows nor the MMA wait is exposed per group.
-    constexpr int NGRP = NB / 4;
-    constexpr int PF = NGRP < 8 ? NGRP : 8;
+    constexpr int PF = NGRP < 4 ? NGRP : 4;
     float zq[PF][4];
-    auto load_group = [&](int tt, int j, float* z) {
+    auto load_group = [&](const char* base, int j, float* z) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int b = b0 + 4 * j + e;
-        z[e] = b < p.B ? gxm[((long long)b * p.T + tt) * (2 * PG)] : 0.f;
-      }
+      for (int e = 0; e < 4; ++e)
+        z[e] = (4 * j + e) < nvalid ? *reinterpret_cast<const float*>(base + (uint32_t)(4 * j + e) * sg) : 0.f;
     };
     {
       const int t_first = dir ? p.T - 1 : 0;
 #pragma unroll
-      for (int j = 0; j < PF; ++j) load_group(t_first, j, zq[j]);
+      for (int j = 0; j < PF; ++j) load_group(gx0 + (size_t)t_first * tg, j, zq[j]);
     }
     for (int step = 0; step < p.T; ++step) {
       const int t = dir ? p.T - 1 - step : step;
       const int t_nxt = dir ? t - 1 : t + 1;
       const bool more = step + 1 < p.T;
+      char* gxt = gx0 + (size_t)t * tg;
+      const char* gxn = gx0 + (size_t)(more ? t_nxt : t) * tg;
+      char* ct = c0p + (size_t)t * tc;
+      char* yt = y0p + (size_t)t * ty;
       if (step > 0) {
         mbar_wait(done_bar, (uint32_t)(step - 1) & 1u);
         tc_fence_after();
@@ -228,8 +240,8 @@ lstm_seq_fwd_kernel(const __grid_constant__ LstmSeqMaps maps, const LstmSeqParam
 #pragma unroll
         for (int e = 0; e < 4; ++e) zin[e] = zq[j % PF][e];
         // refill this FIFO slot: a later group of this step, or an early group of the next step
-        if (j + PF < NGRP) load_group(t, j + PF, zq[j % PF]);
-        else if (more) load_group(t_nxt, j + PF - NGRP, zq[j % PF]);
+        if (j + PF < NGRP) load_group(gxt, j + PF, zq[j % PF]);
+        else if (more) load_group(gxn, j + PF - NGRP, zq[j % PF]);
         uint32_t acc[4] = {0u, 0u, 0u, 0u};
         if (step > 0) {
           tmem_ld4(trow + 4 * j, acc);
@@ -240,8 +252,8 @@ lstm_seq_fwd_kernel(const __grid_constant__ LstmSeqMaps maps, const LstmSeqParam
         for (int e = 0; e < 4; ++e) {
           const float z = zin[e] + bias + __uint_as_float(acc[e]);
           a[e] = fmaf(a_s, sigmoid_fast(a_s * z), a_o);
-          const int b = b0 + 4 * j + e;
-          if (b < p.B) gxm[((long long)b * p.T + t) * (2 * PG)] = a[e];   // activated gate, kept for the backward pass
+          if ((4 * j + e) < nvalid)   // activated gate, kept for the backward pass
+            *reinterpret_cast<float*>(gxt + (uint32_t)(4 * j + e) * sg) = a[e];
         }
         // 4 x 4 transpose over the lanes (gate 0..3, same unit): afterwards this lane holds i, f, g, o of column 4j + gl
         {
@@ -254,21 +266,19 @@ lstm_seq_fwd_kernel(const __grid_constant__ LstmSeqMaps maps, const LstmSeqParam
           const float x0 = __shfl_xor_sync(0xffffffffu, t0, 8), x1 = __shfl_xor_sync(0xffffffffu, t1, 8);
           // column 2 * hi1 + hi0 == gl: gates 0..3
           const float g0 = hi0 ? x0 : b00, g1 = hi0 ? b01 : x0, g2 = hi0 ? x1 : b10, g3 = hi0 ? b11 : x1;
-          const int b = b0 + 4 * j + gl;
           const float cn = fmaf(g1, cst[j], g0 * g2);
           cst[j] = cn;
           const float hn = g3 * tanh_fast(cn);
-          if (b < p.B) {
-            const long long tok = (long long)b * p.T + t;
-            cm[tok * (2 * PH)] = cn;
-            ym[tok * (2 * PH)] = __float2bfloat16(hn);
+          if ((4 * j + gl) < nvalid) {
+            *reinterpret_cast<float*>(ct + (uint32_t)(4 * j) * sc) = cn;
+            *reinterpret_cast<__nv_bfloat16*>(yt + (uint32_t)(4 * j) * sy) = __float2bfloat16(hn);
           }
         }
       }
       // publish h_t: every writer makes its stores visible to the async proxy, then one release-add per CTA
       fence_proxy_async_global();
       tc_fence_before();
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * P_EPI_WARPS) : "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * PF_EPI_WARPS) : "memory");
       if (threadIdx.x == 64) {
         __threadfence();
         red_release_gpu_add(flags + step, 1);
@@ -285,7 +295,7 @@ lstm_seq_fwd_kernel(const __grid_constant__ LstmSeqMaps maps, const LstmSeqParam
 // backward
 // =================================================================================================================
 template <int NB>
-__global__ void __launch_bounds__(P_THREADS, 1)
+__global__ void __launch_bounds__(PlCfg<NB>::BWD_THREADS, 1)
 lstm_seq_bwd_kernel(const __grid_constant__ LstmSeqMaps maps, const LstmSeqParams p) {
   using C = PlCfg<NB>;
   constexpr int KB = PG / 64;  // 24 k-blocks (gate rows) per step
@@ -313,7 +323,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ LstmSeqMaps maps, const LstmSeqParam
     }
     mbar_init(w_bar, 1);
     mbar_init(done_bar, 1);
-    mbar_init(free_bar, P_EPI_WARPS);
+    mbar_init(free_bar, C::BWD_EPI_WARPS);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, TCOLS);
@@ -340,7 +350,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ LstmSeqMaps maps, const LstmSeqParam
           const uint32_t s = it % C::STAGES;
           mbar_wait(&empty_bar[s], ((it / C::STAGES) & 1u) ^ 1u);
           mbar_arrive_expect_tx(&full_bar[s], C::STAGE_B);
-          tma_load_3d(&maps.act[model], &full_bar[s], s_ring + s * C::STAGE_B, dir * PG + kb * 64, t_next, b0);
+          tma_load_3d(&maps.act[model], &full_bar[s], s_ring + s * C::STAGE_B, dir * PG + kb * 64, b0, t_next);
         }
       }
     }
@@ -373,41 +383,49 @@ lstm_seq_bwd_kernel(const __grid_constant__ LstmSeqMaps maps, const LstmSeqParam
       it += KB;
     }
   } else {
-    // epilogue: lane quarter q -> units (q & 1) * 32 + lane (quarters 2, 3 hold the copy); the 4 (copy, warp-half)
-    // combinations split the NB batch columns
-    const int q = warp & 3, half = (warp - 2) >> 2;
+    // epilogue: lane quarter q -> units (q & 1) * 32 + lane (quarters 2, 3 hold the copy); the (copy, warp group)
+    // combinations split the NB batch columns: 8 or 16 warps (wide batch tiles: more warps hide the epilogue's latencies)
+    constexpr int PARTS = C::BWD_EPI_WARPS / 4;           // warps per lane quarter
+    const int q = warp & 3, part = (warp - 2) >> 2;
     const int u = u0 + (q & 1) * 32 + lane;
-    constexpr int NC = P_BWD_DUP ? NB / 4 : NB / 2;       // columns per thread
-    const int col0 = P_BWD_DUP ? ((q >> 1) * 2 + half) * NC : half * NC;
+    constexpr int NC = P_BWD_DUP ? NB / (2 * PARTS) : NB / PARTS;       // columns per thread
+    const int col0 = P_BWD_DUP ? ((q >> 1) * PARTS + part) * NC : part * NC;
     const bool lanes_valid = P_BWD_DUP || q < 2;
     const uint32_t trow = tm + ((uint32_t)(q * 32) << 16) + col0;
     float dcs[NC];
 #pragma unroll
     for (int j = 0; j < NC; ++j) dcs[j] = 0.f;
-    const float* gxm = p.gx[model] + dir * PG + u;
-    const float* cm = p.c[model] + dir * PH + u;
-    const __nv_bfloat16* dym = p.dy[model] + dir * PH + u;
-    __nv_bfloat16* dgm = p.dg[model] + dir * PG + u;
+    // time-major tensors: per-step base pointers + constant byte offsets per batch column
+    const int nvalid = lanes_valid ? min(NB, p.B - b0) - col0 : 0;   // valid columns of this thread's range
+    constexpr uint32_t sg = 2u * PG * 4u, sc = 2u * PH * 4u, sy = 2u * PH * 2u, sd = 2u * PG * 2u;
+    const size_t tg = (size_t)p.B * sg, tcb = (size_t)p.B * sc, ty = (size_t)p.B * sy, td = (size_t)p.B * sd;
+    const char* gx0 = reinterpret_cast<const char*>(p.gx[model] + (long long)(b0 + col0) * (2 * PG) + dir * PG + u);
+    const char* c0p = reinterpret_cast<const char*>(p.c[model] + (long long)(b0 + col0) * (2 * PH) + dir * PH + u);
+    const char* y0p = reinterpret_cast<const char*>(p.dy[model] + (long long)(b0 + col0) * (2 * PH) + dir * PH + u);
+    char* d0p = reinterpret_cast<char*>(p.dg[model] + (long long)(b0 + col0) * (2 * PG) + dir * PG + u);
     // Everything the cell backward needs except the recurrent gradient streams through a register FIFO two groups (of 4
     // batch columns) deep, filled across step boundaries (7 loads per cell: dy, the four gates, c_t, c_{t-1}).
     constexpr int NG4 = NC / 4;                  // groups of 4 columns per thread
-    constexpr int PF = NG4 < 2 ? NG4 : 2;
+    constexpr int PF = (NG4 < 2 || C::BWD_EPI_WARPS == 16) ? 1 : 2;   // 16 warps: 96 registers per thread
     struct Cell { float dy, ig, fg, gg, og, ct, cp; };
     Cell cq[PF][4];
     auto load_group = [&](int tt, int g4, Cell* cc) {
       const int t_pf = dir ? tt + 1 : tt - 1;     // forward-order predecessor (c_{t-1})
       const bool has_prev = dir ? (tt < p.T - 1) : (tt > 0);
+      const char* gp = gx0 + (size_t)tt * tg;
+      const char* cp = c0p + (size_t)tt * tcb;
+      const char* cpp = c0p + (size_t)(has_prev ? t_pf : tt) * tcb;
+      const char* yp = y0p + (size_t)tt * ty;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int b = b0 + col0 + 4 * g4 + e;
+        const int col = 4 * g4 + e;
         Cell c{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (b < p.B && lanes_valid) {
-          const long long tok = (long long)b * p.T + tt;
-          const float* gp = gxm + tok * (2 * PG);
-          c.ig = gp[0]; c.fg = gp[PH]; c.gg = gp[2 * PH]; c.og = gp[3 * PH];
-          c.ct = cm[tok * (2 * PH)];
-          c.cp = has_prev ? cm[((long long)b * p.T + t_pf) * (2 * PH)] : 0.f;
-          c.dy = __bfloat162float(dym[tok * (2 * PH)]);
+        if (col < nvalid) {
+          const float* g = reinterpret_cast<const float*>(gp + (uint32_t)col * sg);
+          c.ig = g[0]; c.fg = g[PH]; c.gg = g[2 * PH]; c.og = g[3 * PH];
+          c.ct = *reinterpret_cast<const float*>(cp + (uint32_t)col * sc);
+          c.cp = has_prev ? *reinterpret_cast<const float*>(cpp + (uint32_t)col * sc) : 0.f;
+          c.dy = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(yp + (uint32_t)col * sy));
         }
         cc[e] = c;
       }
@@ -421,6 +439,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ LstmSeqMaps maps, const LstmSeqParam
       const int t = dir ? step : p.T - 1 - step;
       const int t_nxt = dir ? t + 1 : t - 1;
       const bool more = step + 1 < p.T;
+      char* dgt = d0p + (size_t)t * td;
       if (step > 0) {
         mbar_wait(done_bar, (uint32_t)(step - 1) & 1u);
         tc_fence_after();
@@ -440,14 +459,13 @@ lstm_seq_bwd_kernel(const __grid_constant__ LstmSeqMaps maps, const LstmSeqParam
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int j = 4 * g4 + e;
-          const int b = b0 + col0 + j;
-          if (b < p.B && lanes_valid) {
+          if (j < nvalid) {
             const Cell c = cur[e];
             const float dh = c.dy + __uint_as_float(acc[e]);
             const float tc = tanh_fast(c.ct);
             const float dc = dcs[j] + dh * c.og * (1.f - tc * tc);
             dcs[j] = dc * c.fg;
-            __nv_bfloat16* dp = dgm + ((long long)b * p.T + t) * (2 * PG);
+            __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(dgt + (uint32_t)j * sd);
             dp[0] = __float2bfloat16(dc * c.gg * c.ig * (1.f - c.ig));
             dp[PH] = __float2bfloat16(dc * c.cp * c.fg * (1.f - c.fg));
             dp[2 * PH] = __float2bfloat16(dc * c.ig * (1.f - c.gg * c.gg));
@@ -457,7 +475,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ LstmSeqMaps maps, const LstmSeqParam
       }
       fence_proxy_async_global();
       tc_fence_before();
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * P_EPI_WARPS) : "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * C::BWD_EPI_WARPS) : "memory");
       if (threadIdx.x == 64) {
         __threadfence();
         red_release_gpu_add(flags + step, 1);
@@ -480,9 +498,9 @@ using namespace pe;
 static int seq_maps(LstmSeqMaps* m, const void* const* act, int act_cols, int B, int T, int NB, const void* const* w_hh,
                     bool backward) {
   for (int i = 0; i < 2; ++i) {
-    uint64_t dims[3] = {(uint64_t)act_cols, (uint64_t)T, (uint64_t)B};
-    uint64_t str[2] = {(uint64_t)act_cols * 2, (uint64_t)T * act_cols * 2};
-    uint32_t box[3] = {64, 1, (uint32_t)NB};
+    uint64_t dims[3] = {(uint64_t)act_cols, (uint64_t)B, (uint64_t)T};   // time-major: [T][B][cols]
+    uint64_t str[2] = {(uint64_t)act_cols * 2, (uint64_t)B * act_cols * 2};
+    uint32_t box[3] = {64, (uint32_t)NB, 1};
     if (int rc = pe_host::encode_tmap(&m->act[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, act[i], dims, str, box)) return rc;
   }
   for (int r = 0; r < 4; ++r) {
@@ -508,7 +526,8 @@ static int launch_seq(bool backward, const LstmSeqMaps& maps, LstmSeqParams p, c
   if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PE_ERR_LAUNCH;
   void* args[2] = {(void*)&maps, (void*)&p};
   dim3 grid(PH / 64, p.nbt, 4);
-  if (cudaLaunchCooperativeKernel(fn, grid, dim3(P_THREADS), args, smem, st) != cudaSuccess) return PE_ERR_LAUNCH;
+  if (cudaLaunchCooperativeKernel(fn, grid, dim3(backward ? PlCfg<NB>::BWD_THREADS : PF_THREADS), args, smem, st) != cudaSuccess)
+    return PE_ERR_LAUNCH;
   return PE_OK;
 }
 

@@ -90,6 +90,7 @@ class Engine:
         self.use_graph = os.environ.get("PE_CUDA_GRAPH", "1") != "0"
         # BiLSTM recurrences: persistent kernel (default) or one launch per time step (PE_LSTM_STEPWISE=1)
         self.lstm_persistent = os.environ.get("PE_LSTM_STEPWISE", "0") != "1"
+        self.lstm_persistent_bwd_max_batch = int(os.environ.get("PE_LSTM_BWD_MAXB", "64"))
         self._graphs = {}
         self.bf16_fresh = False
         self._capturing = False
@@ -441,7 +442,13 @@ class Engine:
         V, W16 = self.view, self.bview
         M, Hh, G = B * T, 384, 1536
         drop = self._drop(self.p_lstm, training)
-        X = [Xc, Xd]
+        # Inside the recurrent stacks every token tensor is TIME-MAJOR (row = t * B + b): a time step of the recurrence
+        # then reads / writes one contiguous slab of B rows instead of B rows that lie T rows (megabytes) apart.
+        X = []
+        for mi, Xb in enumerate((Xc, Xd)):
+            Xt = self.buf("lx_tm%d" % mi, (M, Xb.shape[1]))
+            Xt.view(T, B, -1).copy_(Xb.view(B, T, -1).transpose(0, 1))
+            X.append(Xt)
         Y = None
         for l in range(self.num_layers):
             In = 512 if l == 0 else 2 * Hh
@@ -494,7 +501,7 @@ class Engine:
             whh = self._ptrs([W16["%s.model.weight_hh_%s" % n] for n in names])
             # measured on a B200 (profiles/r02_lstm_breakdown.txt): the persistent backward wins while the batch tile is
             # narrow (its epilogue is then latency-bound); at 128-column tiles the per-step launches are faster
-            if self.lstm_persistent and B <= 64:
+            if self.lstm_persistent and B <= self.lstm_persistent_bwd_max_batch:
                 ws = self._lstm_workspace(B, T)
                 call("pe_lstm_seq_bwd", c_int(B), c_int(T), c_int(Hh), gx_a, c_a, dy_a, dg_a, whh, ptr(ws),
                      ctypes.c_size_t(ws.numel() * 4), stream())
@@ -515,11 +522,12 @@ class Engine:
                 # recurrent weights: dW_hh += sum_t dgates_t^T h_{t-1} (time-shifted token views)
                 dg_off, y_off = (1, 0) if d == 0 else (0, 1)
                 gw = self.mat(w_hh, G, Hh, "grad")
-                for c0 in (0, 192):
+                for c0 in (0, 192):  # time-major: "images" = the T - 1 time steps, B token rows each, shifted by B rows
                     call("pe_wgrad_tokens",
-                         ctypes.c_void_p(dG[mi].data_ptr() + 2 * (dg_off * 2 * G + d * G)), c_ll(2 * G), c_ll(T * 2 * G),
-                         ctypes.c_void_p(Y[mi].data_ptr() + 2 * (y_off * 2 * Hh + d * Hh + c0)), c_ll(2 * Hh),
-                         c_ll(T * 2 * Hh), ctypes.c_void_p(gw.data_ptr() + 4 * c0), c_ll(Hh), c_int(B), c_int(T - 1),
+                         ctypes.c_void_p(dG[mi].data_ptr() + 2 * (dg_off * B * 2 * G + d * G)), c_ll(2 * G),
+                         c_ll(B * 2 * G),
+                         ctypes.c_void_p(Y[mi].data_ptr() + 2 * (y_off * B * 2 * Hh + d * Hh + c0)), c_ll(2 * Hh),
+                         c_ll(B * 2 * Hh), ctypes.c_void_p(gw.data_ptr() + 4 * c0), c_ll(Hh), c_int(T - 1), c_int(B),
                          c_int(192), c_int(G), c_int(0), stream())
                 # input gradient (both directions accumulate into the same tensor)
                 if d == 0:
@@ -532,14 +540,32 @@ class Engine:
                     call("pe_dropout_bf16", ptr(dX[mi]), ptr(dX[mi]), c_ll(M * In), c_u(drop[0]), c_f(drop[1]),
                          c_ull(self._seed(128 + 4 * l + mi)), stream())
             dY = dX
-        return dY[0], dY[1]
+        out = []
+        for mi in range(2):  # back to batch-major tokens for the conv trunk
+            d = self.buf("ldx_bm%d" % mi, (M, 512))
+            d.view(B, T, -1).copy_(dY[mi].view(T, B, -1).transpose(0, 1))
+            out.append(d)
+        return out[0], out[1]
 
     # ------------------------------------------------------------------ heads
+    def _tok(self, x):
+        """[M] per-token vector, batch-major (b * T + t) <-> the order of the sequence models' outputs (time-major
+        t * B + b for the BiLSTM stacks); an involution only in shape, so the direction is explicit."""
+        if x is None or self.seq_type != "bilstm":
+            return x
+        return x.view(self._B, self._T).t().contiguous().view(-1)
+
+    def _tok_back(self, x):
+        if self.seq_type != "bilstm":
+            return x
+        return x.view(self._T, self._B).t().contiguous().view(-1)
+
     def _heads(self, f0, sil, lambda_f0, grad_scale, want_grad, gc_ext=None, gd_ext=None):
         V, g = self.view, self.gview
         M, D = self._B * self._T, self.seq_dim
-        self._pred_f0 = self.buf("pred_f0", (M,), torch.float32)
-        self._pred_sil = self.buf("pred_sil", (M,), torch.float32)
+        f0, sil, gc_ext, gd_ext = self._tok(f0), self._tok(sil), self._tok(gc_ext), self._tok(gd_ext)
+        pred_f0 = self.buf("pred_f0", (M,), torch.float32)
+        pred_sil = self.buf("pred_sil", (M,), torch.float32)
         dHc = self.buf("dHc", (M, D)) if want_grad else None
         dHd = self.buf("dHd", (M, D)) if want_grad else None
         self.loss_acc.zero_()
@@ -550,10 +576,11 @@ class Engine:
             gw = lambda n, _gw=gw: (gw_c[n] if n in gw_c and want_grad else _gw(n))
         call("pe_heads_loss", ptr(self._Hc), ptr(self._Hd), c_ll(M), c_int(D), ptr(V["classifier.weight"]),
              ptr(V["classifier.bias"]), ptr(V["detector.weight"]), ptr(V["detector.bias"]), ptr(f0), ptr(sil),
-             c_f(lambda_f0), c_f(grad_scale), ptr(self._pred_f0), ptr(self._pred_sil),
+             c_f(lambda_f0), c_f(grad_scale), ptr(pred_f0), ptr(pred_sil),
              ptr(self.loss_acc) if f0 is not None else None, ptr(self.loss_out) if f0 is not None else None,
              ptr(gc_ext), ptr(gd_ext), ptr(dHc), ptr(dHd), gw("classifier.weight"), gw("classifier.bias"),
              gw("detector.weight"), gw("detector.bias"), stream())
+        self._pred_f0, self._pred_sil = self._tok_back(pred_f0), self._tok_back(pred_sil)   # batch-major for callers
         return dHc, dHd
 
     # ------------------------------------------------------------------ backward
@@ -864,7 +891,11 @@ class Engine:
         B, T = self._B, self._T
         self._predict_only()
         if self.num_class > 1:
-            self._out_cls = self._cls_logits[:, :self.num_class].reshape(B, T, self.num_class)
+            logits = self._cls_logits[:, :self.num_class]
+            if self.seq_type == "bilstm":  # rows are time-major there
+                self._out_cls = logits.reshape(T, B, self.num_class).transpose(0, 1).contiguous()
+            else:
+                self._out_cls = logits.reshape(B, T, self.num_class)
         else:
             self._out_cls = self._pred_f0.view(B, T, 1)
         self._out_det = self._pred_sil.view(B, T)
@@ -909,6 +940,8 @@ class Engine:
         W, _, npad = self._classifier_pad()
         g = self.buf("cls_gpad", (M, npad))
         g.zero_()
+        if self.seq_type == "bilstm":
+            dcls = dcls.reshape(self._B, self._T, nc).transpose(0, 1)
         g[:, :nc].copy_(dcls.reshape(M, nc))
         ops.gemm(g, W, dHc, M, D, npad, b_mn=True)
         dW = self.buf("cls_dw", (npad, D), torch.float32)
