@@ -807,6 +807,16 @@ extern "C" int pe_gemm_bf16(const void* A, long long lda, int a_mn, const void* 
   int bn = N >= 256 ? 256 : ((N + 15) / 16) * 16;
   if (p.b_mn) bn = ((bn + 63) / 64) * 64;
   if (bn > 256) bn = 256;
+  // Wave quantisation: with 256-wide tiles a [12288 x 512] output is 192 tiles = 1.3 waves of 148 CTAs (the second wave
+  // 30 % full); 128-wide tiles make it 384 half-size tiles = 2.6 waves.  Narrow tiles when the last wave would otherwise
+  // be less than two-thirds full and the narrower tiling fills it better.
+  if (bn == 256 && splits == 1 && (N % 128) == 0) {
+    const long long sms = pe_host::num_sms();
+    const long long t256 = (long long)((M + 127) / 128) * ((N + 255) / 256), t128 = (long long)((M + 127) / 128) * (N / 128);
+    auto waste = [&](long long tiles) { return (double)(((tiles + sms - 1) / sms) * sms - tiles) / (double)(((tiles + sms - 1) / sms) * sms); };
+    static const int force = getenv("PE_TC_BN") ? atoi(getenv("PE_TC_BN")) : 0;  // tuning knob: 128 / 256
+    if (force == 128 || (force == 0 && waste(t256) > 0.33 && waste(t128) < waste(t256) - 0.1)) bn = 128;
+  }
   p.block_n = bn;
   p.a_boxes = 2;
   p.b_boxes = bn / 64;
