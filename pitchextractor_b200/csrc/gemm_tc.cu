@@ -810,7 +810,7 @@ extern "C" int pe_gemm_bf16(const void* A, long long lda, int a_mn, const void* 
   // Wave quantisation: with 256-wide tiles a [12288 x 512] output is 192 tiles = 1.3 waves of 148 CTAs (the second wave
   // 30 % full); 128-wide tiles make it 384 half-size tiles = 2.6 waves.  Narrow tiles when the last wave would otherwise
   // be less than two-thirds full and the narrower tiling fills it better.
-  if (bn == 256 && splits == 1 && (N % 128) == 0) {
+  if (bn == 256 && splits == 1 && (N % 128) == 0 && !ep->stats_mode) {  // (column statistics need one tile per row block)
     const long long sms = pe_host::num_sms();
     const long long t256 = (long long)((M + 127) / 128) * ((N + 255) / 256), t128 = (long long)((M + 127) / 128) * (N / 128);
     auto waste = [&](long long tiles) { return (double)(((tiles + sms - 1) / sms) * sms - tiles) / (double)(((tiles + sms - 1) / sms) * sms); };

@@ -672,7 +672,8 @@ static int attn_threads(int T) { return ((T + 31) / 32) * 32; }
 int pe_attn_fwd_tc(const void* qkv, int B, int H, unsigned drop_thresh, float drop_scale, unsigned long long seed,
                    void* ctx, float* lse, cudaStream_t stream);
 int pe_attn_bwd_tc(const void* qkv, const void* ctx, const void* dctx, const float* lse, int B, int H,
-                   unsigned drop_thresh, float drop_scale, unsigned long long seed, void* dqkv, cudaStream_t stream);
+                   unsigned drop_thresh, float drop_scale, unsigned long long seed, void* dqkv, float* delta,
+                   cudaStream_t stream);
 extern "C" int pe_attn_fwd(const void* qkv, int B, int T, int H, int head_dim, unsigned drop_thresh, float drop_scale,
                            unsigned long long seed, void* ctx, float* lse, int force_simt, pe_stream_t stream) {
   if (int rc = pe_host::check_arch()) return rc;
@@ -698,7 +699,7 @@ extern "C" int pe_attn_bwd(const void* qkv, const void* ctx, const void* dctx, c
   if (!qkv || !ctx || !dctx || !lse || !dqkv || !delta || B <= 0 || T <= 0 || T > 256 || H <= 0 || head_dim != HD)
     return PE_ERR_BAD_SHAPE;
   if (T == 192 && !force_simt)
-    return pe_attn_bwd_tc(qkv, ctx, dctx, lse, B, H, drop_thresh, drop_scale, seed, dqkv, PE_ST(stream));
+    return pe_attn_bwd_tc(qkv, ctx, dctx, lse, B, H, drop_thresh, drop_scale, seed, dqkv, delta, PE_ST(stream));
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
