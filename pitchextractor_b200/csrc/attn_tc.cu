@@ -108,7 +108,7 @@ constexpr int AFW_SMEM = 3 * BOX_B + 2 * BOX_B + BOX_B + 3 * BOX_B + 2 * 128 * 4
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, int H, unsigned drop_thresh, float drop_scale,
                    unsigned long long seed, __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse) {
-  seed = pe_salted(seed);
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
   uint8_t* sK = smem;                      // [192 x 64]
@@ -129,6 +129,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, int H, unsigned d
     fence_barrier_init();
   }
   __syncthreads();
+  pdl_wait();
+  seed = pe_salted(seed);
   if (warp == 0) {
     if (elect_one()) {  // loads first: they run while the TMEM allocation (which may wait for a co-resident CTA) settles
       mbar_arrive_expect_tx(&bars[0], 8 * BOX_B);
@@ -241,19 +243,18 @@ constexpr int ABW_SMEM = 12 * BOX_B + 3 * AT * 4 + 64;  // 96 KB of tiles | lse,
 constexpr int ABW_CH = 32, ABW_NCH = AT / ABW_CH;       // chunk width, chunks per unit
 constexpr int ABW_THREADS = ATT_THREADS + 32;
 
-// delta[(b*H + h)*T + t] = sum_d dO[b*T + t][h*64 + d] * O[b*T + t][h*64 + d]; one thread per (token, head)
+// delta[(b*H + h)*T + t] = sum_d dO[b*T + t][h*64 + d] * O[b*T + t][h*64 + d]; eight lanes per (token, head), each one
+// 16-byte load of both tensors (a warp reads 512 contiguous bytes of a token row), summed by three shuffles
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const __nv_bfloat16* __restrict__ ctx, const __nv_bfloat16* __restrict__ dctx, int rows, int H,
                   float* __restrict__ delta) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rows * H) return;
-  const int row = i / H, h = i - row * H;
-  const uint4* po = reinterpret_cast<const uint4*>(ctx + ((long long)row * H + h) * AD);
-  const uint4* pd = reinterpret_cast<const uint4*>(dctx + ((long long)row * H + h) * AD);
+  pdl_trigger();
+  pdl_wait();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one per 8 bf16
+  const long long total = (long long)rows * H * 8;
   float acc = 0.f;
-#pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    const uint4 a = po[u], c = pd[u];
+  if (i < total) {
+    const uint4 a = reinterpret_cast<const uint4*>(ctx)[i], c = reinterpret_cast<const uint4*>(dctx)[i];
     const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
     const __nv_bfloat162* hc = reinterpret_cast<const __nv_bfloat162*>(&c);
 #pragma unroll
@@ -263,15 +264,22 @@ attn_delta_kernel(const __nv_bfloat16* __restrict__ ctx, const __nv_bfloat16* __
       acc = fmaf(x.y, y.y, acc);
     }
   }
-  const int b = row / AT, t = row - b * AT;
-  delta[((long long)b * H + h) * AT + t] = acc;
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  if (i < total && (threadIdx.x & 7) == 0) {
+    const long long rh = i >> 3;  // row * H + h
+    const int row = (int)(rh / H), h = (int)(rh - (long long)row * H);
+    const int b = row / AT, t = row - b * AT;
+    delta[((long long)b * H + h) * AT + t] = acc;
+  }
 }
 
 __global__ void __launch_bounds__(ABW_THREADS, 2)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do, int H,
                    unsigned drop_thresh, float drop_scale, unsigned long long seed, const float* __restrict__ lse,
                    const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv) {
-  seed = pe_salted(seed);
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
   float* sLse = reinterpret_cast<float*>(smem + 12 * BOX_B);  // [192] lse * log2(e)          (unit B only)
@@ -311,6 +319,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     fence_barrier_init();
   }
   __syncthreads();
+  pdl_wait();
+  seed = pe_salted(seed);
   if (warp == 8) {
     if (elect_one()) {
       mbar_arrive_expect_tx(bar_tiles, 10 * BOX_B);
@@ -507,8 +517,8 @@ int pe_attn_fwd_tc(const void* qkv, int B, int H, unsigned drop_thresh, float dr
     if (!attn_attrs(pe::attn_fwd_tc_kernel, pe::AFW_SMEM)) return PE_ERR_LAUNCH;
     attr = true;
   }
-  pe::attn_fwd_tc_kernel<<<dim3(2, H, B), pe::ATT_THREADS, pe::AFW_SMEM, stream>>>(tq, H, drop_thresh, drop_scale, seed,
-                                                                                  (__nv_bfloat16*)ctx, lse);
+  pe_host::launch(pe::attn_fwd_tc_kernel, dim3(2, H, B), dim3(pe::ATT_THREADS), pe::AFW_SMEM, stream, tq, H, drop_thresh,
+                  drop_scale, seed, (__nv_bfloat16*)ctx, lse);
   return cudaGetLastError() == cudaSuccess ? PE_OK : PE_ERR_LAUNCH;
 }
 
@@ -524,9 +534,9 @@ int pe_attn_bwd_tc(const void* qkv, const void* ctx, const void* dctx, const flo
     attr = true;
   }
   const int rows = B * pe::AT;
-  pe::attn_delta_kernel<<<(rows * H + 255) / 256, 256, 0, stream>>>((const __nv_bfloat16*)ctx, (const __nv_bfloat16*)dctx,
-                                                                  rows, H, delta);
-  pe::attn_bwd_tc_kernel<<<dim3(4, H, B), pe::ABW_THREADS, pe::ABW_SMEM, stream>>>(tq, td, H, drop_thresh, drop_scale,
-                                                                                  seed, lse, delta, (__nv_bfloat16*)dqkv);
+  pe_host::launch(pe::attn_delta_kernel, dim3((unsigned)(((long long)rows * H * 8 + 255) / 256)), dim3(256), 0, stream, (const __nv_bfloat16*)ctx,
+                  (const __nv_bfloat16*)dctx, rows, H, delta);
+  pe_host::launch(pe::attn_bwd_tc_kernel, dim3(4, H, B), dim3(pe::ABW_THREADS), pe::ABW_SMEM, stream, tq, td, H,
+                  drop_thresh, drop_scale, seed, (const float*)lse, (const float*)delta, (__nv_bfloat16*)dqkv);
   return cudaGetLastError() == cudaSuccess ? PE_OK : PE_ERR_LAUNCH;
 }

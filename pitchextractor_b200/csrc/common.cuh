@@ -24,6 +24,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
+// Programmatic dependent launch.  Kernels started through pe_host::launch() may begin while the previous kernel of the
+// stream is still running: pdl_wait() blocks until that kernel has completed and its writes are visible, so it must
+// precede every access to memory another kernel produces or still reads; pdl_trigger() lets the NEXT kernel's CTAs
+// be scheduled as soon as every CTA of this grid has passed it (they then park in their own pdl_wait()).  Both are
+// no-ops in a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -90,8 +98,8 @@ __host__ __device__ __forceinline__ uint32_t attn_row_key(unsigned long long see
 }
 __host__ __device__ __forceinline__ uint32_t attn_drop_hash(uint32_t row_key, uint32_t col) {
   uint32_t h = row_key + col * 0x9E3779B1u;
-  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
-  return h;
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u;
+  return h;  // (murmur3's last xor-shift only touches the low 16 bits, which a threshold compare does not see)
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -254,6 +262,30 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, ui
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same with the descriptors given as (low word, high word): only the low word (start address) changes between the
+// MMAs of a main loop, and a 32-bit uniform add per operand is all the issuing thread then spends on it.
+__device__ __forceinline__ void tc_mma_bf16_lh(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_lh(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                             uint32_t accumulate) {
   asm volatile(
@@ -372,6 +404,25 @@ int encode_tmap(CUtensorMap* map, CUtensorMapDataType dt, int rank, const void* 
                 const uint64_t* strides_bytes /* rank-1 entries */, const uint32_t* box, int swizzle_bytes = 128);
 int num_sms();
 int check_arch();  // PE_OK on sm_100, PE_ERR_ARCH otherwise
+bool pdl_enabled();  // programmatic dependent launch between consecutive kernels of a stream (opt-in: PE_PDL=1)
+
+// Kernel launch with the programmatic-stream-serialization attribute: the kernel must call pe::pdl_wait() before it
+// touches memory written (or still read) by earlier kernels.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                          Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // Step-salt registry (see pe::pe_step_salt): each translation unit that draws dropout masks registers a getter
 // for the device address of its own copy; pe_set_step_salt() writes all of them with one tiny kernel.

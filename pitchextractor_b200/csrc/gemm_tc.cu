@@ -39,6 +39,7 @@ struct TcParams {
   int H, W, tw, th, tiles_w, tiles_h;
   int c1_chunks, c2_chunks;
   int taps;  // wgrad: 9 or 1
+  unsigned a_inc, b_inc;  // descriptor start-address step (>> 4) between the four MMAs of a 64-deep k-block (set by launch_tc)
   int kps;           // 64-wide k-blocks per smem stage (1 or 2): narrow tiles amortise the barrier round trip over two
   int commit_group;  // 1, 2 or 4: k-blocks per tcgen05.commit on the smem ring (p.stages is a multiple of it)
   int out_tma;  // bit 0 / 1: ep.out / ep.out2 are written with TMA tensor stores from the staging blocks
@@ -95,6 +96,7 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_trigger();  // the next kernel's CTAs may take this SM as soon as this CTA leaves it (they wait in their own prologue)
   const long long t_entry = p.dbg ? clock64() : 0;
   if (p.dbg && threadIdx.x == 0) {
     unsigned long long ns;
@@ -127,6 +129,7 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the tail of the previous kernel; from here on its results are read
   if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 16 + 5] = clock64() - t_entry;
 
   if (warp == 0 || (MODE == 2 && warp == 10)) {
@@ -135,7 +138,7 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     // 4-6 boxes per k-block and was bound by this warp's issue rate: there warp 0 loads operand A, warp 10 operand B.
     const int part = MODE == 2 ? (warp == 0 ? 1 : 2) : 0;  // 0: both operands, 1: A only, 2: B only
     {
-      const int elems_per_row = p.kind == 0 ? 64 : 32;
+      constexpr int elems_per_row = 64;  // bf16 per 128-byte row
       int stage = 0;
       uint32_t phase = 0;
       long long w_empty = 0;
@@ -256,11 +259,13 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     // ------------------------------------------------------------------ MMA issuer
     // The whole warp walks the loop (uniform control flow), one elected lane issues the tcgen05 instructions.
     {
-      const uint32_t idesc = umma_idesc(p.kind == 0 ? UMMA_BF16 : UMMA_TF32, kBlockM, p.block_n, p.a_mn, p.b_mn);
-      const int k_rows = p.kind == 0 ? 16 : 8;  // UMMA_K
-      const uint32_t a_step = p.a_mn ? (uint32_t)(k_rows * kRowBytes) : 32u;
-      const uint32_t b_step = p.b_mn ? (uint32_t)(k_rows * kRowBytes) : 32u;
-      const int block_k_rows = p.kind == 0 ? 64 : 32;
+      const uint32_t idesc = umma_idesc(UMMA_BF16, kBlockM, p.block_n, p.a_mn, p.b_mn);
+      constexpr int k_rows = 16;  // UMMA_K (bf16)
+      // start-address step (>> 4) between the four MMAs of a 64-deep k-block: 32 B along a K-major row, 16 rows of an
+      // MN-major tile; compile-time for the convolution modes, so the issue loop adds immediates
+      const uint32_t a_inc = MODE == 1 ? 2u : (MODE == 2 ? (uint32_t)(k_rows * kRowBytes) >> 4 : p.a_inc);
+      const uint32_t b_inc = MODE == 1 ? 2u : (MODE == 2 ? (uint32_t)(k_rows * kRowBytes) >> 4 : p.b_inc);
+      constexpr int block_k_rows = 64;
       // MN-major: 64-wide (bf16) MN blocks are separate TMA boxes, block_k_rows * 128 B apart
       const uint32_t a_lbo = p.a_mn ? (uint32_t)(block_k_rows * kRowBytes) : 16u;
       const uint32_t b_lbo = p.b_mn ? (uint32_t)(block_k_rows * kRowBytes) : 16u;
@@ -271,7 +276,7 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const long long t_begin = p.dbg ? clock64() : 0;
       // descriptor templates: everything but the 14-bit start-address field is loop invariant
       const uint64_t da0 = umma_desc_sw128(0, a_lbo, 1024), db0 = umma_desc_sw128(0, b_lbo, 1024);
-      const uint32_t a_inc = a_step >> 4, b_inc = b_step >> 4;
+      const uint32_t da_lo = (uint32_t)da0, da_hi = (uint32_t)(da0 >> 32), db_lo = (uint32_t)db0, db_hi = (uint32_t)(db0 >> 32);
       const uint32_t smem_base = smem_u32(smem);
       const int gmask = p.commit_group - 1;  // smem slots are handed back in groups of 1, 2 or 4 k-blocks
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
@@ -294,21 +299,20 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             mbar_wait(&full_bar[stage], phase);
             if (p.dbg) w_full += clock64() - c2;
             tc_fence_after();
+            // only the low descriptor word (14-bit start address >> 4, no carry: shared memory ends below 256 KB) moves
+            // from MMA to MMA: one 32-bit add per operand, which the compiler keeps on the uniform datapath
+            uint32_t a_sub = da_lo + s0, b_sub = db_lo + s0 + (kATileBytes >> 4);
             for (int sub = 0; sub < nsub; ++sub) {
-              const uint32_t sa = s0 + (uint32_t)sub * ((uint32_t)sub_bytes >> 4);
-              const uint32_t sb = sa + (kATileBytes >> 4);
-              const int i = i0 + sub;
-              if (p.kind == 0) {
+              uint32_t a_lo = a_sub, b_lo = b_sub;
+              const uint32_t first = (i0 + sub) > 0 ? 1u : 0u;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  tc_mma_bf16(d_tmem, da0 | (uint64_t)(sa + k * a_inc), db0 | (uint64_t)(sb + k * b_inc), idesc,
-                              (i > 0 || k > 0) ? 1u : 0u);
-              } else {
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  tc_mma_tf32(d_tmem, da0 | (uint64_t)(sa + k * a_inc), db0 | (uint64_t)(sb + k * b_inc), idesc,
-                              (i > 0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < 4; ++k) {
+                tc_mma_bf16_lh(d_tmem, a_lo, da_hi, b_lo, db_hi, idesc, k > 0 ? 1u : first);
+                a_lo += a_inc;
+                b_lo += b_inc;
               }
+              a_sub += (uint32_t)sub_bytes >> 4;
+              b_sub += (uint32_t)sub_bytes >> 4;
             }
             // tcgen05.commit costs the issuing thread ~200 cycles: narrow tiles (short MMAs) release their slots in
             // groups -- the commit on the group's last slot covers every earlier MMA, the producer waits on that slot
@@ -734,6 +738,8 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtens
   }
   stages -= stages % p.commit_group;
   p.stages = stages;
+  p.a_inc = p.a_mn ? (16 * pe::kRowBytes) >> 4 : 2;  // 16 rows of an MN-major tile / 32 bytes along a K-major row
+  p.b_inc = p.b_mn ? (16 * pe::kRowBytes) >> 4 : 2;
   p.tmem_cols = pow2_cols(2 * p.block_n);
   p.tx_bytes = p.mode == 2 ? (p.a_boxes + p.b_boxes) * 64 * pe::kRowBytes : sub_bytes;  // per k-block
   p.acc_stride = p.tmem_cols / 2;
@@ -771,16 +777,17 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtens
     attr_set = true;
   }
   const int grid = p.num_tiles < pe_host::num_sms() ? p.num_tiles : pe_host::num_sms();
-#define PE_TC_LAUNCH(M, K)                                                                                  \
-  pe::tc_tile_kernel<M, K><<<grid, (M) == 2 ? pe::kNumThreadsWgrad : pe::kNumThreads, smem, stream>>>(ta, ta2, tb, tout, \
-                                                                                                     tout2, p)
+  cudaError_t lerr = cudaSuccess;
+#define PE_TC_LAUNCH(M, K)                                                                                         \
+  lerr = pe_host::launch(pe::tc_tile_kernel<M, K>, dim3(grid), dim3((M) == 2 ? pe::kNumThreadsWgrad : pe::kNumThreads), \
+                         smem, stream, ta, ta2, tb, tout, tout2, p)
   if (p.mode == 0 && p.kps == 1) PE_TC_LAUNCH(0, 1);
   else if (p.mode == 0) PE_TC_LAUNCH(0, 2);
   else if (p.mode == 1 && p.kps == 1) PE_TC_LAUNCH(1, 1);
   else if (p.mode == 1) PE_TC_LAUNCH(1, 2);
   else PE_TC_LAUNCH(2, 1);
 #undef PE_TC_LAUNCH
-  return cudaGetLastError() == cudaSuccess ? PE_OK : PE_ERR_LAUNCH;
+  return (lerr == cudaSuccess && cudaGetLastError() == cudaSuccess) ? PE_OK : PE_ERR_LAUNCH;
 }
 
 static void default_ep(pe_epilogue& e) {

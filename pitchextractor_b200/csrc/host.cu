@@ -1,6 +1,7 @@
 // Host-side plumbing shared by every C-ABI entry point: driver entry-point lookup for the tensor-map
 // encoder, device queries, version.
 #include "common.cuh"
+#include <cstdlib>
 #include "../../include/pitchextractor_b200.h"
 
 #include <cudaTypedefs.h>
@@ -60,6 +61,17 @@ int check_arch() {
     ok = (major == 10) ? PE_OK : PE_ERR_ARCH;
   }
   return ok;
+}
+
+bool pdl_enabled() {
+  static const bool on = []() {
+    // measured on the Transformer step (profiles/r02_phase_times.txt): chains of 20-60 us kernels gain ~1 us per
+    // boundary, but early-scheduled dependents take SM resources from the second stream's kernels (encoder backward
+    // +0.15 ms), so it is opt-in
+    const char* e = getenv("PE_PDL");
+    return e && e[0] == '1';
+  }();
+  return on;
 }
 
 static salt_addr_fn* salt_table(int** count) {

@@ -11,6 +11,8 @@ __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              long long n, float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt,
              float grad_scale, __nv_bfloat16* __restrict__ p_bf16) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
   if (i + 3 < n) {
@@ -50,6 +52,8 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
 
 __global__ void __launch_bounds__(256)
 cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
     const float4 v = *reinterpret_cast<const float4*>(x + i);
@@ -62,6 +66,8 @@ cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, lon
 // forward operand: out[co][0 : 9*C1] = w[co][tap][ci], out[co][9*C1 : 9*C1+C2] = w2[co][ci2]   (bf16)
 __global__ void conv_fwd_weight_kernel(const float* __restrict__ w, int Cout, int K1, const float* __restrict__ w2,
                                        int C2, __nv_bfloat16* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int K = K1 + C2;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)Cout * K) return;
@@ -72,6 +78,8 @@ __global__ void conv_fwd_weight_kernel(const float* __restrict__ w, int Cout, in
 // data-gradient operand: out[ci][tap'][co] = w[co][8 - tap'][ci]; out[ci][9*Cout + co2] = w2[co2][ci]   (bf16)
 __global__ void conv_dgrad_weight_kernel(const float* __restrict__ w, int Cout, int Cin, const float* __restrict__ w2,
                                          int Cout2, __nv_bfloat16* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int K = 9 * Cout + Cout2;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)Cin * K) return;
@@ -100,7 +108,7 @@ extern "C" int pe_adamw(float* p, const float* g, float* m, float* v, long long 
   const double bc1 = 1.0 - pow((double)beta1, (double)step);
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   const long long threads = (n + 3) / 4;
-  adamw_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, PE_ST(stream)>>>(
+  pe_host::launch(adamw_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, PE_ST(stream), 
       p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, (float)bc1, (float)sqrt(bc2), grad_scale,
       (__nv_bfloat16*)p_bf16);
   return PE_LAUNCH_RC();
@@ -110,7 +118,7 @@ extern "C" int pe_cast_bf16(const float* x, void* y, long long n, pe_stream_t st
   if (int rc = pe_host::check_arch()) return rc;
   if (!x || !y || n <= 0) return PE_ERR_BAD_SHAPE;
   const long long threads = (n + 3) / 4;
-  cast_bf16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, PE_ST(stream)>>>(x, (__nv_bfloat16*)y, n);
+  pe_host::launch(cast_bf16_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, PE_ST(stream), x, (__nv_bfloat16*)y, n);
   return PE_LAUNCH_RC();
 }
 
@@ -120,13 +128,13 @@ extern "C" int pe_conv_weight_prep(const float* w, int Cout, int Cin, const floa
   if (!w || Cout <= 0 || Cin <= 0 || (C2 > 0 && !w2) || (!w_fwd && !w_dgrad)) return PE_ERR_BAD_SHAPE;
   if (w_fwd) {
     const long long n = (long long)Cout * (9 * Cin + C2);
-    conv_fwd_weight_kernel<<<(unsigned)((n + 255) / 256), 256, 0, PE_ST(stream)>>>(w, Cout, 9 * Cin, w2, C2,
+    pe_host::launch(conv_fwd_weight_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, PE_ST(stream), w, Cout, 9 * Cin, w2, C2,
                                                                                   (__nv_bfloat16*)w_fwd);
   }
   if (w_dgrad) {
     // fused data gradient of (3x3 conv on x) + (1x1 conv on x2) with respect to ... see header
     const long long n = (long long)Cin * (9 * Cout + C2);
-    conv_dgrad_weight_kernel<<<(unsigned)((n + 255) / 256), 256, 0, PE_ST(stream)>>>(w, Cout, Cin, w2, C2,
+    pe_host::launch(conv_dgrad_weight_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, PE_ST(stream), w, Cout, Cin, w2, C2,
                                                                                     (__nv_bfloat16*)w_dgrad);
   }
   return PE_LAUNCH_RC();

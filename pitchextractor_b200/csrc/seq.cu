@@ -55,6 +55,8 @@ __global__ void __launch_bounds__(256)
 ln_fwd_kernel(const float* __restrict__ xf, const __nv_bfloat16* __restrict__ xb, const float* __restrict__ pe, int T,
               const float* __restrict__ gamma, const float* __restrict__ beta, float eps, long long M,
               __nv_bfloat16* __restrict__ out, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int D = 256 * NCH;
   const int lane = threadIdx.x & 31;
   const long long m = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -101,6 +103,8 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ xf
               const float* __restrict__ rstd_in, long long M, int rows_per_cta, __nv_bfloat16* __restrict__ dx,
               __nv_bfloat16* __restrict__ dxm, unsigned drop_thresh, float drop_scale, unsigned long long seed,
               float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias) {
+  pdl_trigger();
+  pdl_wait();
   seed = pe_salted(seed);
   constexpr int D = 256 * NCH;
   // column partial sums (dgamma, dbeta, dbias) live in a private shared-memory slice per warp instead of 48 registers
@@ -188,6 +192,8 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ xf
 __global__ void __launch_bounds__(256)
 colsum_kernel(const __nv_bfloat16* __restrict__ x, long long M, int N, long long ld, int rows_per_cta,
               float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[4][512];
   const int cg = N >> 3;
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
@@ -267,6 +273,8 @@ __device__ __forceinline__ void load_head(const __nv_bfloat16* src, long long ld
 __global__ void __launch_bounds__(256)
 attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int T, int H, float scale, unsigned drop_thresh,
                 float drop_scale, unsigned long long seed, __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse) {
+  pdl_trigger();
+  pdl_wait();
   seed = pe_salted(seed);
   extern __shared__ __align__(16) float sm[];
   float* Ks = sm;
@@ -334,6 +342,8 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
                    const __nv_bfloat16* __restrict__ dctx, const float* __restrict__ lse, int T, int H, float scale,
                    unsigned drop_thresh, float drop_scale, unsigned long long seed, __nv_bfloat16* __restrict__ dqkv,
                    float* __restrict__ delta) {
+  pdl_trigger();
+  pdl_wait();
   seed = pe_salted(seed);
   extern __shared__ __align__(16) float sm[];
   float* Ks = sm;
@@ -389,6 +399,8 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
                     const float* __restrict__ lse, const float* __restrict__ delta, int T, int H, float scale,
                     unsigned drop_thresh, float drop_scale, unsigned long long seed,
                     __nv_bfloat16* __restrict__ dqkv) {
+  pdl_trigger();
+  pdl_wait();
   seed = pe_salted(seed);
   extern __shared__ __align__(16) float sm[];
   float* Qs = sm;                 // pre-scaled queries
@@ -467,6 +479,8 @@ heads_loss_kernel(const __nv_bfloat16* __restrict__ hc, const __nv_bfloat16* __r
                   const float* __restrict__ gc_ext, const float* __restrict__ gd_ext,
                   __nv_bfloat16* __restrict__ dhc, __nv_bfloat16* __restrict__ dhd, float* __restrict__ dwc,
                   float* __restrict__ dbc, float* __restrict__ dwd, float* __restrict__ dbd) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int D = 256 * NCH;
   __shared__ float red[2][D];
   __shared__ float redb[4];
@@ -583,6 +597,8 @@ heads_loss_kernel(const __nv_bfloat16* __restrict__ hc, const __nv_bfloat16* __r
 
 // loss_out[0] = lambda*sum1/count + sum2/count, [1] = lambda*sum1/count, [2] = sum2/count
 __global__ void loss_finalize_kernel(const double* acc, float lambda_f0, double inv_count, float* loss_out) {
+  pdl_trigger();
+  pdl_wait();
   const double f = (double)lambda_f0 * acc[0] * inv_count, s = acc[1] * inv_count;
   loss_out[0] = (float)(f + s);
   loss_out[1] = (float)f;
@@ -606,13 +622,13 @@ extern "C" int pe_layernorm_fwd(const float* x_f32, const void* x_bf16, const fl
     return PE_ERR_BAD_SHAPE;
   const unsigned grid = (unsigned)((M + 7) / 8);
   if (D == 512)
-    ln_fwd_kernel<2><<<grid, 256, 0, PE_ST(stream)>>>(x_f32, (const __nv_bfloat16*)x_bf16, pe_table, T, gamma, beta,
+    pe_host::launch(ln_fwd_kernel<2>, dim3(grid), dim3(256), 0, PE_ST(stream), x_f32, (const __nv_bfloat16*)x_bf16, pe_table, T, gamma, beta,
                                                       eps, M, (__nv_bfloat16*)out, mean, rstd);
   else if (D == 768)
-    ln_fwd_kernel<3><<<grid, 256, 0, PE_ST(stream)>>>(x_f32, (const __nv_bfloat16*)x_bf16, pe_table, T, gamma, beta,
+    pe_host::launch(ln_fwd_kernel<3>, dim3(grid), dim3(256), 0, PE_ST(stream), x_f32, (const __nv_bfloat16*)x_bf16, pe_table, T, gamma, beta,
                                                       eps, M, (__nv_bfloat16*)out, mean, rstd);
   else if (D == 256)
-    ln_fwd_kernel<1><<<grid, 256, 0, PE_ST(stream)>>>(x_f32, (const __nv_bfloat16*)x_bf16, pe_table, T, gamma, beta,
+    pe_host::launch(ln_fwd_kernel<1>, dim3(grid), dim3(256), 0, PE_ST(stream), x_f32, (const __nv_bfloat16*)x_bf16, pe_table, T, gamma, beta,
                                                       eps, M, (__nv_bfloat16*)out, mean, rstd);
   else
     return PE_ERR_BAD_SHAPE;
@@ -639,7 +655,7 @@ extern "C" int pe_layernorm_bwd(const void* dy, const float* x_f32, const void* 
       cudaFuncSetAttribute(ln_bwd_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 768 * 4);        \
       attr = true;                                                                                                 \
     }                                                                                                              \
-    ln_bwd_kernel<N><<<grid, 256, smem, PE_ST(stream)>>>((const __nv_bfloat16*)dy, x_f32, (const __nv_bfloat16*)x_bf16, \
+    pe_host::launch(ln_bwd_kernel<N>, dim3(grid), dim3(256), smem, PE_ST(stream), (const __nv_bfloat16*)dy, x_f32, (const __nv_bfloat16*)x_bf16, \
                                                          pe_table, T, gamma, mean, rstd, M, per, (__nv_bfloat16*)dx, \
                                                          (__nv_bfloat16*)dx_masked, drop_thresh, drop_scale, seed, \
                                                          dgamma, dbeta, dbias);                                    \
@@ -662,7 +678,7 @@ extern "C" int pe_colsum_bf16(const void* x, long long M, int N, long long ld, f
   if (per_ll < 32) per_ll = 32;
   const int per = (int)per_ll;
   dim3 grid((unsigned)((M + per - 1) / per), gy);
-  colsum_kernel<<<grid, 256, 0, PE_ST(stream)>>>((const __nv_bfloat16*)x, M, N, ld, per, out);
+  pe_host::launch(colsum_kernel, dim3(grid), dim3(256), 0, PE_ST(stream), (const __nv_bfloat16*)x, M, N, ld, per, out);
   return PE_LAUNCH_RC();
 }
 
@@ -686,7 +702,7 @@ extern "C" int pe_attn_fwd(const void* qkv, int B, int T, int H, int head_dim, u
     cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr = true;
   }
-  attn_fwd_kernel<<<dim3(H, B), attn_threads(T), smem, PE_ST(stream)>>>((const __nv_bfloat16*)qkv, T, H, 0.125f,
+  pe_host::launch(attn_fwd_kernel, dim3(dim3(H, B)), dim3(attn_threads(T)), smem, PE_ST(stream), (const __nv_bfloat16*)qkv, T, H, 0.125f,
                                                                         drop_thresh, drop_scale, seed,
                                                                         (__nv_bfloat16*)ctx, lse);
   return PE_LAUNCH_RC();
@@ -707,11 +723,11 @@ extern "C" int pe_attn_bwd(const void* qkv, const void* ctx, const void* dctx, c
     attr = true;
   }
   const size_t smem1 = 2ull * T * HD * sizeof(float);
-  attn_bwd_dq_kernel<<<dim3(H, B), attn_threads(T), smem1, PE_ST(stream)>>>(
+  pe_host::launch(attn_bwd_dq_kernel, dim3(dim3(H, B)), dim3(attn_threads(T)), smem1, PE_ST(stream), 
       (const __nv_bfloat16*)qkv, (const __nv_bfloat16*)ctx, (const __nv_bfloat16*)dctx, lse, T, H, 0.125f, drop_thresh,
       drop_scale, seed, (__nv_bfloat16*)dqkv, delta);
   const size_t smem2 = (2ull * T * HD + 2ull * T) * sizeof(float);
-  attn_bwd_dkv_kernel<<<dim3(H, B), attn_threads(T), smem2, PE_ST(stream)>>>(
+  pe_host::launch(attn_bwd_dkv_kernel, dim3(dim3(H, B)), dim3(attn_threads(T)), smem2, PE_ST(stream), 
       (const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dctx, lse, delta, T, H, 0.125f, drop_thresh, drop_scale, seed,
       (__nv_bfloat16*)dqkv);
   return PE_LAUNCH_RC();
@@ -732,7 +748,7 @@ extern "C" int pe_heads_loss(const void* hc, const void* hd, long long M, int D,
   const unsigned grid = (unsigned)((M + per - 1) / per);
   const float inv = 1.0f / (float)M;
 #define PE_HEADS(N)                                                                                                  \
-  heads_loss_kernel<N><<<grid, 256, 0, PE_ST(stream)>>>((const __nv_bfloat16*)hc, (const __nv_bfloat16*)hd, M, per, \
+  pe_host::launch(heads_loss_kernel<N>, dim3(grid), dim3(256), 0, PE_ST(stream), (const __nv_bfloat16*)hc, (const __nv_bfloat16*)hd, M, per, \
                                                         wc, bc, wd, bd, f0_target, sil_target, lambda_f0, inv,      \
                                                         grad_scale, f0_pred, sil_logit, loss_acc, gc_ext, gd_ext,   \
                                                         (__nv_bfloat16*)dhc, (__nv_bfloat16*)dhd, dwc, dbc, dwd, dbd)
@@ -740,6 +756,6 @@ extern "C" int pe_heads_loss(const void* hc, const void* hd, long long M, int D,
   else if (D == 768) PE_HEADS(3);
   else return PE_ERR_BAD_SHAPE;
 #undef PE_HEADS
-  if (loss_acc && loss_out) loss_finalize_kernel<<<1, 1, 0, PE_ST(stream)>>>(loss_acc, lambda_f0, 1.0 / (double)M, loss_out);
+  if (loss_acc && loss_out) pe_host::launch(loss_finalize_kernel, dim3(1), dim3(1), 0, PE_ST(stream), loss_acc, lambda_f0, 1.0 / (double)M, loss_out);
   return PE_LAUNCH_RC();
 }

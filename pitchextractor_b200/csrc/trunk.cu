@@ -88,6 +88,8 @@ __global__ void __launch_bounds__(256)
 stem_conv_fwd_kernel(const float* __restrict__ x, long long sb, long long st, long long sf, int B, int T, int F,
                      const float* __restrict__ w /*[64][9]*/, __nv_bfloat16* __restrict__ y, int pixels_per_cta,
                      double* __restrict__ stats /* [2][64] or NULL */) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[2][64];
   if (threadIdx.x < 128) (&red[0][0])[threadIdx.x] = 0.f;
   __syncthreads();
@@ -144,6 +146,8 @@ stem_conv_fwd_kernel(const float* __restrict__ x, long long sb, long long st, lo
 __global__ void __launch_bounds__(256)
 stem_conv_wgrad_kernel(const float* __restrict__ x, long long sb, long long st, long long sf, int B, int T, int F,
                        const __nv_bfloat16* __restrict__ dy, float* __restrict__ dw, int pixels_per_cta) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[576];
   for (int i = threadIdx.x; i < 576; i += 256) red[i] = 0.f;
   __syncthreads();
@@ -198,6 +202,8 @@ stem_conv_wgrad_kernel(const float* __restrict__ x, long long sb, long long st, 
 __global__ void __launch_bounds__(256)
 bn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int C, double* __restrict__ sums,
                 int rows_per_cta) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sred[];  // [2][C]
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sred[i] = 0.f;
   __syncthreads();
@@ -248,6 +254,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
                                    const float* __restrict__ beta, float eps, float momentum, float* scale,
                                    float* shift, float* mean_out, float* rstd_out, float* running_mean,
                                    float* running_var, long long* nbt, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c == 0 && nbt) *nbt += 1;
   if (c >= C) return;
@@ -271,6 +279,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
 __global__ void bn_eval_params_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
                                       const float* __restrict__ running_mean, const float* __restrict__ running_var,
                                       float eps, float* scale, float* shift, float* mean_out, float* rstd_out, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float rstd = rsqrtf(running_var[c] + eps);
@@ -295,6 +305,8 @@ bn_act_pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, PoolGeom g, const fl
                        const float* __restrict__ shift, float slope, unsigned drop_thresh, float drop_scale,
                        unsigned long long seed, __nv_bfloat16* __restrict__ out, long long ld_out, int c_off,
                        __nv_bfloat16* __restrict__ out_seq, unsigned char* __restrict__ argmax_out) {
+  pdl_trigger();
+  pdl_wait();
   seed = pe_salted(seed);
   const int cg = g.C >> 3;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -363,6 +375,8 @@ bn_act_pool_fwd_mlp_kernel(const __nv_bfloat16* __restrict__ x, PoolGeom g, cons
                            const float* __restrict__ shift, float slope, unsigned drop_thresh, float drop_scale,
                            unsigned long long seed, __nv_bfloat16* __restrict__ out, long long ld_out, int c_off,
                            __nv_bfloat16* __restrict__ out_seq) {
+  pdl_trigger();
+  pdl_wait();
   seed = pe_salted(seed);
   const int cg = g.C >> 3;
   const int ry = blockDim.x / cg;
@@ -509,6 +523,8 @@ __device__ __forceinline__ void bn_bwd_route(const BnBwdArgs& a, const float* s_
 template <int K, bool EXTRA>
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(BnBwdArgs a, double* __restrict__ sums, int windows_per_cta) {
+  pdl_trigger();
+  pdl_wait();
   a.seed = pe_salted(a.seed);
   extern __shared__ __align__(16) float sm[];  // sc[C] | sh[C] | red[2][C]
   const PoolGeom& g = a.g;
@@ -561,6 +577,8 @@ bn_bwd_reduce_kernel(BnBwdArgs a, double* __restrict__ sums, int windows_per_cta
 __global__ void bn_bwd_params_kernel(const double* __restrict__ sums, double count, const float* __restrict__ scale,
                                      const float* __restrict__ mean, const float* __restrict__ rstd, float* dgamma,
                                      float* dbeta, float* __restrict__ coef, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double sg = sums[c], sgx = sums[C + c];
@@ -579,6 +597,8 @@ __global__ void bn_bwd_params_kernel(const double* __restrict__ sums, double cou
 template <int K>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(BnBwdArgs a, const float* __restrict__ coef, __nv_bfloat16* __restrict__ dx) {
+  pdl_trigger();
+  pdl_wait();
   a.seed = pe_salted(a.seed);
   extern __shared__ __align__(16) float sm[];  // sc | sh | A | B
   const PoolGeom& g = a.g;
@@ -637,6 +657,8 @@ bn_bwd_apply_kernel(BnBwdArgs a, const float* __restrict__ coef, __nv_bfloat16* 
 template <int K, int U, bool EXTRA, bool AUX>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_mlp_kernel(BnBwdArgs a, const float* __restrict__ coef, __nv_bfloat16* __restrict__ dx) {
+  pdl_trigger();
+  pdl_wait();
   a.seed = pe_salted(a.seed);
   const PoolGeom& g = a.g;
   const int cg = g.C >> 3;
@@ -745,6 +767,8 @@ bn_bwd_apply_mlp_kernel(BnBwdArgs a, const float* __restrict__ coef, __nv_bfloat
 __global__ void __launch_bounds__(256)
 maxpool_bwd_add_kernel(const __nv_bfloat16* __restrict__ x, PoolGeom g, const __nv_bfloat16* __restrict__ dout,
                        long long ld_dout, int c_off, __nv_bfloat16* __restrict__ dx) {
+  pdl_trigger();
+  pdl_wait();
   const int cg = g.C >> 3;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = g.rows * g.Wo * cg;
@@ -783,6 +807,8 @@ maxpool_bwd_add_kernel(const __nv_bfloat16* __restrict__ x, PoolGeom g, const __
 __global__ void __launch_bounds__(256)
 maxpool_bwd_idx_kernel(const unsigned char* __restrict__ argmax, PoolGeom g, const __nv_bfloat16* __restrict__ dout,
                        long long ld_dout, int c_off, __nv_bfloat16* __restrict__ dx) {
+  pdl_trigger();
+  pdl_wait();
   const int cg = g.C >> 3;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = g.rows * g.Wo * cg;
@@ -826,7 +852,7 @@ extern "C" int pe_stem_conv_fwd(const float* x, long long sb, long long st, long
   const long long P = (long long)B * T * F;
   if (P >= (1ll << 31)) return PE_ERR_BAD_SHAPE;
   const int per = stem_pixels_per_cta(P);
-  stem_conv_fwd_kernel<<<(unsigned)((P + per - 1) / per), 256, 0, PE_ST(stream)>>>(x, sb, st, sf, B, T, F, w,
+  pe_host::launch(stem_conv_fwd_kernel, dim3((unsigned)((P + per - 1) / per)), dim3(256), 0, PE_ST(stream), x, sb, st, sf, B, T, F, w,
                                                                                    (__nv_bfloat16*)y, per, stats);
   return PE_LAUNCH_RC();
 }
@@ -838,7 +864,7 @@ extern "C" int pe_stem_conv_wgrad(const float* x, long long sb, long long st, lo
   const long long P = (long long)B * T * F;
   if (P >= (1ll << 31)) return PE_ERR_BAD_SHAPE;
   const int per = stem_pixels_per_cta(P);
-  stem_conv_wgrad_kernel<<<(unsigned)((P + per - 1) / per), 256, 0, PE_ST(stream)>>>(
+  pe_host::launch(stem_conv_wgrad_kernel, dim3((unsigned)((P + per - 1) / per)), dim3(256), 0, PE_ST(stream), 
       x, sb, st, sf, B, T, F, (const __nv_bfloat16*)dy, dw, per);
   return PE_LAUNCH_RC();
 }
@@ -849,7 +875,7 @@ extern "C" int pe_bn_stats(const void* x, long long rows, int C, double* sums, p
   if (int rc = pe_host::check_arch()) return rc;
   if (!x || !sums || rows <= 0 || !chan_ok(C) || C / 8 > 256) return PE_ERR_BAD_SHAPE;
   const int per = 2048;
-  bn_stats_kernel<<<(unsigned)((rows + per - 1) / per), 256, 2 * C * sizeof(float), PE_ST(stream)>>>(
+  pe_host::launch(bn_stats_kernel, dim3((unsigned)((rows + per - 1) / per)), dim3(256), 2 * C * sizeof(float), PE_ST(stream), 
       (const __nv_bfloat16*)x, rows, C, sums, per);
   return PE_LAUNCH_RC();
 }
@@ -860,7 +886,7 @@ extern "C" int pe_bn_finalize(const double* sums, double count, const float* gam
                               pe_stream_t stream) {
   if (int rc = pe_host::check_arch()) return rc;
   if (!sums || !gamma || !beta || !scale || !shift || !mean || !rstd || C <= 0 || count <= 0) return PE_ERR_BAD_SHAPE;
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, PE_ST(stream)>>>(sums, count, gamma, beta, eps, momentum, scale, shift,
+  pe_host::launch(bn_finalize_kernel, dim3((C + 127) / 128), dim3(128), 0, PE_ST(stream), sums, count, gamma, beta, eps, momentum, scale, shift,
                                                                  mean, rstd, running_mean, running_var,
                                                                  num_batches_tracked, C);
   return PE_LAUNCH_RC();
@@ -871,7 +897,7 @@ extern "C" int pe_bn_eval_params(const float* gamma, const float* beta, const fl
                                  float* rstd, int C, pe_stream_t stream) {
   if (int rc = pe_host::check_arch()) return rc;
   if (!gamma || !beta || !running_mean || !running_var || !scale || !shift || C <= 0) return PE_ERR_BAD_SHAPE;
-  bn_eval_params_kernel<<<(C + 127) / 128, 128, 0, PE_ST(stream)>>>(gamma, beta, running_mean, running_var, eps, scale,
+  pe_host::launch(bn_eval_params_kernel, dim3((C + 127) / 128), dim3(128), 0, PE_ST(stream), gamma, beta, running_mean, running_var, eps, scale,
                                                                     shift, mean, rstd, C);
   return PE_LAUNCH_RC();
 }
@@ -894,11 +920,11 @@ extern "C" int pe_bn_act_pool_fwd(const void* x, long long rows, int W, int C, i
   do {                                                                                                             \
     const unsigned grid = (unsigned)((nwin + (long long)ry * U - 1) / ((long long)ry * U));                        \
     if (extra)                                                                                                     \
-      bn_act_pool_fwd_mlp_kernel<K, U, true><<<grid, threads, 0, PE_ST(stream)>>>(                                 \
+      pe_host::launch(bn_act_pool_fwd_mlp_kernel<K, U, true>, dim3(grid), dim3(threads), 0, PE_ST(stream),                                  \
           (const __nv_bfloat16*)x, g, scale, shift, slope, drop_thresh, drop_scale, seed, (__nv_bfloat16*)out,     \
           ld_out, c_off, (__nv_bfloat16*)out_seq);                                                                 \
     else                                                                                                           \
-      bn_act_pool_fwd_mlp_kernel<K, U, false><<<grid, threads, 0, PE_ST(stream)>>>(                                \
+      pe_host::launch(bn_act_pool_fwd_mlp_kernel<K, U, false>, dim3(grid), dim3(threads), 0, PE_ST(stream),                                 \
           (const __nv_bfloat16*)x, g, scale, shift, slope, drop_thresh, drop_scale, seed, (__nv_bfloat16*)out,     \
           ld_out, c_off, (__nv_bfloat16*)out_seq);                                                                 \
   } while (0)
@@ -908,7 +934,7 @@ extern "C" int pe_bn_act_pool_fwd(const void* x, long long rows, int W, int C, i
 #undef PE_FWD
     return PE_LAUNCH_RC();
   }
-  bn_act_pool_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, PE_ST(stream)>>>(
+  pe_host::launch(bn_act_pool_fwd_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, PE_ST(stream), 
       (const __nv_bfloat16*)x, g, scale, shift, slope, drop_thresh, drop_scale, seed, (__nv_bfloat16*)out, ld_out, c_off,
       (__nv_bfloat16*)out_seq, (unsigned char*)argmax_out);
   return PE_LAUNCH_RC();
@@ -954,17 +980,17 @@ extern "C" int pe_bn_act_pool_bwd(const void* x, long long rows, int W, int C, i
   cudaStream_t st = PE_ST(stream);
 #define PE_BN_BWD(K, U)                                                                                    \
   do {                                                                                                    \
-    if (!sums_ready && extra) bn_bwd_reduce_kernel<K, true><<<g1, 256, sm1, st>>>(a, sums, per);          \
-    else if (!sums_ready) bn_bwd_reduce_kernel<K, false><<<g1, 256, sm1, st>>>(a, sums, per);             \
-    bn_bwd_params_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, (double)rows * W, scale, mean, rstd, dgamma, dbeta, \
+    if (!sums_ready && extra) pe_host::launch(bn_bwd_reduce_kernel<K, true>, dim3(g1), dim3(256), sm1, st, a, sums, per);          \
+    else if (!sums_ready) pe_host::launch(bn_bwd_reduce_kernel<K, false>, dim3(g1), dim3(256), sm1, st, a, sums, per);             \
+    pe_host::launch(bn_bwd_params_kernel, dim3((C + 127) / 128), dim3(128), 0, st, sums, (double)rows * W, scale, mean, rstd, dgamma, dbeta, \
                                                           coef, C);                                       \
     const unsigned ga = (unsigned)((nwin + (long long)ry * U - 1) / ((long long)ry * U));                 \
     if (aux)                                                                                              \
-      bn_bwd_apply_mlp_kernel<K, U, false, true><<<ga, cgs * ry, 0, st>>>(a, coef, (__nv_bfloat16*)dx);   \
+      pe_host::launch(bn_bwd_apply_mlp_kernel<K, U, false, true>, dim3(ga), dim3(cgs * ry), 0, st, a, coef, (__nv_bfloat16*)dx);   \
     else if (extra)                                                                                       \
-      bn_bwd_apply_mlp_kernel<K, U, true, false><<<ga, cgs * ry, 0, st>>>(a, coef, (__nv_bfloat16*)dx);   \
+      pe_host::launch(bn_bwd_apply_mlp_kernel<K, U, true, false>, dim3(ga), dim3(cgs * ry), 0, st, a, coef, (__nv_bfloat16*)dx);   \
     else                                                                                                  \
-      bn_bwd_apply_mlp_kernel<K, U, false, false><<<ga, cgs * ry, 0, st>>>(a, coef, (__nv_bfloat16*)dx);  \
+      pe_host::launch(bn_bwd_apply_mlp_kernel<K, U, false, false>, dim3(ga), dim3(cgs * ry), 0, st, a, coef, (__nv_bfloat16*)dx);  \
   } while (0)
   const int cgs = C / 8, ry = 256 / cgs;
   const bool extra = drop_thresh != 0 || dout_seq != nullptr;
@@ -983,11 +1009,11 @@ extern "C" int pe_maxpool_bwd_add(const void* x, const void* argmax, long long r
   PoolGeom g{rows, W, C, k, W / k};
   const long long total = rows * g.Wo * (C / 8);
   if (argmax) {
-    maxpool_bwd_idx_kernel<<<(unsigned)((total + 255) / 256), 256, 0, PE_ST(stream)>>>(
+    pe_host::launch(maxpool_bwd_idx_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, PE_ST(stream), 
         (const unsigned char*)argmax, g, (const __nv_bfloat16*)dout, ld_dout, c_off, (__nv_bfloat16*)dx);
     return PE_LAUNCH_RC();
   }
-  maxpool_bwd_add_kernel<<<(unsigned)((total + 255) / 256), 256, 0, PE_ST(stream)>>>(
+  pe_host::launch(maxpool_bwd_add_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, PE_ST(stream), 
       (const __nv_bfloat16*)x, g, (const __nv_bfloat16*)dout, ld_dout, c_off, (__nv_bfloat16*)dx);
   return PE_LAUNCH_RC();
 }

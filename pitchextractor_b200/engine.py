@@ -83,6 +83,9 @@ class Engine:
         self._fwd_token = 0
         self.on_grads_ready = None  # callback(tag) for the data-parallel gradient reducer
         self._side_stream = None
+        self._wg_streams = {}     # per encoder stack: helper stream of the weight-gradient GEMMs
+        self._phase_cb = None     # see _mark()
+        self.phase_events = None  # PE_PHASES=1: per replayed step, [(tag, start event, end event), ...]
         self._side_pending = False
         self.reducer = None         # GradReducer: begin_step() / ready(tag) / wait() bracket every training step
         # Training steps are captured into a CUDA graph after two eager warm-up steps and replayed from then on
@@ -332,6 +335,7 @@ class Engine:
         SEQD = self.buf("SEQD", (BT, 512))
         self._act_pool(DD, BT, 2, 256, 1, aff, out=None, out_seq=SEQD, drop=self._drop(self.p_trunk, training),
                        seed=self._seed(2))
+        self._mark("trunk_fwd")
         # ---- sequence models (model.py:94,113)
         if self.seq_type == "transformer":
             # the two encoder stacks are independent: the detector's runs on a second stream, so that the tail of one
@@ -343,7 +347,13 @@ class Engine:
         else:
             Hc, Hd = self._bilstm_fwd(SEQC, SEQD, B, T, training)
         self._Hc, self._Hd = Hc, Hd
+        self._mark("encoder_fwd")
         return Hc, Hd
+
+    def _mark(self, tag):
+        """Phase boundary (all streams joined here): tools/phase_times.py cuts the captured step at these points."""
+        if self._phase_cb is not None:
+            self._phase_cb(tag)
 
     @contextlib.contextmanager
     def _forked(self, join=True):
@@ -592,64 +602,100 @@ class Engine:
                  out_mode=L.PE_OUT_F32_ATOMIC)
 
     def _transformer_bwd(self, prefix, tag, X, dH, B, T, site0):
+        """Backward of one encoder stack.  The data-gradient chain (LayerNorm, dgrad GEMMs, attention) runs on the
+        current stream; weight / bias gradients, which nothing reads before the optimizer, go to a per-stack helper
+        stream behind events (graph branches under capture).  Gradient buffers alternate between two sets by layer
+        parity, and layer l first waits for the helper work of layer l + 2, which read the set it is about to overwrite."""
         V, W16, g = self.view, self.bview, self.gview
         M, D, FF, H = B * T, 512, self.ff, self.nhead
         training = self._training
         drop = self._drop(self.p_seq, training)
         adrop = L.attn_drop_thresh(self.p_seq if drop[0] else 0.0)
-        pdrop = self.p_seq if drop[0] else 0.0
         stats = self._bufs[tag + "lnstats"]
         sm = self.model.get_submodule(prefix)
         dS = self.buf(tag + "dS", (M, D))
-        dSm = self.buf(tag + "dSm", (M, D))
-        dU = self.buf(tag + "dU", (M, FF))
         dH1 = self.buf(tag + "dH1", (M, D))
         dCTX = self.buf(tag + "dCTX", (M, D))
-        dQKV = self.buf(tag + "dQKV", (M, 3 * D))
         delta = self.buf(tag + "delta", (B, H, T), torch.float32)
+        main = torch.cuda.current_stream()
+        floating = os.environ.get("PE_TWO_STREAMS", "1") != "0" and os.environ.get("PE_WGRAD_STREAMS", "1") != "0"
+        if floating:
+            if tag not in self._wg_streams:
+                self._wg_streams[tag] = torch.cuda.Stream(device=self.device)
+            helper = self._wg_streams[tag]
+        done = {}
+
+        @contextlib.contextmanager
+        def off_chain():
+            """Work that depends on everything enqueued so far on the chain but that the chain does not wait for."""
+            if not floating:
+                yield
+                return
+            ev = torch.cuda.Event()
+            ev.record(main)
+            helper.wait_event(ev)
+            with torch.cuda.stream(helper):
+                yield
+
         for l in reversed(range(self.num_layers)):
             q = "%s.model.layers.%d." % (prefix, l)
             t = "%s%d" % (tag, l)
             site = site0 + 8 * l
+            par = l & 1
+            dSm2 = self.buf(tag + "dSm2_%d" % par, (M, D))
+            dSm1 = self.buf(tag + "dSm1_%d" % par, (M, D))
+            dU = self.buf(tag + "dU_%d" % par, (M, FF))
+            dQKV = self.buf(tag + "dQKV_%d" % par, (M, 3 * D))
+            if floating and (l + 2) in done:
+                main.wait_event(done.pop(l + 2))
             Hin = self._bufs[tag + "H0"] if l == 0 else self._bufs["%s%dH2" % (tag, l - 1)]
             QKV, CTX, LSE = self._bufs[t + "QKV"], self._bufs[t + "CTX"], self._bufs[t + "LSE"]
             S1, H1, U, G, S2 = (self._bufs[t + k] for k in ("S1", "H1", "U", "G", "S2"))
             # norm2 backward (+ linear2 output dropout, linear2.bias gradient)
             call("pe_layernorm_bwd", ptr(dH), ptr(S2), None, None, c_int(T), c_int(D), ptr(V[q + "norm2.weight"]),
-                 ptr(stats[2 * l + 2, 0]), ptr(stats[2 * l + 2, 1]), c_ll(M), ptr(dS), ptr(dSm), c_u(drop[0]),
+                 ptr(stats[2 * l + 2, 0]), ptr(stats[2 * l + 2, 1]), c_ll(M), ptr(dS), ptr(dSm2), c_u(drop[0]),
                  c_f(drop[1]), c_ull(self._seed(site + 3)), ptr(g[q + "norm2.weight"]), ptr(g[q + "norm2.bias"]),
                  ptr(g[q + "linear2.bias"]), stream())
-            # linear2: dG -> through dropout and GELU' -> dU ; weight gradient
-            ops.gemm(dSm, W16[q + "linear2.weight"], dU, M, FF, D, b_mn=True, aux=U, aux_mode=L.PE_AUX_MUL)
-            self._wgrad_linear(dSm, G, q + "linear2.weight", D, FF, M)
-            # linear1: dH1 = dU W1 + dS (residual) ; weight / bias gradients
+            with off_chain():
+                self._wgrad_linear(dSm2, G, q + "linear2.weight", D, FF, M)
+            # linear2: dG -> through dropout and GELU' -> dU
+            ops.gemm(dSm2, W16[q + "linear2.weight"], dU, M, FF, D, b_mn=True, aux=U, aux_mode=L.PE_AUX_MUL)
+            with off_chain():
+                self._wgrad_linear(dU, H1, q + "linear1.weight", FF, D, M)
+                call("pe_colsum_bf16", ptr(dU), c_ll(M), c_int(FF), c_ll(FF), ptr(g[q + "linear1.bias"]), stream())
+            # linear1: dH1 = dU W1 + dS (residual)
             ops.gemm(dU, W16[q + "linear1.weight"], dH1, M, D, FF, b_mn=True, aux=dS, aux_mode=L.PE_AUX_ADD)
-            self._wgrad_linear(dU, H1, q + "linear1.weight", FF, D, M)
-            call("pe_colsum_bf16", ptr(dU), c_ll(M), c_int(FF), c_ll(FF), ptr(g[q + "linear1.bias"]), stream())
             # norm1 backward (+ out_proj output dropout, out_proj.bias gradient)
             call("pe_layernorm_bwd", ptr(dH1), ptr(S1), None, None, c_int(T), c_int(D), ptr(V[q + "norm1.weight"]),
-                 ptr(stats[2 * l + 1, 0]), ptr(stats[2 * l + 1, 1]), c_ll(M), ptr(dS), ptr(dSm), c_u(drop[0]),
+                 ptr(stats[2 * l + 1, 0]), ptr(stats[2 * l + 1, 1]), c_ll(M), ptr(dS), ptr(dSm1), c_u(drop[0]),
                  c_f(drop[1]), c_ull(self._seed(site + 1)), ptr(g[q + "norm1.weight"]), ptr(g[q + "norm1.bias"]),
                  ptr(g[q + "self_attn.out_proj.bias"]), stream())
+            with off_chain():
+                self._wgrad_linear(dSm1, CTX, q + "self_attn.out_proj.weight", D, D, M)
             # out_proj
-            ops.gemm(dSm, W16[q + "self_attn.out_proj.weight"], dCTX, M, D, D, b_mn=True)
-            self._wgrad_linear(dSm, CTX, q + "self_attn.out_proj.weight", D, D, M)
+            ops.gemm(dSm1, W16[q + "self_attn.out_proj.weight"], dCTX, M, D, D, b_mn=True)
             # attention
             call("pe_attn_bwd", ptr(QKV), ptr(CTX), ptr(dCTX), ptr(LSE), c_int(B), c_int(T), c_int(H), c_int(64),
                  c_u(adrop[0]), c_f(adrop[1]), c_ull(self._seed(site + 0)), ptr(dQKV), ptr(delta), c_int(0), stream())
+            with off_chain():
+                self._wgrad_linear(dQKV, Hin, q + "self_attn.in_proj_weight", 3 * D, D, M)
+                call("pe_colsum_bf16", ptr(dQKV), c_ll(M), c_int(3 * D), c_ll(3 * D),
+                     ptr(g[q + "self_attn.in_proj_bias"]), stream())
+                if floating:
+                    done[l] = torch.cuda.Event()
+                    done[l].record(helper)
             # in_proj: dH = dQKV Wqkv + dS (residual)
             dHn = self.buf(tag + "dHin%d" % (l & 1), (M, D))
             ops.gemm(dQKV, W16[q + "self_attn.in_proj_weight"], dHn, M, D, 3 * D, b_mn=True, aux=dS,
                      aux_mode=L.PE_AUX_ADD)
-            self._wgrad_linear(dQKV, Hin, q + "self_attn.in_proj_weight", 3 * D, D, M)
-            call("pe_colsum_bf16", ptr(dQKV), c_ll(M), c_int(3 * D), c_ll(3 * D), ptr(g[q + "self_attn.in_proj_bias"]),
-                 stream())
             dH = dHn
         dX = self.buf(tag + "dX", (M, D))
         call("pe_layernorm_bwd", ptr(dH), None, ptr(X), ptr(sm.pos_encoding.pe), c_int(T), c_int(D),
              ptr(V[prefix + ".layer_norm.weight"]), ptr(stats[0, 0]), ptr(stats[0, 1]), c_ll(M), ptr(dX), None, c_u(0),
              c_f(1.0), c_ull(0), ptr(g[prefix + ".layer_norm.weight"]), ptr(g[prefix + ".layer_norm.bias"]), None,
              stream())
+        for ev in done.values():  # the stack's gradients are complete when this function returns (stream order)
+            main.wait_event(ev)
         return dX
 
     def backward_core(self, dHc, dHd):
@@ -670,6 +716,7 @@ class Engine:
             dSEQC, dSEQD = self._bilstm_bwd(dHc, dHd, B, T)
             notify("sequence_detector+heads")
             notify("sequence_classifier")
+        self._mark("encoder_bwd")
         tdrop = self._drop(self.p_trunk, training)
         # detector_conv
         dDD = self.buf("dDD", (BT * 2, 256))
@@ -728,6 +775,7 @@ class Engine:
              c_int(80), ptr(dY1), ptr(g["conv_block.0.weight"]), stream())
         self._join_side()
         notify("trunk")
+        self._mark("trunk_bwd")
 
     # ------------------------------------------------------------------ public entry points
     def train_step(self, mel, f0, sil, lambda_f0=0.1, grad_scale=1.0):
@@ -750,6 +798,7 @@ class Engine:
         f0 = f0.to(self.device, torch.float32).contiguous().view(-1)
         sil = sil.to(self.device, torch.float32).contiguous().view(-1)
         dHc, dHd = self._heads(f0, sil, lambda_f0, grad_scale, want_grad=True)
+        self._mark("heads_loss")
         self.backward_core(dHc, dHd)
         if self.reducer is not None:
             self.reducer.wait()  # the current stream waits for the bucket all-reduces (captured as graph edges)
@@ -785,6 +834,17 @@ class Engine:
         self.cast_weights()  # not part of the graph: skipped when FusedAdamW.step already wrote the bf16 copy
         if self.reducer is not None:
             self.reducer.begin_step()
+        if ent.get("phases"):  # profiling mode: the step was cut at the phase marks, time every segment
+            cs, evs = torch.cuda.current_stream(), []
+            for graph, tags in ent["segments"]:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(cs)
+                graph.replay()
+                e1.record(cs)
+                evs.append((tags[0] if tags else "tail", e0, e1))
+            self.phase_events.append(evs)
+            L.launch_count += ent["launches"]
+            return self.loss_out
         for graph, tags in ent["segments"]:
             graph.replay()
             for tag in tags:  # gradient buckets completed by this segment: their all-reduces go out from the host
@@ -834,6 +894,10 @@ class Engine:
                 pass
 
         real = self.reducer
+        if real is None and os.environ.get("PE_PHASES") == "1":  # profiling: cut the graph at the phase marks
+            ent["phases"] = True
+            self.phase_events = []
+            self._phase_cb = lambda tag: (end(tag), begin())
         side = torch.cuda.Stream(device=self.device)
         self.cast_weights()
         self._capturing = True
@@ -854,6 +918,7 @@ class Engine:
         except Exception as e:  # stay on the eager CUDA path (still no CPU fallback)
             self.reducer = real
             self._capturing = False
+            self._phase_cb = None
             if "g" in cur:
                 try:
                     cur["g"].capture_end()
@@ -868,6 +933,7 @@ class Engine:
             return
         self.reducer = real
         self._capturing = False
+        self._phase_cb = None
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         ent["segments"] = segments
