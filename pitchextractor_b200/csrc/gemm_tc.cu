@@ -73,7 +73,11 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile) {
 // the TMA + MMA main loop of tile i + 1.
 // MODE and KPS are compile-time copies of p.mode and p.kps: the producer / MMA warps are single instruction streams whose per-k-block
 // latency bounds narrow tiles, so their loops must not carry the other modes' branches.
-template <int MODE, int KPS>
+// PAIR = 1: the kernel runs as clusters of two CTAs and every tile is 256 rows tall (tcgen05 cta_group::2): CTA r of the
+// pair loads its own 128 rows of A and half of the B tile and keeps its 128 accumulator rows in its own TMEM; only the
+// leader (rank 0) issues MMAs.  Each SM then fills / reads half of B per MMA, which is what the shared-memory port of a
+// single SM cannot sustain at full tensor rate (operand reads + TMA fills of a 128 x 256 x 64 step: 96 KB per 512 cycles).
+template <int MODE, int KPS, int PAIR>
 __global__ void __launch_bounds__(kNumThreadsWgrad, 1)
 tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_a2,
                const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_out,
@@ -82,7 +86,11 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   // swizzle of the operand tiles needs), and all 227 KB are usable.
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
-  const int b_tile_bytes = p.block_n * kRowBytes;
+  constexpr int NC = PAIR ? 2 : 1;  // CTAs per tile
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int first_tile = PAIR ? (int)cluster_id_x() : (int)blockIdx.x;
+  const int tile_step = PAIR ? (int)cluster_count_x() : (int)gridDim.x;
+  const int b_tile_bytes = (p.block_n / NC) * kRowBytes;  // this CTA's part of the B tile
   const int sub_bytes = kATileBytes + b_tile_bytes;  // one 64-wide k-block of both operands
   const int stage_bytes = KPS * sub_bytes;
   // layout: operand ring | epilogue staging (8 warps x 2 blocks of 32 rows x 64 B) | barriers | TMEM slot | column statistics
@@ -118,15 +126,19 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], kNumEpiWarps);
+      mbar_init(&tmem_empty_bar[s], kNumEpiWarps * NC);  // pair: the peer's epilogue warps arrive on the leader's barrier
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  if (warp == 2) {
+    if (PAIR) tmem_alloc_pair(tmem_slot, (uint32_t)p.tmem_cols);
+    else tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  }
   if (p.ep.stats_mode)
     for (int i = threadIdx.x; i < 512; i += (int)blockDim.x) s_stats[i] = 0.f;
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // (the peer's barriers are signalled remotely: their initialisation must be visible)
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // everything above overlapped the tail of the previous kernel; from here on its results are read
@@ -142,17 +154,20 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       long long w_empty = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      // pair: both CTAs' loads complete on the leader's full barriers (the leader alone announces the byte count)
+      const uint32_t full_leader = PAIR ? mapa_shared(smem_u32(full_bar), 0) : 0u;
+      for (int tile = first_tile; tile < p.num_tiles; tile += tile_step) {
         const TileCoord tc = decode_tile(p, tile);
+        const int tx = PAIR ? tc.tx * 2 + (int)rank : tc.tx;  // (an odd tile count leaves the last peer an empty tile)
         const int kb_begin = tc.tz * p.kb_per_split;
         const int kb_end = min(p.kb_total, kb_begin + p.kb_per_split);
         int m0 = 0, n0 = 0, img = 0, h0 = 0, w0 = 0;
         if (MODE == 0) {
-          m0 = tc.tx * kBlockM;
-          n0 = tc.ty * p.block_n;
+          m0 = tx * kBlockM;
+          n0 = tc.ty * p.block_n + (int)rank * (p.block_n / NC);
         } else if (MODE == 1) {
-          decode_conv_tile(p, tc.tx, img, h0, w0);
-          n0 = tc.ty * p.block_n;
+          decode_conv_tile(p, tx, img, h0, w0);
+          n0 = tc.ty * p.block_n + (int)rank * (p.block_n / NC);
         } else {
           m0 = tc.tx * kBlockM;  // Cout tile; tc.ty = tap
         }
@@ -191,8 +206,19 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           if (leader) {
             const int bytes = part == 0 ? p.tx_bytes
                                         : (part == 1 ? p.a_boxes : p.b_boxes) * 64 * kRowBytes;  // (mode 2: KPS == 1)
-            mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(nsub * bytes));
+            if (!PAIR || rank == 0) mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(nsub * bytes * NC));
           }
+          const uint32_t fb = full_leader + 8u * (uint32_t)s;
+#define PE_LOAD_2D(map, dst, c0, c1)                                  \
+  do {                                                                \
+    if (PAIR) tma_load_2d_pair(map, fb, dst, c0, c1);                 \
+    else tma_load_2d(map, &full_bar[s], dst, c0, c1);                 \
+  } while (0)
+#define PE_LOAD_4D(map, dst, c0, c1, c2, c3)                          \
+  do {                                                                \
+    if (PAIR) tma_load_4d_pair(map, fb, dst, c0, c1, c2, c3);         \
+    else tma_load_4d(map, &full_bar[s], dst, c0, c1, c2, c3);         \
+  } while (0)
           for (int sub = 0; sub < nsub; ++sub) {
           const int kb = kb0 + sub;
           uint8_t* sa = smem + (size_t)s * stage_bytes + (size_t)sub * sub_bytes;
@@ -202,25 +228,25 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           } else if (MODE == 0) {
             const int k0 = kb * elems_per_row;
             if (!p.a_mn) {
-              tma_load_2d(&tma_a, &full_bar[s], sa, k0, m0);
+              PE_LOAD_2D(&tma_a, sa, k0, m0);
             } else {
               for (int j = 0; j < p.a_boxes; ++j)
-                tma_load_2d(&tma_a, &full_bar[s], sa + j * (elems_per_row * kRowBytes), m0 + j * elems_per_row, k0);
+                PE_LOAD_2D(&tma_a, sa + j * (elems_per_row * kRowBytes), m0 + j * elems_per_row, k0);
             }
             if (!p.b_mn) {
-              tma_load_2d(&tma_b, &full_bar[s], sb, k0, n0);
+              PE_LOAD_2D(&tma_b, sb, k0, n0);
             } else {
               for (int j = 0; j < p.b_boxes; ++j)
-                tma_load_2d(&tma_b, &full_bar[s], sb + j * (elems_per_row * kRowBytes), n0 + j * elems_per_row, k0);
+                PE_LOAD_2D(&tma_b, sb + j * (elems_per_row * kRowBytes), n0 + j * elems_per_row, k0);
             }
           } else if (MODE == 1) {
             if (kb < main_kb) {
               const int kh = c_tap >= 6 ? 2 : (c_tap >= 3 ? 1 : 0);
-              tma_load_4d(&tma_a, &full_bar[s], sa, c_chunk * 64, w0 + (c_tap - 3 * kh) - 1, h0 + kh - 1, img);
+              PE_LOAD_4D(&tma_a, sa, c_chunk * 64, w0 + (c_tap - 3 * kh) - 1, h0 + kh - 1, img);
             } else {
-              tma_load_4d(&tma_a2, &full_bar[s], sa, (kb - main_kb) * 64, w0, h0, img);
+              PE_LOAD_4D(&tma_a2, sa, (kb - main_kb) * 64, w0, h0, img);
             }
-            tma_load_2d(&tma_b, &full_bar[s], sb, kb * 64, n0);
+            PE_LOAD_2D(&tma_b, sb, kb * 64, n0);
           } else {
             // k-block = one 64-pixel patch; A = dy (Cout-major); B = x shifted by the tap(s) this tile owns: output
             // column n = tap * Cin + ci, 64-wide boxes, several taps per tile when Cin is small (A is loaded once)
@@ -250,16 +276,18 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
           }
           }  // sub
+#undef PE_LOAD_2D
+#undef PE_LOAD_4D
           __syncwarp();
         }
       }
       if (p.dbg && lane == 0 && warp == 0) p.dbg[blockIdx.x * 16 + 3] = w_empty;
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp == 1 && (!PAIR || rank == 0)) {
+    // ------------------------------------------------------------------ MMA issuer (pair: the leader CTA's)
     // The whole warp walks the loop (uniform control flow), one elected lane issues the tcgen05 instructions.
     {
-      const uint32_t idesc = umma_idesc(UMMA_BF16, kBlockM, p.block_n, p.a_mn, p.b_mn);
+      const uint32_t idesc = umma_idesc(UMMA_BF16, kBlockM * NC, p.block_n, p.a_mn, p.b_mn);
       constexpr int k_rows = 16;  // UMMA_K (bf16)
       // start-address step (>> 4) between the four MMAs of a 64-deep k-block: 32 B along a K-major row, 16 rows of an
       // MN-major tile; compile-time for the convolution modes, so the issue loop adds immediates
@@ -279,7 +307,7 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const uint32_t da_lo = (uint32_t)da0, da_hi = (uint32_t)(da0 >> 32), db_lo = (uint32_t)db0, db_hi = (uint32_t)(db0 >> 32);
       const uint32_t smem_base = smem_u32(smem);
       const int gmask = p.commit_group - 1;  // smem slots are handed back in groups of 1, 2 or 4 k-blocks
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
+      for (int tile = first_tile; tile < p.num_tiles; tile += tile_step, ++local) {
         const TileCoord tc = decode_tile(p, tile);
         const int kb_begin = tc.tz * p.kb_per_split;
         const int num_kb = min(p.kb_total, kb_begin + p.kb_per_split) - kb_begin;
@@ -307,7 +335,8 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               const uint32_t first = (i0 + sub) > 0 ? 1u : 0u;
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                tc_mma_bf16_lh(d_tmem, a_lo, da_hi, b_lo, db_hi, idesc, k > 0 ? 1u : first);
+                if (PAIR) tc_mma_bf16_pair_lh(d_tmem, a_lo, da_hi, b_lo, db_hi, idesc, k > 0 ? 1u : first);
+                else tc_mma_bf16_lh(d_tmem, a_lo, da_hi, b_lo, db_hi, idesc, k > 0 ? 1u : first);
                 a_lo += a_inc;
                 b_lo += b_inc;
               }
@@ -316,8 +345,13 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
             // tcgen05.commit costs the issuing thread ~200 cycles: narrow tiles (short MMAs) release their slots in
             // groups -- the commit on the group's last slot covers every earlier MMA, the producer waits on that slot
-            if ((stage & gmask) == gmask) tc_commit(&empty_bar[stage]);
-            if (i0 + nsub >= num_kb) tc_commit(&tmem_full_bar[acc]);
+            if (PAIR) {  // multicast commits: the slot is free / the accumulator is ready in both CTAs
+              if ((stage & gmask) == gmask) tc_commit_pair(&empty_bar[stage], 3);
+              if (i0 + nsub >= num_kb) tc_commit_pair(&tmem_full_bar[acc], 3);
+            } else {
+              if ((stage & gmask) == gmask) tc_commit(&empty_bar[stage]);
+              if (i0 + nsub >= num_kb) tc_commit(&tmem_full_bar[acc]);
+            }
           }
           __syncwarp();
           if (++stage == p.stages) {
@@ -333,7 +367,7 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         p.dbg[blockIdx.x * 16 + 6] = clock64() - t_entry;
       }
     }
-  } else {
+  } else if (warp >= 2 && warp < 2 + kNumEpiWarps) {
     // -------------------------------------------------------------------- epilogue (8 warps, 2 per TMEM lane quarter)
     const pe_epilogue& ep = p.ep;
     const unsigned long long drop_seed = pe_salted(ep.drop_seed);
@@ -345,20 +379,22 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     uint32_t stg_flip = 0;
     uint32_t local = 0;
     long long e_wait = 0, e_ld = 0, e_work = 0, e_last = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
+    const uint32_t tmem_empty_leader = PAIR ? mapa_shared(smem_u32(tmem_empty_bar), 0) : 0u;
+    for (int tile = first_tile; tile < p.num_tiles; tile += tile_step, ++local) {
       const TileCoord tc = decode_tile(p, tile);
+      const int tx = PAIR ? tc.tx * 2 + (int)rank : tc.tx;
       int m0 = 0, n0 = 0, img = 0, h0 = 0, w0 = 0;
       long long grow;
       bool row_ok;
       long long out_col_off = 0;
       if (MODE == 1) {
-        decode_conv_tile(p, tc.tx, img, h0, w0);
+        decode_conv_tile(p, tx, img, h0, w0);
         n0 = tc.ty * p.block_n;
         const int h = h0 + r / p.tw, w = w0 + r % p.tw;
-        row_ok = (h < p.H) && (w < p.W);
         grow = ((long long)img * p.H + h) * p.W + w;
+        row_ok = (h < p.H) && (w < p.W) && (grow < (long long)p.M);  // (pair: the last peer tile may lie past the batch)
       } else {
-        m0 = tc.tx * kBlockM;
+        m0 = tx * kBlockM;
         n0 = tc.ty * p.block_n;  // wgrad: columns are tap-major (n = tap * Cin + ci), several taps per tile
         grow = m0 + r;
         row_ok = grow < p.M;
@@ -534,7 +570,10 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           }
         }
         }
-        if (ep.stats_mode) {
+        // BatchNorm batch statistics of a bf16 output that leaves through the staging block: summed column-wise out of
+        // the staged block after the store below (32 two-byte loads per lane instead of the 62-shuffle butterfly)
+        const bool stats_from_block = ep.stats_mode == 1 && (p.out_tma & 1) && ep.out_mode == PE_OUT_BF16;
+        if (ep.stats_mode && !stats_from_block) {
           // per-column sums over the 32 rows of this warp by a transposing butterfly (31 shuffles per quantity), then
           // one shared-memory atomic per column; the CTA flushes its partials to the fp64 global sums once, at the end
           float sa[32], sb[32];
@@ -613,6 +652,36 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (p.out_tma & 1) {
           if (ep.out_mode == PE_OUT_BF16) stage_and_store(&tma_out, f, col0);
           else stage_and_store_f32(&tma_out, f, col0, ep.out_mode == PE_OUT_F32_ATOMIC);
+          if (stats_from_block) {
+            // lane = column: element (row j, column lane) of the block just staged (SWIZZLE_64B: 16-byte unit index
+            // XOR bits 1-2 of the row); rows outside the tensor hold junk and are skipped
+            const uint8_t* blk = stg + (stg_flip ^ 1u) * (kStagingBytes / 2) + (lane & 7) * 2;
+            const uint32_t rowmask = __ballot_sync(0xffffffffu, row_ok);
+            const int u0 = lane >> 3;
+            const uint8_t* bk[4] = {blk + ((u0 ^ 0) << 4), blk + ((u0 ^ 1) << 4), blk + ((u0 ^ 2) << 4), blk + ((u0 ^ 3) << 4)};
+            float s1 = 0.f, s2 = 0.f;
+            if (rowmask == 0xffffffffu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float v = __uint_as_float((uint32_t)(*reinterpret_cast<const unsigned short*>(bk[(j >> 1) & 3] + j * 64)) << 16);
+                s1 += v;
+                s2 = fmaf(v, v, s2);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float v = __uint_as_float((uint32_t)(*reinterpret_cast<const unsigned short*>(bk[(j >> 1) & 3] + j * 64)) << 16);
+                if ((rowmask >> j) & 1u) {
+                  s1 += v;
+                  s2 = fmaf(v, v, s2);
+                }
+              }
+            }
+            if (full) {
+              atomicAdd(&s_stats[col0 + lane], s1);
+              atomicAdd(&s_stats[256 + col0 + lane], s2);
+            }
+          }
         } else if (!row_ok) {
           // nothing to write for rows outside the tensor
         } else if (ep.out_mode == PE_OUT_BF16) {
@@ -651,7 +720,10 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       // hand the accumulator stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(tmem_empty_leader + 8u * acc);
+        else mbar_arrive(&tmem_empty_bar[acc]);
+      }
       if (p.dbg) { e_last = clock64() - e_t1; e_work += e_last; }
     }
     if (p.out_tma && lane == 0) bulk_wait_all();  // staged stores have landed before the CTA may exit
@@ -671,9 +743,13 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // the leader's MMAs read the peer's shared memory and write its TMEM until the very end
+  else __syncthreads();
   if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 16 + 7] = clock64() - t_entry;
-  if (warp == 2) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  if (warp == 2) {
+    if (PAIR) tmem_dealloc_pair(tmem_base, (uint32_t)p.tmem_cols);
+    else tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
 }
 
 }  // namespace pe
@@ -709,9 +785,24 @@ static bool out_tmap(CUtensorMap* m, const TcParams& p, void* base, long long ld
   return pe_host::encode_tmap(m, dt, 2, base, dims, str, box, 64) == PE_OK;
 }
 
+// CTA-pair (cta_group::2) execution of a launch: 256-row tiles, each CTA of a cluster of two holds half of the B tile.
+// K-major B is split by rows of the N x 64 box, MN-major B by its 64-wide column boxes.
+static bool want_pair(int mode, int block_n, int b_mn, int m_tiles) {
+  // Measured (profiles/r02_tile_engine_notes.md): the main loop of 256-wide tiles gets 9 % shorter, narrower tiles do not
+  // change (they are bound by the ~85-cycle issue interval of SS-operand MMAs, not by operand traffic), and the training
+  // step is unchanged within noise -- so pairs are opt-in: PE_TC_PAIR=1 every eligible launch, 2 only N = 256.
+  static const int knob = getenv("PE_TC_PAIR") ? atoi(getenv("PE_TC_PAIR")) : 0;
+  if (!knob || mode == 2 || m_tiles < 2) return false;
+  if (knob == 2 && block_n != 256) return false;
+  if (block_n % 32 || block_n < 32) return false;   // N / 2 per CTA, multiples of 16 (the MMA's N is block_n)
+  if (b_mn && (block_n % 128)) return false;        // whole 64-wide boxes per CTA
+  return pe_host::num_sms() % 2 == 0;
+}
+
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, TcParams& p, dim3 tiles,
-                     cudaStream_t stream, int conv_B = 0) {
-  const int sub_bytes = pe::kATileBytes + p.block_n * pe::kRowBytes;
+                     cudaStream_t stream, int conv_B = 0, bool pair = false) {
+  const int nc = pair ? 2 : 1;
+  const int sub_bytes = pe::kATileBytes + (p.block_n / nc) * pe::kRowBytes;  // per CTA
   // narrow tiles (short MMAs) are bound by the per-stage barrier round trip of the producer / MMA threads: two k-blocks
   // per stage halve it (wide tiles keep one: two 96 KB stages would not cover the TMA latency)
   p.kps = (p.block_n <= 128 && p.mode != 2) ? 2 : 1;
@@ -743,7 +834,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtens
   p.tmem_cols = pow2_cols(2 * p.block_n);
   p.tx_bytes = p.mode == 2 ? (p.a_boxes + p.b_boxes) * 64 * pe::kRowBytes : sub_bytes;  // per k-block
   p.acc_stride = p.tmem_cols / 2;
-  p.tiles_x = (int)tiles.x;
+  p.tiles_x = ((int)tiles.x + nc - 1) / nc;  // pair: columns of 256-row tiles
   p.tiles_y = (int)tiles.y;
   p.tiles_z = (int)tiles.z;
   p.num_tiles = p.tiles_x * p.tiles_y * p.tiles_z;
@@ -768,24 +859,35 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtens
   static bool attr_set = false;
   if (!attr_set) {
     const int sz = 227 * 1024;
-    if (cudaFuncSetAttribute(pe::tc_tile_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz) != cudaSuccess ||
-        cudaFuncSetAttribute(pe::tc_tile_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz) != cudaSuccess ||
-        cudaFuncSetAttribute(pe::tc_tile_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz) != cudaSuccess ||
-        cudaFuncSetAttribute(pe::tc_tile_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz) != cudaSuccess ||
-        cudaFuncSetAttribute(pe::tc_tile_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz) != cudaSuccess)
+    if (cudaFuncSetAttribute(pe::tc_tile_kernel<0, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz) != cudaSuccess ||
+        cudaFuncSetAttribute(pe::tc_tile_kernel<0, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz) != cudaSuccess ||
+        cudaFuncSetAttribute(pe::tc_tile_kernel<1, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz) != cudaSuccess ||
+        cudaFuncSetAttribute(pe::tc_tile_kernel<1, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz) != cudaSuccess ||
+        cudaFuncSetAttribute(pe::tc_tile_kernel<2, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz) != cudaSuccess ||
+        cudaFuncSetAttribute(pe::tc_tile_kernel<0, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz) != cudaSuccess ||
+        cudaFuncSetAttribute(pe::tc_tile_kernel<0, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz) != cudaSuccess ||
+        cudaFuncSetAttribute(pe::tc_tile_kernel<1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz) != cudaSuccess ||
+        cudaFuncSetAttribute(pe::tc_tile_kernel<1, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz) != cudaSuccess)
       return PE_ERR_LAUNCH;
     attr_set = true;
   }
-  const int grid = p.num_tiles < pe_host::num_sms() ? p.num_tiles : pe_host::num_sms();
+  const int units = pe_host::num_sms() / nc;  // CTAs or CTA pairs
+  const int grid = (p.num_tiles < units ? p.num_tiles : units) * nc;
   cudaError_t lerr = cudaSuccess;
-#define PE_TC_LAUNCH(M, K)                                                                                         \
-  lerr = pe_host::launch(pe::tc_tile_kernel<M, K>, dim3(grid), dim3((M) == 2 ? pe::kNumThreadsWgrad : pe::kNumThreads), \
-                         smem, stream, ta, ta2, tb, tout, tout2, p)
-  if (p.mode == 0 && p.kps == 1) PE_TC_LAUNCH(0, 1);
-  else if (p.mode == 0) PE_TC_LAUNCH(0, 2);
-  else if (p.mode == 1 && p.kps == 1) PE_TC_LAUNCH(1, 1);
-  else if (p.mode == 1) PE_TC_LAUNCH(1, 2);
-  else PE_TC_LAUNCH(2, 1);
+#define PE_TC_LAUNCH(M, K, P)                                                                                        \
+  lerr = pe_host::launch_cluster(pe::tc_tile_kernel<M, K, P>, dim3(grid),                                             \
+                                 dim3((M) == 2 ? pe::kNumThreadsWgrad : pe::kNumThreads), smem, stream, (P) ? 2 : 1, ta, \
+                                 ta2, tb, tout, tout2, p)
+  if (pair) {
+    if (p.mode == 0 && p.kps == 1) PE_TC_LAUNCH(0, 1, 1);
+    else if (p.mode == 0) PE_TC_LAUNCH(0, 2, 1);
+    else if (p.kps == 1) PE_TC_LAUNCH(1, 1, 1);
+    else PE_TC_LAUNCH(1, 2, 1);
+  } else if (p.mode == 0 && p.kps == 1) PE_TC_LAUNCH(0, 1, 0);
+  else if (p.mode == 0) PE_TC_LAUNCH(0, 2, 0);
+  else if (p.mode == 1 && p.kps == 1) PE_TC_LAUNCH(1, 1, 0);
+  else if (p.mode == 1) PE_TC_LAUNCH(1, 2, 0);
+  else PE_TC_LAUNCH(2, 1, 0);
 #undef PE_TC_LAUNCH
   return (lerr == cudaSuccess && cudaGetLastError() == cudaSuccess) ? PE_OK : PE_ERR_LAUNCH;
 }
@@ -825,8 +927,10 @@ extern "C" int pe_gemm_bf16(const void* A, long long lda, int a_mn, const void* 
     if (force == 128 || (force == 0 && waste(t256) > 0.33 && waste(t128) < waste(t256) - 0.1)) bn = 128;
   }
   p.block_n = bn;
+  const bool pair = want_pair(0, bn, p.b_mn, (M + 127) / 128);
+  const int nc = pair ? 2 : 1;
   p.a_boxes = 2;
-  p.b_boxes = bn / 64;
+  p.b_boxes = bn / 64 / nc;  // (MN-major B: 64-wide boxes per CTA)
   p.kb_total = (K + 63) / 64;
   p.kb_per_split = (p.kb_total + splits - 1) / splits;
   splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
@@ -841,13 +945,13 @@ extern "C" int pe_gemm_bf16(const void* A, long long lda, int a_mn, const void* 
     else         { dims[0] = (uint64_t)M; dims[1] = (uint64_t)K; box[0] = 64; box[1] = 64; }
     str[0] = (uint64_t)lda * 2;
     if (int rc = pe_host::encode_tmap(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, dims, str, box)) return rc;
-    if (!p.b_mn) { dims[0] = (uint64_t)K; dims[1] = (uint64_t)N; box[0] = 64; box[1] = (uint32_t)bn; }
+    if (!p.b_mn) { dims[0] = (uint64_t)K; dims[1] = (uint64_t)N; box[0] = 64; box[1] = (uint32_t)(bn / nc); }
     else         { dims[0] = (uint64_t)N; dims[1] = (uint64_t)K; box[0] = 64; box[1] = 64; }
     str[0] = (uint64_t)ldb * 2;
     if (int rc = pe_host::encode_tmap(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, B, dims, str, box)) return rc;
   }
   dim3 grid((M + 127) / 128, (N + bn - 1) / bn, splits);
-  return launch_tc(ta, ta, tb, p, grid, reinterpret_cast<cudaStream_t>(stream));
+  return launch_tc(ta, ta, tb, p, grid, reinterpret_cast<cudaStream_t>(stream), 0, pair);
 }
 
 // patch shapes: 128-pixel output tiles (fwd) and 64-pixel contraction blocks (wgrad) that tile W in 5 columns
@@ -889,6 +993,7 @@ extern "C" int pe_conv3x3_nhwc(const void* x, const void* x2, const void* w, int
   p.M = B * H * W;
   p.N = Cout;
   p.block_n = Cout > 256 ? 256 : Cout;
+  const bool pair = want_pair(1, p.block_n, 0, B * p.tiles_h * p.tiles_w);
   p.kb_total = 9 * p.c1_chunks + p.c2_chunks;
   p.kb_per_split = p.kb_total;
   p.ep = *ep;
@@ -902,11 +1007,11 @@ extern "C" int pe_conv3x3_nhwc(const void* x, const void* x2, const void* w, int
     const int Ktot = 9 * C1 + C2;
     uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)Cout};
     uint64_t str[1] = {(uint64_t)Ktot * 2};
-    uint32_t box[2] = {64, (uint32_t)p.block_n};
+    uint32_t box[2] = {64, (uint32_t)(p.block_n / (pair ? 2 : 1))};
     if (int rc = pe_host::encode_tmap(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w, dims, str, box)) return rc;
   }
   dim3 grid(B * p.tiles_h * p.tiles_w, (Cout + p.block_n - 1) / p.block_n, 1);
-  return launch_tc(ta, ta2, tb, p, grid, reinterpret_cast<cudaStream_t>(stream), B);
+  return launch_tc(ta, ta2, tb, p, grid, reinterpret_cast<cudaStream_t>(stream), B, pair);
 }
 
 extern "C" int pe_conv_wgrad_nhwc(const void* dy, const void* x, float* dw, long long ldw, int B, int H, int W, int C,

@@ -180,3 +180,18 @@ def test_conv_epilogue_column_statistics(built_lib):
     g3 = out.float().reshape(-1, Cout) * torch.where(pre_s > 0, 1.0, 0.01)
     assert torch.allclose(sums3[0], g3.double().sum(0), rtol=1e-3, atol=1e-2)
     assert torch.allclose(sums3[1], (g3.double() * x_s.double()).sum(0), rtol=1e-3, atol=1e-2)
+
+
+@pytest.mark.parametrize("env", [{"PE_TC_PAIR": "1"}, {"PE_PDL": "1"}])
+def test_opt_in_launch_modes(built_lib, env):
+    """The opt-in launch modes of the tile engine -- CTA pairs (tcgen05 cta_group::2, clusters of two) and programmatic
+    dependent launch -- are switched by environment variables read once per process, so they are exercised by re-running
+    this file's GEMM / convolution / column-statistics checks in a child process."""
+    import os
+    import subprocess
+    import sys
+    child = dict(os.environ, **env)
+    cmd = [sys.executable, "-m", "pytest", __file__, "-q", "-x", "-m", "gpu", "-k",
+           "kmajor or mn_major or conv3x3 or column_statistics or epilogues", "-p", "no:cacheprovider"]
+    r = subprocess.run(cmd, env=child, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
