@@ -101,6 +101,7 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);  // [2][256] per-CTA column partial sums (ep.stats)
+  uint32_t* s_sign = reinterpret_cast<uint32_t*>(s_stats + 512);  // [128] stats mode 3: per column pair, 0xffff where scale >= 0
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -136,12 +137,18 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   }
   if (p.ep.stats_mode)
     for (int i = threadIdx.x; i < 512; i += (int)blockDim.x) s_stats[i] = 0.f;
+
   tc_fence_before();
   if (PAIR) cluster_sync_all();  // (the peer's barriers are signalled remotely: their initialisation must be visible)
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // everything above overlapped the tail of the previous kernel; from here on its results are read
+  if (p.ep.stats_mode == 3) {
+    for (int i = threadIdx.x; i < p.N / 2; i += (int)blockDim.x)
+      s_sign[i] = (p.ep.stats_scale[2 * i] >= 0.f ? 0x0000ffffu : 0u) | (p.ep.stats_scale[2 * i + 1] >= 0.f ? 0xffff0000u : 0u);
+    __syncthreads();
+  }
   if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 16 + 5] = clock64() - t_entry;
 
   if (warp == 0 || (MODE == 2 && warp == 10)) {
@@ -380,6 +387,9 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     uint32_t local = 0;
     long long e_wait = 0, e_ld = 0, e_work = 0, e_last = 0;
     const uint32_t tmem_empty_leader = PAIR ? mapa_shared(smem_u32(tmem_empty_bar), 0) : 0u;
+    // BatchNorm-backward sums read column-wise out of the staging blocks (every 32-column chunk of the launch is whole)
+    const bool stats_x_block = ep.stats_mode >= 2 && (p.out_tma & 1) && ep.out_mode == PE_OUT_BF16 && (p.N % 32) == 0 &&
+                               (p.block_n % 32) == 0;
     for (int tile = first_tile; tile < p.num_tiles; tile += tile_step, ++local) {
       const TileCoord tc = decode_tile(p, tile);
       const int tx = PAIR ? tc.tx * 2 + (int)rank : tc.tx;
@@ -402,10 +412,15 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       // 64-byte row blocks -> one of this warp's two staging blocks (each lane its own row; 16-byte units XOR-swizzled
       // as SWIZZLE_64B expects, which also makes the writes bank-conflict free) -> one TMA tensor store / reduction.
       // Rows and columns outside the tensor are clipped by the TMA unit, so every lane takes part regardless of row_ok.
+      // (stats_x_block: the first staging block holds the BatchNorm input of this chunk, see below; outputs then leave
+      // through the second block alone, which is free again once the previous chunk's store has been read)
       auto stage_block = [&](const CUtensorMap* map, const uint4 (&w)[4], int col, bool reduce) {
-        uint8_t* buf = stg + stg_flip * (kStagingBytes / 2);
+        uint8_t* buf = stg + (stats_x_block ? 1u : stg_flip) * (kStagingBytes / 2);
         stg_flip ^= 1u;
-        if (lane == 0) bulk_wait_read_1();  // the store issued two blocks ago (same buffer) has been read
+        if (lane == 0) {
+          if (stats_x_block) bulk_wait_read_all();
+          else bulk_wait_read_1();  // the store issued two blocks ago (same buffer) has been read
+        }
         __syncwarp();
 #pragma unroll
         for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(buf + lane * 64 + ((u ^ ((lane >> 1) & 3)) << 4)) = w[u];
@@ -572,7 +587,47 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
         // BatchNorm batch statistics of a bf16 output that leaves through the staging block: summed column-wise out of
         // the staged block after the store below (32 two-byte loads per lane instead of the 62-shuffle butterfly)
-        const bool stats_from_block = ep.stats_mode == 1 && (p.out_tma & 1) && ep.out_mode == PE_OUT_BF16;
+        // The first BatchNorm-backward pass (modes 2 / 3) goes the same way: the lanes first put the BatchNorm input of
+        // their rows (mode 3: of the pooled pair, the element MaxPool selected) into the other staging block.
+        const bool stats_from_block = stats_x_block || (ep.stats_mode == 1 && (p.out_tma & 1) && ep.out_mode == PE_OUT_BF16);
+        if (stats_x_block) {
+          __syncwarp();  // (the previous chunk's column pass has finished reading the block)
+          uint4 xs[4];
+          if (ep.stats_mode == 2) {
+            const uint4* xp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(ep.stats_x) +
+                                                             grow * (long long)p.N + col0);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) xs[u] = row_ok ? xp[u] : make_uint4(0u, 0u, 0u, 0u);
+          } else {
+            // the BatchNorm input is twice as wide as this gradient (MaxPool (1,2) in between): output pixel `grow` owns
+            // input pixels 2*grow and 2*grow+1 and the gradient goes to the maximum of the activated pair.  LeakyReLU of
+            // an affine map is monotonic, so that is the larger input where the BatchNorm scale is positive and the
+            // smaller one where it is negative: packed bf16 max / min and a per-column sign mask, no arithmetic.
+            const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(ep.stats_x) + grow * 2LL * p.N + col0;
+            const uint4* sg = reinterpret_cast<const uint4*>(s_sign + (col0 >> 1));
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              uint4 u0 = make_uint4(0u, 0u, 0u, 0u), u1 = u0;
+              if (row_ok) {
+                u0 = *reinterpret_cast<const uint4*>(xp + 8 * u);
+                u1 = *reinterpret_cast<const uint4*>(xp + p.N + 8 * u);
+              }
+              const uint4 m = sg[u];
+              const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&u0);
+              const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u1);
+              const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+              uint32_t sel[4];
+#pragma unroll
+              for (int t2 = 0; t2 < 4; ++t2) {
+                const __nv_bfloat162 mx = __hmax2(a2[t2], b2[t2]), mn = __hmin2(a2[t2], b2[t2]);
+                sel[t2] = (*reinterpret_cast<const uint32_t*>(&mx) & mw[t2]) | (*reinterpret_cast<const uint32_t*>(&mn) & ~mw[t2]);
+              }
+              xs[u] = make_uint4(sel[0], sel[1], sel[2], sel[3]);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(stg + lane * 64 + ((u ^ ((lane >> 1) & 3)) << 4)) = xs[u];
+        }
         if (ep.stats_mode && !stats_from_block) {
           // per-column sums over the 32 rows of this warp by a transposing butterfly (31 shuffles per quantity), then
           // one shared-memory atomic per column; the CTA flushes its partials to the fp64 global sums once, at the end
@@ -652,7 +707,28 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (p.out_tma & 1) {
           if (ep.out_mode == PE_OUT_BF16) stage_and_store(&tma_out, f, col0);
           else stage_and_store_f32(&tma_out, f, col0, ep.out_mode == PE_OUT_F32_ATOMIC);
-          if (stats_from_block) {
+          if (stats_x_block) {
+            // lane = column: g = v * lrelu'(x * scale + shift) over the 32 rows; sums of g and g * x
+            const uint8_t* vb = stg + kStagingBytes / 2 + (lane & 7) * 2;
+            const uint8_t* xb = stg + (lane & 7) * 2;
+            const uint32_t rowmask = __ballot_sync(0xffffffffu, row_ok);
+            const int u0 = lane >> 3;
+            const int uo[4] = {(u0 ^ 0) << 4, (u0 ^ 1) << 4, (u0 ^ 2) << 4, (u0 ^ 3) << 4};
+            const float sc = __ldg(ep.stats_scale + col0 + lane), sh = __ldg(ep.stats_shift + col0 + lane);
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int off = uo[(j >> 1) & 3] + j * 64;
+              const float v = __uint_as_float((uint32_t)(*reinterpret_cast<const unsigned short*>(vb + off)) << 16);
+              const float x = __uint_as_float((uint32_t)(*reinterpret_cast<const unsigned short*>(xb + off)) << 16);
+              float g = v * (fmaf(x, sc, sh) > 0.f ? 1.f : ep.stats_slope);
+              if (rowmask != 0xffffffffu && !((rowmask >> j) & 1u)) g = 0.f;
+              s1 += g;
+              s2 = fmaf(g, x, s2);
+            }
+            atomicAdd(&s_stats[col0 + lane], s1);
+            atomicAdd(&s_stats[256 + col0 + lane], s2);
+          } else if (stats_from_block) {
             // lane = column: element (row j, column lane) of the block just staged (SWIZZLE_64B: 16-byte unit index
             // XOR bits 1-2 of the row); rows outside the tensor hold junk and are skipped
             const uint8_t* blk = stg + (stg_flip ^ 1u) * (kStagingBytes / 2) + (lane & 7) * 2;
@@ -855,7 +931,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtens
     if (p.ep.out2 && p.ep.act != PE_ACT_NONE && out_tmap(&tout2, p, p.ep.out2, p.ep.ld2, conv_B, 2)) p.out_tma |= 2;
   }
   const size_t smem = (size_t)stages * stage_bytes + pe::kNumEpiWarps * pe::kStagingBytes +
-                      (2 * stages + 4) * sizeof(uint64_t) + 16 + 2048;
+                      (2 * stages + 4) * sizeof(uint64_t) + 16 + 2048 + 512;
   static bool attr_set = false;
   if (!attr_set) {
     const int sz = 227 * 1024;
