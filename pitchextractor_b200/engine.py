@@ -83,7 +83,6 @@ class Engine:
         self._fwd_token = 0
         self.on_grads_ready = None  # callback(tag) for the data-parallel gradient reducer
         self._side_stream = None
-        self._wg_streams = {}     # per encoder stack: helper stream of the weight-gradient GEMMs
         self._phase_cb = None     # see _mark()
         self.phase_events = None  # PE_PHASES=1: per replayed step, [(tag, start event, end event), ...]
         self._side_pending = False
@@ -602,10 +601,9 @@ class Engine:
                  out_mode=L.PE_OUT_F32_ATOMIC)
 
     def _transformer_bwd(self, prefix, tag, X, dH, B, T, site0):
-        """Backward of one encoder stack.  The data-gradient chain (LayerNorm, dgrad GEMMs, attention) runs on the
-        current stream; weight / bias gradients, which nothing reads before the optimizer, go to a per-stack helper
-        stream behind events (graph branches under capture).  Gradient buffers alternate between two sets by layer
-        parity, and layer l first waits for the helper work of layer l + 2, which read the set it is about to overwrite."""
+        """Backward of one encoder stack (the two stacks run on two streams, see backward_core).  Weight / bias gradients
+        stay on the stack's stream: floating them on helper streams behind the data-gradient chain was measured and
+        gave nothing (the phase is throughput-bound: 2.61 ms either way, profiles/r02_phase_times.txt)."""
         V, W16, g = self.view, self.bview, self.gview
         M, D, FF, H = B * T, 512, self.ff, self.nhead
         training = self._training
@@ -617,37 +615,13 @@ class Engine:
         dH1 = self.buf(tag + "dH1", (M, D))
         dCTX = self.buf(tag + "dCTX", (M, D))
         delta = self.buf(tag + "delta", (B, H, T), torch.float32)
-        main = torch.cuda.current_stream()
-        floating = os.environ.get("PE_TWO_STREAMS", "1") != "0" and os.environ.get("PE_WGRAD_STREAMS", "1") != "0"
-        if floating:
-            if tag not in self._wg_streams:
-                self._wg_streams[tag] = torch.cuda.Stream(device=self.device)
-            helper = self._wg_streams[tag]
-        done = {}
-
-        @contextlib.contextmanager
-        def off_chain():
-            """Work that depends on everything enqueued so far on the chain but that the chain does not wait for."""
-            if not floating:
-                yield
-                return
-            ev = torch.cuda.Event()
-            ev.record(main)
-            helper.wait_event(ev)
-            with torch.cuda.stream(helper):
-                yield
-
         for l in reversed(range(self.num_layers)):
             q = "%s.model.layers.%d." % (prefix, l)
             t = "%s%d" % (tag, l)
             site = site0 + 8 * l
-            par = l & 1
-            dSm2 = self.buf(tag + "dSm2_%d" % par, (M, D))
-            dSm1 = self.buf(tag + "dSm1_%d" % par, (M, D))
-            dU = self.buf(tag + "dU_%d" % par, (M, FF))
-            dQKV = self.buf(tag + "dQKV_%d" % par, (M, 3 * D))
-            if floating and (l + 2) in done:
-                main.wait_event(done.pop(l + 2))
+            dSm2 = dSm1 = self.buf(tag + "dSm", (M, D))
+            dU = self.buf(tag + "dU", (M, FF))
+            dQKV = self.buf(tag + "dQKV", (M, 3 * D))
             Hin = self._bufs[tag + "H0"] if l == 0 else self._bufs["%s%dH2" % (tag, l - 1)]
             QKV, CTX, LSE = self._bufs[t + "QKV"], self._bufs[t + "CTX"], self._bufs[t + "LSE"]
             S1, H1, U, G, S2 = (self._bufs[t + k] for k in ("S1", "H1", "U", "G", "S2"))
@@ -656,13 +630,11 @@ class Engine:
                  ptr(stats[2 * l + 2, 0]), ptr(stats[2 * l + 2, 1]), c_ll(M), ptr(dS), ptr(dSm2), c_u(drop[0]),
                  c_f(drop[1]), c_ull(self._seed(site + 3)), ptr(g[q + "norm2.weight"]), ptr(g[q + "norm2.bias"]),
                  ptr(g[q + "linear2.bias"]), stream())
-            with off_chain():
-                self._wgrad_linear(dSm2, G, q + "linear2.weight", D, FF, M)
+            self._wgrad_linear(dSm2, G, q + "linear2.weight", D, FF, M)
             # linear2: dG -> through dropout and GELU' -> dU
             ops.gemm(dSm2, W16[q + "linear2.weight"], dU, M, FF, D, b_mn=True, aux=U, aux_mode=L.PE_AUX_MUL)
-            with off_chain():
-                self._wgrad_linear(dU, H1, q + "linear1.weight", FF, D, M)
-                call("pe_colsum_bf16", ptr(dU), c_ll(M), c_int(FF), c_ll(FF), ptr(g[q + "linear1.bias"]), stream())
+            self._wgrad_linear(dU, H1, q + "linear1.weight", FF, D, M)
+            call("pe_colsum_bf16", ptr(dU), c_ll(M), c_int(FF), c_ll(FF), ptr(g[q + "linear1.bias"]), stream())
             # linear1: dH1 = dU W1 + dS (residual)
             ops.gemm(dU, W16[q + "linear1.weight"], dH1, M, D, FF, b_mn=True, aux=dS, aux_mode=L.PE_AUX_ADD)
             # norm1 backward (+ out_proj output dropout, out_proj.bias gradient)
@@ -670,20 +642,15 @@ class Engine:
                  ptr(stats[2 * l + 1, 0]), ptr(stats[2 * l + 1, 1]), c_ll(M), ptr(dS), ptr(dSm1), c_u(drop[0]),
                  c_f(drop[1]), c_ull(self._seed(site + 1)), ptr(g[q + "norm1.weight"]), ptr(g[q + "norm1.bias"]),
                  ptr(g[q + "self_attn.out_proj.bias"]), stream())
-            with off_chain():
-                self._wgrad_linear(dSm1, CTX, q + "self_attn.out_proj.weight", D, D, M)
+            self._wgrad_linear(dSm1, CTX, q + "self_attn.out_proj.weight", D, D, M)
             # out_proj
             ops.gemm(dSm1, W16[q + "self_attn.out_proj.weight"], dCTX, M, D, D, b_mn=True)
             # attention
             call("pe_attn_bwd", ptr(QKV), ptr(CTX), ptr(dCTX), ptr(LSE), c_int(B), c_int(T), c_int(H), c_int(64),
                  c_u(adrop[0]), c_f(adrop[1]), c_ull(self._seed(site + 0)), ptr(dQKV), ptr(delta), c_int(0), stream())
-            with off_chain():
-                self._wgrad_linear(dQKV, Hin, q + "self_attn.in_proj_weight", 3 * D, D, M)
-                call("pe_colsum_bf16", ptr(dQKV), c_ll(M), c_int(3 * D), c_ll(3 * D),
-                     ptr(g[q + "self_attn.in_proj_bias"]), stream())
-                if floating:
-                    done[l] = torch.cuda.Event()
-                    done[l].record(helper)
+            self._wgrad_linear(dQKV, Hin, q + "self_attn.in_proj_weight", 3 * D, D, M)
+            call("pe_colsum_bf16", ptr(dQKV), c_ll(M), c_int(3 * D), c_ll(3 * D),
+                 ptr(g[q + "self_attn.in_proj_bias"]), stream())
             # in_proj: dH = dQKV Wqkv + dS (residual)
             dHn = self.buf(tag + "dHin%d" % (l & 1), (M, D))
             ops.gemm(dQKV, W16[q + "self_attn.in_proj_weight"], dHn, M, D, 3 * D, b_mn=True, aux=dS,
@@ -694,8 +661,6 @@ class Engine:
              ptr(V[prefix + ".layer_norm.weight"]), ptr(stats[0, 0]), ptr(stats[0, 1]), c_ll(M), ptr(dX), None, c_u(0),
              c_f(1.0), c_ull(0), ptr(g[prefix + ".layer_norm.weight"]), ptr(g[prefix + ".layer_norm.bias"]), None,
              stream())
-        for ev in done.values():  # the stack's gradients are complete when this function returns (stream order)
-            main.wait_event(ev)
         return dX
 
     def backward_core(self, dHc, dHd):
