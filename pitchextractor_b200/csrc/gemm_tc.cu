@@ -77,7 +77,9 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile) {
 // pair loads its own 128 rows of A and half of the B tile and keeps its 128 accumulator rows in its own TMEM; only the
 // leader (rank 0) issues MMAs.  Each SM then fills / reads half of B per MMA, which is what the shared-memory port of a
 // single SM cannot sustain at full tensor rate (operand reads + TMA fills of a 128 x 256 x 64 step: 96 KB per 512 cycles).
-template <int MODE, int KPS, int PAIR>
+// STATS = 1: the epilogue carries the column-statistics code (BatchNorm batch statistics / BatchNorm-backward sums).  The
+// encoder GEMMs are instantiated without it: with the statistics paths compiled in, FFN1's epilogue was 8 % slower.
+template <int MODE, int KPS, int PAIR, int STATS>
 __global__ void __launch_bounds__(kNumThreadsWgrad, 1)
 tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_a2,
                const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_out,
@@ -135,7 +137,7 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (PAIR) tmem_alloc_pair(tmem_slot, (uint32_t)p.tmem_cols);
     else tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   }
-  if (p.ep.stats_mode)
+  if (STATS && p.ep.stats_mode)
     for (int i = threadIdx.x; i < 512; i += (int)blockDim.x) s_stats[i] = 0.f;
 
   tc_fence_before();
@@ -144,7 +146,7 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // everything above overlapped the tail of the previous kernel; from here on its results are read
-  if (p.ep.stats_mode == 3) {
+  if (STATS && p.ep.stats_mode == 3) {
     for (int i = threadIdx.x; i < p.N / 2; i += (int)blockDim.x)
       s_sign[i] = (p.ep.stats_scale[2 * i] >= 0.f ? 0x0000ffffu : 0u) | (p.ep.stats_scale[2 * i + 1] >= 0.f ? 0xffff0000u : 0u);
     __syncthreads();
@@ -377,6 +379,7 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   } else if (warp >= 2 && warp < 2 + kNumEpiWarps) {
     // -------------------------------------------------------------------- epilogue (8 warps, 2 per TMEM lane quarter)
     const pe_epilogue& ep = p.ep;
+    const int stats_mode = STATS ? ep.stats_mode : 0;  // (compiled out of the instantiations without statistics)
     const unsigned long long drop_seed = pe_salted(ep.drop_seed);
     const int q = warp & 3;              // TMEM lane quarter this warp may access
     const int pair = (warp - 2) >> 2;    // which of the two warps of the quarter: takes chunks c with (c & 1) == pair
@@ -388,7 +391,7 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     long long e_wait = 0, e_ld = 0, e_work = 0, e_last = 0;
     const uint32_t tmem_empty_leader = PAIR ? mapa_shared(smem_u32(tmem_empty_bar), 0) : 0u;
     // BatchNorm-backward sums read column-wise out of the staging blocks (every 32-column chunk of the launch is whole)
-    const bool stats_x_block = ep.stats_mode >= 2 && (p.out_tma & 1) && ep.out_mode == PE_OUT_BF16 && (p.N % 32) == 0 &&
+    const bool stats_x_block = stats_mode >= 2 && (p.out_tma & 1) && ep.out_mode == PE_OUT_BF16 && (p.N % 32) == 0 &&
                                (p.block_n % 32) == 0;
     for (int tile = first_tile; tile < p.num_tiles; tile += tile_step, ++local) {
       const TileCoord tc = decode_tile(p, tile);
@@ -469,7 +472,7 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         tmem_ld32(t_row + (uint32_t)(c * 32), v);
         tmem_ld_wait();
         e_ld += p.dbg ? clock64() - e_t2 : 0;
-        if (!row_ok && !ep.stats_mode && !p.out_tma) continue;  // (warp-uniform paths below need every lane)
+        if (!row_ok && !stats_mode && !p.out_tma) continue;  // (warp-uniform paths below need every lane)
         const int col0 = n0 + c * 32;
         float f[32];
 #pragma unroll
@@ -589,11 +592,11 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         // the staged block after the store below (32 two-byte loads per lane instead of the 62-shuffle butterfly)
         // The first BatchNorm-backward pass (modes 2 / 3) goes the same way: the lanes first put the BatchNorm input of
         // their rows (mode 3: of the pooled pair, the element MaxPool selected) into the other staging block.
-        const bool stats_from_block = stats_x_block || (ep.stats_mode == 1 && (p.out_tma & 1) && ep.out_mode == PE_OUT_BF16);
+        const bool stats_from_block = stats_x_block || (stats_mode == 1 && (p.out_tma & 1) && ep.out_mode == PE_OUT_BF16);
         if (stats_x_block) {
           __syncwarp();  // (the previous chunk's column pass has finished reading the block)
           uint4 xs[4];
-          if (ep.stats_mode == 2) {
+          if (stats_mode == 2) {
             const uint4* xp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(ep.stats_x) +
                                                              grow * (long long)p.N + col0);
 #pragma unroll
@@ -628,19 +631,19 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
           for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(stg + lane * 64 + ((u ^ ((lane >> 1) & 3)) << 4)) = xs[u];
         }
-        if (ep.stats_mode && !stats_from_block) {
+        if (stats_mode && !stats_from_block) {
           // per-column sums over the 32 rows of this warp by a transposing butterfly (31 shuffles per quantity), then
           // one shared-memory atomic per column; the CTA flushes its partials to the fp64 global sums once, at the end
           float sa[32], sb[32];
           const bool colok = full;
-          if (ep.stats_mode == 1) {
+          if (stats_mode == 1) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const float v = (row_ok && colok) ? (ep.out_mode == PE_OUT_BF16 ? __bfloat162float(__float2bfloat16(f[j])) : f[j]) : 0.f;
               sa[j] = v;
               sb[j] = v * v;
             }
-          } else if (ep.stats_mode == 3) {
+          } else if (stats_mode == 3) {
             // the BatchNorm input is twice as wide as this gradient (MaxPool (1,2) in between): output pixel `grow`
             // owns input pixels 2*grow and 2*grow+1; the gradient goes to the first maximum of the activated pair
             const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(ep.stats_x) + grow * 2LL * p.N + col0;
@@ -809,7 +812,7 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       p.dbg[blockIdx.x * 16 + 10] = e_work;
       p.dbg[blockIdx.x * 16 + 11] = e_last;
     }
-    if (ep.stats_mode) {
+    if (stats_mode) {
       asm volatile("bar.sync 2, 256;" ::: "memory");  // the 8 epilogue warps
       for (int i = threadIdx.x - 64; i < 2 * p.N; i += 32 * kNumEpiWarps) {
         const int which = i / p.N, col = i - which * p.N;
@@ -932,38 +935,43 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtens
   }
   const size_t smem = (size_t)stages * stage_bytes + pe::kNumEpiWarps * pe::kStagingBytes +
                       (2 * stages + 4) * sizeof(uint64_t) + 16 + 2048 + 512;
+  const int st = p.ep.stats_mode ? 1 : 0;
+  if (st && (pair || p.mode == 2)) return PE_ERR_BAD_SHAPE;  // (statistics: single-CTA GEMM / convolution launches only)
   static bool attr_set = false;
   if (!attr_set) {
     const int sz = 227 * 1024;
-    if (cudaFuncSetAttribute(pe::tc_tile_kernel<0, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz) != cudaSuccess ||
-        cudaFuncSetAttribute(pe::tc_tile_kernel<0, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz) != cudaSuccess ||
-        cudaFuncSetAttribute(pe::tc_tile_kernel<1, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz) != cudaSuccess ||
-        cudaFuncSetAttribute(pe::tc_tile_kernel<1, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz) != cudaSuccess ||
-        cudaFuncSetAttribute(pe::tc_tile_kernel<2, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz) != cudaSuccess ||
-        cudaFuncSetAttribute(pe::tc_tile_kernel<0, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz) != cudaSuccess ||
-        cudaFuncSetAttribute(pe::tc_tile_kernel<0, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz) != cudaSuccess ||
-        cudaFuncSetAttribute(pe::tc_tile_kernel<1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz) != cudaSuccess ||
-        cudaFuncSetAttribute(pe::tc_tile_kernel<1, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz) != cudaSuccess)
+#define PE_TC_ATTR(M, K, P, S) \
+  (cudaFuncSetAttribute(pe::tc_tile_kernel<M, K, P, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz) == cudaSuccess)
+    if (!(PE_TC_ATTR(0, 1, 0, 0) && PE_TC_ATTR(0, 2, 0, 0) && PE_TC_ATTR(1, 1, 0, 0) && PE_TC_ATTR(1, 2, 0, 0) &&
+          PE_TC_ATTR(2, 1, 0, 0) && PE_TC_ATTR(0, 1, 0, 1) && PE_TC_ATTR(0, 2, 0, 1) && PE_TC_ATTR(1, 1, 0, 1) &&
+          PE_TC_ATTR(1, 2, 0, 1) && PE_TC_ATTR(0, 1, 1, 0) && PE_TC_ATTR(0, 2, 1, 0) && PE_TC_ATTR(1, 1, 1, 0) &&
+          PE_TC_ATTR(1, 2, 1, 0)))
       return PE_ERR_LAUNCH;
+#undef PE_TC_ATTR
     attr_set = true;
   }
   const int units = pe_host::num_sms() / nc;  // CTAs or CTA pairs
   const int grid = (p.num_tiles < units ? p.num_tiles : units) * nc;
   cudaError_t lerr = cudaSuccess;
-#define PE_TC_LAUNCH(M, K, P)                                                                                        \
-  lerr = pe_host::launch_cluster(pe::tc_tile_kernel<M, K, P>, dim3(grid),                                             \
+#define PE_TC_LAUNCH(M, K, P, S)                                                                                     \
+  lerr = pe_host::launch_cluster(pe::tc_tile_kernel<M, K, P, S>, dim3(grid),                                          \
                                  dim3((M) == 2 ? pe::kNumThreadsWgrad : pe::kNumThreads), smem, stream, (P) ? 2 : 1, ta, \
                                  ta2, tb, tout, tout2, p)
   if (pair) {
-    if (p.mode == 0 && p.kps == 1) PE_TC_LAUNCH(0, 1, 1);
-    else if (p.mode == 0) PE_TC_LAUNCH(0, 2, 1);
-    else if (p.kps == 1) PE_TC_LAUNCH(1, 1, 1);
-    else PE_TC_LAUNCH(1, 2, 1);
-  } else if (p.mode == 0 && p.kps == 1) PE_TC_LAUNCH(0, 1, 0);
-  else if (p.mode == 0) PE_TC_LAUNCH(0, 2, 0);
-  else if (p.mode == 1 && p.kps == 1) PE_TC_LAUNCH(1, 1, 0);
-  else if (p.mode == 1) PE_TC_LAUNCH(1, 2, 0);
-  else PE_TC_LAUNCH(2, 1, 0);
+    if (p.mode == 0 && p.kps == 1) PE_TC_LAUNCH(0, 1, 1, 0);
+    else if (p.mode == 0) PE_TC_LAUNCH(0, 2, 1, 0);
+    else if (p.kps == 1) PE_TC_LAUNCH(1, 1, 1, 0);
+    else PE_TC_LAUNCH(1, 2, 1, 0);
+  } else if (st) {
+    if (p.mode == 0 && p.kps == 1) PE_TC_LAUNCH(0, 1, 0, 1);
+    else if (p.mode == 0) PE_TC_LAUNCH(0, 2, 0, 1);
+    else if (p.kps == 1) PE_TC_LAUNCH(1, 1, 0, 1);
+    else PE_TC_LAUNCH(1, 2, 0, 1);
+  } else if (p.mode == 0 && p.kps == 1) PE_TC_LAUNCH(0, 1, 0, 0);
+  else if (p.mode == 0) PE_TC_LAUNCH(0, 2, 0, 0);
+  else if (p.mode == 1 && p.kps == 1) PE_TC_LAUNCH(1, 1, 0, 0);
+  else if (p.mode == 1) PE_TC_LAUNCH(1, 2, 0, 0);
+  else PE_TC_LAUNCH(2, 1, 0, 0);
 #undef PE_TC_LAUNCH
   return (lerr == cudaSuccess && cudaGetLastError() == cudaSuccess) ? PE_OK : PE_ERR_LAUNCH;
 }
@@ -1003,7 +1011,7 @@ extern "C" int pe_gemm_bf16(const void* A, long long lda, int a_mn, const void* 
     if (force == 128 || (force == 0 && waste(t256) > 0.33 && waste(t128) < waste(t256) - 0.1)) bn = 128;
   }
   p.block_n = bn;
-  const bool pair = want_pair(0, bn, p.b_mn, (M + 127) / 128);
+  const bool pair = !ep->stats_mode && want_pair(0, bn, p.b_mn, (M + 127) / 128);
   const int nc = pair ? 2 : 1;
   p.a_boxes = 2;
   p.b_boxes = bn / 64 / nc;  // (MN-major B: 64-wide boxes per CTA)
@@ -1069,7 +1077,7 @@ extern "C" int pe_conv3x3_nhwc(const void* x, const void* x2, const void* w, int
   p.M = B * H * W;
   p.N = Cout;
   p.block_n = Cout > 256 ? 256 : Cout;
-  const bool pair = want_pair(1, p.block_n, 0, B * p.tiles_h * p.tiles_w);
+  const bool pair = !ep->stats_mode && want_pair(1, p.block_n, 0, B * p.tiles_h * p.tiles_w);
   p.kb_total = 9 * p.c1_chunks + p.c2_chunks;
   p.kb_per_split = p.kb_total;
   p.ep = *ep;
