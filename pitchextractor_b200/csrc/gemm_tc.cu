@@ -77,9 +77,11 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile) {
 // pair loads its own 128 rows of A and half of the B tile and keeps its 128 accumulator rows in its own TMEM; only the
 // leader (rank 0) issues MMAs.  Each SM then fills / reads half of B per MMA, which is what the shared-memory port of a
 // single SM cannot sustain at full tensor rate (operand reads + TMA fills of a 128 x 256 x 64 step: 96 KB per 512 cycles).
-// STATS = 1: the epilogue carries the column-statistics code (BatchNorm batch statistics / BatchNorm-backward sums).  The
-// encoder GEMMs are instantiated without it: with the statistics paths compiled in, FFN1's epilogue was 8 % slower.
-template <int MODE, int KPS, int PAIR, int STATS>
+// FEAT selects what the epilogue is compiled with: bit 0 = column statistics (BatchNorm batch statistics / BatchNorm-backward
+// sums), bit 1 = the "heavy" element-wise paths (GELU and its derivative, Philox dropout, second output).  An epilogue that
+// carries code it does not run is measurably slower (registers, instruction cache): with the statistics paths compiled in,
+// FFN1's epilogue took 60 us instead of 52.
+template <int MODE, int KPS, int PAIR, int FEAT>
 __global__ void __launch_bounds__(kNumThreadsWgrad, 1)
 tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_a2,
                const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_out,
@@ -88,6 +90,7 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   // swizzle of the operand tiles needs), and all 227 KB are usable.
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  constexpr bool STATS = (FEAT & 1) != 0, HEAVY = (FEAT & 2) != 0;
   constexpr int NC = PAIR ? 2 : 1;  // CTAs per tile
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   const int first_tile = PAIR ? (int)cluster_id_x() : (int)blockIdx.x;
@@ -380,6 +383,9 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     // -------------------------------------------------------------------- epilogue (8 warps, 2 per TMEM lane quarter)
     const pe_epilogue& ep = p.ep;
     const int stats_mode = STATS ? ep.stats_mode : 0;  // (compiled out of the instantiations without statistics)
+    const int act = HEAVY ? ep.act : PE_ACT_NONE;
+    const unsigned drop_thresh = HEAVY ? ep.drop_thresh : 0u;
+    const int aux_mode = (!HEAVY && ep.aux_mode == PE_AUX_GELU_GRAD) ? PE_AUX_NONE : ep.aux_mode;
     const unsigned long long drop_seed = pe_salted(ep.drop_seed);
     const int q = warp & 3;              // TMEM lane quarter this warp may access
     const int pair = (warp - 2) >> 2;    // which of the two warps of the quarter: takes chunks c with (c & 1) == pair
@@ -493,16 +499,16 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               if (col0 + j < p.N) f[j] += __ldg(ep.bias + col0 + j);
           }
         }
-        if (ep.act == PE_ACT_GELU_SAVE_GRAD) {
+        if (act == PE_ACT_GELU_SAVE_GRAD) {
           // out = dropout(gelu(v)); out2 = d out / d v = gelu'(v) * dropout factor (the backward GEMM just multiplies)
           float gp[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) gelu_erf_both(f[j], f[j], gp[j]);
-          if (ep.drop_thresh) {
+          if (drop_thresh) {
             const unsigned long long e0 = (unsigned long long)grow * (unsigned long long)p.N + (unsigned long long)col0;
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
-              const uint32_t km = dropout_keep8(drop_seed, (e0 + j) >> 3, ep.drop_thresh);
+              const uint32_t km = dropout_keep8(drop_seed, (e0 + j) >> 3, drop_thresh);
 #pragma unroll
               for (int t = 0; t < 8; ++t) {
                 const float sc = ((km >> t) & 1u) ? ep.drop_scale : 0.f;
@@ -525,7 +531,7 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               if (col0 + j < p.N && c * 32 + j < p.block_n) o2[j] = __float2bfloat16(gp[j]);
           }
         } else {
-        if (ep.act == PE_ACT_GELU) {
+        if (act == PE_ACT_GELU) {
           if (ep.out2) {
             __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(ep.out2) + grow * ep.ld2 + col0;
             if (p.out_tma & 2) {
@@ -544,17 +550,17 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
         }
-        if (ep.drop_thresh) {  // element index row * N + col; N % 8 == 0 is enforced by the launcher
+        if (drop_thresh) {  // element index row * N + col; N % 8 == 0 is enforced by the launcher
           const unsigned long long e0 = (unsigned long long)grow * (unsigned long long)p.N + (unsigned long long)col0;
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
-            const uint32_t km = dropout_keep8(drop_seed, (e0 + j) >> 3, ep.drop_thresh);
+            const uint32_t km = dropout_keep8(drop_seed, (e0 + j) >> 3, drop_thresh);
 #pragma unroll
             for (int t = 0; t < 8; ++t) f[j + t] = ((km >> t) & 1u) ? f[j + t] * ep.drop_scale : 0.f;
           }
         }
         }
-        if (ep.aux_mode != PE_AUX_NONE) {
+        if (aux_mode != PE_AUX_NONE) {
           const __nv_bfloat16* ax = reinterpret_cast<const __nv_bfloat16*>(ep.aux) + grow * ep.ld_aux + col0;
           float a[32];
           if (!row_ok) {
@@ -576,10 +582,10 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             for (int j = 0; j < 32; ++j)
               a[j] = (col0 + j < p.N && c * 32 + j < p.block_n) ? __bfloat162float(ax[j]) : 0.f;
           }
-          if (ep.aux_mode == PE_AUX_ADD) {
+          if (aux_mode == PE_AUX_ADD) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] += a[j];
-          } else if (ep.aux_mode == PE_AUX_MUL) {
+          } else if (aux_mode == PE_AUX_MUL) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] *= a[j];
           } else {
@@ -935,43 +941,51 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtens
   }
   const size_t smem = (size_t)stages * stage_bytes + pe::kNumEpiWarps * pe::kStagingBytes +
                       (2 * stages + 4) * sizeof(uint64_t) + 16 + 2048 + 512;
-  const int st = p.ep.stats_mode ? 1 : 0;
-  if (st && (pair || p.mode == 2)) return PE_ERR_BAD_SHAPE;  // (statistics: single-CTA GEMM / convolution launches only)
+  const bool heavy = p.ep.act != PE_ACT_NONE || p.ep.drop_thresh != 0 || p.ep.aux_mode == PE_AUX_GELU_GRAD;
+  int feat = (p.ep.stats_mode ? 1 : 0) | (heavy ? 2 : 0);
+  if (p.mode == 1 && (feat & 2)) feat = 3;  // (convolutions: the element-wise paths only exist in the full instantiation)
+  if (p.mode == 2 && feat) return PE_ERR_BAD_SHAPE;
+  if (pair && ((feat & 1) || (p.mode == 1 && feat))) return PE_ERR_BAD_SHAPE;  // (callers switch pairs off for these)
   static bool attr_set = false;
   if (!attr_set) {
     const int sz = 227 * 1024;
-#define PE_TC_ATTR(M, K, P, S) \
-  (cudaFuncSetAttribute(pe::tc_tile_kernel<M, K, P, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz) == cudaSuccess)
-    if (!(PE_TC_ATTR(0, 1, 0, 0) && PE_TC_ATTR(0, 2, 0, 0) && PE_TC_ATTR(1, 1, 0, 0) && PE_TC_ATTR(1, 2, 0, 0) &&
-          PE_TC_ATTR(2, 1, 0, 0) && PE_TC_ATTR(0, 1, 0, 1) && PE_TC_ATTR(0, 2, 0, 1) && PE_TC_ATTR(1, 1, 0, 1) &&
-          PE_TC_ATTR(1, 2, 0, 1) && PE_TC_ATTR(0, 1, 1, 0) && PE_TC_ATTR(0, 2, 1, 0) && PE_TC_ATTR(1, 1, 1, 0) &&
-          PE_TC_ATTR(1, 2, 1, 0)))
+#define PE_TC_ATTR(M, K, P, F) \
+  (cudaFuncSetAttribute(pe::tc_tile_kernel<M, K, P, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz) == cudaSuccess)
+#define PE_TC_ATTR_K(M, P, F) (PE_TC_ATTR(M, 1, P, F) && PE_TC_ATTR(M, 2, P, F))
+    if (!(PE_TC_ATTR_K(0, 0, 0) && PE_TC_ATTR_K(0, 0, 1) && PE_TC_ATTR_K(0, 0, 2) && PE_TC_ATTR_K(0, 0, 3) &&
+          PE_TC_ATTR_K(0, 1, 0) && PE_TC_ATTR_K(0, 1, 2) && PE_TC_ATTR_K(1, 0, 0) && PE_TC_ATTR_K(1, 0, 1) &&
+          PE_TC_ATTR_K(1, 0, 3) && PE_TC_ATTR_K(1, 1, 0) && PE_TC_ATTR(2, 1, 0, 0)))
       return PE_ERR_LAUNCH;
+#undef PE_TC_ATTR_K
 #undef PE_TC_ATTR
     attr_set = true;
   }
   const int units = pe_host::num_sms() / nc;  // CTAs or CTA pairs
   const int grid = (p.num_tiles < units ? p.num_tiles : units) * nc;
   cudaError_t lerr = cudaSuccess;
-#define PE_TC_LAUNCH(M, K, P, S)                                                                                     \
-  lerr = pe_host::launch_cluster(pe::tc_tile_kernel<M, K, P, S>, dim3(grid),                                          \
+#define PE_TC_LAUNCH(M, K, P, F)                                                                                     \
+  lerr = pe_host::launch_cluster(pe::tc_tile_kernel<M, K, P, F>, dim3(grid),                                          \
                                  dim3((M) == 2 ? pe::kNumThreadsWgrad : pe::kNumThreads), smem, stream, (P) ? 2 : 1, ta, \
                                  ta2, tb, tout, tout2, p)
-  if (pair) {
-    if (p.mode == 0 && p.kps == 1) PE_TC_LAUNCH(0, 1, 1, 0);
-    else if (p.mode == 0) PE_TC_LAUNCH(0, 2, 1, 0);
-    else if (p.kps == 1) PE_TC_LAUNCH(1, 1, 1, 0);
-    else PE_TC_LAUNCH(1, 2, 1, 0);
-  } else if (st) {
-    if (p.mode == 0 && p.kps == 1) PE_TC_LAUNCH(0, 1, 0, 1);
-    else if (p.mode == 0) PE_TC_LAUNCH(0, 2, 0, 1);
-    else if (p.kps == 1) PE_TC_LAUNCH(1, 1, 0, 1);
-    else PE_TC_LAUNCH(1, 2, 0, 1);
-  } else if (p.mode == 0 && p.kps == 1) PE_TC_LAUNCH(0, 1, 0, 0);
-  else if (p.mode == 0) PE_TC_LAUNCH(0, 2, 0, 0);
-  else if (p.mode == 1 && p.kps == 1) PE_TC_LAUNCH(1, 1, 0, 0);
-  else if (p.mode == 1) PE_TC_LAUNCH(1, 2, 0, 0);
-  else PE_TC_LAUNCH(2, 1, 0, 0);
+#define PE_TC_LAUNCH_K(M, P, F)          \
+  do {                                   \
+    if (p.kps == 1) PE_TC_LAUNCH(M, 1, P, F); \
+    else PE_TC_LAUNCH(M, 2, P, F);       \
+  } while (0)
+  if (p.mode == 2) PE_TC_LAUNCH(2, 1, 0, 0);
+  else if (p.mode == 0 && pair) {
+    if (feat == 0) PE_TC_LAUNCH_K(0, 1, 0);
+    else PE_TC_LAUNCH_K(0, 1, 2);
+  } else if (p.mode == 0) {
+    if (feat == 0) PE_TC_LAUNCH_K(0, 0, 0);
+    else if (feat == 1) PE_TC_LAUNCH_K(0, 0, 1);
+    else if (feat == 2) PE_TC_LAUNCH_K(0, 0, 2);
+    else PE_TC_LAUNCH_K(0, 0, 3);
+  } else if (pair) PE_TC_LAUNCH_K(1, 1, 0);
+  else if (feat == 0) PE_TC_LAUNCH_K(1, 0, 0);
+  else if (feat == 1) PE_TC_LAUNCH_K(1, 0, 1);
+  else PE_TC_LAUNCH_K(1, 0, 3);
+#undef PE_TC_LAUNCH_K
 #undef PE_TC_LAUNCH
   return (lerr == cudaSuccess && cudaGetLastError() == cudaSuccess) ? PE_OK : PE_ERR_LAUNCH;
 }
@@ -1077,7 +1091,8 @@ extern "C" int pe_conv3x3_nhwc(const void* x, const void* x2, const void* w, int
   p.M = B * H * W;
   p.N = Cout;
   p.block_n = Cout > 256 ? 256 : Cout;
-  const bool pair = !ep->stats_mode && want_pair(1, p.block_n, 0, B * p.tiles_h * p.tiles_w);
+  const bool conv_plain = !ep->stats_mode && ep->act == PE_ACT_NONE && !ep->drop_thresh && ep->aux_mode != PE_AUX_GELU_GRAD;
+  const bool pair = conv_plain && want_pair(1, p.block_n, 0, B * p.tiles_h * p.tiles_w);
   p.kb_total = 9 * p.c1_chunks + p.c2_chunks;
   p.kb_per_split = p.kb_total;
   p.ep = *ep;
