@@ -637,82 +637,6 @@ tc_tile_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
           for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(stg + lane * 64 + ((u ^ ((lane >> 1) & 3)) << 4)) = xs[u];
         }
-        if (stats_mode && !stats_from_block) {
-          // per-column sums over the 32 rows of this warp by a transposing butterfly (31 shuffles per quantity), then
-          // one shared-memory atomic per column; the CTA flushes its partials to the fp64 global sums once, at the end
-          float sa[32], sb[32];
-          const bool colok = full;
-          if (stats_mode == 1) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float v = (row_ok && colok) ? (ep.out_mode == PE_OUT_BF16 ? __bfloat162float(__float2bfloat16(f[j])) : f[j]) : 0.f;
-              sa[j] = v;
-              sb[j] = v * v;
-            }
-          } else if (stats_mode == 3) {
-            // the BatchNorm input is twice as wide as this gradient (MaxPool (1,2) in between): output pixel `grow`
-            // owns input pixels 2*grow and 2*grow+1; the gradient goes to the first maximum of the activated pair
-            const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(ep.stats_x) + grow * 2LL * p.N + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 u0 = make_uint4(0u, 0u, 0u, 0u), u1 = u0;
-              if (row_ok && colok) {
-                u0 = *reinterpret_cast<const uint4*>(xp + j);
-                u1 = *reinterpret_cast<const uint4*>(xp + p.N + j);
-              }
-              const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&u0);
-              const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&u1);
-#pragma unroll
-              for (int t = 0; t < 8; ++t) {
-                const float2 a2 = __bfloat1622float2(h0[t >> 1]), b2 = __bfloat1622float2(h1[t >> 1]);
-                const float x0 = (t & 1) ? a2.y : a2.x, x1 = (t & 1) ? b2.y : b2.x;
-                const float sc = __ldg(ep.stats_scale + min(col0 + j + t, p.N - 1));
-                const float sh = __ldg(ep.stats_shift + min(col0 + j + t, p.N - 1));
-                const float p0 = fmaf(x0, sc, sh), p1 = fmaf(x1, sc, sh);
-                const float z0 = p0 > 0.f ? p0 : p0 * ep.stats_slope, z1 = p1 > 0.f ? p1 : p1 * ep.stats_slope;
-                const bool second = z1 > z0;
-                const float pre = second ? p1 : p0, x = second ? x1 : x0;
-                const float v = (row_ok && colok) ? __bfloat162float(__float2bfloat16(f[j + t])) : 0.f;
-                const float g = v * (pre > 0.f ? 1.f : ep.stats_slope);
-                sa[j + t] = g;
-                sb[j + t] = g * x;
-              }
-            }
-          } else {
-            const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(ep.stats_x) + grow * (long long)p.N + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 u = make_uint4(0u, 0u, 0u, 0u);
-              if (row_ok && colok) u = *reinterpret_cast<const uint4*>(xp + j);
-              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-              for (int t = 0; t < 8; ++t) {
-                const float2 x2 = __bfloat1622float2(h2[t >> 1]);
-                const float x = (t & 1) ? x2.y : x2.x;
-                const float z = fmaf(x, __ldg(ep.stats_scale + min(col0 + j + t, p.N - 1)), __ldg(ep.stats_shift + min(col0 + j + t, p.N - 1)));
-                const float v = (row_ok && colok) ? __bfloat162float(__float2bfloat16(f[j + t])) : 0.f;
-                const float g = v * (z > 0.f ? 1.f : ep.stats_slope);
-                sa[j + t] = g;
-                sb[j + t] = g * x;
-              }
-            }
-          }
-#pragma unroll
-          for (int s = 16; s >= 1; s >>= 1) {
-            const bool up = (lane & s) != 0;
-#pragma unroll
-            for (int i = 0; i < s; ++i) {
-              const float send_a = up ? sa[i] : sa[i + s], keep_a = up ? sa[i + s] : sa[i];
-              const float send_b = up ? sb[i] : sb[i + s], keep_b = up ? sb[i + s] : sb[i];
-              sa[i] = keep_a + __shfl_xor_sync(0xffffffffu, send_a, s);
-              sb[i] = keep_b + __shfl_xor_sync(0xffffffffu, send_b, s);
-            }
-          }
-          if (colok) {
-            atomicAdd(&s_stats[col0 + lane], sa[0]);
-            atomicAdd(&s_stats[256 + col0 + lane], sb[0]);
-          }
-        }
         if (p.out_tma & 1) {
           if (ep.out_mode == PE_OUT_BF16) stage_and_store(&tma_out, f, col0);
           else stage_and_store_f32(&tma_out, f, col0, ep.out_mode == PE_OUT_F32_ATOMIC);
@@ -930,6 +854,8 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtens
     if (!p.ep.stats || p.N > 256 || (p.N % 32) || p.tiles_y != 1 || p.mode == 2) return PE_ERR_BAD_SHAPE;
     if (p.ep.stats_mode < 1 || p.ep.stats_mode > 3) return PE_ERR_BAD_SHAPE;
     if (p.ep.stats_mode >= 2 && (!p.ep.stats_x || !p.ep.stats_scale || !p.ep.stats_shift)) return PE_ERR_BAD_SHAPE;
+    // the sums are read out of the staged bf16 output blocks (whole 32-column chunks, TMA-addressable output)
+    if (p.ep.out_mode != PE_OUT_BF16 || (p.block_n % 32)) return PE_ERR_BAD_SHAPE;
   }
   // staged TMA stores for bf16 outputs of the GEMM / conv modes (whole 32-column chunks only)
   CUtensorMap tout = ta, tout2 = ta;
@@ -939,6 +865,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtens
     if (out_tmap(&tout, p, p.ep.out, p.ep.ldc, conv_B, p.ep.out_mode == PE_OUT_BF16 ? 2 : 4)) p.out_tma |= 1;
     if (p.ep.out2 && p.ep.act != PE_ACT_NONE && out_tmap(&tout2, p, p.ep.out2, p.ep.ld2, conv_B, 2)) p.out_tma |= 2;
   }
+  if (p.ep.stats_mode && !(p.out_tma & 1)) return PE_ERR_BAD_SHAPE;
   const size_t smem = (size_t)stages * stage_bytes + pe::kNumEpiWarps * pe::kStagingBytes +
                       (2 * stages + 4) * sizeof(uint64_t) + 16 + 2048 + 512;
   const bool heavy = p.ep.act != PE_ACT_NONE || p.ep.drop_thresh != 0 || p.ep.aux_mode == PE_AUX_GELU_GRAD;
