@@ -84,6 +84,8 @@ class Engine:
         self.on_grads_ready = None  # callback(tag) for the data-parallel gradient reducer
         self._side_stream = None
         self._phase_cb = None     # see _mark()
+        self._nvtx = os.environ.get("PE_NVTX") == "1"
+        self._nvtx_open = False
         self.phase_events = None  # PE_PHASES=1: per replayed step, [(tag, start event, end event), ...]
         self._side_pending = False
         self.reducer = None         # GradReducer: begin_step() / ready(tag) / wait() bracket every training step
@@ -349,8 +351,17 @@ class Engine:
         self._mark("encoder_fwd")
         return Hc, Hd
 
+    _PHASES = ("trunk_fwd", "encoder_fwd", "heads_loss", "encoder_bwd", "trunk_bwd")
+
     def _mark(self, tag):
-        """Phase boundary (all streams joined here): tools/phase_times.py cuts the captured step at these points."""
+        """Phase boundary (all streams joined here): tools/phase_times.py cuts the captured step at these points; with
+        PE_NVTX=1 the phases of an eagerly launched step (PE_CUDA_GRAPH=0) show up as NVTX ranges in a timeline."""
+        if self._nvtx_open:  # (only inside a training step: forward_core alone also passes its marks)
+            torch.cuda.nvtx.range_pop()
+            i = self._PHASES.index(tag)
+            self._nvtx_open = i + 1 < len(self._PHASES)
+            if self._nvtx_open:
+                torch.cuda.nvtx.range_push(self._PHASES[i + 1])
         if self._phase_cb is not None:
             self._phase_cb(tag)
 
@@ -756,6 +767,9 @@ class Engine:
         return self._train_step_eager(x, f0, sil, lambda_f0, grad_scale)
 
     def _train_step_eager(self, x, f0, sil, lambda_f0, grad_scale):
+        if self._nvtx and not self._nvtx_open:
+            torch.cuda.nvtx.range_push(self._PHASES[0])
+            self._nvtx_open = True
         if self.reducer is not None:
             self.reducer.begin_step()
         self.zero_grad()
