@@ -1,8 +1,9 @@
 // Persistent BiLSTM recurrence (reference model.py:218-228 -> torch.nn.LSTM, gate order i,f,g,o): ONE launch runs all T
 // time steps of the four independent recurrences of a layer (2 sequence models x 2 directions).
 //
-// Work split: CTA (unit tile of 64, batch tile of NB, recurrence).  The CTA's slice of W_hh -- forward: the 4 x 64 gate
-// rows of its units (192 KB bf16); backward: the 64 unit columns of all 1536 gate rows (192 KB) -- is loaded into shared
+// Work split: CTA (unit tile, batch tile of NB, recurrence); a unit tile is 64 hidden units (backward; forward when the
+// batch needs more than three batch tiles) or 32 (forward otherwise).  The CTA's slice of W_hh -- forward: the 4 x 64 (32)
+// gate rows of its units (192 / 96 KB bf16); backward: the 64 unit columns of all 1536 gate rows (192 KB) -- is loaded into shared
 // memory ONCE and stays there for every time step; only h_{t-1} (forward) / dgates_{t+1} (backward), 12 - 96 KB per step,
 // streams through a small TMA ring.  The MMA is "transposed": weights are the A operand (gate rows / units on the 128 TMEM
 // lanes), the batch is the N dimension, so that a batch of 16 keeps all 128 lanes of the epilogue busy.
@@ -15,19 +16,18 @@
 //            M = 64 units are presented twice (the two 64-row atoms of the A descriptor alias each other), so lanes 64-127
 //            hold a copy and the second half of the epilogue warps takes the second half of the batch columns; dc is
 //            carried in registers.
-// The six unit-tile CTAs of a (recurrence, batch tile) exchange h_t / dgates_t through global memory (L2) and a per-step
+// The six (twelve) unit-tile CTAs of a (recurrence, batch tile) exchange h_t / dgates_t through global memory (L2) and a per-step
 // arrival counter: writers store, fence, barrier, one release-add; the loader thread of every CTA acquire-polls the
 // counter before it issues the TMA loads of the next step.  All CTAs must be co-resident: the launch is cooperative and
 // the grid is at most one CTA per SM.
 #include "common.cuh"
+#include <cstdlib>
 #include "../../include/pitchextractor_b200.h"
 
 namespace pe {
 
 constexpr int PH = 384;          // hidden size
 constexpr int PG = 4 * PH;       // gate rows per direction
-constexpr int PF_EPI_WARPS = 16;                   // forward: 2 M-tiles x 4 lane quarters x 2 column halves
-constexpr int PF_THREADS = 64 + 32 * PF_EPI_WARPS;
 constexpr int P_W_BYTES = 6 * 32768;               // resident weight slice (both directions of use: 192 KB)
 constexpr int P_RING_BYTES = 32768;
 // backward: the M = 128 MMA sees the CTA's 64 units twice (A descriptor atom stride 0), so that TMEM lanes 64..127 hold a
@@ -93,11 +93,17 @@ struct PlCfg {
 // =================================================================================================================
 // forward
 // =================================================================================================================
-template <int NB>
-__global__ void __launch_bounds__(PF_THREADS, 1)
+// UT = hidden units per CTA: 64 (two M tiles of 4 gates x 32 units) or 32 (one M tile).  At small batch tiles a time
+// step is bound by the issue interval of its MMAs (>= 85 cycles each, whatever N is: 48 per step at UT = 64), so small
+// batches use twice as many CTAs with half the MMAs each.
+template <int NB, int UT>
+__global__ void __launch_bounds__(64 + 32 * (UT / 4), 1)
 lstm_seq_fwd_kernel(const __grid_constant__ LstmSeqMaps maps, const LstmSeqParams p) {
   using C = PlCfg<NB>;
   constexpr int KB = PH / 64;  // 6 k-blocks per step
+  constexpr int MT = UT / 32;                 // M tiles (128 gate rows each)
+  constexpr int EPI_WARPS = 8 * MT;           // M tiles x 4 lane quarters x 2 column halves
+  constexpr int W_KB_BYTES = MT * 16384;      // weight bytes per k-block
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* s_w = smem;                        // [KB][2 M-tiles][128 rows x 128 B]
@@ -109,11 +115,11 @@ lstm_seq_fwd_kernel(const __grid_constant__ LstmSeqMaps maps, const LstmSeqParam
   uint64_t* free_bar = done_bar + 1;          // accumulator drained by the epilogue warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(free_bar + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int u0 = blockIdx.x * 64, bt = blockIdx.y, rec = blockIdx.z;
+  const int u0 = blockIdx.x * UT, bt = blockIdx.y, rec = blockIdx.z;
   const int b0 = p.b_first + bt * NB;
   const int model = rec >> 1, dir = rec & 1;
   int* flags = p.flags + ((size_t)rec * p.nbt + bt) * p.T;
-  constexpr uint32_t TCOLS = 2 * NB < 32 ? 32 : 2 * NB;
+  constexpr uint32_t TCOLS = MT * NB < 32 ? 32 : MT * NB;
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -122,7 +128,7 @@ lstm_seq_fwd_kernel(const __grid_constant__ LstmSeqMaps maps, const LstmSeqParam
     }
     mbar_init(w_bar, 1);
     mbar_init(done_bar, 1);
-    mbar_init(free_bar, PF_EPI_WARPS);
+    mbar_init(free_bar, EPI_WARPS);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, TCOLS);
@@ -134,17 +140,17 @@ lstm_seq_fwd_kernel(const __grid_constant__ LstmSeqMaps maps, const LstmSeqParam
   if (warp == 0) {
     // ------------------------------------------------------------ loader: weights once, then h_{t-1} per step
     if (elect_one()) {
-      mbar_arrive_expect_tx(w_bar, P_W_BYTES);
+      mbar_arrive_expect_tx(w_bar, KB * W_KB_BYTES);
       for (int kb = 0; kb < KB; ++kb)
-        for (int mq = 0; mq < 8; ++mq)
-          tma_load_3d(&maps.w[rec], w_bar, s_w + kb * 32768 + mq * 4096, kb * 64, u0 + mq * 8, 0);
+        for (int mq = 0; mq < UT / 8; ++mq)
+          tma_load_3d(&maps.w[rec], w_bar, s_w + kb * W_KB_BYTES + mq * 4096, kb * 64, u0 + mq * 8, 0);
     }
     __syncwarp();
     if (elect_one()) {
       uint32_t it = 0;
       for (int step = 1; step < p.T; ++step) {
         const int t_prev = dir ? p.T - step : step - 1;
-        wait_counter(flags + (step - 1), 6);   // h_{t-1} of all six unit tiles is in global memory
+        wait_counter(flags + (step - 1), PH / UT);   // h_{t-1} of all unit tiles is in global memory
         fence_proxy_async_global();
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const uint32_t s = it % C::STAGES;
@@ -169,9 +175,9 @@ lstm_seq_fwd_kernel(const __grid_constant__ LstmSeqMaps maps, const LstmSeqParam
           const uint32_t s = (it + kb) % C::STAGES;
           mbar_wait(&full_bar[s], ((it + kb) / C::STAGES) & 1u);
           tc_fence_after();
-          const uint32_t sb = smem_u32(s_ring + s * C::STAGE_B), sa = smem_u32(s_w + kb * 32768);
+          const uint32_t sb = smem_u32(s_ring + s * C::STAGE_B), sa = smem_u32(s_w + kb * W_KB_BYTES);
 #pragma unroll
-          for (int m = 0; m < 2; ++m)
+          for (int m = 0; m < MT; ++m)
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               tc_mma_bf16(tm + m * NB, umma_desc_sw128(sa + m * 16384 + k * 32, 16, 1024),
@@ -187,7 +193,7 @@ lstm_seq_fwd_kernel(const __grid_constant__ LstmSeqMaps maps, const LstmSeqParam
     // ------------------------------------------------------------ epilogue: 16 warps = 2 M-tiles x 4 lane quarters x
     // 2 column halves (the epilogue is the longest part of a step at wide batch tiles: twice the warps hide its latencies)
     const int ew = warp - 2;
-    const int q = warp & 3, m = (ew >> 2) & 1, ch = ew >> 3;
+    const int q = warp & 3, m = MT == 2 ? (ew >> 2) & 1 : 0, ch = MT == 2 ? ew >> 3 : ew >> 2;
     const int gl = lane >> 3, ul = lane & 7;             // this lane's gate and unit inside the quarter
     const int u = u0 + (m * 4 + q) * 8 + ul;
     constexpr int NGRP = NB / 8;                         // groups of 4 batch columns handled by this warp
@@ -278,7 +284,7 @@ lstm_seq_fwd_kernel(const __grid_constant__ LstmSeqMaps maps, const LstmSeqParam
       // publish h_t: every writer makes its stores visible to the async proxy, then one release-add per CTA
       fence_proxy_async_global();
       tc_fence_before();
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * PF_EPI_WARPS) : "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
       if (threadIdx.x == 64) {
         __threadfence();
         red_release_gpu_add(flags + step, 1);
@@ -519,15 +525,25 @@ static int seq_maps(LstmSeqMaps* m, const void* const* act, int act_cols, int B,
   return PE_OK;
 }
 
+// Units per CTA of the forward kernel: 32 (twelve unit tiles, half the MMAs and half the epilogue per CTA and step) while
+// all batch tiles still fit one cooperative launch (12 unit tiles x 4 recurrences x <= 3 batch tiles on 148 SMs), else 64.
+// Measured: forward layers 3.76 -> 3.16 ms at B = 16, 6.90 -> 5.84 ms at B = 64, 11.7 -> 9.75 ms at B = 128.
+static int fwd_unit_tile(int nbt_total) {
+  static const int knob = getenv("PE_LSTM_UT") ? atoi(getenv("PE_LSTM_UT")) : 0;  // tuning knob: 32 / 64
+  if (knob == 32 || knob == 64) return knob;
+  return nbt_total <= pe_host::num_sms() / 48 ? 32 : 64;
+}
+
 template <int NB>
-static int launch_seq(bool backward, const LstmSeqMaps& maps, LstmSeqParams p, cudaStream_t st) {
-  const void* fn = backward ? (const void*)lstm_seq_bwd_kernel<NB> : (const void*)lstm_seq_fwd_kernel<NB>;
+static int launch_seq(bool backward, int ut, const LstmSeqMaps& maps, LstmSeqParams p, cudaStream_t st) {
+  const void* fn = backward ? (const void*)lstm_seq_bwd_kernel<NB>
+                            : (ut == 32 ? (const void*)lstm_seq_fwd_kernel<NB, 32> : (const void*)lstm_seq_fwd_kernel<NB, 64>);
   const size_t smem = PlCfg<NB>::SMEM;
   if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PE_ERR_LAUNCH;
   void* args[2] = {(void*)&maps, (void*)&p};
-  dim3 grid(PH / 64, p.nbt, 4);
-  if (cudaLaunchCooperativeKernel(fn, grid, dim3(backward ? PlCfg<NB>::BWD_THREADS : PF_THREADS), args, smem, st) != cudaSuccess)
-    return PE_ERR_LAUNCH;
+  dim3 grid(PH / ut, p.nbt, 4);
+  const int threads = backward ? PlCfg<NB>::BWD_THREADS : 64 + 32 * (ut / 4);
+  if (cudaLaunchCooperativeKernel(fn, grid, dim3(threads), args, smem, st) != cudaSuccess) return PE_ERR_LAUNCH;
   return PE_OK;
 }
 
@@ -535,9 +551,10 @@ static int run_seq(bool backward, LstmSeqParams p, const void* const* act, int a
                    int* flags, size_t flags_bytes, cudaStream_t st) {
   const int B = p.B, T = p.T;
   const int NB = B <= 16 ? 16 : B <= 32 ? 32 : B <= 64 ? 64 : 128;
-  const int max_bt = pe_host::num_sms() / 24;   // 6 unit tiles x 4 recurrences per batch tile, one CTA per SM
-  if (max_bt < 1) return PE_ERR_ARCH;
   const int nbt_total = (B + NB - 1) / NB;
+  const int ut = backward ? 64 : fwd_unit_tile(nbt_total);
+  const int max_bt = pe_host::num_sms() / (4 * (PH / ut));   // unit tiles x 4 recurrences per batch tile, one CTA per SM
+  if (max_bt < 1) return PE_ERR_ARCH;
   const int nbt_launch = nbt_total < max_bt ? nbt_total : max_bt;
   if (!flags || flags_bytes < (size_t)4 * nbt_launch * T * sizeof(int)) return PE_ERR_WORKSPACE;
   LstmSeqMaps maps;
@@ -549,10 +566,10 @@ static int run_seq(bool backward, LstmSeqParams p, const void* const* act, int a
     if (cudaMemsetAsync(flags, 0, (size_t)4 * p.nbt * T * sizeof(int), st) != cudaSuccess) return PE_ERR_LAUNCH;
     int rc;
     switch (NB) {
-      case 16: rc = launch_seq<16>(backward, maps, p, st); break;
-      case 32: rc = launch_seq<32>(backward, maps, p, st); break;
-      case 64: rc = launch_seq<64>(backward, maps, p, st); break;
-      default: rc = launch_seq<128>(backward, maps, p, st); break;
+      case 16: rc = launch_seq<16>(backward, ut, maps, p, st); break;
+      case 32: rc = launch_seq<32>(backward, ut, maps, p, st); break;
+      case 64: rc = launch_seq<64>(backward, ut, maps, p, st); break;
+      default: rc = launch_seq<128>(backward, ut, maps, p, st); break;
     }
     if (rc) return rc;
   }
