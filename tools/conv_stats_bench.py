@@ -1,5 +1,5 @@
 """Narrow-output convolutions (Cout <= 128): time per call with the plain epilogue and with the fused column statistics
-(BatchNorm forward sums; BatchNorm-backward first pass, direct and through MaxPool(1,2)).  Run with PE_CONV_SWAP=0 / 1."""
+(BatchNorm forward sums; BatchNorm-backward first pass, direct and through MaxPool(1,2)).  """
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pitchextractor_b200 import ops
@@ -25,5 +25,5 @@ def run(B, H, W, C1, C2, Cout):
         us = e0.elapsed_time(e1) * 100
         res.append("%s %6.1f us (%4.0f TF/s)" % (name, us, 2.0 * B * H * W * Cout * (9 * C1 + C2) / us / 1e6))
     print("conv W=%d %d(+%d)->%d: " % (W, C1, C2, Cout) + " | ".join(res))
-print("PE_CONV_SWAP =", os.environ.get("PE_CONV_SWAP", "default"))
+
 run(64, 192, 80, 64, 0, 64); run(64, 192, 40, 64, 0, 128); run(64, 192, 40, 128, 64, 128); run(64, 192, 40, 128, 0, 64)
