@@ -122,8 +122,8 @@ extern "C" long long pe_workspace_bytes(const char* op, int B, int T, int L) {
   };
   if (is("pe_lstm_seq_fwd") || is("pe_lstm_seq_bwd")) {  // per-step arrival counters of the launch's batch tiles
     if (T <= 0) return -1;
-    const int NB = B <= 16 ? 16 : B <= 32 ? 32 : B <= 64 ? 64 : 128;
-    int nbt = (B + NB - 1) / NB;
+    // (at most num_sms / 24 batch tiles per launch, whatever tile width the launcher picks)
+    int nbt = (B + 15) / 16;
     const int max_bt = pe_host::num_sms() / 24 > 0 ? pe_host::num_sms() / 24 : 6;
     if (nbt > max_bt) nbt = max_bt;
     return (long long)4 * nbt * T * (long long)sizeof(int);

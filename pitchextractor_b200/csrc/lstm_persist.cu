@@ -525,13 +525,45 @@ static int seq_maps(LstmSeqMaps* m, const void* const* act, int act_cols, int B,
   return PE_OK;
 }
 
-// Units per CTA of the forward kernel: 32 (twelve unit tiles, half the MMAs and half the epilogue per CTA and step) while
-// all batch tiles still fit one cooperative launch (12 unit tiles x 4 recurrences x <= 3 batch tiles on 148 SMs), else 64.
-// Measured: forward layers 3.76 -> 3.16 ms at B = 16, 6.90 -> 5.84 ms at B = 64, 11.7 -> 9.75 ms at B = 128.
-static int fwd_unit_tile(int nbt_total) {
-  static const int knob = getenv("PE_LSTM_UT") ? atoi(getenv("PE_LSTM_UT")) : 0;  // tuning knob: 32 / 64
-  if (knob == 32 || knob == 64) return knob;
-  return nbt_total <= pe_host::num_sms() / 48 ? 32 : 64;
+// Tiling of a launch.  A time step costs a CTA roughly in proportion to its batch-tile width NB (the h / dgates tile streams
+// through a 32 KB ring, the epilogue is NB columns wide) and hardly depends on the number of batch tiles, which run side by
+// side on their own CTAs -- so the narrowest tile whose batch tiles still fit ONE cooperative launch wins.  Forward: 32
+// units per CTA (12 unit tiles x 4 recurrences x <= 3 batch tiles on 148 SMs; half the MMAs and half the epilogue per CTA
+// and step) or 64 units (<= 6 batch tiles), whichever allows the cheaper tile.  Measured forward layer times (ms, four
+// layer calls): UT = 32: 3.16 / 3.75 / 5.84 / 9.75 at NB = 16 / 32 / 64 / 128; UT = 64: 3.76 / 4.57 / 6.90 / 11.7.
+// Backward (64 units): 6.9 / 8.5 / 11.4 / 20.2 ms at NB = 16 / 32 / 64 / 128.
+struct SeqTiling {
+  int ut, nb;
+};
+static int narrowest_nb(int B, int max_tiles) {
+  for (int nb = 16; nb < 128; nb *= 2)
+    if ((B + nb - 1) / nb <= max_tiles) return nb;
+  return 128;
+}
+static SeqTiling seq_tiling(bool backward, int B) {
+  static const int k_ut = getenv("PE_LSTM_UT") ? atoi(getenv("PE_LSTM_UT")) : 0;          // tuning knobs
+  static const int k_fnb = getenv("PE_LSTM_FWD_NB") ? atoi(getenv("PE_LSTM_FWD_NB")) : 0;
+  static const int k_bnb = getenv("PE_LSTM_BWD_NB") ? atoi(getenv("PE_LSTM_BWD_NB")) : 0;
+  auto valid_nb = [](int v) { return v == 16 || v == 32 || v == 64 || v == 128; };
+  const int sms = pe_host::num_sms();
+  if (backward) return SeqTiling{64, valid_nb(k_bnb) ? k_bnb : narrowest_nb(B, sms / 24 > 0 ? sms / 24 : 1)};
+  const int nb32 = narrowest_nb(B, sms / 48 > 0 ? sms / 48 : 1), nb64 = narrowest_nb(B, sms / 24 > 0 ? sms / 24 : 1);
+  // relative cost of a step at (UT, NB), from the measurements above
+  auto cost = [](int ut, int nb) {
+    const float c32[4] = {3.16f, 3.75f, 5.84f, 9.75f}, c64[4] = {3.76f, 4.57f, 6.90f, 11.7f};
+    const int i = nb == 16 ? 0 : nb == 32 ? 1 : nb == 64 ? 2 : 3;
+    return ut == 32 ? c32[i] : c64[i];
+  };
+  // (a tile width whose batch tiles do not fit one launch is run in chunks: cost x chunks)
+  auto total = [&](int ut, int nb) {
+    const int max_bt = sms / (4 * (PH / ut)) > 0 ? sms / (4 * (PH / ut)) : 1;
+    const int tiles = (B + nb - 1) / nb;
+    return cost(ut, nb) * (float)((tiles + max_bt - 1) / max_bt);
+  };
+  SeqTiling t = total(32, nb32) <= total(64, nb64) ? SeqTiling{32, nb32} : SeqTiling{64, nb64};
+  if (k_ut == 32 || k_ut == 64) t = SeqTiling{k_ut, k_ut == 32 ? nb32 : nb64};
+  if (valid_nb(k_fnb)) t.nb = k_fnb;
+  return t;
 }
 
 template <int NB>
@@ -550,9 +582,9 @@ static int launch_seq(bool backward, int ut, const LstmSeqMaps& maps, LstmSeqPar
 static int run_seq(bool backward, LstmSeqParams p, const void* const* act, int act_cols, const void* const* w_hh,
                    int* flags, size_t flags_bytes, cudaStream_t st) {
   const int B = p.B, T = p.T;
-  const int NB = B <= 16 ? 16 : B <= 32 ? 32 : B <= 64 ? 64 : 128;
+  const SeqTiling tl = seq_tiling(backward, B);
+  const int NB = tl.nb, ut = tl.ut;
   const int nbt_total = (B + NB - 1) / NB;
-  const int ut = backward ? 64 : fwd_unit_tile(nbt_total);
   const int max_bt = pe_host::num_sms() / (4 * (PH / ut));   // unit tiles x 4 recurrences per batch tile, one CTA per SM
   if (max_bt < 1) return PE_ERR_ARCH;
   const int nbt_launch = nbt_total < max_bt ? nbt_total : max_bt;

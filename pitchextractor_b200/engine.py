@@ -94,7 +94,9 @@ class Engine:
         self.use_graph = os.environ.get("PE_CUDA_GRAPH", "1") != "0"
         # BiLSTM recurrences: persistent kernel (default) or one launch per time step (PE_LSTM_STEPWISE=1)
         self.lstm_persistent = os.environ.get("PE_LSTM_STEPWISE", "0") != "1"
-        self.lstm_persistent_bwd_max_batch = int(os.environ.get("PE_LSTM_BWD_MAXB", "64"))
+        # persistent backward while its batch tiles (64 columns at most, 6 per launch) fit one launch; above that the
+        # 128-column tiles lose to one launch per time step (20.2 vs 17.0 ms at B = 512)
+        self.lstm_persistent_bwd_max_batch = int(os.environ.get("PE_LSTM_BWD_MAXB", "384"))
         self._graphs = {}
         self.bf16_fresh = False
         self._capturing = False
