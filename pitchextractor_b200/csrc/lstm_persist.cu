@@ -81,6 +81,12 @@ __device__ __forceinline__ void wait_counter(const int* p, int target) {
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float tanh_fast(float x) { return fmaf(2.f, __fdividef(1.f, 1.f + __expf(-2.f * x)), -1.f); }
 
+__host__ __device__ constexpr uint32_t tmem_pow2(uint32_t cols) {  // tcgen05.alloc takes powers of two >= 32
+  uint32_t c = 32;
+  while (c < cols) c <<= 1;
+  return c;
+}
+
 template <int NB>
 struct PlCfg {
   static constexpr int STAGE_B = NB * 128;                                  // one [NB x 64] bf16 k-block
@@ -119,7 +125,7 @@ lstm_seq_fwd_kernel(const __grid_constant__ LstmSeqMaps maps, const LstmSeqParam
   const int b0 = p.b_first + bt * NB;
   const int model = rec >> 1, dir = rec & 1;
   int* flags = p.flags + ((size_t)rec * p.nbt + bt) * p.T;
-  constexpr uint32_t TCOLS = MT * NB < 32 ? 32 : MT * NB;
+  constexpr uint32_t TCOLS = tmem_pow2(MT * NB);
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -320,7 +326,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ LstmSeqMaps maps, const LstmSeqParam
   const int b0 = p.b_first + bt * NB;
   const int model = rec >> 1, dir = rec & 1;
   int* flags = p.flags + ((size_t)rec * p.nbt + bt) * p.T;
-  constexpr uint32_t TCOLS = NB < 32 ? 32 : NB;
+  constexpr uint32_t TCOLS = tmem_pow2(NB);
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -535,23 +541,24 @@ static int seq_maps(LstmSeqMaps* m, const void* const* act, int act_cols, int B,
 struct SeqTiling {
   int ut, nb;
 };
+static const int kSeqNB[5] = {16, 32, 64, 96, 128};
 static int narrowest_nb(int B, int max_tiles) {
-  for (int nb = 16; nb < 128; nb *= 2)
-    if ((B + nb - 1) / nb <= max_tiles) return nb;
+  for (int i = 0; i < 4; ++i)
+    if ((B + kSeqNB[i] - 1) / kSeqNB[i] <= max_tiles) return kSeqNB[i];
   return 128;
 }
 static SeqTiling seq_tiling(bool backward, int B) {
   static const int k_ut = getenv("PE_LSTM_UT") ? atoi(getenv("PE_LSTM_UT")) : 0;          // tuning knobs
   static const int k_fnb = getenv("PE_LSTM_FWD_NB") ? atoi(getenv("PE_LSTM_FWD_NB")) : 0;
   static const int k_bnb = getenv("PE_LSTM_BWD_NB") ? atoi(getenv("PE_LSTM_BWD_NB")) : 0;
-  auto valid_nb = [](int v) { return v == 16 || v == 32 || v == 64 || v == 128; };
+  auto valid_nb = [](int v) { return v == 16 || v == 32 || v == 64 || v == 96 || v == 128; };
   const int sms = pe_host::num_sms();
   if (backward) return SeqTiling{64, valid_nb(k_bnb) ? k_bnb : narrowest_nb(B, sms / 24 > 0 ? sms / 24 : 1)};
   const int nb32 = narrowest_nb(B, sms / 48 > 0 ? sms / 48 : 1), nb64 = narrowest_nb(B, sms / 24 > 0 ? sms / 24 : 1);
   // relative cost of a step at (UT, NB), from the measurements above
   auto cost = [](int ut, int nb) {
-    const float c32[4] = {3.16f, 3.75f, 5.84f, 9.75f}, c64[4] = {3.76f, 4.57f, 6.90f, 11.7f};
-    const int i = nb == 16 ? 0 : nb == 32 ? 1 : nb == 64 ? 2 : 3;
+    const float c32[5] = {3.16f, 3.75f, 5.84f, 7.8f, 9.75f}, c64[5] = {3.76f, 4.57f, 6.90f, 9.3f, 11.7f};  // (96: interpolated)
+    const int i = nb == 16 ? 0 : nb == 32 ? 1 : nb == 64 ? 2 : nb == 96 ? 3 : 4;
     return ut == 32 ? c32[i] : c64[i];
   };
   // (a tile width whose batch tiles do not fit one launch is run in chunks: cost x chunks)
@@ -601,6 +608,7 @@ static int run_seq(bool backward, LstmSeqParams p, const void* const* act, int a
       case 16: rc = launch_seq<16>(backward, ut, maps, p, st); break;
       case 32: rc = launch_seq<32>(backward, ut, maps, p, st); break;
       case 64: rc = launch_seq<64>(backward, ut, maps, p, st); break;
+      case 96: rc = launch_seq<96>(backward, ut, maps, p, st); break;
       default: rc = launch_seq<128>(backward, ut, maps, p, st); break;
     }
     if (rc) return rc;
