@@ -123,10 +123,11 @@ extern "C" long long pe_workspace_bytes(const char* op, int B, int T, int L) {
   if (is("pe_lstm_seq_fwd") || is("pe_lstm_seq_bwd")) {  // per-step arrival counters of the launch's batch tiles
     if (T <= 0) return -1;
     // (at most num_sms / 24 batch tiles per launch, whatever tile width the launcher picks)
-    int nbt = (B + 15) / 16;
     const int max_bt = pe_host::num_sms() / 24 > 0 ? pe_host::num_sms() / 24 : 6;
-    if (nbt > max_bt) nbt = max_bt;
-    return (long long)4 * nbt * T * (long long)sizeof(int);
+    long long bytes = (((long long)4 * max_bt * T * (long long)sizeof(int)) + 255) & ~255LL;
+    // backward: + the four transposed recurrent weight matrices of the gate-stacked kernel (narrow batch tiles)
+    if (is("pe_lstm_seq_bwd")) bytes += (long long)4 * 1536 * 384 * 2;
+    return bytes;
   }
   if (is("pe_logmel_tc")) {  // re-strided waveform copy, only used when rows are not 16-byte aligned
     if (L <= 0) return -1;

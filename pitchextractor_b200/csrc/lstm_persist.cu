@@ -12,6 +12,7 @@
 //            activation (tanh(x) = 2 sigmoid(2x) - 1: one formula, per-lane constants), stores the activated gate (kept for
 //            the backward pass); a 4 x 4 register transpose over the four gate lanes of a unit (two rounds of warp shuffles)
 //            then gives every lane all four gates of one batch column: c_t (kept in registers across the steps), h_t.
+//   backward, batch tiles of 16 / 32 columns: gate-stacked formulation on a transposed weight copy, see lstm_seq_bwd_gs_kernel
 //   backward D[unit, b] = sum_j W_hh[j, unit] dgates_{t+1}[b, j]                  (K = 1536; A = W_hh^T, MN-major)
 //            M = 64 units are presented twice (the two 64-row atoms of the A descriptor alias each other), so lanes 64-127
 //            hold a copy and the second half of the epilogue warps takes the second half of the batch columns; dc is
@@ -500,6 +501,230 @@ lstm_seq_bwd_kernel(const __grid_constant__ LstmSeqMaps maps, const LstmSeqParam
   if (warp == 2) tmem_dealloc(tm, TCOLS);
 }
 
+
+// =================================================================================================================
+// backward, narrow batch tiles (NB <= 32): gate-stacked formulation
+// =================================================================================================================
+// dh[u, b] = sum_j W_hh[j, u] dgates[b, j] has K = 1536: 96 MMAs per step whatever the batch tile holds, and an MMA
+// cannot be issued more often than every ~85 cycles.  Stacking the four gate blocks on BOTH output dimensions --
+// D[(g, u), (g', b)] = sum_k W_hh[g*384 + k, u] dgates[b, g'*384 + k], K = 384 -- needs 48 MMAs of N = 4 NB columns
+// (still at the issue floor for NB <= 32) and the wanted sum is the diagonal g == g'.  A = W_hh^T (a transposed copy made
+// by the launcher) in the same [4 gates x 8 units] x 64 k layout per TMEM lane quarter as the forward kernel, so the four
+// diagonal terms of a unit sit on four lanes of one warp: two shuffle rounds add them, and (as in the forward kernel) each
+// of the four lanes then does the cell backward of one of four batch columns.
+template <int NB, int UT>
+__global__ void __launch_bounds__(64 + 32 * (UT / 4), 1)
+lstm_seq_bwd_gs_kernel(const __grid_constant__ LstmSeqMaps maps, const LstmSeqParams p) {
+  constexpr int KB = PH / 64;                 // 6 k-blocks per step
+  constexpr int MT = UT / 32;                 // M tiles (4 gate blocks x 32 units each): 64 or 32 units per CTA, as forward
+  constexpr int W_KB_BYTES = MT * 16384;
+  constexpr int NN = 4 * NB;                  // MMA width: (gate, batch column)
+  constexpr int STAGE_B = NN * 128;           // one [4 NB x 64] bf16 k-block
+  constexpr int STAGES = P_RING_BYTES / STAGE_B;
+  constexpr int EPI_WARPS = 8 * MT;           // M tiles x 4 lane quarters x 2 column halves
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* s_w = smem;                        // [KB][2 M-tiles][128 rows x 128 B]
+  uint8_t* s_ring = smem + P_W_BYTES;         // [STAGES][4 gate blocks][NB rows x 128 B]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_ring + STAGES * STAGE_B);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* w_bar = empty_bar + STAGES;
+  uint64_t* done_bar = w_bar + 1;
+  uint64_t* free_bar = done_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(free_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u0 = blockIdx.x * UT, bt = blockIdx.y, rec = blockIdx.z;
+  const int b0 = p.b_first + bt * NB;
+  const int model = rec >> 1, dir = rec & 1;
+  int* flags = p.flags + ((size_t)rec * p.nbt + bt) * p.T;
+  constexpr uint32_t TCOLS = tmem_pow2(MT * NN);
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(w_bar, 1);
+    mbar_init(done_bar, 1);
+    mbar_init(free_bar, EPI_WARPS);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, TCOLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ loader: W_hh^T slice once, then dgates_{t+1} per step
+    if (elect_one()) {
+      mbar_arrive_expect_tx(w_bar, KB * W_KB_BYTES);
+      for (int kb = 0; kb < KB; ++kb)
+        for (int mq = 0; mq < UT / 8; ++mq)
+          tma_load_3d(&maps.w[rec], w_bar, s_w + kb * W_KB_BYTES + mq * 4096, kb * 64, u0 + mq * 8, 0);
+    }
+    __syncwarp();
+    if (elect_one()) {
+      uint32_t it = 0;
+      for (int step = 1; step < p.T; ++step) {
+        const int t = dir ? step : p.T - 1 - step;
+        const int t_next = dir ? t - 1 : t + 1;
+        wait_counter(flags + (step - 1), PH / UT);
+        fence_proxy_async_global();
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const uint32_t s = it % STAGES;
+          mbar_wait(&empty_bar[s], ((it / STAGES) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[s], STAGE_B);
+          for (int g = 0; g < 4; ++g)   // the k-block of every gate block: rows (g, b) of the B operand
+            tma_load_3d(&maps.act[model], &full_bar[s], s_ring + s * STAGE_B + g * (NB * 128), dir * PG + g * PH + kb * 64, b0,
+                        t_next);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    constexpr uint32_t IDESC = umma_idesc(UMMA_BF16, 128, NN, 0, 0);
+    if (elect_one()) mbar_wait(w_bar, 0);
+    __syncwarp();
+    uint32_t it = 0;
+    for (int step = 1; step < p.T; ++step) {
+      if (elect_one()) {
+        mbar_wait(free_bar, (uint32_t)(step - 1) & 1u);
+        tc_fence_after();
+        for (int kb = 0; kb < KB; ++kb) {
+          const uint32_t s = (it + kb) % STAGES;
+          mbar_wait(&full_bar[s], ((it + kb) / STAGES) & 1u);
+          tc_fence_after();
+          const uint32_t sb = smem_u32(s_ring + s * STAGE_B), sa = smem_u32(s_w + kb * W_KB_BYTES);
+#pragma unroll
+          for (int m = 0; m < MT; ++m)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc_mma_bf16(tm + m * NN, umma_desc_sw128(sa + m * 16384 + k * 32, 16, 1024),
+                          umma_desc_sw128(sb + k * 32, 16, 1024), IDESC, (kb > 0 || k > 0) ? 1u : 0u);
+          tc_commit(&empty_bar[s]);
+        }
+        tc_commit(done_bar);
+      }
+      __syncwarp();
+      it += KB;
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue
+    const int ew = warp - 2;
+    const int q = warp & 3, m = MT == 2 ? (ew >> 2) & 1 : 0, ch = MT == 2 ? ew >> 3 : ew >> 2;
+    const int gl = lane >> 3, ul = lane & 7;             // this lane's gate block and unit inside the quarter
+    const int u = u0 + (m * 4 + q) * 8 + ul;
+    constexpr int NGRP = NB / 8;                         // groups of 4 batch columns handled by this warp
+    const int colw = ch * (NB / 2);                      // its first column
+    const uint32_t trow = tm + ((uint32_t)(q * 32) << 16) + m * NN + colw;
+    float dcs[NGRP];
+#pragma unroll
+    for (int j = 0; j < NGRP; ++j) dcs[j] = 0.f;
+    const int nvalid = min(NB, p.B - b0) - colw;         // valid columns of this warp's range (may be <= 0)
+    constexpr uint32_t sg = 2u * PG * 4u, sc = 2u * PH * 4u, sy = 2u * PH * 2u, sd = 2u * PG * 2u;
+    const size_t tg = (size_t)p.B * sg, tcb = (size_t)p.B * sc, ty = (size_t)p.B * sy, td = (size_t)p.B * sd;
+    // this lane's cell of group j is (unit u, batch column b0 + colw + 4 j + gl)
+    const char* gx0 = reinterpret_cast<const char*>(p.gx[model] + (long long)(b0 + colw + gl) * (2 * PG) + dir * PG + u);
+    const char* c0p = reinterpret_cast<const char*>(p.c[model] + (long long)(b0 + colw + gl) * (2 * PH) + dir * PH + u);
+    const char* y0p = reinterpret_cast<const char*>(p.dy[model] + (long long)(b0 + colw + gl) * (2 * PH) + dir * PH + u);
+    char* d0p = reinterpret_cast<char*>(p.dg[model] + (long long)(b0 + colw + gl) * (2 * PG) + dir * PG + u);
+    struct Cell { float dy, ig, fg, gg, og, ct, cp; };
+    Cell cq[NGRP];
+    auto load_cell = [&](int tt, int j) {
+      Cell c{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (4 * j + gl < nvalid) {
+        const int t_pf = dir ? tt + 1 : tt - 1;     // forward-order predecessor (c_{t-1})
+        const bool has_prev = dir ? (tt < p.T - 1) : (tt > 0);
+        const float* g = reinterpret_cast<const float*>(gx0 + (size_t)tt * tg + (uint32_t)(4 * j) * sg);
+        c.ig = g[0]; c.fg = g[PH]; c.gg = g[2 * PH]; c.og = g[3 * PH];
+        c.ct = *reinterpret_cast<const float*>(c0p + (size_t)tt * tcb + (uint32_t)(4 * j) * sc);
+        c.cp = has_prev ? *reinterpret_cast<const float*>(c0p + (size_t)t_pf * tcb + (uint32_t)(4 * j) * sc) : 0.f;
+        c.dy = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(y0p + (size_t)tt * ty + (uint32_t)(4 * j) * sy));
+      }
+      return c;
+    };
+    {
+      const int t_first = dir ? 0 : p.T - 1;
+#pragma unroll
+      for (int j = 0; j < NGRP; ++j) cq[j] = load_cell(t_first, j);
+    }
+    for (int step = 0; step < p.T; ++step) {
+      const int t = dir ? step : p.T - 1 - step;
+      const int t_nxt = dir ? t + 1 : t - 1;
+      const bool more = step + 1 < p.T;
+      char* dgt = d0p + (size_t)t * td;
+      if (step > 0) {
+        mbar_wait(done_bar, (uint32_t)(step - 1) & 1u);
+        tc_fence_after();
+      }
+#pragma unroll
+      for (int j = 0; j < NGRP; ++j) {
+        const Cell c = cq[j];
+        if (more) cq[j] = load_cell(t_nxt, j);   // next step's operands are in flight during this step's arithmetic
+        float dhr = 0.f;
+        if (step > 0) {
+          // the lane's own gate block of the four (g', b) column blocks: D[(gl, u), (gl, 4j .. 4j+3)]
+          uint32_t a0[4], a1[4], a2[4], a3[4];
+          tmem_ld4(trow + 0 * NB + 4 * j, a0);
+          tmem_ld4(trow + 1 * NB + 4 * j, a1);
+          tmem_ld4(trow + 2 * NB + 4 * j, a2);
+          tmem_ld4(trow + 3 * NB + 4 * j, a3);
+          tmem_ld_wait();
+          float v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            v[e] = __uint_as_float(gl == 0 ? a0[e] : gl == 1 ? a1[e] : gl == 2 ? a2[e] : a3[e]);
+          // sum over the four gate lanes of the unit (lanes ul + 8 g): afterwards every lane holds dh for columns 4j..4j+3
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            v[e] += __shfl_xor_sync(0xffffffffu, v[e], 8);
+            v[e] += __shfl_xor_sync(0xffffffffu, v[e], 16);
+          }
+          dhr = gl == 0 ? v[0] : gl == 1 ? v[1] : gl == 2 ? v[2] : v[3];   // this lane's column: 4j + gl
+        }
+        if (4 * j + gl < nvalid) {
+          const float dh = c.dy + dhr;
+          const float tc = tanh_fast(c.ct);
+          const float dc = dcs[j] + dh * c.og * (1.f - tc * tc);
+          dcs[j] = dc * c.fg;
+          __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(dgt + (uint32_t)(4 * j) * sd);
+          dp[0] = __float2bfloat16(dc * c.gg * c.ig * (1.f - c.ig));
+          dp[PH] = __float2bfloat16(dc * c.cp * c.fg * (1.f - c.fg));
+          dp[2 * PH] = __float2bfloat16(dc * c.ig * (1.f - c.gg * c.gg));
+          dp[3 * PH] = __float2bfloat16(dh * tc * c.og * (1.f - c.og));
+        }
+      }
+      fence_proxy_async_global();
+      tc_fence_before();
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+      if (threadIdx.x == 64) {
+        __threadfence();
+        red_release_gpu_add(flags + step, 1);
+      }
+      if (lane == 0) mbar_arrive(free_bar);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tm, TCOLS);
+}
+
+// W_hh [1536][384] bf16 -> W_hh^T [384][1536] (one recurrence per blockIdx.z), 32 x 32 tiles through shared memory
+__global__ void __launch_bounds__(256)
+lstm_whh_transpose_kernel(const __nv_bfloat16* const w0, const __nv_bfloat16* const w1, const __nv_bfloat16* const w2,
+                          const __nv_bfloat16* const w3, __nv_bfloat16* __restrict__ out) {
+  __shared__ __nv_bfloat16 tile[32][33];
+  const __nv_bfloat16* w = blockIdx.z == 0 ? w0 : blockIdx.z == 1 ? w1 : blockIdx.z == 2 ? w2 : w3;
+  __nv_bfloat16* o = out + (size_t)blockIdx.z * PG * PH;
+  const int j0 = blockIdx.y * 32, u0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) tile[r][tx] = w[(size_t)(j0 + r) * PH + u0 + tx];
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) o[(size_t)(u0 + r) * PG + j0 + tx] = tile[tx][r];
+}
+
 }  // namespace pe
 
 // =================================================================================================================
@@ -507,8 +732,9 @@ lstm_seq_bwd_kernel(const __grid_constant__ LstmSeqMaps maps, const LstmSeqParam
 // =================================================================================================================
 using namespace pe;
 
+// mode: 0 forward, 1 backward (W_hh as stored, MN-major operand), 2 gate-stacked backward (w_hh = the transposed copies)
 static int seq_maps(LstmSeqMaps* m, const void* const* act, int act_cols, int B, int T, int NB, const void* const* w_hh,
-                    bool backward) {
+                    int mode) {
   for (int i = 0; i < 2; ++i) {
     uint64_t dims[3] = {(uint64_t)act_cols, (uint64_t)B, (uint64_t)T};   // time-major: [T][B][cols]
     uint64_t str[2] = {(uint64_t)act_cols * 2, (uint64_t)B * act_cols * 2};
@@ -516,7 +742,12 @@ static int seq_maps(LstmSeqMaps* m, const void* const* act, int act_cols, int B,
     if (int rc = pe_host::encode_tmap(&m->act[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, act[i], dims, str, box)) return rc;
   }
   for (int r = 0; r < 4; ++r) {
-    if (backward) {
+    if (mode == 2) {  // W_hh^T [unit][gate * 384 + k]: the same (k, unit, gate) box as the forward kernel's
+      uint64_t dims[3] = {(uint64_t)PH, (uint64_t)PH, 4};
+      uint64_t str[2] = {(uint64_t)PG * 2, (uint64_t)PH * 2};
+      uint32_t box[3] = {64, 8, 4};
+      if (int rc = pe_host::encode_tmap(&m->w[r], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, w_hh[r], dims, str, box)) return rc;
+    } else if (mode == 1) {
       uint64_t dims[2] = {(uint64_t)PH, (uint64_t)PG};
       uint64_t str[1] = {(uint64_t)PH * 2};
       uint32_t box[2] = {64, 64};
@@ -553,7 +784,19 @@ static SeqTiling seq_tiling(bool backward, int B) {
   static const int k_bnb = getenv("PE_LSTM_BWD_NB") ? atoi(getenv("PE_LSTM_BWD_NB")) : 0;
   auto valid_nb = [](int v) { return v == 16 || v == 32 || v == 64 || v == 96 || v == 128; };
   const int sms = pe_host::num_sms();
-  if (backward) return SeqTiling{64, valid_nb(k_bnb) ? k_bnb : narrowest_nb(B, sms / 24 > 0 ? sms / 24 : 1)};
+  if (backward) {
+    // gate-stacked kernel at 16- / 32-column tiles (measured backward layers, ms: 32 units x 16 columns 4.4, 64 x 16 5.1,
+    // 64 x 32 8.1; the 64 / 128-column tiles of the plain kernel 11.4 / 20.2)
+    static const int k_but = getenv("PE_LSTM_BWD_UT") ? atoi(getenv("PE_LSTM_BWD_UT")) : 0;
+    const int t32 = sms / 48 > 0 ? sms / 48 : 1, t64 = sms / 24 > 0 ? sms / 24 : 1;
+    SeqTiling t{64, narrowest_nb(B, t64)};
+    if ((B + 15) / 16 <= t32) t = SeqTiling{32, 16};
+    if (k_but == 32) t = SeqTiling{32, narrowest_nb(B, t32)};
+    if (k_but == 64) t = SeqTiling{64, narrowest_nb(B, t64)};
+    if (valid_nb(k_bnb)) t.nb = k_bnb;
+    if (t.nb > 32) t.ut = 64;  // (only the gate-stacked kernel of the narrow tiles has the 32-unit variant)
+    return t;
+  }
   const int nb32 = narrowest_nb(B, sms / 48 > 0 ? sms / 48 : 1), nb64 = narrowest_nb(B, sms / 24 > 0 ? sms / 24 : 1);
   // relative cost of a step at (UT, NB), from the measurements above
   auto cost = [](int ut, int nb) {
@@ -586,6 +829,23 @@ static int launch_seq(bool backward, int ut, const LstmSeqMaps& maps, LstmSeqPar
   return PE_OK;
 }
 
+template <int NB>
+static int launch_seq_gs(int ut, const LstmSeqMaps& maps, LstmSeqParams p, cudaStream_t st) {
+  const void* fn = ut == 32 ? (const void*)lstm_seq_bwd_gs_kernel<NB, 32> : (const void*)lstm_seq_bwd_gs_kernel<NB, 64>;
+  const size_t smem = (size_t)P_W_BYTES + P_RING_BYTES + 256 + 1024;
+  if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PE_ERR_LAUNCH;
+  void* args[2] = {(void*)&maps, (void*)&p};
+  if (cudaLaunchCooperativeKernel(fn, dim3(PH / ut, p.nbt, 4), dim3(64 + 32 * (ut / 4)), args, smem, st) != cudaSuccess)
+    return PE_ERR_LAUNCH;
+  return PE_OK;
+}
+
+// bytes of the arrival counters at the head of the workspace (the transposed weights of the gate-stacked backward follow)
+static size_t seq_flags_bytes(int T) {
+  const int max_bt = pe_host::num_sms() / 24 > 0 ? pe_host::num_sms() / 24 : 1;
+  return (((size_t)4 * max_bt * T * sizeof(int)) + 255) & ~(size_t)255;
+}
+
 static int run_seq(bool backward, LstmSeqParams p, const void* const* act, int act_cols, const void* const* w_hh,
                    int* flags, size_t flags_bytes, cudaStream_t st) {
   const int B = p.B, T = p.T;
@@ -596,14 +856,30 @@ static int run_seq(bool backward, LstmSeqParams p, const void* const* act, int a
   if (max_bt < 1) return PE_ERR_ARCH;
   const int nbt_launch = nbt_total < max_bt ? nbt_total : max_bt;
   if (!flags || flags_bytes < (size_t)4 * nbt_launch * T * sizeof(int)) return PE_ERR_WORKSPACE;
+  // narrow batch tiles: gate-stacked backward on a transposed copy of the weights (kept behind the counters)
+  static const bool gs_off = getenv("PE_LSTM_BWD_GS") && atoi(getenv("PE_LSTM_BWD_GS")) == 0;  // tuning knob
+  const bool gs = backward && NB <= 32 && !gs_off && flags_bytes >= seq_flags_bytes(T) + (size_t)4 * PG * PH * 2;
+  const void* wt[4];
+  if (gs) {
+    __nv_bfloat16* wbase = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(flags) + seq_flags_bytes(T));
+    lstm_whh_transpose_kernel<<<dim3(PH / 32, PG / 32, 4), 256, 0, st>>>(
+        (const __nv_bfloat16*)w_hh[0], (const __nv_bfloat16*)w_hh[1], (const __nv_bfloat16*)w_hh[2],
+        (const __nv_bfloat16*)w_hh[3], wbase);
+    for (int r = 0; r < 4; ++r) wt[r] = wbase + (size_t)r * PG * PH;
+  }
   LstmSeqMaps maps;
-  if (int rc = seq_maps(&maps, act, act_cols, B, T, NB, w_hh, backward)) return rc;
+  if (int rc = seq_maps(&maps, act, act_cols, B, T, NB, gs ? wt : w_hh, gs ? 2 : (backward ? 1 : 0))) return rc;
   for (int bt0 = 0; bt0 < nbt_total; bt0 += nbt_launch) {   // batch tiles are independent: chunk them if B is huge
     p.nbt = nbt_total - bt0 < nbt_launch ? nbt_total - bt0 : nbt_launch;
     p.b_first = bt0 * NB;
     p.flags = flags;
     if (cudaMemsetAsync(flags, 0, (size_t)4 * p.nbt * T * sizeof(int), st) != cudaSuccess) return PE_ERR_LAUNCH;
     int rc;
+    if (gs) {
+      rc = NB == 16 ? launch_seq_gs<16>(ut, maps, p, st) : launch_seq_gs<32>(ut, maps, p, st);
+      if (rc) return rc;
+      continue;
+    }
     switch (NB) {
       case 16: rc = launch_seq<16>(backward, ut, maps, p, st); break;
       case 32: rc = launch_seq<32>(backward, ut, maps, p, st); break;

@@ -454,11 +454,11 @@ class Engine:
                 out.append((prefix, "l%d%s" % (layer, sfx)))
         return out  # index = model * 2 + direction
 
-    def _lstm_workspace(self, B, T):
+    def _lstm_workspace(self, B, T, op=b"pe_lstm_seq_fwd"):
         fn = L.lib().pe_workspace_bytes
         fn.restype = ctypes.c_longlong
-        need = int(fn(b"pe_lstm_seq_fwd", c_int(B), c_int(T), c_int(0)))
-        return self.buf("lstm_flags", (max(need, 4) // 4,), torch.int32)
+        need = int(fn(op, c_int(B), c_int(T), c_int(0)))
+        return self.buf("lstm_ws_" + op.decode(), ((max(need, 4) + 3) // 4,), torch.int32)
 
     def _bilstm_fwd(self, Xc, Xd, B, T, training):
         V, W16 = self.view, self.bview
@@ -524,7 +524,7 @@ class Engine:
             # measured on a B200 (profiles/r02_lstm_breakdown.txt): the persistent backward wins while the batch tile is
             # narrow (its epilogue is then latency-bound); at 128-column tiles the per-step launches are faster
             if self.lstm_persistent and B <= self.lstm_persistent_bwd_max_batch:
-                ws = self._lstm_workspace(B, T)
+                ws = self._lstm_workspace(B, T, b"pe_lstm_seq_bwd")
                 call("pe_lstm_seq_bwd", c_int(B), c_int(T), c_int(Hh), gx_a, c_a, dy_a, dg_a, whh, ptr(ws),
                      ctypes.c_size_t(ws.numel() * 4), stream())
             else:
