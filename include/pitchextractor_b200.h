@@ -256,7 +256,10 @@ int pe_lstm_steps_bwd(int B, int T, int hidden, int step_begin, int step_end, co
 /* The same recurrences as ONE persistent launch per layer over all T steps (north_star: "persistent kernel with its
  * weights resident in shared memory"): every CTA keeps its 192 KB slice of W_hh in shared memory, h_t / dgates_t are
  * exchanged through L2 with a per-step arrival counter.  Same tensors as above; the cell-state gradient is carried in
- * registers.  workspace: pe_workspace_bytes("pe_lstm_seq_fwd", B, T, 0) bytes of device memory (zeroed by the call). */
+ * registers.  workspace: pe_workspace_bytes("pe_lstm_seq_fwd" / "pe_lstm_seq_bwd", B, T, 0) bytes of device memory: the
+ * arrival counters (zeroed by the call) and, for the backward, room for a transposed copy of the four W_hh (written by
+ * the call; used by the gate-stacked kernel of narrow batch tiles -- with a workspace that only holds the counters the
+ * call falls back to the plain kernel). */
 int pe_lstm_seq_fwd(int B, int T, int hidden, float* const* gx, float* const* c, void* const* y,
                     const void* const* w_hh, const float* const* b_ih, const float* const* b_hh, void* workspace,
                     size_t workspace_bytes, pe_stream_t stream);
