@@ -520,12 +520,13 @@ lstm_seq_bwd_gs_kernel(const __grid_constant__ LstmSeqMaps maps, const LstmSeqPa
   constexpr int W_KB_BYTES = MT * 16384;
   constexpr int NN = 4 * NB;                  // MMA width: (gate, batch column)
   constexpr int STAGE_B = NN * 128;           // one [4 NB x 64] bf16 k-block
-  constexpr int STAGES = P_RING_BYTES / STAGE_B;
+  // ring: with 32 units per CTA the weights take 96 KB, so a whole step's six k-blocks can be in flight
+  constexpr int STAGES = UT == 32 ? (6 * STAGE_B <= 98304 ? 6 : 98304 / STAGE_B) : P_RING_BYTES / STAGE_B;
   constexpr int EPI_WARPS = 8 * MT;           // M tiles x 4 lane quarters x 2 column halves
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* s_w = smem;                        // [KB][2 M-tiles][128 rows x 128 B]
-  uint8_t* s_ring = smem + P_W_BYTES;         // [STAGES][4 gate blocks][NB rows x 128 B]
+  uint8_t* s_w = smem;                        // [KB][M tiles][128 rows x 128 B]
+  uint8_t* s_ring = smem + KB * W_KB_BYTES;   // [STAGES][4 gate blocks][NB rows x 128 B]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_ring + STAGES * STAGE_B);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* w_bar = empty_bar + STAGES;
@@ -832,7 +833,7 @@ static int launch_seq(bool backward, int ut, const LstmSeqMaps& maps, LstmSeqPar
 template <int NB>
 static int launch_seq_gs(int ut, const LstmSeqMaps& maps, LstmSeqParams p, cudaStream_t st) {
   const void* fn = ut == 32 ? (const void*)lstm_seq_bwd_gs_kernel<NB, 32> : (const void*)lstm_seq_bwd_gs_kernel<NB, 64>;
-  const size_t smem = (size_t)P_W_BYTES + P_RING_BYTES + 256 + 1024;
+  const size_t smem = (size_t)P_W_BYTES + P_RING_BYTES + 256 + 1024;  // (32 units: 96 KB of weights + up to 96 KB of ring)
   if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PE_ERR_LAUNCH;
   void* args[2] = {(void*)&maps, (void*)&p};
   if (cudaLaunchCooperativeKernel(fn, dim3(PH / ut, p.nbt, 4), dim3(64 + 32 * (ut / 4)), args, smem, st) != cudaSuccess)
