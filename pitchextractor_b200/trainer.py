@@ -9,6 +9,7 @@ Differences that follow from the B200 design (documented, not hidden):
   * under torch.distributed (one process per GPU) gradients are all-reduced in overlapped buckets.
 """
 import logging
+import collections
 import os
 from collections import defaultdict
 
@@ -48,6 +49,7 @@ class Trainer(object):
             self.logger.info("gradient_checkpointing ignored: activations stay resident in HBM")
         self._logmel = None
         self._copy_stream = None
+        self._loss_ring = []   # pinned [3] buffers of run_pipelined
         self._reducer = None
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.sync_every_step = True  # reference semantics: run() returns python floats (3 .item() syncs there, 1 here)
@@ -215,13 +217,21 @@ class Trainer(object):
         losses = self.run_async(batch).tolist()  # one device->host read of 3 floats
         return {"loss": losses[0], "f0": losses[1], "sil": losses[2]}
 
-    def run_pipelined(self, batches):
-        """``run`` over an iterable of host batches, yielding the same ``{'loss','f0','sil'}`` floats per batch, but one
-        step behind the GPU: step i+1 (its host->device copies, log-mel, graph replay, optimizer) is enqueued before the
-        host waits for the three loss floats of step i, which travel through a small ring of pinned buffers.  The GPU
-        never idles while Python prepares the next step; every batch is still copied in and every loss read back."""
-        ring = [torch.empty(3, dtype=torch.float32).pin_memory() for _ in range(3)]
-        pending, k = None, 0
+    def run_pipelined(self, batches, depth=None):
+        """``run`` over an iterable of host batches, yielding the same ``{'loss','f0','sil'}`` floats per batch, but up to
+        ``depth`` steps behind the GPU (default 4, ``PE_PIPELINE_DEPTH``): steps i+1 .. i+depth (host->device copies,
+        log-mel, graph replay, optimizer) are enqueued before the host waits for the three loss floats of step i, which
+        travel through a small ring of pinned buffers.  The GPU does not idle while Python prepares the next step, and a
+        host hiccup shorter than ``depth`` steps (a descheduled thread, a garbage collection) is absorbed by the queue;
+        every batch is still copied in and every loss read back, in order."""
+        if depth is None:
+            depth = int(os.environ.get("PE_PIPELINE_DEPTH", "4"))
+        depth = max(1, depth)
+        if len(self._loss_ring) < depth + 2:  # pinned once: a pinned allocation inside the loop can stall the GPU queue
+            self._loss_ring += [torch.empty(3, dtype=torch.float32).pin_memory()
+                                for _ in range(depth + 2 - len(self._loss_ring))]
+        ring = self._loss_ring[:depth + 2]
+        pending, k = collections.deque(), 0
 
         def resolve(item):
             host, ev = item
@@ -236,11 +246,11 @@ class Trainer(object):
             host.copy_(dev_losses, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record()
-            if pending is not None:
-                yield resolve(pending)
-            pending = (host, ev)
-        if pending is not None:
-            yield resolve(pending)
+            pending.append((host, ev))
+            if len(pending) > depth:
+                yield resolve(pending.popleft())
+        while pending:
+            yield resolve(pending.popleft())
 
     def _train_epoch(self):
         self.epochs += 1
